@@ -1,0 +1,167 @@
+"""ctypes front end of the oracle (test infrastructure).
+
+* `Oracle`      -- oracle/sdr_oracle.c, the plain-C restatement (one object = one stream)
+* `run_ref`     -- oracle/_ref/sdr_ref_{i16,f32}, the unmodified reference hot path
+* `ref_prims()` -- oracle/_ref/libref_prims.so, the reference's own DSP classes
+
+Only tests/, __graft_entry__.smoke() and bench.py's CPU legs import this module.
+"""
+import ctypes as C
+import os
+import subprocess
+import tempfile
+
+import numpy as np
+
+HERE = os.path.dirname(os.path.abspath(__file__))
+REF_DIR = os.path.join(HERE, "_ref")
+_lib = None
+_prims = None
+
+
+def build(force=False):
+    """make -C oracle (C restatement always; _ref only where /root/reference exists)."""
+    if force or not os.path.exists(os.path.join(HERE, "libsdr_oracle.so")) \
+            or (os.path.exists("/root/reference/vfo.cpp") and not have_ref()):
+        subprocess.run(["make", "-C", HERE, "all"], check=True, capture_output=True)
+
+
+def have_ref():
+    return all(os.path.exists(os.path.join(REF_DIR, f))
+               for f in ("sdr_ref_i16", "sdr_ref_f32", "libref_prims.so"))
+
+
+def lib():
+    global _lib
+    if _lib is None:
+        build()
+        L = C.CDLL(os.path.join(HERE, "libsdr_oracle.so"))
+        vp, i, d, f, l = C.c_void_p, C.c_int, C.c_double, C.c_float, C.c_long
+        L.orc_create.restype = vp; L.orc_create.argtypes = [i, i, i]
+        L.orc_add_main.restype = i; L.orc_add_main.argtypes = [vp, d, i, i]
+        L.orc_add_sub.restype = i; L.orc_add_sub.argtypes = [vp, i, i, d, i, i, i, i, f]
+        L.orc_process.restype = None; L.orc_process.argtypes = [vp, vp, l]
+        L.orc_sub_count.restype = l; L.orc_sub_count.argtypes = [vp, i]
+        L.orc_sub_pcm.restype = vp; L.orc_sub_pcm.argtypes = [vp, i]
+        L.orc_sub_tap.restype = vp; L.orc_sub_tap.argtypes = [vp, i]
+        L.orc_main_count.restype = l; L.orc_main_count.argtypes = [vp, i]
+        L.orc_main_tap.restype = vp; L.orc_main_tap.argtypes = [vp, i]
+        L.orc_clear_outputs.restype = None; L.orc_clear_outputs.argtypes = [vp]
+        L.orc_destroy.restype = None; L.orc_destroy.argtypes = [vp]
+        L.orc_oscillator.restype = None; L.orc_oscillator.argtypes = [d, d, vp, l]
+        L.orc_oscillator_table.restype = i; L.orc_oscillator_table.argtypes = [d, d, vp, l]
+        L.orc_halfband.restype = None; L.orc_halfband.argtypes = [vp, i, i, vp]
+        L.orc_fir.restype = None; L.orc_fir.argtypes = [i, vp, vp, l, i, vp]
+        L.orc_hilbert_points.restype = None; L.orc_hilbert_points.argtypes = [i, i, vp]
+        L.orc_usb.restype = None; L.orc_usb.argtypes = [i, i, vp, l, vp]
+        L.orc_low_pass.restype = i; L.orc_low_pass.argtypes = [d, d, d, d, vp, i]
+        _lib = L
+    return _lib
+
+
+def ref_prims():
+    global _prims
+    if _prims is None:
+        L = C.CDLL(os.path.join(REF_DIR, "libref_prims.so"))
+        vp, i, d, l = C.c_void_p, C.c_int, C.c_double, C.c_long
+        L.ref_oscillator.restype = None; L.ref_oscillator.argtypes = [d, d, vp, l]
+        L.ref_halfband.restype = None; L.ref_halfband.argtypes = [i, i, vp, i, i, vp]
+        L.ref_fir.restype = None; L.ref_fir.argtypes = [i, vp, vp, l, i, vp]
+        L.ref_hilbert_points.restype = None; L.ref_hilbert_points.argtypes = [i, i, vp]
+        L.ref_usb.restype = None; L.ref_usb.argtypes = [i, i, vp, l, vp]
+        L.ref_low_pass.restype = i; L.ref_low_pass.argtypes = [d, d, d, d, vp, i]
+        L.ref_kiss_fft.restype = None; L.ref_kiss_fft.argtypes = [i, vp, vp]
+        _prims = L
+    return _prims
+
+
+def _p(a):
+    return a.ctypes.data_as(C.c_void_p)
+
+
+class Oracle:
+    """One stream of one plan through the C restatement."""
+
+    def __init__(self, plan, main_tap=False):
+        L = lib()
+        self.plan = plan
+        self.h = L.orc_create(plan["Fs"], plan["block"], int(plan["dc"]))
+        for m in plan["mains"]:
+            assert L.orc_add_main(self.h, m["mixer"], m["decim"], int(main_tap)) >= 0
+        for s in plan["subs"]:
+            assert L.orc_add_sub(self.h, s["main"], s["Fs"], s["mixer"], s["decim"],
+                                 s["samples_per_buffer"], s["late"], s["filterbw"], s["gain"]) >= 0
+
+    def process(self, iq_u8):
+        iq = np.ascontiguousarray(iq_u8, dtype=np.uint8)
+        nblocks = iq.size // (2 * self.plan["block"])
+        lib().orc_process(self.h, _p(iq), nblocks)
+        return nblocks
+
+    def _arr(self, ptr, n, dtype):
+        if n == 0:
+            return np.zeros(0, dtype)
+        buf = (C.c_char * (n * np.dtype(dtype).itemsize)).from_address(ptr)
+        return np.frombuffer(buf, dtype=dtype).copy()
+
+    def pcm(self, s):
+        L = lib()
+        return self._arr(L.orc_sub_pcm(self.h, s), L.orc_sub_count(self.h, s), np.int16)
+
+    def tap(self, s):
+        L = lib()
+        return self._arr(L.orc_sub_tap(self.h, s), L.orc_sub_count(self.h, s), np.float32)
+
+    def main_tap(self, m):
+        L = lib()
+        n = L.orc_main_count(self.h, m)
+        return self._arr(L.orc_main_tap(self.h, m), 2 * n, np.float32).view(np.complex64)
+
+    def clear(self):
+        lib().orc_clear_outputs(self.h)
+
+    def close(self):
+        if self.h:
+            lib().orc_destroy(self.h)
+            self.h = None
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass
+
+
+def run_ref(ini_path, iq_u8, float_tap=False, main_tap=False, blocks=None):
+    """Run the unmodified reference on `iq_u8`. Returns (outputs, frames, mains):
+    outputs[topic] = int16 (or float32) array, frames = list of (topic_bytes, rate,
+    payload_bytes, parts), mains[k] = complex64 decimate[decimateCount] of main k."""
+    exe = os.path.join(REF_DIR, "sdr_ref_f32" if float_tap else "sdr_ref_i16")
+    with tempfile.TemporaryDirectory() as d:
+        inp = os.path.join(d, "iq.u8")
+        np.ascontiguousarray(iq_u8, dtype=np.uint8).tofile(inp)
+        cmd = [exe, "--ini", ini_path, "--in", inp, "--out", d]
+        if main_tap:
+            cmd.append("--main-tap")
+        if blocks is not None:
+            cmd += ["--blocks", str(blocks)]
+        subprocess.run(cmd, check=True)
+        outs, frames, mains = {}, [], {}
+        for fn in sorted(os.listdir(d)):
+            if fn.endswith(".pcm"):
+                outs[fn[:-4]] = np.fromfile(os.path.join(d, fn), dtype=np.float32 if float_tap else np.int16)
+            elif fn.startswith("main") and fn.endswith(".cf32"):
+                mains[int(fn[4:-5])] = np.fromfile(os.path.join(d, fn), dtype=np.complex64)
+        with open(os.path.join(d, "frames.txt")) as f:
+            for line in f:
+                t, rate, nb, parts = line.split()
+                frames.append((bytes.fromhex(t), int(rate), int(nb), int(parts)))
+    return outs, frames, mains
+
+
+def time_ref(ini_path, iq_path, blocks):
+    """Seconds the reference spends in byte->float + demodData for `blocks` callbacks."""
+    exe = os.path.join(REF_DIR, "sdr_ref_i16")
+    out = subprocess.run([exe, "--ini", ini_path, "--in", iq_path, "--time", "--blocks", str(blocks)],
+                         check=True, capture_output=True, text=True).stdout.split()
+    return int(out[0]), float(out[1])

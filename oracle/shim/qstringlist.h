@@ -1,0 +1,1 @@
+#include "qshim_core.h"
