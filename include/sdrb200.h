@@ -1,0 +1,197 @@
+/*
+ * sdrb200.h -- C ABI of libsdrb200.so, the B200 (sm_100a) channelizer that replaces the
+ * CPU hot path of jeroenbeijer/SDRReceiver:
+ *
+ *   uint8 IQ -> (x-127) -> DC removal -> per main VFO: NCO mix + 11-tap half-band cascade
+ *            -> per sub VFO: NCO mix + half-band cascade [+ /5 or /6 FIR] -> USB demod
+ *               (delay62 - Hilbert125) [-> filter_bandwidth low-pass] -> gain -> int16
+ *
+ * The reference has no FFI layer; its boundary is the C++ class surface.
+ * Each entry point below names the reference code it stands in for (paths relative to the
+ * SDRReceiver source tree). The header-compatible C++ facades (sdrreceiver_b200/host/) and
+ * the Python binding (sdrreceiver_b200/binding.py) are thin layers over exactly this ABI.
+ *
+ * Conventions: plain C, caller-owned buffers, every function returns 0 on success or a
+ * negative SDRB_E_* code and never throws; sdrb_last_error() gives the message of the last
+ * failure on the calling thread. There is no CPU fallback: without a CUDA device the
+ * compute entry points fail with SDRB_E_CUDA.
+ */
+#ifndef SDRB200_H
+#define SDRB200_H
+
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define SDRB_OK 0
+#define SDRB_E_INVALID (-1)     /* bad argument / unsupported plan */
+#define SDRB_E_IO (-2)          /* ini file unreadable */
+#define SDRB_E_CUDA (-3)        /* CUDA runtime error or no device */
+#define SDRB_E_NOMEM (-4)
+#define SDRB_E_ZMQ (-5)         /* libzmq not loadable / socket error */
+
+#define SDRB_MAX_MAIN 8         /* the reference caps main VFOs at 3 (mainwindow.h:82) */
+#define SDRB_MAX_SUB 256
+#define SDRB_TOPIC_LEN 5        /* ZMQ topic frame is exactly 5 bytes (zmqpublisher.cpp:91) */
+
+typedef struct sdrb_plan sdrb_plan;   /* immutable VFO plan: rates, tree, NCO tables, taps */
+typedef struct sdrb_bank sdrb_bank;   /* n_streams receivers of one plan on one GPU: carry
+                                         state (DC, sample counters, filter tails) + work buffers */
+
+/* ---- plan description (what MainWindow::MainWindow computes, mainwindow.cpp:29-235) ---- */
+typedef struct {
+    double mixer_hz;        /* center_frequency - frequency          (mainwindow.cpp:131) */
+    int32_t decim;          /* half-band stages                      (mainwindow.cpp:130) */
+} sdrb_main_desc;
+
+typedef struct {
+    char topic[8];          /* zmq topic, first 5 bytes are sent     (mainwindow.cpp:193) */
+    int32_t main_idx;       /* parent main VFO                       (mainwindow.cpp:178-191) */
+    double mixer_hz;        /* main_freq - (frequency + mix_offset)  (mainwindow.cpp:220) */
+    int32_t decim;          /* half-band stages                      (mainwindow.cpp:197-216) */
+    int32_t late;           /* 0, or the /5 or /6 FIR decimation     (mainwindow.cpp:197-210) */
+    int32_t filter_bw;      /* filter_bandwidth Hz, 0 = off          (mainwindow.cpp:218) */
+    float gain;             /* ini gain / 100                        (mainwindow.cpp:219) */
+} sdrb_sub_desc;
+
+typedef struct {
+    int32_t sample_rate;    /* 288000 | 1536000 | 1920000            (mainwindow.h:29) */
+    int32_t block;          /* complex samples per callback = buflen/2 (mainwindow.cpp:67-80) */
+    int32_t bufsplit;       /* callbacks per second, 4 or 5 */
+    int32_t correct_dc;     /* correct_dc_bias                       (mainwindow.cpp:96) */
+    int32_t n_main, n_sub;
+    sdrb_main_desc mains[SDRB_MAX_MAIN];
+    sdrb_sub_desc subs[SDRB_MAX_SUB];
+} sdrb_plan_desc;
+
+typedef struct {
+    int32_t sample_rate, block, bufsplit, correct_dc, n_main, n_sub;
+    int32_t center_frequency;     /* 0 when the plan was not built from an ini */
+    int32_t pcm_per_block;        /* int16 samples per stream per callback, all sub VFOs */
+    double alg_bytes_per_sample;  /* 2 + 2*sum(out_rate)/Fs             */
+    double alg_flops_per_sample;  /* SURVEY.md 8(d) counting rule */
+    char zmq_address[128];
+} sdrb_plan_info;
+
+typedef struct {
+    double mixer_hz;
+    int32_t frequency;            /* absolute Hz (ini plans), else 0 */
+    int32_t decim, out_rate, block_out;   /* block_out = block >> decim */
+} sdrb_main_info;
+
+typedef struct {
+    char topic[8];
+    int32_t frequency, data_rate; /* ini values (0 when built from a desc) */
+    int32_t main_idx, decim, late, filter_bw;
+    float gain;
+    double mixer_hz;
+    int32_t in_rate;              /* parent's output rate = this VFO's Fs */
+    int32_t out_rate;             /* audio rate sent as ZMQ frame 2 */
+    int32_t samples_out;          /* int16 samples per callback = ZMQ frame 3 / 2 */
+    int32_t pcm_offset;           /* offset of this VFO inside one stream-callback record */
+    int32_t n_dec_taps, n_lpf_taps;
+} sdrb_sub_info;
+
+/* Plan compiler: QSettings ini grammar + mainwindow.cpp:29-235, Qt-free. */
+int sdrb_plan_from_ini(const char *ini_path, sdrb_plan **out);
+/* Same plan from explicit numbers (what the vfo setters carry, vfo.cpp:177-233). */
+int sdrb_plan_create(const sdrb_plan_desc *desc, sdrb_plan **out);
+void sdrb_plan_destroy(sdrb_plan *plan);
+int sdrb_plan_get_info(const sdrb_plan *plan, sdrb_plan_info *info);
+int sdrb_plan_get_main(const sdrb_plan *plan, int idx, sdrb_main_info *info);
+int sdrb_plan_get_sub(const sdrb_plan *plan, int idx, sdrb_sub_info *info);
+/* Host copies of the tables vfo::init builds (vfo.cpp:60-137), for inspection/tests:
+ * kind 0 = main NCO table (cf32, (int)Fs entries), 1 = sub NCO table, 2 = sub /late FIR
+ * taps, 3 = sub low-pass taps, 4 = Hilbert points (125). Returns the element count
+ * (complex entries for 0/1, floats otherwise); copies at most max_elems. */
+long sdrb_plan_copy_table(const sdrb_plan *plan, int kind, int idx, float *dst, long max_elems);
+
+/* ---- receiver bank: replaces sdrj + the vfo tree for n_streams independent dongles ---- */
+int sdrb_bank_create(const sdrb_plan *plan, int device, int n_streams, int max_blocks, sdrb_bank **out);
+void sdrb_bank_destroy(sdrb_bank *bank);
+/* Fresh filter/NCO/DC state, as after constructing the reference objects. stream = -1: all. */
+int sdrb_bank_reset(sdrb_bank *bank, int stream);
+/* Per-stream blocks consumed so far (sample counter / block). */
+int sdrb_bank_blocks_done(sdrb_bank *bank, int stream, int64_t *blocks);
+
+/*
+ * n_blocks callbacks for every stream of the bank, everything resident on the device.
+ * Stands in for n_blocks x { sdr::rtlsdr_callback (jonti/sdr.cpp:100-145) -> sdrj::demodData
+ * (sdrj.cpp:266-305) -> vfo::process tree (vfo.cpp:235-296) } per stream.
+ *   d_iq   device, stream s at d_iq + s*iq_stride, n_blocks*block*2 bytes of uint8 I,Q
+ *   d_pcm  device int16 [n_streams][n_blocks][pcm_per_block]; VFO v of callback b of stream s
+ *          starts at ((s*n_blocks + b)*pcm_per_block + pcm_offset[v]) -- each slice is one
+ *          ready-made ZMQ payload (vfo::transmitData, vfo.cpp:426-453)
+ *   d_tap  optional (NULL = off) float32, same layout: usb*gain*32768 before conversion
+ *   stream cudaStream_t (NULL = default stream); the call only enqueues work
+ */
+int sdrb_bank_process_device(sdrb_bank *bank, const uint8_t *d_iq, size_t iq_stride, int n_blocks,
+                             int16_t *d_pcm, float *d_tap, void *cuda_stream);
+/* Copy out the main VFO outputs (vfo::decimate[decimateCount], vfo.h:39) of the last
+ * process call: cf32 [n_streams][n_blocks*block_out] on the device. */
+int sdrb_bank_copy_main(sdrb_bank *bank, int main_idx, int n_blocks, float *d_out_cf32, void *cuda_stream);
+
+/*
+ * Host-facing call: same work with HOST buffers (pinned from sdrb_host_alloc for full
+ * speed; pageable memory works but is staged by the driver). Copies in, runs, copies out
+ * and returns when h_pcm is complete. Streams are split into groups whose H2D copy,
+ * kernels and D2H copy overlap on separate CUDA streams.
+ */
+int sdrb_bank_process_host(sdrb_bank *bank, const uint8_t *h_iq, size_t iq_stride, int n_blocks,
+                           int16_t *h_pcm, float *h_tap);
+/* Kernel launches issued by the last process_* call (for bench.py's gpu_launches). */
+int sdrb_bank_last_launches(const sdrb_bank *bank);
+
+void *sdrb_host_alloc(size_t bytes);   /* cudaHostAlloc'd (pinned) */
+void sdrb_host_free(void *p);
+
+/* ---- per-class primitives backing the C++ facades (device pointers, batch of `n_ch`
+ *      independent channels laid out channel-major) ---- */
+/* Oscillator (oscillator.cpp:4-50): host-built table, bit-identical to the reference. */
+long sdrb_nco_table(double sample_rate, double frequency, float *dst_cf32, long max_entries);
+/* vfo::process mix loop (vfo.cpp:237-245): out[i] = table[idx(n0+i)] * in[i]. */
+int sdrb_nco_mix(const float *d_table_cf32, int table_len, int64_t n0, const float *d_in_cf32,
+                 float *d_out_cf32, int n_ch, int n, void *cuda_stream);
+/* HalfBandDecimator::decimate (halfbanddecimator.cpp:43-72), taps = 11: one call = one
+ * block of n (even) samples per channel; d_hist holds the 11-sample queue head per channel
+ * and is updated with the reference's off-by-one carry (jonti/dsp.cpp:163-173). */
+int sdrb_halfband11(const float *d_in_cf32, float *d_out_cf32, float *d_hist_cf32, int n_ch, int n,
+                    void *cuda_stream);
+/* FIR::FIRUpdateAndProcess over a block (jonti/dsp.cpp:59-71): newest sample excluded;
+ * d_hist = last ntaps inputs per channel (updated); decim >= 1 keeps every decim-th output
+ * starting with the first (vfo::usb_decimdemod, vfo.cpp:334-387). */
+int sdrb_fir(const float *d_taps, int ntaps, const float *d_in, float *d_out, float *d_hist, int n_ch,
+             int n, int decim, void *cuda_stream);
+/* delay(62)(re) - FIRHilbert125(im) (vfo.cpp:316-324; jonti/dsp.cpp:184-231); d_points = the
+ * 125 FIRHilbert coefficients on the device (sdrb_hilbert_points), d_hist = last 124 complex
+ * inputs per channel (updated). */
+int sdrb_usb_demod(const float *d_points, const float *d_in_cf32, float *d_out, float *d_hist_cf32,
+                   int n_ch, int n, void *cuda_stream);
+/* gnuradio firdes low_pass, Hamming (gnuradio/firfilter.cpp:64-108). Returns ntaps or
+ * SDRB_E_INVALID where the reference throws std::out_of_range. Host only. */
+int sdrb_low_pass(double gain, double fs, double cutoff, double tw, float *taps, int max_taps);
+/* FIRHilbert coefficients (jonti/dsp.cpp:198-216). Host only. */
+int sdrb_hilbert_points(int len, int fs, float *points);
+
+/* ---- spectrum path: Hann window + 8192-point FFT (mainwindow.cpp:411-455, kiss_fft) ---- */
+int sdrb_spectrum_fft(const float *d_in_cf32, float *d_out_cf32, int n_batch, int nfft, int apply_hann,
+                      void *cuda_stream);
+
+/* ---- ZMQ output (zmqpublisher.cpp:15-96), libzmq loaded at run time ---- */
+typedef struct sdrb_publisher sdrb_publisher;
+int sdrb_publisher_open(const char *address, int bind, sdrb_publisher **out);
+int sdrb_publisher_send(sdrb_publisher *p, const char *topic, uint32_t rate, const void *payload, uint32_t len);
+/* One multipart message per sub VFO per callback per stream from a process_host result. */
+int sdrb_publisher_send_block(sdrb_publisher *p, const sdrb_plan *plan, const int16_t *h_pcm_record);
+void sdrb_publisher_close(sdrb_publisher *p);
+
+const char *sdrb_last_error(void);
+const char *sdrb_version(void);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* SDRB200_H */

@@ -1,0 +1,685 @@
+// C ABI of libsdrb200.so (include/sdrb200.h): plan upload, receiver bank, launches.
+// Host logic only; the kernels live in kernels.cuh / prims.cuh. No CPU compute path exists
+// here: every process_* entry point fails with SDRB_E_CUDA when no device is usable.
+#include <cuda_runtime.h>
+
+#include <algorithm>
+#include <cmath>
+#include <cstdio>
+#include <cstring>
+#include <map>
+#include <new>
+#include <string>
+#include <vector>
+
+#include "plan.hpp"
+#include "kernels.cuh"
+#include "prims.cuh"
+
+namespace sdrb {
+const char *last_error_cstr();
+}
+using namespace sdrb;
+
+#define CU_TRY(expr)                                                                           \
+    do {                                                                                       \
+        cudaError_t e_ = (expr);                                                               \
+        if (e_ != cudaSuccess) {                                                               \
+            set_error(std::string(#expr) + ": " + cudaGetErrorString(e_));                     \
+            return SDRB_E_CUDA;                                                                \
+        }                                                                                      \
+    } while (0)
+
+// ------------------------------------------------------------------------------------
+// plan
+// ------------------------------------------------------------------------------------
+struct sdrb_plan {
+    HostPlan h;
+};
+
+extern "C" int sdrb_plan_from_ini(const char *ini_path, sdrb_plan **out) {
+    if (!out) { set_error("sdrb_plan_from_ini: out is NULL"); return SDRB_E_INVALID; }
+    *out = nullptr;
+    sdrb_plan *p = new (std::nothrow) sdrb_plan();
+    if (!p) return SDRB_E_NOMEM;
+    const int rc = plan_from_ini(ini_path, p->h);
+    if (rc != SDRB_OK) { delete p; return rc; }
+    *out = p;
+    return SDRB_OK;
+}
+
+extern "C" int sdrb_plan_create(const sdrb_plan_desc *desc, sdrb_plan **out) {
+    if (!desc || !out) { set_error("sdrb_plan_create: NULL argument"); return SDRB_E_INVALID; }
+    *out = nullptr;
+    sdrb_plan *p = new (std::nothrow) sdrb_plan();
+    if (!p) return SDRB_E_NOMEM;
+    const int rc = plan_from_desc(*desc, p->h);
+    if (rc != SDRB_OK) { delete p; return rc; }
+    *out = p;
+    return SDRB_OK;
+}
+
+extern "C" void sdrb_plan_destroy(sdrb_plan *plan) { delete plan; }
+
+extern "C" int sdrb_plan_get_info(const sdrb_plan *plan, sdrb_plan_info *info) {
+    if (!plan || !info) { set_error("sdrb_plan_get_info: NULL argument"); return SDRB_E_INVALID; }
+    const HostPlan &h = plan->h;
+    memset(info, 0, sizeof(*info));
+    info->sample_rate = h.fs; info->block = h.block; info->bufsplit = h.bufsplit;
+    info->correct_dc = h.correct_dc; info->n_main = (int)h.mains.size(); info->n_sub = (int)h.subs.size();
+    info->center_frequency = h.center; info->pcm_per_block = h.pcm_per_block;
+    info->alg_bytes_per_sample = h.alg_bytes; info->alg_flops_per_sample = h.alg_flops;
+    strncpy(info->zmq_address, h.zmq_address.c_str(), sizeof(info->zmq_address) - 1);
+    return SDRB_OK;
+}
+
+extern "C" int sdrb_plan_get_main(const sdrb_plan *plan, int idx, sdrb_main_info *info) {
+    if (!plan || !info || idx < 0 || idx >= (int)plan->h.mains.size()) {
+        set_error("sdrb_plan_get_main: bad argument"); return SDRB_E_INVALID;
+    }
+    const MainVfo &m = plan->h.mains[(size_t)idx];
+    info->mixer_hz = m.mixer; info->frequency = m.frequency; info->decim = m.decim;
+    info->out_rate = m.out_rate; info->block_out = m.block_out;
+    return SDRB_OK;
+}
+
+extern "C" int sdrb_plan_get_sub(const sdrb_plan *plan, int idx, sdrb_sub_info *info) {
+    if (!plan || !info || idx < 0 || idx >= (int)plan->h.subs.size()) {
+        set_error("sdrb_plan_get_sub: bad argument"); return SDRB_E_INVALID;
+    }
+    const SubVfo &s = plan->h.subs[(size_t)idx];
+    memset(info, 0, sizeof(*info));
+    strncpy(info->topic, s.topic.c_str(), sizeof(info->topic) - 1);
+    info->frequency = s.frequency; info->data_rate = s.data_rate; info->main_idx = s.main_idx;
+    info->decim = s.decim; info->late = s.late; info->filter_bw = s.filter_bw; info->gain = s.gain;
+    info->mixer_hz = s.mixer; info->in_rate = s.fs; info->out_rate = s.out_rate;
+    info->samples_out = s.samples_out; info->pcm_offset = s.pcm_offset;
+    info->n_dec_taps = (int)s.dec_taps.size(); info->n_lpf_taps = (int)s.lpf_taps.size();
+    return SDRB_OK;
+}
+
+extern "C" long sdrb_plan_copy_table(const sdrb_plan *plan, int kind, int idx, float *dst, long max_elems) {
+    if (!plan) { set_error("sdrb_plan_copy_table: NULL plan"); return SDRB_E_INVALID; }
+    const HostPlan &h = plan->h;
+    const float *src = nullptr;
+    long n = 0, width = 1;
+    if (kind == 0 && idx >= 0 && idx < (int)h.mains.size()) {
+        src = &h.mains[(size_t)idx].lut[0].re; n = (long)h.mains[(size_t)idx].lut.size(); width = 2;
+    } else if (idx >= 0 && idx < (int)h.subs.size()) {
+        const SubVfo &s = h.subs[(size_t)idx];
+        if (kind == 1) { src = &s.lut[0].re; n = (long)s.lut.size(); width = 2; }
+        else if (kind == 2) { src = s.dec_taps.data(); n = (long)s.dec_taps.size(); }
+        else if (kind == 3) { src = s.lpf_taps.data(); n = (long)s.lpf_taps.size(); }
+        else if (kind == 4) { src = s.hilbert.data(); n = (long)s.hilbert.size(); }
+        else { set_error("sdrb_plan_copy_table: unknown kind"); return SDRB_E_INVALID; }
+    } else { set_error("sdrb_plan_copy_table: index out of range"); return SDRB_E_INVALID; }
+    if (dst && n > 0) memcpy(dst, src, sizeof(float) * (size_t)(std::min(n, max_elems) * width));
+    return n;
+}
+
+// ------------------------------------------------------------------------------------
+// bank
+// ------------------------------------------------------------------------------------
+namespace {
+
+struct DevBuf {
+    void *p = nullptr;
+    size_t bytes = 0;
+    int alloc(size_t n) {
+        bytes = n;
+        cudaError_t e = cudaMalloc(&p, n ? n : 16);
+        if (e != cudaSuccess) { set_error(std::string("cudaMalloc: ") + cudaGetErrorString(e)); return SDRB_E_NOMEM; }
+        return SDRB_OK;
+    }
+    void release() { if (p) cudaFree(p); p = nullptr; }
+};
+
+struct SubGroup {           // sub VFOs sharing (stage count) -> one K2A launch
+    int decim;
+    int tiles;              // K2A tiles per callback
+    int first, count;       // range in the device SubDev array (sorted by group)
+};
+
+inline size_t round_up(size_t v, size_t m) { return (v + m - 1) / m * m; }
+
+}  // namespace
+
+struct sdrb_bank {
+    const sdrb_plan *plan = nullptr;
+    int device = 0, n_streams = 0, max_blocks = 0;
+    int last_launches = 0;
+    // tables
+    DevBuf luts, taps;
+    // state
+    DevBuf blocks_done, dc_state, raw_tail;
+    // work
+    DevBuf dc_part, dc_start, main_out, zbuf, dbuf;
+    int dc_stride = 0;
+    // descriptors
+    K1Params k1{};
+    DevBuf subdev, latedev, usbdev, carry;
+    std::vector<SubGroup> groups;
+    int n_late = 0, n_usb = 0, n_carry = 0;
+    int max_usb_samples = 0, max_late_samples = 0;
+    std::vector<size_t> main_off;           // per main: offset (float2 units) inside main_out per stream
+    size_t main_stride = 0;                 // float2 per stream
+    // host staging for process_host
+    DevBuf d_iq, d_pcm, d_tap;
+    cudaStream_t s_copy_in = nullptr, s_compute = nullptr, s_copy_out = nullptr;
+    std::vector<cudaEvent_t> ev_in, ev_done;
+    bool dc_consts_set = false;
+};
+
+static int upload_dc_consts() {
+    DcConsts c;
+    const float a = 1.0f - 0.000001f;       // sdrj.cpp:281, evaluated in float like the reference
+    c.a = a;
+    c.c = 0.000001f;
+    const double ad = (double)a;
+    for (int j = 0; j <= 8; j++) c.apow[j] = (float)std::pow(ad, j);
+    for (int l = 0; l < 32; l++) { c.apow8[l] = (float)std::pow(ad, 8 * l); c.rpow8[l] = (float)std::pow(ad, 8 * (31 - l)); }
+    for (int d = 0; d < 5; d++) c.wscan[d] = (float)std::pow(ad, 8 * (1 << d));
+    c.a256 = std::pow(ad, 256);
+    CU_TRY(cudaMemcpyToSymbol(c_dc, &c, sizeof(c)));
+    return SDRB_OK;
+}
+
+extern "C" void sdrb_bank_destroy(sdrb_bank *b) {
+    if (!b) return;
+    cudaSetDevice(b->device);
+    DevBuf *all[] = {&b->luts, &b->taps, &b->blocks_done, &b->dc_state, &b->raw_tail, &b->dc_part, &b->dc_start,
+                     &b->main_out, &b->zbuf, &b->dbuf, &b->subdev, &b->latedev, &b->usbdev, &b->carry,
+                     &b->d_iq, &b->d_pcm, &b->d_tap};
+    for (DevBuf *d : all) d->release();
+    for (cudaEvent_t e : b->ev_in) cudaEventDestroy(e);
+    for (cudaEvent_t e : b->ev_done) cudaEventDestroy(e);
+    if (b->s_copy_in) cudaStreamDestroy(b->s_copy_in);
+    if (b->s_compute) cudaStreamDestroy(b->s_compute);
+    if (b->s_copy_out) cudaStreamDestroy(b->s_copy_out);
+    delete b;
+}
+
+extern "C" int sdrb_bank_create(const sdrb_plan *plan, int device, int n_streams, int max_blocks, sdrb_bank **out) {
+    if (!plan || !out || n_streams <= 0 || max_blocks <= 0) {
+        set_error("sdrb_bank_create: bad argument"); return SDRB_E_INVALID;
+    }
+    *out = nullptr;
+    int ndev = 0;
+    if (cudaGetDeviceCount(&ndev) != cudaSuccess || ndev == 0) {
+        set_error("sdrb_bank_create: no CUDA device (this library has no CPU path)");
+        return SDRB_E_CUDA;
+    }
+    if (device < 0 || device >= ndev) { set_error("sdrb_bank_create: device index out of range"); return SDRB_E_INVALID; }
+    CU_TRY(cudaSetDevice(device));
+    const HostPlan &h = plan->h;
+    sdrb_bank *b = new (std::nothrow) sdrb_bank();
+    if (!b) return SDRB_E_NOMEM;
+    b->plan = plan; b->device = device; b->n_streams = n_streams; b->max_blocks = max_blocks;
+    int rc = upload_dc_consts();
+    if (rc != SDRB_OK) { sdrb_bank_destroy(b); return rc; }
+
+#define BANK_TRY(x) do { rc = (x); if (rc != SDRB_OK) { sdrb_bank_destroy(b); return rc; } } while (0)
+#define BANK_CU(x) do { cudaError_t e_ = (x); if (e_ != cudaSuccess) { set_error(std::string(#x) + ": " + cudaGetErrorString(e_)); sdrb_bank_destroy(b); return SDRB_E_CUDA; } } while (0)
+
+    // ---- tables: all NCO tables in one buffer, all taps in another ----
+    size_t lut_elems = 0;
+    for (const MainVfo &m : h.mains) lut_elems += round_up(m.lut.size(), 2);
+    for (const SubVfo &s : h.subs) lut_elems += round_up(s.lut.size(), 2);
+    BANK_TRY(b->luts.alloc(lut_elems * sizeof(float2)));
+    std::vector<size_t> main_lut_off, sub_lut_off;
+    {
+        size_t at = 0;
+        for (const MainVfo &m : h.mains) {
+            main_lut_off.push_back(at);
+            BANK_CU(cudaMemcpy((float2 *)b->luts.p + at, m.lut.data(), m.lut.size() * sizeof(float2), cudaMemcpyHostToDevice));
+            at += round_up(m.lut.size(), 2);
+        }
+        for (const SubVfo &s : h.subs) {
+            sub_lut_off.push_back(at);
+            BANK_CU(cudaMemcpy((float2 *)b->luts.p + at, s.lut.data(), s.lut.size() * sizeof(float2), cudaMemcpyHostToDevice));
+            at += round_up(s.lut.size(), 2);
+        }
+    }
+    // taps per sub: hil[64] | lpf[np] | dec[ntaps]  (16-byte aligned pieces)
+    std::vector<float> taps_host;
+    std::vector<size_t> hil_off, lpf_off, dec_off;
+    std::vector<int> np_of;
+    for (const SubVfo &s : h.subs) {
+        hil_off.push_back(taps_host.size());
+        taps_host.push_back(0.f); taps_host.push_back(0.f);
+        for (int j = 0; j < 62; j++) taps_host.push_back(s.hilbert[(size_t)(2 * j + 1)]);
+        const int n = (int)s.lpf_taps.size(), np = (int)round_up((size_t)n, 4);
+        if (np > MAX_FIR_TAPS || (int)s.dec_taps.size() > MAX_FIR_TAPS) {
+            set_error("bank: filter longer than 512 taps"); sdrb_bank_destroy(b); return SDRB_E_INVALID;
+        }
+        np_of.push_back(np);
+        lpf_off.push_back(taps_host.size());
+        for (int j = 0; j < np - n; j++) taps_host.push_back(0.f);
+        for (int j = 0; j < n; j++) taps_host.push_back(s.lpf_taps[(size_t)j]);
+        dec_off.push_back(taps_host.size());
+        for (float v : s.dec_taps) taps_host.push_back(v);
+        while (taps_host.size() % 4) taps_host.push_back(0.f);
+    }
+    BANK_TRY(b->taps.alloc(taps_host.size() * sizeof(float)));
+    if (!taps_host.empty())
+        BANK_CU(cudaMemcpy(b->taps.p, taps_host.data(), taps_host.size() * sizeof(float), cudaMemcpyHostToDevice));
+
+    // ---- state ----
+    BANK_TRY(b->blocks_done.alloc(sizeof(long long) * (size_t)n_streams));
+    BANK_TRY(b->dc_state.alloc(sizeof(double2) * 2 * (size_t)n_streams));
+    BANK_TRY(b->raw_tail.alloc((size_t)n_streams * 2 * RAW_TAIL));
+
+    // ---- work buffers ----
+    const int n_seg_max = max_blocks * (h.block / DC_SEG);
+    b->dc_stride = n_seg_max + 2;
+    BANK_TRY(b->dc_part.alloc(sizeof(float2) * (size_t)n_streams * (size_t)b->dc_stride));
+    BANK_TRY(b->dc_start.alloc(sizeof(float2) * (size_t)n_streams * (size_t)b->dc_stride));
+    {
+        size_t at = 0;
+        for (const MainVfo &m : h.mains) {
+            b->main_off.push_back(at);
+            at += round_up((size_t)MAIN_HIST + (size_t)max_blocks * m.block_out, 2);
+        }
+        b->main_stride = at;
+    }
+    BANK_TRY(b->main_out.alloc(sizeof(float2) * b->main_stride * (size_t)n_streams));
+
+    // z / d buffers per sub
+    std::vector<size_t> z_off, d_off;
+    std::vector<int> z_hist, d_hist;
+    size_t z_stride = 0, d_stride = 0;
+    for (size_t i = 0; i < h.subs.size(); i++) {
+        const SubVfo &s = h.subs[i];
+        int zh, dh = 0;
+        if (s.late > 0) { zh = (int)round_up(s.dec_taps.size(), 64); dh = (int)round_up((size_t)np_of[i] + 128, 64); }
+        else zh = (int)round_up((size_t)np_of[i] + 128, 64);
+        z_hist.push_back(zh); d_hist.push_back(dh);
+        z_off.push_back(z_stride);
+        z_stride += round_up((size_t)zh + (size_t)max_blocks * s.block_z, 2);
+        d_off.push_back(d_stride);
+        if (s.late > 0) d_stride += round_up((size_t)dh + (size_t)max_blocks * s.samples_out, 2);
+    }
+    BANK_TRY(b->zbuf.alloc(sizeof(float2) * z_stride * (size_t)n_streams));
+    BANK_TRY(b->dbuf.alloc(sizeof(float2) * d_stride * (size_t)n_streams));
+
+    // ---- descriptors ----
+    K1Params &k1 = b->k1;
+    k1.tail = (const uint8_t *)b->raw_tail.p;
+    k1.dc_start = (const float2 *)b->dc_start.p;
+    k1.blocks_done = (const long long *)b->blocks_done.p;
+    k1.dc_stride = b->dc_stride; k1.block = h.block; k1.correct_dc = h.correct_dc; k1.n_main = (int)h.mains.size();
+    for (size_t i = 0; i < h.mains.size(); i++) {
+        MainDev &M = k1.mains[i];
+        M.lut = (const float2 *)b->luts.p + main_lut_off[i];
+        M.out = (float2 *)b->main_out.p + b->main_off[i];
+        M.out_stride = (long long)b->main_stride;
+        M.lut_len = (int)h.mains[i].lut.size(); M.decim = h.mains[i].decim; M.block_out = h.mains[i].block_out;
+    }
+    // sub VFOs grouped by stage count
+    std::vector<int> order;
+    for (int dcm = 0; dcm <= 5; dcm++) {
+        SubGroup g; g.decim = dcm; g.first = (int)order.size(); g.count = 0; g.tiles = 0;
+        for (size_t i = 0; i < h.subs.size(); i++) {
+            if (h.subs[i].decim != dcm) continue;
+            order.push_back((int)i); g.count++;
+            int tiles;
+            if (dcm == 0) tiles = (h.subs[i].block_in + 2047) / 2048;
+            else {
+                const int ht = dcm <= 2 ? 1 : dcm == 3 ? 3 : dcm == 4 ? 5 : 11;
+                const int adv = (K2A_THREADS - ht) * K2A_CHUNK;
+                tiles = (h.subs[i].block_in + adv - 1) / adv;
+            }
+            g.tiles = std::max(g.tiles, tiles);
+        }
+        if (g.count) b->groups.push_back(g);
+    }
+    std::vector<SubDev> subdev;
+    std::vector<LateDev> latedev;
+    std::vector<UsbDev> usbdev;
+    std::vector<CarryItem> carry;
+    for (int i : order) {
+        const SubVfo &s = h.subs[(size_t)i];
+        SubDev D;
+        D.lut = (const float2 *)b->luts.p + sub_lut_off[(size_t)i];
+        D.in = (const float2 *)b->main_out.p + b->main_off[(size_t)s.main_idx];
+        D.z = (float2 *)b->zbuf.p + z_off[(size_t)i];
+        D.in_stride = (long long)b->main_stride; D.z_stride = (long long)z_stride;
+        D.lut_len = (int)s.lut.size(); D.block_in = s.block_in; D.block_z = s.block_z; D.z_hist = z_hist[(size_t)i];
+        subdev.push_back(D);
+    }
+    for (size_t i = 0; i < h.subs.size(); i++) {
+        const SubVfo &s = h.subs[i];
+        UsbDev U;
+        if (s.late > 0) {
+            LateDev L;
+            L.z = (const float2 *)b->zbuf.p + z_off[i];
+            L.d = (float2 *)b->dbuf.p + d_off[i];
+            L.taps = (const float *)b->taps.p + dec_off[i];
+            L.z_stride = (long long)z_stride; L.d_stride = (long long)d_stride;
+            L.z_hist = z_hist[i]; L.d_hist = d_hist[i]; L.block_z = s.block_z; L.samples_out = s.samples_out;
+            L.late = s.late; L.ntaps = (int)s.dec_taps.size();
+            latedev.push_back(L);
+            b->max_late_samples = std::max(b->max_late_samples, s.samples_out);
+            U.src = L.d; U.src_stride = L.d_stride; U.src_hist = L.d_hist;
+            CarryItem c; c.base = L.d; c.stride = (long long)(d_stride * sizeof(float2));
+            c.hist_bytes = L.d_hist * (int)sizeof(float2); c.block_bytes = s.samples_out * (int)sizeof(float2);
+            carry.push_back(c);
+        } else {
+            U.src = (const float2 *)b->zbuf.p + z_off[i]; U.src_stride = (long long)z_stride; U.src_hist = z_hist[i];
+        }
+        U.samples_out = s.samples_out; U.np = np_of[i]; U.pcm_offset = s.pcm_offset;
+        U.hil = (const float *)b->taps.p + hil_off[i];
+        U.lpf = (const float *)b->taps.p + lpf_off[i];
+        U.gain = s.gain;
+        usbdev.push_back(U);
+        b->max_usb_samples = std::max(b->max_usb_samples, s.samples_out);
+        CarryItem c; c.base = (float2 *)b->zbuf.p + z_off[i]; c.stride = (long long)(z_stride * sizeof(float2));
+        c.hist_bytes = z_hist[i] * (int)sizeof(float2); c.block_bytes = s.block_z * (int)sizeof(float2);
+        carry.push_back(c);
+    }
+    for (size_t i = 0; i < h.mains.size(); i++) {
+        CarryItem c; c.base = (float2 *)b->main_out.p + b->main_off[i];
+        c.stride = (long long)(b->main_stride * sizeof(float2));
+        c.hist_bytes = MAIN_HIST * (int)sizeof(float2); c.block_bytes = h.mains[i].block_out * (int)sizeof(float2);
+        carry.push_back(c);
+    }
+    b->n_late = (int)latedev.size(); b->n_usb = (int)usbdev.size(); b->n_carry = (int)carry.size();
+    BANK_TRY(b->subdev.alloc(sizeof(SubDev) * std::max<size_t>(subdev.size(), 1)));
+    BANK_TRY(b->latedev.alloc(sizeof(LateDev) * std::max<size_t>(latedev.size(), 1)));
+    BANK_TRY(b->usbdev.alloc(sizeof(UsbDev) * std::max<size_t>(usbdev.size(), 1)));
+    BANK_TRY(b->carry.alloc(sizeof(CarryItem) * std::max<size_t>(carry.size(), 1)));
+    if (!subdev.empty()) BANK_CU(cudaMemcpy(b->subdev.p, subdev.data(), sizeof(SubDev) * subdev.size(), cudaMemcpyHostToDevice));
+    if (!latedev.empty()) BANK_CU(cudaMemcpy(b->latedev.p, latedev.data(), sizeof(LateDev) * latedev.size(), cudaMemcpyHostToDevice));
+    if (!usbdev.empty()) BANK_CU(cudaMemcpy(b->usbdev.p, usbdev.data(), sizeof(UsbDev) * usbdev.size(), cudaMemcpyHostToDevice));
+    BANK_CU(cudaMemcpy(b->carry.p, carry.data(), sizeof(CarryItem) * carry.size(), cudaMemcpyHostToDevice));
+
+    BANK_CU(cudaFuncSetAttribute(k2a_sub_cascade<1>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)K2A_SMEM));
+    BANK_CU(cudaFuncSetAttribute(k2a_sub_cascade<2>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)K2A_SMEM));
+    BANK_CU(cudaFuncSetAttribute(k2a_sub_cascade<3>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)K2A_SMEM));
+    BANK_CU(cudaFuncSetAttribute(k2a_sub_cascade<4>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)K2A_SMEM));
+    BANK_CU(cudaFuncSetAttribute(k2a_sub_cascade<5>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)K2A_SMEM));
+    BANK_CU(cudaStreamCreateWithFlags(&b->s_copy_in, cudaStreamNonBlocking));
+    BANK_CU(cudaStreamCreateWithFlags(&b->s_compute, cudaStreamNonBlocking));
+    BANK_CU(cudaStreamCreateWithFlags(&b->s_copy_out, cudaStreamNonBlocking));
+#undef BANK_TRY
+#undef BANK_CU
+    rc = sdrb_bank_reset(b, -1);
+    if (rc != SDRB_OK) { sdrb_bank_destroy(b); return rc; }
+    *out = b;
+    return SDRB_OK;
+}
+
+extern "C" int sdrb_bank_reset(sdrb_bank *b, int stream) {
+    if (!b || stream < -1 || stream >= b->n_streams) { set_error("sdrb_bank_reset: bad argument"); return SDRB_E_INVALID; }
+    CU_TRY(cudaSetDevice(b->device));
+    const int s0 = stream < 0 ? 0 : stream, ns = stream < 0 ? b->n_streams : 1;
+    CU_TRY(cudaMemset((long long *)b->blocks_done.p + s0, 0, sizeof(long long) * (size_t)ns));
+    CU_TRY(cudaMemset((double2 *)b->dc_state.p + 2 * (size_t)s0, 0, sizeof(double2) * 2 * (size_t)ns));
+    CU_TRY(cudaMemset((uint8_t *)b->raw_tail.p + (size_t)s0 * 2 * RAW_TAIL, 0, (size_t)ns * 2 * RAW_TAIL));
+    // history regions: zero whole per-stream slices (cheap, and only done on reset)
+    const size_t ms = b->main_stride * sizeof(float2);
+    CU_TRY(cudaMemset((char *)b->main_out.p + ms * (size_t)s0, 0, ms * (size_t)ns));
+    const size_t zs = b->zbuf.bytes / (size_t)b->n_streams, ds = b->dbuf.bytes / (size_t)b->n_streams;
+    if (zs) CU_TRY(cudaMemset((char *)b->zbuf.p + zs * (size_t)s0, 0, zs * (size_t)ns));
+    if (ds) CU_TRY(cudaMemset((char *)b->dbuf.p + ds * (size_t)s0, 0, ds * (size_t)ns));
+    CU_TRY(cudaDeviceSynchronize());
+    return SDRB_OK;
+}
+
+extern "C" int sdrb_bank_blocks_done(sdrb_bank *b, int stream, int64_t *blocks) {
+    if (!b || !blocks || stream < 0 || stream >= b->n_streams) { set_error("sdrb_bank_blocks_done: bad argument"); return SDRB_E_INVALID; }
+    CU_TRY(cudaSetDevice(b->device));
+    long long v = 0;
+    CU_TRY(cudaMemcpy(&v, (long long *)b->blocks_done.p + stream, sizeof(v), cudaMemcpyDeviceToHost));
+    *blocks = v;
+    return SDRB_OK;
+}
+
+// Enqueue the whole pipeline for streams [s0, s0+ns) on `st`. Returns launches issued.
+static int enqueue(sdrb_bank *b, const uint8_t *d_iq, size_t iq_stride, int n_blocks, int16_t *d_pcm, float *d_tap,
+                   int s0, int ns, cudaStream_t st, int *launches) {
+    const HostPlan &h = b->plan->h;
+    int nl = 0;
+    const int n_seg = n_blocks * (h.block / DC_SEG);
+    if (h.correct_dc) {
+        k0_dc_partial<<<dim3((unsigned)((n_seg + 7) / 8), (unsigned)ns), 256, 0, st>>>(
+            d_iq, iq_stride, (float2 *)b->dc_part.p, b->dc_stride, n_seg, s0);
+        k0_dc_scan<<<(unsigned)ns, 32, 0, st>>>((const float2 *)b->dc_part.p, b->dc_stride, (float2 *)b->dc_start.p,
+                                                b->dc_stride, (double2 *)b->dc_state.p, n_seg, s0);
+        nl += 2;
+    }
+    K1Params k1 = b->k1;
+    k1.iq = d_iq; k1.iq_stride = iq_stride; k1.n_blocks = n_blocks; k1.stream0 = s0;
+    const int k1_tiles = (h.block + K1_TILE - 1) / K1_TILE;
+    k1_ingest_main<<<dim3((unsigned)ns, (unsigned)k1_tiles, (unsigned)n_blocks), K1_THREADS, 0, st>>>(k1);
+    nl++;
+    for (const SubGroup &g : b->groups) {
+        K2aParams kp;
+        kp.subs = (const SubDev *)b->subdev.p + g.first;
+        kp.blocks_done = (const long long *)b->blocks_done.p;
+        kp.n_blocks = n_blocks; kp.tiles = g.tiles; kp.stream0 = s0;
+        const dim3 grid((unsigned)ns, (unsigned)g.count, (unsigned)(g.tiles * n_blocks));
+        switch (g.decim) {
+        case 0: k2a_mix_only<<<grid, 256, 0, st>>>(kp); break;
+        case 1: k2a_sub_cascade<1><<<grid, K2A_THREADS, K2A_SMEM, st>>>(kp); break;
+        case 2: k2a_sub_cascade<2><<<grid, K2A_THREADS, K2A_SMEM, st>>>(kp); break;
+        case 3: k2a_sub_cascade<3><<<grid, K2A_THREADS, K2A_SMEM, st>>>(kp); break;
+        case 4: k2a_sub_cascade<4><<<grid, K2A_THREADS, K2A_SMEM, st>>>(kp); break;
+        default: k2a_sub_cascade<5><<<grid, K2A_THREADS, K2A_SMEM, st>>>(kp); break;
+        }
+        nl++;
+    }
+    if (b->n_late) {
+        const int tiles = (n_blocks * b->max_late_samples + LATE_TILE - 1) / LATE_TILE;
+        k2_late_fir<<<dim3((unsigned)ns, (unsigned)b->n_late, (unsigned)tiles), LATE_TILE, 0, st>>>(
+            (const LateDev *)b->latedev.p, n_blocks, s0);
+        nl++;
+    }
+    if (b->n_usb) {
+        const int tiles = (n_blocks * b->max_usb_samples + USB_TILE - 1) / USB_TILE;
+        k2b_usb_audio<<<dim3((unsigned)ns, (unsigned)b->n_usb, (unsigned)tiles), 256, 0, st>>>(
+            (const UsbDev *)b->usbdev.p, n_blocks, s0, b->n_streams, h.pcm_per_block, d_pcm, d_tap);
+        nl++;
+    }
+    k3_carry<<<dim3((unsigned)ns, (unsigned)(b->n_carry + 1)), 128, 0, st>>>(
+        (const CarryItem *)b->carry.p, b->n_carry, n_blocks, d_iq, iq_stride, h.block, (uint8_t *)b->raw_tail.p,
+        (long long *)b->blocks_done.p, s0);
+    nl++;
+    CU_TRY(cudaGetLastError());
+    *launches += nl;
+    return SDRB_OK;
+}
+
+static int check_process_args(sdrb_bank *b, const void *iq, size_t iq_stride, int n_blocks, const void *pcm) {
+    if (!b || !iq || !pcm) { set_error("process: NULL argument"); return SDRB_E_INVALID; }
+    if (n_blocks <= 0 || n_blocks > b->max_blocks) { set_error("process: n_blocks outside 1..max_blocks"); return SDRB_E_INVALID; }
+    const size_t need = (size_t)n_blocks * (size_t)b->plan->h.block * 2;
+    if (iq_stride < need || iq_stride % 16 != 0 || ((uintptr_t)iq) % 16 != 0) {
+        set_error("process: iq_stride must be >= n_blocks*block*2 and, like the base pointer, 16-byte aligned");
+        return SDRB_E_INVALID;
+    }
+    return SDRB_OK;
+}
+
+extern "C" int sdrb_bank_process_device(sdrb_bank *b, const uint8_t *d_iq, size_t iq_stride, int n_blocks,
+                                        int16_t *d_pcm, float *d_tap, void *cuda_stream) {
+    int rc = check_process_args(b, d_iq, iq_stride, n_blocks, d_pcm);
+    if (rc != SDRB_OK) return rc;
+    CU_TRY(cudaSetDevice(b->device));
+    b->last_launches = 0;
+    return enqueue(b, d_iq, iq_stride, n_blocks, d_pcm, d_tap, 0, b->n_streams, (cudaStream_t)cuda_stream, &b->last_launches);
+}
+
+extern "C" int sdrb_bank_copy_main(sdrb_bank *b, int main_idx, int n_blocks, float *d_out, void *cuda_stream) {
+    if (!b || !d_out || main_idx < 0 || main_idx >= (int)b->plan->h.mains.size() || n_blocks <= 0 || n_blocks > b->max_blocks) {
+        set_error("sdrb_bank_copy_main: bad argument"); return SDRB_E_INVALID;
+    }
+    CU_TRY(cudaSetDevice(b->device));
+    const MainVfo &m = b->plan->h.mains[(size_t)main_idx];
+    // The carry kernel has already moved the tail to the front, but the body is intact.
+    const size_t row = (size_t)n_blocks * m.block_out * sizeof(float2);
+    CU_TRY(cudaMemcpy2DAsync(d_out, row, (float2 *)b->main_out.p + b->main_off[(size_t)main_idx] + MAIN_HIST,
+                             b->main_stride * sizeof(float2), row, (size_t)b->n_streams, cudaMemcpyDeviceToDevice,
+                             (cudaStream_t)cuda_stream));
+    return SDRB_OK;
+}
+
+extern "C" int sdrb_bank_process_host(sdrb_bank *b, const uint8_t *h_iq, size_t iq_stride, int n_blocks,
+                                      int16_t *h_pcm, float *h_tap) {
+    int rc = check_process_args(b, h_iq, iq_stride, n_blocks, h_pcm);
+    if (rc != SDRB_OK) return rc;
+    CU_TRY(cudaSetDevice(b->device));
+    const HostPlan &h = b->plan->h;
+    const size_t in_row = (size_t)n_blocks * h.block * 2;
+    const size_t rec = (size_t)n_blocks * h.pcm_per_block;
+    const size_t in_max = (size_t)b->max_blocks * h.block * 2;
+    if (!b->d_iq.p) {
+        rc = b->d_iq.alloc(in_max * (size_t)b->n_streams); if (rc) return rc;
+        rc = b->d_pcm.alloc((size_t)b->max_blocks * h.pcm_per_block * sizeof(int16_t) * (size_t)b->n_streams); if (rc) return rc;
+    }
+    if (h_tap && !b->d_tap.p) {
+        rc = b->d_tap.alloc((size_t)b->max_blocks * h.pcm_per_block * sizeof(float) * (size_t)b->n_streams); if (rc) return rc;
+    }
+    // stream groups: copy-in / compute / copy-out overlap across groups
+    const int n_groups = std::min(b->n_streams, 8);
+    while ((int)b->ev_in.size() < n_groups) {
+        cudaEvent_t e1, e2;
+        CU_TRY(cudaEventCreateWithFlags(&e1, cudaEventDisableTiming));
+        CU_TRY(cudaEventCreateWithFlags(&e2, cudaEventDisableTiming));
+        b->ev_in.push_back(e1); b->ev_done.push_back(e2);
+    }
+    b->last_launches = 0;
+    const int per = (b->n_streams + n_groups - 1) / n_groups;
+    for (int g = 0; g < n_groups; g++) {
+        const int s0 = g * per, ns = std::min(per, b->n_streams - s0);
+        if (ns <= 0) break;
+        uint8_t *din = (uint8_t *)b->d_iq.p + (size_t)s0 * in_max;
+        CU_TRY(cudaMemcpy2DAsync(din, in_max, h_iq + (size_t)s0 * iq_stride, iq_stride, in_row, (size_t)ns,
+                                 cudaMemcpyHostToDevice, b->s_copy_in));
+        CU_TRY(cudaEventRecord(b->ev_in[(size_t)g], b->s_copy_in));
+        CU_TRY(cudaStreamWaitEvent(b->s_compute, b->ev_in[(size_t)g], 0));
+        // kernels index streams absolutely: pass the bank-wide base pointers
+        rc = enqueue(b, (const uint8_t *)b->d_iq.p, in_max, n_blocks, (int16_t *)b->d_pcm.p,
+                     h_tap ? (float *)b->d_tap.p : nullptr, s0, ns, b->s_compute, &b->last_launches);
+        if (rc != SDRB_OK) return rc;
+        CU_TRY(cudaEventRecord(b->ev_done[(size_t)g], b->s_compute));
+        CU_TRY(cudaStreamWaitEvent(b->s_copy_out, b->ev_done[(size_t)g], 0));
+        CU_TRY(cudaMemcpyAsync(h_pcm + (size_t)s0 * rec, (int16_t *)b->d_pcm.p + (size_t)s0 * rec,
+                               rec * sizeof(int16_t) * (size_t)ns, cudaMemcpyDeviceToHost, b->s_copy_out));
+        if (h_tap)
+            CU_TRY(cudaMemcpyAsync(h_tap + (size_t)s0 * rec, (float *)b->d_tap.p + (size_t)s0 * rec,
+                                   rec * sizeof(float) * (size_t)ns, cudaMemcpyDeviceToHost, b->s_copy_out));
+    }
+    CU_TRY(cudaStreamSynchronize(b->s_copy_out));
+    CU_TRY(cudaStreamSynchronize(b->s_compute));
+    return SDRB_OK;
+}
+
+extern "C" int sdrb_bank_last_launches(const sdrb_bank *b) { return b ? b->last_launches : 0; }
+
+extern "C" void *sdrb_host_alloc(size_t bytes) {
+    void *p = nullptr;
+    if (cudaHostAlloc(&p, bytes, cudaHostAllocDefault) != cudaSuccess) {
+        set_error("sdrb_host_alloc: cudaHostAlloc failed");
+        return nullptr;
+    }
+    return p;
+}
+
+extern "C" void sdrb_host_free(void *p) { if (p) cudaFreeHost(p); }
+
+extern "C" const char *sdrb_last_error(void) { return last_error_cstr(); }
+extern "C" const char *sdrb_version(void) { return "sdrb200 0.1 (sm_100a)"; }
+
+// ------------------------------------------------------------------------------------
+// host-only table builders
+// ------------------------------------------------------------------------------------
+extern "C" long sdrb_nco_table(double sample_rate, double frequency, float *dst, long max_entries) {
+    if (sample_rate < 1.0) { set_error("sdrb_nco_table: sample_rate < 1"); return SDRB_E_INVALID; }
+    const std::vector<cf32> q = nco_table(sample_rate, frequency);
+    if (dst) memcpy(dst, q.data(), sizeof(cf32) * (size_t)std::min<long>((long)q.size(), max_entries));
+    return (long)q.size();
+}
+
+extern "C" int sdrb_low_pass(double gain, double fs, double cutoff, double tw, float *taps, int max_taps) {
+    std::vector<float> t;
+    const int n = low_pass_hamming(gain, fs, cutoff, tw, t);
+    if (n < 0) return n;
+    if (taps) memcpy(taps, t.data(), sizeof(float) * (size_t)std::min(n, max_taps));
+    return n;
+}
+
+extern "C" int sdrb_hilbert_points(int len, int fs, float *points) {
+    if (len <= 0 || !points) { set_error("sdrb_hilbert_points: bad argument"); return SDRB_E_INVALID; }
+    std::vector<float> p;
+    hilbert_points(len, fs, p);
+    memcpy(points, p.data(), sizeof(float) * (size_t)len);
+    return SDRB_OK;
+}
+
+// ------------------------------------------------------------------------------------
+// per-class primitives (prims.cuh)
+// ------------------------------------------------------------------------------------
+extern "C" int sdrb_nco_mix(const float *d_table, int table_len, int64_t n0, const float *d_in, float *d_out,
+                            int n_ch, int n, void *cuda_stream) {
+    if (!d_table || !d_in || !d_out || table_len <= 0 || n_ch <= 0 || n <= 0 || n0 < 0) {
+        set_error("sdrb_nco_mix: bad argument"); return SDRB_E_INVALID;
+    }
+    prim_nco_mix<<<dim3((unsigned)((n + 255) / 256), (unsigned)n_ch), 256, 0, (cudaStream_t)cuda_stream>>>(
+        (const float2 *)d_table, table_len, (long long)n0, (const float2 *)d_in, (float2 *)d_out, n);
+    CU_TRY(cudaGetLastError());
+    return SDRB_OK;
+}
+
+extern "C" int sdrb_halfband11(const float *d_in, float *d_out, float *d_hist, int n_ch, int n, void *cuda_stream) {
+    if (!d_in || !d_out || !d_hist || n_ch <= 0 || n < 12 || (n & 1)) {
+        set_error("sdrb_halfband11: needs an even block of at least 12 samples"); return SDRB_E_INVALID;
+    }
+    cudaStream_t st = (cudaStream_t)cuda_stream;
+    prim_halfband11<<<dim3((unsigned)((n / 2 + 255) / 256), (unsigned)n_ch), 256, 0, st>>>(
+        (const float2 *)d_in, (float2 *)d_out, (const float2 *)d_hist, n);
+    prim_halfband11_carry<<<(unsigned)n_ch, 32, 0, st>>>((const float2 *)d_in, (float2 *)d_hist, n);
+    CU_TRY(cudaGetLastError());
+    return SDRB_OK;
+}
+
+extern "C" int sdrb_fir(const float *d_taps, int ntaps, const float *d_in, float *d_out, float *d_hist, int n_ch,
+                        int n, int decim, void *cuda_stream) {
+    if (!d_taps || !d_in || !d_out || !d_hist || ntaps <= 0 || ntaps > 4096 || n_ch <= 0 || n < ntaps || decim < 1) {
+        set_error("sdrb_fir: bad argument (block must be at least ntaps long)"); return SDRB_E_INVALID;
+    }
+    cudaStream_t st = (cudaStream_t)cuda_stream;
+    const int n_out = (n + decim - 1) / decim;
+    prim_fir<<<dim3((unsigned)((n_out + 255) / 256), (unsigned)n_ch), 256, 0, st>>>(d_taps, ntaps, d_in, d_out, d_hist, n, decim, n_out);
+    prim_tail_carry<<<(unsigned)n_ch, 128, 0, st>>>(d_in, d_hist, n, ntaps, 1);
+    CU_TRY(cudaGetLastError());
+    return SDRB_OK;
+}
+
+extern "C" int sdrb_usb_demod(const float *d_points, const float *d_in, float *d_out, float *d_hist, int n_ch, int n,
+                              void *cuda_stream) {
+    if (!d_points || !d_in || !d_out || !d_hist || n_ch <= 0 || n < 124) {
+        set_error("sdrb_usb_demod: bad argument (block must be at least 124 long)"); return SDRB_E_INVALID;
+    }
+    cudaStream_t st = (cudaStream_t)cuda_stream;
+    prim_usb<<<dim3((unsigned)((n + 255) / 256), (unsigned)n_ch), 256, 0, st>>>(
+        d_points, (const float2 *)d_in, d_out, (const float2 *)d_hist, n);
+    prim_tail_carry<<<(unsigned)n_ch, 128, 0, st>>>(d_in, d_hist, n, 124, 2);
+    CU_TRY(cudaGetLastError());
+    return SDRB_OK;
+}
+
+extern "C" int sdrb_spectrum_fft(const float *d_in, float *d_out, int n_batch, int nfft, int apply_hann, void *cuda_stream) {
+    if (!d_in || !d_out || n_batch <= 0 || nfft != 8192) {
+        set_error("sdrb_spectrum_fft: nfft must be 8192 (mainwindow.cpp:241)"); return SDRB_E_INVALID;
+    }
+    static bool attr = false;
+    if (!attr) {
+        CU_TRY(cudaFuncSetAttribute(prim_fft8192, cudaFuncAttributeMaxDynamicSharedMemorySize, 8192 * (int)sizeof(float2)));
+        attr = true;
+    }
+    prim_fft8192<<<(unsigned)n_batch, 512, 8192 * sizeof(float2), (cudaStream_t)cuda_stream>>>(
+        (const float2 *)d_in, (float2 *)d_out, apply_hann);
+    CU_TRY(cudaGetLastError());
+    return SDRB_OK;
+}

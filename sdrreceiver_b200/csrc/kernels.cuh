@@ -1,0 +1,738 @@
+// Hand-written sm_100a kernels of the SDRReceiver channelizer hot path.
+//
+// Pipeline per process call (all streams of a bank, n_blocks callbacks each):
+//   k0_dc_partial  -> k0_dc_scan           DC-removal IIR (sdrj.cpp:277-283) as a 2-level scan
+//   k1_ingest_main                          u8 -> f32 (sdr.cpp:43-49), DC, per main VFO NCO mix
+//                                           (vfo.cpp:237-245) + 11-tap half-band cascade
+//                                           (halfbanddecimator.cpp:43-72) -> cf32 main output
+//   k2a_sub_cascade<S>                      per sub VFO: NCO mix + S half-band stages -> cf32 z
+//   k2_late_fir                             /5 or /6 decimating FIR (vfo.cpp:334-387)
+//   k2b_usb_audio                           delay62 - Hilbert125 (vfo.cpp:316-324), optional
+//                                           low-pass, gain, int16 (vfo.cpp:328)
+//   k3_carry                                filter tails / raw tail / counters for the next call
+//
+// Reference quirks reproduced on purpose:
+//   * FIRQueueBackToFront copies one slot early (dsp.cpp:169): at every callback edge, at
+//     every half-band stage, window slots that fall before the callback read one sample
+//     further back ("HEAD" path of hb_stage).
+//   * NCO = 1-second lookup table with |v| -> sqrt(0.95); stream sample 0 uses entry L-1.
+//   * FIR::FIRUpdateAndProcess excludes the newest sample; FIRHilbert includes it.
+#pragma once
+#include <cuda_runtime.h>
+#include <stdint.h>
+
+namespace sdrb {
+
+// ------------------------------------------------------------------------------------
+// constants
+// ------------------------------------------------------------------------------------
+// hbcoeff11 (halfbanddecimator.h:66-79)
+#define HB_P0 0.0060431029837374152f
+#define HB_P2 (-0.049372515458761493f)
+#define HB_P4 0.29332944952052842f
+#define HB_P5 0.5f
+
+constexpr int DC_SEG = 256;            // samples per DC scan segment (= one K1 warp)
+constexpr int RAW_TAIL = 256;          // raw samples carried between calls (K1 halo warp)
+constexpr int K1_WARPS = 8;            // active warps per K1 CTA (+1 halo warp)
+constexpr int K1_THREADS = (K1_WARPS + 1) * 32;
+constexpr int K1_TILE = K1_WARPS * 256;
+constexpr int K2A_THREADS = 256;
+constexpr int K2A_CHUNK = 32;          // main-output samples owned by one K2A thread
+constexpr int HB_PAD = 8;              // leading pad chunks of every smem stage array
+constexpr int MAIN_HIST = 512;         // main-output samples kept in front of each call
+constexpr int USB_TILE = 1024;         // audio samples per K2B CTA
+constexpr int LATE_TILE = 256;
+constexpr int MAX_FIR_TAPS = 512;
+
+struct DcConsts {
+    float a;            // 1.0f - 0.000001f
+    float c;            // 0.000001f
+    float apow[9];      // a^j, j = 0..8
+    float apow8[32];    // a^(8*lane)
+    float wscan[5];     // a^(8*2^d)
+    float rpow8[32];    // a^(8*(31-lane))
+    double a256;        // a^256
+};
+__constant__ DcConsts c_dc;
+
+struct MainDev {
+    const float2 *lut;      // Oscillator table
+    float2 *out;            // [n_streams][out_stride]: MAIN_HIST history + n_blocks*block_out
+    long long out_stride;
+    int lut_len, decim, block_out;
+};
+
+struct K1Params {
+    const uint8_t *iq;
+    size_t iq_stride;
+    const uint8_t *tail;            // [n_streams][2*RAW_TAIL]
+    const float2 *dc_start;         // [n_streams][dc_stride]; entry seg+1 = state entering seg
+    const long long *blocks_done;   // [n_streams]
+    int dc_stride, block, n_blocks, correct_dc, n_main, stream0;
+    MainDev mains[SDRB_MAX_MAIN];
+};
+
+struct SubDev {
+    const float2 *lut;
+    const float2 *in;               // parent main output (with MAIN_HIST history)
+    float2 *z;                      // [n_streams][z_stride]: z_hist history + n_blocks*block_z
+    long long in_stride, z_stride;
+    int lut_len, block_in, block_z, z_hist;
+};
+
+struct K2aParams {
+    const SubDev *subs;             // device array, this launch's group
+    const long long *blocks_done;
+    int n_blocks, tiles, stream0;
+};
+
+struct LateDev {
+    const float2 *z;                // pre-decimation samples (K2A output)
+    float2 *d;                      // [n_streams][d_stride]: d_hist + n_blocks*samples_out
+    const float *taps;              // ntaps floats
+    long long z_stride, d_stride;
+    int z_hist, d_hist, block_z, samples_out, late, ntaps;
+};
+
+struct UsbDev {
+    const float2 *src;              // z (plain path) or d (late path), with history in front
+    long long src_stride;
+    int src_hist, samples_out, np, pcm_offset;
+    const float *hil;               // 64 floats: 0,0, points[1], points[3], ... points[123]
+    const float *lpf;               // np floats, leading zeros then the low-pass taps
+    float gain;
+};
+
+struct CarryItem {
+    void *base;                     // per-stream buffers of `stride` bytes
+    long long stride;
+    int hist_bytes, block_bytes;    // copy [hist + n*block - hist, hist + n*block) -> [0, hist)
+};
+
+// ------------------------------------------------------------------------------------
+// small helpers
+// ------------------------------------------------------------------------------------
+__device__ __forceinline__ float2 cmul(float2 a, float2 b) {
+    return make_float2(a.x * b.x - a.y * b.y, a.x * b.y + a.y * b.x);
+}
+
+// byte k of w -> (float)byte - 127  without the conversion pipe: splice the byte into the
+// mantissa of 2^23 and subtract 2^23 + 127.
+template <int K>
+__device__ __forceinline__ float u8_to_f(uint32_t w) {
+    return __uint_as_float(__byte_perm(w, 0x4B000000u, 0x7540 | K)) - 8388735.0f;
+}
+
+__device__ __forceinline__ void unpack8(const uint4 raw, float2 (&x)[8]) {
+    x[0] = make_float2(u8_to_f<0>(raw.x), u8_to_f<1>(raw.x));
+    x[1] = make_float2(u8_to_f<2>(raw.x), u8_to_f<3>(raw.x));
+    x[2] = make_float2(u8_to_f<0>(raw.y), u8_to_f<1>(raw.y));
+    x[3] = make_float2(u8_to_f<2>(raw.y), u8_to_f<3>(raw.y));
+    x[4] = make_float2(u8_to_f<0>(raw.z), u8_to_f<1>(raw.z));
+    x[5] = make_float2(u8_to_f<2>(raw.z), u8_to_f<3>(raw.z));
+    x[6] = make_float2(u8_to_f<0>(raw.w), u8_to_f<1>(raw.w));
+    x[7] = make_float2(u8_to_f<2>(raw.w), u8_to_f<3>(raw.w));
+}
+
+template <int N> struct Log2 { static constexpr int v = 1 + Log2<N / 2>::v; };
+template <> struct Log2<1> { static constexpr int v = 0; };
+
+// Position of natural sample u (relative to the CTA's first chunk, may be negative down to
+// -HB_PAD chunks) inside a padded smem stage array: chunks of CH samples, of which the last
+// P are stored, STR float2 apart.
+template <int CH, int P, int STR>
+__device__ __forceinline__ int hb_pos(int u) {
+    return ((u >> Log2<CH>::v) + HB_PAD) * STR + ((u & (CH - 1)) - (CH - P));
+}
+
+// One 11-tap half-band stage for the thread that owns input samples in[0..2R-1] (natural
+// order, first one at callback coordinate v0) and produces out[0..R-1].
+// Window of output m = v0/2 + r is callback coordinates 2m-10 .. 2m, taps at +0,2,4,5,6,8,10
+// (dsp.cpp:139-142). Samples the thread does not own come from the previous chunks through
+// `sm`. HEAD: for outputs of this callback (m >= 0), window slots with a negative coordinate
+// read one sample further back -- the FIRQueueBackToFront off-by-one (dsp.cpp:163-173).
+template <int R, int P, int STR, bool HEAD>
+__device__ __forceinline__ void hb_stage(const float2 (&in)[2 * R], float2 (&out)[R],
+                                         const float2 *__restrict__ sm, int t, int v0) {
+    constexpr int CH = 2 * R;
+#define HB_TAP(dst, K)                                                          \
+    {                                                                           \
+        const int p_ = 2 * r - 10 + (K);                                        \
+        if (p_ >= 0) {                                                          \
+            dst = in[p_ >= 0 ? p_ : 0];                                         \
+        } else {                                                                \
+            int u_ = t * CH + p_;                                               \
+            if (HEAD) { if (m >= 0 && v0 + p_ < 0) u_ -= 1; }                   \
+            dst = sm[hb_pos<CH, P, STR>(u_)];                                   \
+        }                                                                       \
+    }
+    const int m0 = v0 >> 1;
+#pragma unroll
+    for (int r = 0; r < R; ++r) {
+        const int m = m0 + r;
+        (void)m;
+        float2 w0, w2, w4, w5, w6, w8, w10;
+        HB_TAP(w0, 0) HB_TAP(w2, 2) HB_TAP(w4, 4) HB_TAP(w5, 5) HB_TAP(w6, 6) HB_TAP(w8, 8) HB_TAP(w10, 10)
+        out[r].x = HB_P0 * (w0.x + w10.x) + HB_P2 * (w2.x + w8.x) + HB_P4 * (w4.x + w6.x) + HB_P5 * w5.x;
+        out[r].y = HB_P0 * (w0.y + w10.y) + HB_P2 * (w2.y + w8.y) + HB_P4 * (w4.y + w6.y) + HB_P5 * w5.y;
+    }
+#undef HB_TAP
+}
+
+template <int R, int P, int STR>
+__device__ __forceinline__ void hb_run(const float2 (&in)[2 * R], float2 (&out)[R],
+                                       const float2 *__restrict__ sm, int t, int v0) {
+    const int m0 = v0 >> 1;
+    if (m0 >= 0 && m0 < 5) hb_stage<R, P, STR, true>(in, out, sm, t, v0);
+    else hb_stage<R, P, STR, false>(in, out, sm, t, v0);
+}
+
+// store the last P of a thread's R stage outputs for its right-hand neighbours
+template <int R, int P, int STR>
+__device__ __forceinline__ void hb_publish(const float2 (&v)[R], float2 *__restrict__ sm, int t) {
+#pragma unroll
+    for (int k = R - P; k < R; ++k) sm[(t + HB_PAD) * STR + (k - (R - P))] = v[k];
+}
+
+// ------------------------------------------------------------------------------------
+// K0: DC-removal IIR  avept = avept*a + c*x  (sdrj.cpp:277-283) as a scan.
+// Pass 1: per 256-sample segment, P = sum_k a^(255-k) * c * x_k. One warp per segment.
+// ------------------------------------------------------------------------------------
+__global__ void __launch_bounds__(256) k0_dc_partial(const uint8_t *__restrict__ iq, size_t iq_stride,
+                                                      float2 *__restrict__ part, int part_stride,
+                                                      int n_seg, int stream0) {
+    const int stream = stream0 + blockIdx.y;
+    const int seg = blockIdx.x * 8 + (threadIdx.x >> 5);
+    const int lane = threadIdx.x & 31;
+    if (seg >= n_seg) return;
+    const uint4 raw = __ldg(reinterpret_cast<const uint4 *>(iq + (size_t)stream * iq_stride + (size_t)seg * (DC_SEG * 2)) + lane);
+    float2 x[8];
+    unpack8(raw, x);
+    const float a = c_dc.a, c = c_dc.c;
+    float2 acc = make_float2(c * x[0].x, c * x[0].y);
+#pragma unroll
+    for (int k = 1; k < 8; ++k) {
+        acc.x = fmaf(a, acc.x, c * x[k].x);
+        acc.y = fmaf(a, acc.y, c * x[k].y);
+    }
+    const float w = c_dc.rpow8[lane];
+    acc.x *= w;
+    acc.y *= w;
+#pragma unroll
+    for (int d = 16; d > 0; d >>= 1) {
+        acc.x += __shfl_xor_sync(0xffffffffu, acc.x, d);
+        acc.y += __shfl_xor_sync(0xffffffffu, acc.y, d);
+    }
+    if (lane == 0) part[(size_t)stream * part_stride + seg] = acc;
+}
+
+// Pass 2: one warp per stream walks the segment partials (double precision) and writes
+// the state entering every segment: start[0] = state entering the last segment of the
+// previous call (for K1's halo warp), start[1 + s] = state entering segment s.
+// dc_state[stream] = {A_next (entering sample 0 of the next call), A_prevseg}.
+__global__ void __launch_bounds__(32) k0_dc_scan(const float2 *__restrict__ part, int part_stride,
+                                                  float2 *__restrict__ start, int start_stride,
+                                                  double2 *__restrict__ dc_state, int n_seg, int stream0) {
+    const int stream = stream0 + blockIdx.x;
+    const int lane = threadIdx.x;
+    const int per = (n_seg + 31) / 32;
+    const int s_lo = min(lane * per, n_seg), s_hi = min(s_lo + per, n_seg);
+    const float2 *p = part + (size_t)stream * part_stride;
+    float2 *o = start + (size_t)stream * start_stride;
+    const double w = c_dc.a256;
+    // local composite: state_out = wl * state_in + sl
+    double wl = 1.0, sx = 0.0, sy = 0.0;
+    for (int s = s_lo; s < s_hi; ++s) {
+        const float2 v = p[s];
+        sx = sx * w + (double)v.x;
+        sy = sy * w + (double)v.y;
+        wl *= w;
+    }
+    // inclusive scan of composites over lanes
+    double cw = wl, cx = sx, cy = sy;
+#pragma unroll
+    for (int d = 1; d < 32; d <<= 1) {
+        const double pw = __shfl_up_sync(0xffffffffu, cw, d);
+        const double px = __shfl_up_sync(0xffffffffu, cx, d);
+        const double py = __shfl_up_sync(0xffffffffu, cy, d);
+        if (lane >= d) {
+            cx = cw * px + cx;
+            cy = cw * py + cy;
+            cw = cw * pw;
+        }
+    }
+    // exclusive composite for this lane
+    double ew = __shfl_up_sync(0xffffffffu, cw, 1);
+    double ex = __shfl_up_sync(0xffffffffu, cx, 1);
+    double ey = __shfl_up_sync(0xffffffffu, cy, 1);
+    if (lane == 0) { ew = 1.0; ex = 0.0; ey = 0.0; }
+    const double2 st0 = dc_state[2 * (size_t)stream];        // entering sample 0
+    const double2 stp = dc_state[2 * (size_t)stream + 1];    // entering previous call's last segment
+    __syncwarp();
+    double ax = ew * st0.x + ex, ay = ew * st0.y + ey;
+    if (lane == 0) o[0] = make_float2((float)stp.x, (float)stp.y);
+    double lx = ax, ly = ay;   // state entering the last processed segment
+    for (int s = s_lo; s < s_hi; ++s) {
+        o[1 + s] = make_float2((float)ax, (float)ay);
+        lx = ax; ly = ay;
+        const float2 v = p[s];
+        ax = ax * w + (double)v.x;
+        ay = ay * w + (double)v.y;
+    }
+    // the lane that owns the last segment publishes the carry
+    if (s_hi == n_seg && s_lo < n_seg) {
+        dc_state[2 * (size_t)stream] = make_double2(ax, ay);
+        dc_state[2 * (size_t)stream + 1] = make_double2(lx, ly);
+    }
+}
+
+// ------------------------------------------------------------------------------------
+// K1: fused ingest + main VFOs.
+// CTA = 9 warps: warp 0 recomputes the 256 samples in front of the tile (filter halo, or
+// the tail of the previous callback for tile 0), warps 1..8 own 256 samples each; every
+// thread owns 8 consecutive samples = one 16-byte load.
+// ------------------------------------------------------------------------------------
+constexpr int K1_A0_STR = 10, K1_A1_STR = 6, K1_A2_STR = 2;
+
+__global__ void __launch_bounds__(K1_THREADS, 2) k1_ingest_main(const K1Params p) {
+    __shared__ __align__(16) float2 sA0[(K1_THREADS + HB_PAD) * K1_A0_STR];
+    __shared__ __align__(16) float2 sA1[(K1_THREADS + HB_PAD) * K1_A1_STR];
+    __shared__ __align__(16) float2 sA2[(K1_THREADS + HB_PAD) * K1_A2_STR];
+
+    const int stream = p.stream0 + blockIdx.x;
+    const int tile = blockIdx.y, b = blockIdx.z;
+    const int t = threadIdx.x, lane = t & 31;
+    const int B = p.block;
+    const int i0 = tile * K1_TILE - 256 + t * 8;          // callback coordinate of the chunk
+    const long long blk = p.blocks_done[stream] + b;
+    const bool in_block = i0 < B;
+    const bool first_ever = (blk == 0);                    // nothing exists before sample 0
+    const bool exists = in_block && !(first_ever && i0 < 0);
+    const bool halo = t < 32;
+
+    float2 x[8];
+#pragma unroll
+    for (int k = 0; k < 8; ++k) x[k] = make_float2(0.f, 0.f);
+    if (exists) {
+        const uint8_t *src = (b == 0 && i0 < 0)
+            ? p.tail + (size_t)stream * (2 * RAW_TAIL) + (2 * RAW_TAIL + 2 * i0)
+            : p.iq + (size_t)stream * p.iq_stride + ((size_t)b * B + i0) * 2;
+        const uint4 raw = __ldg(reinterpret_cast<const uint4 *>(src));
+        unpack8(raw, x);
+        if (p.correct_dc) {
+            const float a = c_dc.a, c = c_dc.c;
+            float2 L[8];
+            L[0] = make_float2(c * x[0].x, c * x[0].y);
+#pragma unroll
+            for (int k = 1; k < 8; ++k) {
+                L[k].x = fmaf(a, L[k - 1].x, c * x[k].x);
+                L[k].y = fmaf(a, L[k - 1].y, c * x[k].y);
+            }
+            // the whole warp exists or not together (256-aligned), so full-mask shuffles are safe
+            float2 inc = L[7];
+#pragma unroll
+            for (int d = 0; d < 5; ++d) {
+                const float vx = __shfl_up_sync(0xffffffffu, inc.x, 1 << d);
+                const float vy = __shfl_up_sync(0xffffffffu, inc.y, 1 << d);
+                if (lane >= (1 << d)) {
+                    inc.x = fmaf(c_dc.wscan[d], vx, inc.x);
+                    inc.y = fmaf(c_dc.wscan[d], vy, inc.y);
+                }
+            }
+            float px = __shfl_up_sync(0xffffffffu, inc.x, 1);
+            float py = __shfl_up_sync(0xffffffffu, inc.y, 1);
+            if (lane == 0) { px = 0.f; py = 0.f; }
+            const int seg = (b * B + i0 - 8 * lane) >> 8;      // -1: last segment of the previous call
+            const float2 aseg = __ldg(p.dc_start + (size_t)stream * p.dc_stride + (seg + 1));
+            const float sx = fmaf(c_dc.apow8[lane], aseg.x, px);
+            const float sy = fmaf(c_dc.apow8[lane], aseg.y, py);
+#pragma unroll
+            for (int k = 0; k < 8; ++k) {
+                x[k].x -= fmaf(c_dc.apow[k + 1], sx, L[k].x);
+                x[k].y -= fmaf(c_dc.apow[k + 1], sy, L[k].y);
+            }
+        }
+    }
+    const long long n_abs = blk * (long long)B + i0;
+    // every main VFO table has (int)Fs entries, so one modulo serves them all
+    const int lut_idx = exists ? (int)(n_abs % p.mains[0].lut_len) : 0;
+
+    for (int mi = 0; mi < p.n_main; ++mi) {
+        const MainDev &M = p.mains[mi];
+        float2 mixed[8];
+#pragma unroll
+        for (int k = 0; k < 8; ++k) mixed[k] = make_float2(0.f, 0.f);
+        if (exists) {
+            const float4 *lp = reinterpret_cast<const float4 *>(M.lut + lut_idx);
+            float4 l01 = __ldg(lp), l23 = __ldg(lp + 1), l45 = __ldg(lp + 2), l67 = __ldg(lp + 3);
+            if (n_abs == 0) {                       // Oscillator start-up quirk (oscillator.cpp:26-30)
+                const float2 last = __ldg(M.lut + (M.lut_len - 1));
+                l01.x = last.x; l01.y = last.y;
+            }
+            mixed[0] = cmul(make_float2(l01.x, l01.y), x[0]);
+            mixed[1] = cmul(make_float2(l01.z, l01.w), x[1]);
+            mixed[2] = cmul(make_float2(l23.x, l23.y), x[2]);
+            mixed[3] = cmul(make_float2(l23.z, l23.w), x[3]);
+            mixed[4] = cmul(make_float2(l45.x, l45.y), x[4]);
+            mixed[5] = cmul(make_float2(l45.z, l45.w), x[5]);
+            mixed[6] = cmul(make_float2(l67.x, l67.y), x[6]);
+            mixed[7] = cmul(make_float2(l67.z, l67.w), x[7]);
+        }
+        const bool store = in_block && !halo;
+        float2 *outp = M.out + (size_t)stream * M.out_stride + MAIN_HIST + (size_t)b * M.block_out;
+        if (M.decim == 0) {
+            if (store) {
+                float4 *o4 = reinterpret_cast<float4 *>(outp + i0);
+#pragma unroll
+                for (int k = 0; k < 4; ++k)
+                    o4[k] = make_float4(mixed[2 * k].x, mixed[2 * k].y, mixed[2 * k + 1].x, mixed[2 * k + 1].y);
+            }
+            continue;
+        }
+        __syncthreads();                            // previous main done with sA0
+        {
+            float4 *s4 = reinterpret_cast<float4 *>(sA0 + (t + HB_PAD) * K1_A0_STR);
+#pragma unroll
+            for (int k = 0; k < 4; ++k)
+                s4[k] = make_float4(mixed[2 * k].x, mixed[2 * k].y, mixed[2 * k + 1].x, mixed[2 * k + 1].y);
+        }
+        __syncthreads();
+        float2 o1[4];
+        hb_run<4, 8, K1_A0_STR>(mixed, o1, sA0, t, i0);
+        if (M.decim == 1) {
+            if (store) {
+                float4 *o4 = reinterpret_cast<float4 *>(outp + (i0 >> 1));
+                o4[0] = make_float4(o1[0].x, o1[0].y, o1[1].x, o1[1].y);
+                o4[1] = make_float4(o1[2].x, o1[2].y, o1[3].x, o1[3].y);
+            }
+            continue;
+        }
+        hb_publish<4, 4, K1_A1_STR>(o1, sA1, t);
+        __syncthreads();
+        float2 o2[2];
+        hb_run<2, 4, K1_A1_STR>(o1, o2, sA1, t, i0 >> 1);
+        if (M.decim == 2) {
+            if (store)
+                *reinterpret_cast<float4 *>(outp + (i0 >> 2)) = make_float4(o2[0].x, o2[0].y, o2[1].x, o2[1].y);
+            continue;
+        }
+        hb_publish<2, 2, K1_A2_STR>(o2, sA2, t);
+        __syncthreads();
+        float2 o3[1];
+        hb_run<1, 2, K1_A2_STR>(o2, o3, sA2, t, i0 >> 2);
+        if (store) outp[i0 >> 3] = o3[0];
+    }
+}
+
+// ------------------------------------------------------------------------------------
+// K2A: per sub VFO NCO mix + S half-band stages.
+// Phase 1 (coalesced): every thread loads pairs of parent samples and table entries, mixes,
+// and stores into a padded smem array. Phase 2: every thread owns 32 consecutive mixed
+// samples in registers and runs the whole cascade (16, 8, 4, 2, 1 outputs per stage);
+// only the <= 12 trailing outputs per stage go through smem for the neighbours.
+// The first HT threads of a CTA recompute the filter halo in front of the tile.
+// ------------------------------------------------------------------------------------
+template <int S> struct K2aHalo { static constexpr int v = S <= 2 ? 1 : S == 3 ? 3 : S == 4 ? 5 : 11; };
+constexpr int K2A_A0_STR = 34;
+constexpr size_t K2A_SMEM_X = (size_t)(K2A_THREADS + HB_PAD) * K2A_A0_STR * sizeof(float2);
+constexpr size_t K2A_SMEM_Y = (size_t)(K2A_THREADS + HB_PAD) * 13 * sizeof(float2);
+constexpr size_t K2A_SMEM = K2A_SMEM_X + K2A_SMEM_Y + 16;
+
+template <int S>
+__global__ void __launch_bounds__(K2A_THREADS, 2) k2a_sub_cascade(const K2aParams p) {
+    extern __shared__ __align__(16) unsigned char smem_raw[];
+    float2 *sX = reinterpret_cast<float2 *>(smem_raw);
+    float2 *sY = reinterpret_cast<float2 *>(smem_raw + K2A_SMEM_X);
+    int *sBase = reinterpret_cast<int *>(smem_raw + K2A_SMEM_X + K2A_SMEM_Y);
+
+    constexpr int HT = K2aHalo<S>::v;
+    constexpr int ADV = (K2A_THREADS - HT) * K2A_CHUNK;
+    const SubDev &D = p.subs[blockIdx.y];
+    const int stream = p.stream0 + blockIdx.x;
+    const int tile = blockIdx.z % p.tiles, b = blockIdx.z / p.tiles;
+    const int t = threadIdx.x;
+    const int B = D.block_in;
+    const int r0 = tile * ADV - HT * K2A_CHUNK;           // callback coordinate of thread 0's chunk
+    const long long blk = p.blocks_done[stream] + b;
+    if (t == 0) sBase[0] = (int)((blk * (long long)B) % D.lut_len);
+    __syncthreads();
+    const int lut_base = sBase[0];
+    const bool first_ever = (blk == 0);
+    const float2 *inp = D.in + (size_t)stream * D.in_stride + MAIN_HIST + (size_t)b * B;
+
+    // ---- phase 1: coalesced load + mix ----
+#pragma unroll 4
+    for (int j = 0; j < K2A_CHUNK / 2; ++j) {
+        const int g = j * (2 * K2A_THREADS) + 2 * t;      // CTA-relative sample (even)
+        const int i = r0 + g;
+        float4 m = make_float4(0.f, 0.f, 0.f, 0.f);
+        if (i < B && !(first_ever && i < 0)) {
+            const float4 xv = __ldg(reinterpret_cast<const float4 *>(inp + i));
+            int idx = lut_base + i;
+            if (idx < 0) idx += D.lut_len;
+            if (idx >= D.lut_len) idx -= D.lut_len;
+            float4 lv = __ldg(reinterpret_cast<const float4 *>(D.lut + idx));
+            if (first_ever && i == 0) {
+                const float2 last = __ldg(D.lut + (D.lut_len - 1));
+                lv.x = last.x; lv.y = last.y;
+            }
+            const float2 m0 = cmul(make_float2(lv.x, lv.y), make_float2(xv.x, xv.y));
+            const float2 m1 = cmul(make_float2(lv.z, lv.w), make_float2(xv.z, xv.w));
+            m = make_float4(m0.x, m0.y, m1.x, m1.y);
+        }
+        *reinterpret_cast<float4 *>(sX + ((g >> 5) + HB_PAD) * K2A_A0_STR + (g & 31)) = m;
+    }
+    __syncthreads();
+
+    // ---- phase 2: register-resident cascade ----
+    const int v0 = r0 + t * K2A_CHUNK;
+    const bool store = (t >= HT) && (v0 < B);
+    float2 a0[32];
+    {
+        const float4 *s4 = reinterpret_cast<const float4 *>(sX + (t + HB_PAD) * K2A_A0_STR);
+#pragma unroll
+        for (int k = 0; k < 16; ++k) {
+            const float4 v = s4[k];
+            a0[2 * k] = make_float2(v.x, v.y);
+            a0[2 * k + 1] = make_float2(v.z, v.w);
+        }
+    }
+    float2 *zp = D.z + (size_t)stream * D.z_stride + D.z_hist + (size_t)b * D.block_z;
+    float2 a1[16];
+    hb_run<16, 32, K2A_A0_STR>(a0, a1, sX, t, v0);
+    if constexpr (S == 1) {
+        if (store) {
+            float4 *o4 = reinterpret_cast<float4 *>(zp + (v0 >> 1));
+#pragma unroll
+            for (int k = 0; k < 8; ++k) o4[k] = make_float4(a1[2 * k].x, a1[2 * k].y, a1[2 * k + 1].x, a1[2 * k + 1].y);
+        }
+        return;
+    }
+    hb_publish<16, 12, 13>(a1, sY, t);
+    __syncthreads();                                       // sX free from here on
+    float2 a2[8];
+    hb_run<8, 12, 13>(a1, a2, sY, t, v0 >> 1);
+    if constexpr (S == 2) {
+        if (store) {
+            float4 *o4 = reinterpret_cast<float4 *>(zp + (v0 >> 2));
+#pragma unroll
+            for (int k = 0; k < 4; ++k) o4[k] = make_float4(a2[2 * k].x, a2[2 * k].y, a2[2 * k + 1].x, a2[2 * k + 1].y);
+        }
+        return;
+    }
+    hb_publish<8, 8, 9>(a2, sX, t);
+    __syncthreads();                                       // sY free
+    float2 a3[4];
+    hb_run<4, 8, 9>(a2, a3, sX, t, v0 >> 2);
+    if constexpr (S == 3) {
+        if (store) {
+            float4 *o4 = reinterpret_cast<float4 *>(zp + (v0 >> 3));
+            o4[0] = make_float4(a3[0].x, a3[0].y, a3[1].x, a3[1].y);
+            o4[1] = make_float4(a3[2].x, a3[2].y, a3[3].x, a3[3].y);
+        }
+        return;
+    }
+    hb_publish<4, 4, 5>(a3, sY, t);
+    __syncthreads();                                       // sX free
+    float2 a4[2];
+    hb_run<2, 4, 5>(a3, a4, sY, t, v0 >> 3);
+    if constexpr (S == 4) {
+        if (store) *reinterpret_cast<float4 *>(zp + (v0 >> 4)) = make_float4(a4[0].x, a4[0].y, a4[1].x, a4[1].y);
+        return;
+    }
+    hb_publish<2, 2, 3>(a4, sX, t);
+    __syncthreads();
+    float2 a5[1];
+    hb_run<1, 2, 3>(a4, a5, sX, t, v0 >> 4);
+    if (store) zp[v0 >> 5] = a5[0];
+}
+
+// S = 0 (e.g. the 288 kS/s plan): the sub VFO only mixes.
+__global__ void __launch_bounds__(256) k2a_mix_only(const K2aParams p) {
+    const SubDev &D = p.subs[blockIdx.y];
+    const int stream = p.stream0 + blockIdx.x;
+    const int tile = blockIdx.z % p.tiles, b = blockIdx.z / p.tiles;
+    const int B = D.block_in;
+    const long long blk = p.blocks_done[stream] + b;
+    const int lut_base = (int)((blk * (long long)B) % D.lut_len);
+    const float2 *inp = D.in + (size_t)stream * D.in_stride + MAIN_HIST + (size_t)b * B;
+    float2 *zp = D.z + (size_t)stream * D.z_stride + D.z_hist + (size_t)b * D.block_z;
+    const int i = tile * 2048 + 2 * threadIdx.x;
+#pragma unroll
+    for (int j = 0; j < 4; ++j) {
+        const int ii = i + j * 512;
+        if (ii < B) {
+            const float4 xv = __ldg(reinterpret_cast<const float4 *>(inp + ii));
+            int idx = lut_base + ii;
+            if (idx >= D.lut_len) idx -= D.lut_len;
+            float4 lv = __ldg(reinterpret_cast<const float4 *>(D.lut + idx));
+            if (blk == 0 && ii == 0) {
+                const float2 last = __ldg(D.lut + (D.lut_len - 1));
+                lv.x = last.x; lv.y = last.y;
+            }
+            const float2 m0 = cmul(make_float2(lv.x, lv.y), make_float2(xv.x, xv.y));
+            const float2 m1 = cmul(make_float2(lv.z, lv.w), make_float2(xv.z, xv.w));
+            *reinterpret_cast<float4 *>(zp + ii) = make_float4(m0.x, m0.y, m1.x, m1.y);
+        }
+    }
+}
+
+// ------------------------------------------------------------------------------------
+// K2 late: d[m] = sum_i taps[i] * z[late*m - ntaps + i]  on both arms
+// (fir_decI/Q FIRUpdateAndProcess on the first sample of each group of `late`, FIRUpdate
+// on the others: vfo.cpp:346-384; newest sample excluded: dsp.cpp:59-71).
+// ------------------------------------------------------------------------------------
+__global__ void __launch_bounds__(LATE_TILE) k2_late_fir(const LateDev *__restrict__ devs, int n_blocks, int stream0) {
+    __shared__ float2 sz[LATE_TILE * 6 + MAX_FIR_TAPS];
+    __shared__ float st[MAX_FIR_TAPS];
+    const LateDev &D = devs[blockIdx.y];
+    const int stream = stream0 + blockIdx.x;
+    const int n_total = n_blocks * D.samples_out;
+    const int m0 = blockIdx.z * LATE_TILE;
+    if (m0 >= n_total) return;
+    const int t = threadIdx.x;
+    const int span = D.late * LATE_TILE + D.ntaps;
+    const long long zlo = (long long)D.late * m0 - D.ntaps;       // may be negative: history
+    const long long zmax = (long long)n_blocks * D.block_z;
+    const float2 *zp = D.z + (size_t)stream * D.z_stride + D.z_hist;
+    for (int e = t; e < span; e += LATE_TILE) {
+        const long long zi = zlo + e;
+        sz[e] = (zi < zmax) ? zp[zi] : make_float2(0.f, 0.f);
+    }
+    for (int e = t; e < D.ntaps; e += LATE_TILE) st[e] = D.taps[e];
+    __syncthreads();
+    const int m = m0 + t;
+    if (m >= n_total) return;
+    const float2 *w = sz + D.late * t;
+    float ax = 0.f, ay = 0.f;
+    for (int i = 0; i < D.ntaps; ++i) {
+        const float c = st[i];
+        const float2 v = w[i];
+        ax = fmaf(c, v.x, ax);
+        ay = fmaf(c, v.y, ay);
+    }
+    D.d[(size_t)stream * D.d_stride + D.d_hist + m] = make_float2(ax, ay);
+}
+
+// ------------------------------------------------------------------------------------
+// K2B: USB demodulation + optional low-pass + gain + int16.
+//   usb[n] = re[n-62] - sum_{i=0..124} points[i]*im[n-124+i]      (vfo.cpp:316-324)
+// only odd i are non-zero, so every output touches 62 samples of one parity: the imaginary
+// arm is split into two parity planes and each thread produces 4 consecutive plane outputs
+// from a sliding register window (float4 smem loads, 16 FMA per load pair).
+//   out[n] = sum_{i<N} lpf[i]*usb[n-N+i]                           (dsp.cpp:59-71)
+//   pcm = (short)(out*gain*32768.0)                                (vfo.cpp:328)
+// ------------------------------------------------------------------------------------
+__device__ __forceinline__ void fir4(const float *__restrict__ x, const float *__restrict__ taps, int ntaps, float (&acc)[4]) {
+    float4 cur = *reinterpret_cast<const float4 *>(x);
+    acc[0] = acc[1] = acc[2] = acc[3] = 0.f;
+    for (int j = 0; j < ntaps; j += 4) {
+        const float4 nxt = *reinterpret_cast<const float4 *>(x + j + 4);
+        const float4 c = *reinterpret_cast<const float4 *>(taps + j);
+        acc[0] = fmaf(c.x, cur.x, acc[0]); acc[0] = fmaf(c.y, cur.y, acc[0]); acc[0] = fmaf(c.z, cur.z, acc[0]); acc[0] = fmaf(c.w, cur.w, acc[0]);
+        acc[1] = fmaf(c.x, cur.y, acc[1]); acc[1] = fmaf(c.y, cur.z, acc[1]); acc[1] = fmaf(c.z, cur.w, acc[1]); acc[1] = fmaf(c.w, nxt.x, acc[1]);
+        acc[2] = fmaf(c.x, cur.z, acc[2]); acc[2] = fmaf(c.y, cur.w, acc[2]); acc[2] = fmaf(c.z, nxt.x, acc[2]); acc[2] = fmaf(c.w, nxt.y, acc[2]);
+        acc[3] = fmaf(c.x, cur.w, acc[3]); acc[3] = fmaf(c.y, nxt.x, acc[3]); acc[3] = fmaf(c.z, nxt.y, acc[3]); acc[3] = fmaf(c.w, nxt.z, acc[3]);
+        cur = nxt;
+    }
+}
+
+constexpr int USB_SPAN = USB_TILE + MAX_FIR_TAPS + 128;     // z samples a CTA may need
+
+__global__ void __launch_bounds__(256) k2b_usb_audio(const UsbDev *__restrict__ devs, int n_blocks, int stream0,
+                                                      int n_streams_total, int pcm_per_block,
+                                                      int16_t *__restrict__ pcm, float *__restrict__ tap) {
+    __shared__ __align__(16) float sPlaneA[USB_SPAN / 2 + 8];    // im[zlo + 2j + 1]
+    __shared__ __align__(16) float sPlaneB[USB_SPAN / 2 + 8];    // im[zlo + 2j + 2]
+    __shared__ __align__(16) float sRe[USB_SPAN + 8];
+    __shared__ __align__(16) float sUsb[USB_TILE + MAX_FIR_TAPS + 8];
+    __shared__ __align__(16) float sHil[64];
+    __shared__ __align__(16) float sLpf[MAX_FIR_TAPS];
+
+    const UsbDev &D = devs[blockIdx.y];
+    const int stream = stream0 + blockIdx.x;
+    const int n_total = n_blocks * D.samples_out;
+    const int n0 = blockIdx.z * USB_TILE;
+    if (n0 >= n_total) return;
+    const int t = threadIdx.x;
+    const int NP = D.np;
+    const int span = USB_TILE + NP + 128;                   // z-local q in [0, span)
+    const long long zlo = (long long)n0 - NP - 128;
+    const float2 *zp = D.src + (size_t)stream * D.src_stride + D.src_hist;
+    for (int e = t; e < span; e += 256) {
+        const long long zi = zlo + e;
+        const float2 v = (zi < n_total) ? zp[zi] : make_float2(0.f, 0.f);
+        sRe[e] = v.x;
+        if (e & 1) sPlaneA[e >> 1] = v.y;
+        else if (e >= 2) sPlaneB[(e >> 1) - 1] = v.y;
+    }
+    if (t < 64) sHil[t] = D.hil[t];
+    for (int e = t; e < NP; e += 256) sLpf[e] = D.lpf[e];
+    __syncthreads();
+
+    // Hilbert: usb index i = q - 128, q = 2w + par, i in [0, USB_TILE + NP)
+    const int n_usb = USB_TILE + NP;
+    const int per_par = (n_usb / 2 + 3) / 4;               // threads needed per parity
+    for (int it = t; it < 2 * per_par; it += 256) {
+        const int par = it >= per_par;
+        const int w0 = 64 + 4 * (par ? it - per_par : it); // first plane output of this thread
+        const float *plane = par ? sPlaneB : sPlaneA;
+        float acc[4];
+        fir4(plane + (w0 - 64), sHil, 64, acc);
+#pragma unroll
+        for (int r = 0; r < 4; ++r) {
+            const int q = 2 * (w0 + r) + par;
+            const int i = q - 128;
+            if (i < n_usb) sUsb[i] = sRe[q - 62] - acc[r];
+        }
+    }
+    __syncthreads();
+
+    // low-pass (or identity), gain, quantise, store 4 consecutive samples per thread
+    const int i4 = 4 * t;
+    float o[4];
+    if (NP > 0) {
+        fir4(sUsb + i4, sLpf, NP, o);
+    } else {
+        const float4 v = *reinterpret_cast<const float4 *>(sUsb + i4);
+        o[0] = v.x; o[1] = v.y; o[2] = v.z; o[3] = v.w;
+    }
+#pragma unroll
+    for (int r = 0; r < 4; ++r) {
+        const int n = n0 + i4 + r;
+        if (n < n_total) {
+            const int blk = n / D.samples_out, i = n - blk * D.samples_out;
+            const size_t at = ((size_t)stream * n_blocks + blk) * pcm_per_block + D.pcm_offset + i;
+            const float v = (o[r] * D.gain) * 32768.0f;     // exact power-of-two scaling
+            pcm[at] = (int16_t)__float2int_rz(v);
+            if (tap) tap[at] = v;
+        }
+    }
+}
+
+// ------------------------------------------------------------------------------------
+// K3: carry. Copies the trailing `hist` bytes of what this call produced to the front of
+// each buffer (main outputs, z, d) and keeps the last RAW_TAIL raw samples.
+// ------------------------------------------------------------------------------------
+__global__ void __launch_bounds__(128) k3_carry(const CarryItem *__restrict__ items, int n_items, int n_blocks,
+                                                 const uint8_t *__restrict__ iq, size_t iq_stride, int block,
+                                                 uint8_t *__restrict__ tail, long long *__restrict__ blocks_done,
+                                                 int stream0) {
+    const int stream = stream0 + blockIdx.x;
+    const int item = blockIdx.y;
+    if (item < n_items) {
+        const CarryItem it = items[item];
+        unsigned char *base = reinterpret_cast<unsigned char *>(it.base) + (size_t)stream * it.stride;
+        const uint4 *src = reinterpret_cast<const uint4 *>(base + (size_t)n_blocks * it.block_bytes);
+        uint4 *dst = reinterpret_cast<uint4 *>(base);
+        for (int e = threadIdx.x; e < it.hist_bytes / 16; e += 128) dst[e] = src[e];
+    } else {
+        const uint4 *src = reinterpret_cast<const uint4 *>(iq + (size_t)stream * iq_stride + ((size_t)n_blocks * block - RAW_TAIL) * 2);
+        uint4 *dst = reinterpret_cast<uint4 *>(tail + (size_t)stream * (2 * RAW_TAIL));
+        for (int e = threadIdx.x; e < (2 * RAW_TAIL) / 16; e += 128) dst[e] = src[e];
+        if (threadIdx.x == 0) blocks_done[stream] += n_blocks;
+    }
+}
+
+}  // namespace sdrb

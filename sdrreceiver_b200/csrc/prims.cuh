@@ -1,0 +1,117 @@
+// Per-class device primitives behind the C++ facades (Oscillator/vfo mix loop,
+// HalfBandDecimator, FIR, FIRHilbert+DelayThing, FFTWrapper). One CTA row per channel;
+// state is explicit (history arrays), exactly what the reference objects hold.
+#pragma once
+#include <cuda_runtime.h>
+#include "kernels.cuh"
+
+namespace sdrb {
+
+// vfo::process mix loop (vfo.cpp:237-245) with Oscillator::tick indexing (oscillator.cpp:39-50)
+__global__ void __launch_bounds__(256) prim_nco_mix(const float2 *__restrict__ table, int L, long long n0,
+                                                     const float2 *__restrict__ in, float2 *__restrict__ out, int n) {
+    const int i = blockIdx.x * 256 + threadIdx.x;
+    if (i >= n) return;
+    const long long g = n0 + i;
+    const int idx = (g == 0) ? L - 1 : (int)(g % L);
+    const size_t at = (size_t)blockIdx.y * n + i;
+    out[at] = cmul(__ldg(table + idx), in[at]);
+}
+
+// HalfBandDecimator::decimate, 11 taps (halfbanddecimator.cpp:43-72; dsp.cpp:96-148):
+// queue = [hist(11) | block]; output m reads queue[2m+1 .. 2m+11].
+__global__ void __launch_bounds__(256) prim_halfband11(const float2 *__restrict__ in, float2 *__restrict__ out,
+                                                        const float2 *__restrict__ hist, int n) {
+    const int m = blockIdx.x * 256 + threadIdx.x;
+    if (m >= n / 2) return;
+    const float2 *x = in + (size_t)blockIdx.y * n;
+    const float2 *h = hist + (size_t)blockIdx.y * 11;
+    auto q = [&](int j) -> float2 { return j < 11 ? h[j] : x[j - 11]; };
+    const int t = 2 * m + 1;
+    const float2 w0 = q(t), w2 = q(t + 2), w4 = q(t + 4), w5 = q(t + 5), w6 = q(t + 6), w8 = q(t + 8), w10 = q(t + 10);
+    float2 y;
+    y.x = HB_P0 * (w0.x + w10.x) + HB_P2 * (w2.x + w8.x) + HB_P4 * (w4.x + w6.x) + HB_P5 * w5.x;
+    y.y = HB_P0 * (w0.y + w10.y) + HB_P2 * (w2.y + w8.y) + HB_P4 * (w4.y + w6.y) + HB_P5 * w5.y;
+    out[(size_t)blockIdx.y * (n / 2) + m] = y;
+}
+
+// FIRQueueBackToFront (dsp.cpp:163-173): new head = queue[B-1 .. B+9] = block[B-12 .. B-2].
+__global__ void prim_halfband11_carry(const float2 *__restrict__ in, float2 *__restrict__ hist, int n) {
+    if (threadIdx.x < 11) hist[(size_t)blockIdx.x * 11 + threadIdx.x] = in[(size_t)blockIdx.x * n + (n - 12 + threadIdx.x)];
+}
+
+// FIR::FIRUpdateAndProcess (dsp.cpp:59-71): y[m] = sum_i taps[i] * x[decim*m - N + i]
+__global__ void __launch_bounds__(256) prim_fir(const float *__restrict__ taps, int N, const float *__restrict__ in,
+                                                 float *__restrict__ out, const float *__restrict__ hist, int n,
+                                                 int decim, int n_out) {
+    const int m = blockIdx.x * 256 + threadIdx.x;
+    if (m >= n_out) return;
+    const float *x = in + (size_t)blockIdx.y * n;
+    const float *h = hist + (size_t)blockIdx.y * N;
+    const int base = decim * m - N;
+    float acc = 0.f;
+    for (int i = 0; i < N; ++i) {
+        const int j = base + i;
+        acc = fmaf(__ldg(taps + i), j < 0 ? h[N + j] : x[j], acc);
+    }
+    out[(size_t)blockIdx.y * n_out + m] = acc;
+}
+
+// keep the last `count` elements (of `width` floats) of every channel's block
+__global__ void prim_tail_carry(const float *__restrict__ in, float *__restrict__ hist, int n, int count, int width) {
+    const float *x = in + (size_t)blockIdx.x * n * width + (size_t)(n - count) * width;
+    float *h = hist + (size_t)blockIdx.x * count * width;
+    for (int e = threadIdx.x; e < count * width; e += blockDim.x) h[e] = x[e];
+}
+
+// usb = DelayThing(62)(re) - FIRHilbert125(im)  (vfo.cpp:316-324; dsp.cpp:218-231)
+__global__ void __launch_bounds__(256) prim_usb(const float *__restrict__ pts, const float2 *__restrict__ in,
+                                                 float *__restrict__ out, const float2 *__restrict__ hist, int n) {
+    __shared__ float sp[125];
+    if (threadIdx.x < 125) sp[threadIdx.x] = pts[threadIdx.x];
+    __syncthreads();
+    const int i = blockIdx.x * 256 + threadIdx.x;
+    if (i >= n) return;
+    const float2 *x = in + (size_t)blockIdx.y * n;
+    const float2 *h = hist + (size_t)blockIdx.y * 124;
+    auto at = [&](int j) -> float2 { return j < 0 ? h[124 + j] : x[j]; };
+    float acc = 0.f;
+    for (int k = 1; k < 125; k += 2) acc = fmaf(sp[k], at(i - 124 + k).y, acc);   // even points are exactly 0
+    out[(size_t)blockIdx.y * n + i] = at(i - 62).x - acc;
+}
+
+// Spectrum path: optional Hann window (mainwindow.cpp:284-288, 416-423) and an 8192-point
+// forward complex FFT, unscaled like kiss_fft (kiss_fft.c:339-388). One CTA per transform,
+// whole transform in shared memory: bit-reversed load, 13 radix-2 stages.
+__global__ void __launch_bounds__(512) prim_fft8192(const float2 *__restrict__ in, float2 *__restrict__ out, int hann) {
+    extern __shared__ float2 s[];
+    constexpr int N = 8192, LOGN = 13;
+    const float2 *x = in + (size_t)blockIdx.x * N;
+    for (int i = threadIdx.x; i < N; i += 512) {
+        float2 v = x[i];
+        if (hann) {
+            const float w = (float)(0.5 * (1.0 - cos(2.0 * 3.14159265358979323846 * (double)(float)i / (N - 1.0))));
+            v.x *= w; v.y *= w;
+        }
+        s[__brev((unsigned)i) >> (32 - LOGN)] = v;
+    }
+    __syncthreads();
+    for (int st = 0; st < LOGN; ++st) {
+        const int half = 1 << st;
+        for (int bfly = threadIdx.x; bfly < N / 2; bfly += 512) {
+            const int k = bfly & (half - 1);
+            const int i0 = ((bfly >> st) << (st + 1)) + k, i1 = i0 + half;
+            float sn, cs;
+            sincospif(-(float)k / (float)half, &sn, &cs);
+            const float2 a = s[i0], b = s[i1];
+            const float2 tw = make_float2(b.x * cs - b.y * sn, b.x * sn + b.y * cs);
+            s[i0] = make_float2(a.x + tw.x, a.y + tw.y);
+            s[i1] = make_float2(a.x - tw.x, a.y - tw.y);
+        }
+        __syncthreads();
+    }
+    float2 *y = out + (size_t)blockIdx.x * N;
+    for (int i = threadIdx.x; i < N; i += 512) y[i] = s[i];
+}
+
+}  // namespace sdrb

@@ -1,0 +1,130 @@
+// ZMQ output, wire-compatible with ZmqPublisher (zmqpublisher.cpp:15-96): one PUB socket,
+// the same keepalive / reconnect socket options, and per message three frames
+//   [topic, exactly 5 bytes][sample rate, uint32 little endian][int16 LE mono PCM].
+// libzmq has no headers in this image, so the eight entry points are resolved at run time
+// from SDRB_LIBZMQ, the system libzmq, or the copy bundled with pyzmq.
+#include <dlfcn.h>
+#include <glob.h>
+
+#include <cstring>
+#include <string>
+
+#include "plan.hpp"
+
+struct sdrb_plan { sdrb::HostPlan h; };
+
+namespace {
+struct ZmqApi {
+    void *lib = nullptr;
+    void *(*ctx_new)() = nullptr;
+    int (*ctx_term)(void *) = nullptr;
+    void *(*socket)(void *, int) = nullptr;
+    int (*close)(void *) = nullptr;
+    int (*setsockopt)(void *, int, const void *, size_t) = nullptr;
+    int (*bind)(void *, const char *) = nullptr;
+    int (*connect)(void *, const char *) = nullptr;
+    int (*send)(void *, const void *, size_t, int) = nullptr;
+    int (*err)() = nullptr;
+};
+ZmqApi g_zmq;
+
+bool load_zmq() {
+    if (g_zmq.lib) return true;
+    std::string cands[8];
+    int n = 0;
+    if (const char *e = getenv("SDRB_LIBZMQ")) cands[n++] = e;
+    cands[n++] = "libzmq.so.5";
+    cands[n++] = "libzmq.so";
+    glob_t g;
+    const char *pats[] = {"/opt/prime-rl/.venv/lib/python3*/site-packages/pyzmq.libs/libzmq-*.so*",
+                          "/usr/lib/python3/dist-packages/pyzmq.libs/libzmq-*.so*",
+                          "/usr/local/lib/python3*/site-packages/pyzmq.libs/libzmq-*.so*"};
+    for (const char *pat : pats)
+        if (n < 8 && glob(pat, 0, nullptr, &g) == 0) {
+            if (g.gl_pathc > 0) cands[n++] = g.gl_pathv[0];
+            globfree(&g);
+        }
+    for (int i = 0; i < n && !g_zmq.lib; i++) g_zmq.lib = dlopen(cands[i].c_str(), RTLD_NOW | RTLD_LOCAL);
+    if (!g_zmq.lib) { sdrb::set_error("libzmq not found (set SDRB_LIBZMQ to its path)"); return false; }
+#define SYM(field, name) g_zmq.field = (decltype(g_zmq.field))dlsym(g_zmq.lib, name)
+    SYM(ctx_new, "zmq_ctx_new"); SYM(ctx_term, "zmq_ctx_term"); SYM(socket, "zmq_socket"); SYM(close, "zmq_close");
+    SYM(setsockopt, "zmq_setsockopt"); SYM(bind, "zmq_bind"); SYM(connect, "zmq_connect"); SYM(send, "zmq_send");
+    SYM(err, "zmq_errno");
+#undef SYM
+    if (!g_zmq.ctx_new || !g_zmq.socket || !g_zmq.setsockopt || !g_zmq.bind || !g_zmq.connect || !g_zmq.send) {
+        sdrb::set_error("libzmq is missing required symbols");
+        dlclose(g_zmq.lib); g_zmq.lib = nullptr;
+        return false;
+    }
+    return true;
+}
+// libzmq 4.x constants (zmq.h)
+constexpr int kPUB = 1, kSNDMORE = 2, kRECONNECT_IVL = 18, kRECONNECT_IVL_MAX = 21;
+constexpr int kKEEPALIVE = 34, kKEEPALIVE_CNT = 35, kKEEPALIVE_IDLE = 36, kKEEPALIVE_INTVL = 37, kLINGER = 17;
+}  // namespace
+
+struct sdrb_publisher {
+    void *ctx = nullptr, *sock = nullptr;
+};
+
+extern "C" int sdrb_publisher_open(const char *address, int bind, sdrb_publisher **out) {
+    if (!address || !out) { sdrb::set_error("sdrb_publisher_open: NULL argument"); return SDRB_E_INVALID; }
+    *out = nullptr;
+    if (!load_zmq()) return SDRB_E_ZMQ;
+    sdrb_publisher *p = new sdrb_publisher();
+    p->ctx = g_zmq.ctx_new();
+    p->sock = p->ctx ? g_zmq.socket(p->ctx, kPUB) : nullptr;
+    if (!p->sock) { sdrb::set_error("zmq_socket failed"); delete p; return SDRB_E_ZMQ; }
+    // same options, same values as ZmqPublisher::connect (zmqpublisher.cpp:24-37)
+    const int keepalive = 1, cnt = 10, idle = 1, intvl = 1, reconnect = 1000, reconnect_max = 0, linger = 0;
+    g_zmq.setsockopt(p->sock, kKEEPALIVE, &keepalive, sizeof(int));
+    g_zmq.setsockopt(p->sock, kKEEPALIVE_CNT, &cnt, sizeof(int));
+    g_zmq.setsockopt(p->sock, kKEEPALIVE_IDLE, &idle, sizeof(int));
+    g_zmq.setsockopt(p->sock, kKEEPALIVE_INTVL, &intvl, sizeof(int));
+    g_zmq.setsockopt(p->sock, kRECONNECT_IVL, &reconnect, sizeof(int));
+    g_zmq.setsockopt(p->sock, kRECONNECT_IVL_MAX, &reconnect_max, sizeof(int));
+    g_zmq.setsockopt(p->sock, kLINGER, &linger, sizeof(int));
+    const int rc = bind ? g_zmq.bind(p->sock, address) : g_zmq.connect(p->sock, address);
+    if (rc < 0) {
+        sdrb::set_error(std::string("ZeroMQ could not ") + (bind ? "bind to " : "connect to ") + address +
+                        " error code: " + std::to_string(g_zmq.err ? g_zmq.err() : -1));
+        if (g_zmq.close) g_zmq.close(p->sock);
+        if (g_zmq.ctx_term) g_zmq.ctx_term(p->ctx);
+        delete p;
+        return SDRB_E_ZMQ;
+    }
+    *out = p;
+    return SDRB_OK;
+}
+
+extern "C" int sdrb_publisher_send(sdrb_publisher *p, const char *topic, uint32_t rate, const void *payload, uint32_t len) {
+    if (!p || !topic || (!payload && len)) { sdrb::set_error("sdrb_publisher_send: NULL argument"); return SDRB_E_INVALID; }
+    if (len == 0) return SDRB_OK;                                 // zmqpublisher.cpp:88
+    char t[SDRB_TOPIC_LEN] = {0, 0, 0, 0, 0};                     // always 5 bytes on the wire (line 91)
+    memcpy(t, topic, strnlen(topic, SDRB_TOPIC_LEN));
+    unsigned char r[4];
+    memcpy(r, &rate, 4);
+    if (g_zmq.send(p->sock, t, SDRB_TOPIC_LEN, kSNDMORE) < 0 || g_zmq.send(p->sock, r, 4, kSNDMORE) < 0 ||
+        g_zmq.send(p->sock, payload, len, 0) < 0) {
+        sdrb::set_error("zmq_send failed, errno " + std::to_string(g_zmq.err ? g_zmq.err() : -1));
+        return SDRB_E_ZMQ;
+    }
+    return SDRB_OK;
+}
+
+extern "C" int sdrb_publisher_send_block(sdrb_publisher *p, const sdrb_plan *plan, const int16_t *rec) {
+    if (!p || !plan || !rec) { sdrb::set_error("sdrb_publisher_send_block: NULL argument"); return SDRB_E_INVALID; }
+    for (const sdrb::SubVfo &s : plan->h.subs) {                  // vfo::transmitData, vfo.cpp:426-437
+        const int rc = sdrb_publisher_send(p, s.topic.c_str(), (uint32_t)s.out_rate, rec + s.pcm_offset,
+                                           (uint32_t)s.samples_out * 2u);
+        if (rc != SDRB_OK) return rc;
+    }
+    return SDRB_OK;
+}
+
+extern "C" void sdrb_publisher_close(sdrb_publisher *p) {
+    if (!p) return;
+    if (p->sock && g_zmq.close) g_zmq.close(p->sock);
+    if (p->ctx && g_zmq.ctx_term) g_zmq.ctx_term(p->ctx);
+    delete p;
+}
