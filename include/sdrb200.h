@@ -144,6 +144,13 @@ int sdrb_bank_process_host(sdrb_bank *bank, const uint8_t *h_iq, size_t iq_strid
                            int16_t *h_pcm, float *h_tap);
 /* Kernel launches issued by the last process_* call (for bench.py's gpu_launches). */
 int sdrb_bank_last_launches(const sdrb_bank *bank);
+/* Per-kernel-class device timing (CUDA events on the launching stream), for roofline
+ * reporting: classes 0 DC scan, 1 ingest+main VFOs, 2 sub-VFO cascades, 3 /late FIR,
+ * 4 USB audio, 5 carry. set_timing(.., 1) starts/clears; kernel_times synchronises the
+ * device and returns accumulated milliseconds and number of timed calls per class. */
+#define SDRB_N_KERNEL_CLASSES 6
+int sdrb_bank_set_timing(sdrb_bank *bank, int on);
+int sdrb_bank_kernel_times(sdrb_bank *bank, double *ms, long *calls);
 
 void *sdrb_host_alloc(size_t bytes);   /* cudaHostAlloc'd (pinned) */
 void sdrb_host_free(void *p);

@@ -20,6 +20,7 @@
 //   DIR/frames.txt    one line per ZMQ message: topic-bytes(hex) rate payload-bytes parts
 //   DIR/main<k>.cf32  (--main-tap) decimate[decimateCount] of main VFO k, every block
 //   --time            no files; prints "samples seconds" for the demodData loop only
+//   --skip N          (with --time) first N callbacks run untimed (warm-up)
 #include <chrono>
 #include <cstdio>
 #include <fstream>
@@ -110,7 +111,7 @@ struct Ini {
 
 int main(int argc, char **argv) {
     const char *ini_path = 0, *in_path = 0, *out_dir = 0;
-    long max_blocks = -1;
+    long max_blocks = -1, skip_blocks = 0;
     bool main_tap = false, timing = false;
     for (int i = 1; i < argc; i++) {
         std::string a = argv[i];
@@ -120,6 +121,7 @@ int main(int argc, char **argv) {
         else if (a == "--blocks" && i + 1 < argc) max_blocks = atol(argv[++i]);
         else if (a == "--main-tap") main_tap = true;
         else if (a == "--time") timing = true;
+        else if (a == "--skip" && i + 1 < argc) skip_blocks = atol(argv[++i]);
         else { fprintf(stderr, "unknown argument %s\n", argv[i]); return 2; }
     }
     if (!ini_path || !in_path || (!out_dir && !timing)) {
@@ -250,7 +252,7 @@ int main(int argc, char **argv) {
         for (int i = 0; i < buflen; i++) fl[i] = radio->floats.at(src[i]);   // sdr.cpp:122-129
         radio->demodData(fl.data(), buflen);
         auto t1 = std::chrono::steady_clock::now();
-        seconds += std::chrono::duration<double>(t1 - t0).count();
+        if (b >= skip_blocks) seconds += std::chrono::duration<double>(t1 - t0).count();
         if (timing) continue;
         for (const ZmqMessage &m : g_messages) {
             std::string topic = m.parts.size() > 0 ? m.parts[0] : "";
@@ -274,7 +276,7 @@ int main(int argc, char **argv) {
         }
     }
     if (timing) {
-        printf("%ld %.6f\n", nblocks * (long)(buflen / 2), seconds);
+        printf("%ld %.6f\n", (nblocks - skip_blocks) * (long)(buflen / 2), seconds);
         return 0;
     }
     for (auto &kv : pcm) if (kv.second) fclose(kv.second);

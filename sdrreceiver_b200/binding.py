@@ -84,6 +84,8 @@ def lib():
         "sdrb_bank_copy_main": (i, [vp, i, i, vp, vp]),
         "sdrb_bank_process_host": (i, [vp, vp, sz, i, vp, vp]),
         "sdrb_bank_last_launches": (i, [vp]),
+        "sdrb_bank_set_timing": (i, [vp, i]),
+        "sdrb_bank_kernel_times": (i, [vp, vp, vp]),
         "sdrb_host_alloc": (vp, [sz]),
         "sdrb_host_free": (None, [vp]),
         "sdrb_nco_table": (l, [d, d, vp, l]),
@@ -223,6 +225,17 @@ class Bank:
         self.process_host(buf.ctypes.data_as(C.c_void_p), stride, n_blocks, pcm.ctypes.data_as(C.c_void_p),
                           tap.ctypes.data_as(C.c_void_p) if want_tap else None)
         return pcm, tap
+
+    def set_timing(self, on=True):
+        _check(lib().sdrb_bank_set_timing(self.h, int(on)), "sdrb_bank_set_timing")
+
+    def kernel_times(self):
+        """{class name: (total ms, timed calls)} since set_timing(True)."""
+        ms = (C.c_double * 6)()
+        calls = (C.c_long * 6)()
+        _check(lib().sdrb_bank_kernel_times(self.h, ms, calls), "sdrb_bank_kernel_times")
+        names = ["dc_scan", "ingest_main", "sub_cascade", "late_fir", "usb_audio", "carry"]
+        return {n: (ms[k], calls[k]) for k, n in enumerate(names)}
 
     @property
     def last_launches(self):

@@ -167,7 +167,12 @@ struct sdrb_bank {
     DevBuf d_iq, d_pcm, d_tap;
     cudaStream_t s_copy_in = nullptr, s_compute = nullptr, s_copy_out = nullptr;
     std::vector<cudaEvent_t> ev_in, ev_done;
-    bool dc_consts_set = false;
+    // optional per-kernel timing (bench.py roofline): event pairs around each kernel class
+    bool timing = false;
+    std::vector<cudaEvent_t> tev;           // 2 * SDRB_N_KERNEL_CLASSES * calls, recycled
+    size_t tev_used = 0;
+    double kernel_ms[SDRB_N_KERNEL_CLASSES] = {0};
+    long kernel_calls[SDRB_N_KERNEL_CLASSES] = {0};
 };
 
 static int upload_dc_consts() {
@@ -193,6 +198,7 @@ extern "C" void sdrb_bank_destroy(sdrb_bank *b) {
     for (DevBuf *d : all) d->release();
     for (cudaEvent_t e : b->ev_in) cudaEventDestroy(e);
     for (cudaEvent_t e : b->ev_done) cudaEventDestroy(e);
+    for (cudaEvent_t e : b->tev) cudaEventDestroy(e);
     if (b->s_copy_in) cudaStreamDestroy(b->s_copy_in);
     if (b->s_compute) cudaStreamDestroy(b->s_compute);
     if (b->s_copy_out) cudaStreamDestroy(b->s_copy_out);
@@ -435,12 +441,25 @@ extern "C" int sdrb_bank_blocks_done(sdrb_bank *b, int stream, int64_t *blocks) 
     return SDRB_OK;
 }
 
+// Timing marks: when enabled, a cudaEvent pair brackets every kernel class on the launching
+// stream; sdrb_bank_kernel_times() folds them into per-class totals after a synchronize.
+static void mark(sdrb_bank *b, cudaStream_t st) {
+    if (!b->timing) return;
+    if (b->tev_used == b->tev.size()) {
+        cudaEvent_t e;
+        if (cudaEventCreate(&e) != cudaSuccess) return;
+        b->tev.push_back(e);
+    }
+    cudaEventRecord(b->tev[b->tev_used++], st);
+}
+
 // Enqueue the whole pipeline for streams [s0, s0+ns) on `st`. Returns launches issued.
 static int enqueue(sdrb_bank *b, const uint8_t *d_iq, size_t iq_stride, int n_blocks, int16_t *d_pcm, float *d_tap,
                    int s0, int ns, cudaStream_t st, int *launches) {
     const HostPlan &h = b->plan->h;
     int nl = 0;
     const int n_seg = n_blocks * (h.block / DC_SEG);
+    mark(b, st);                                            // class 0: DC scan
     if (h.correct_dc) {
         k0_dc_partial<<<dim3((unsigned)((n_seg + 7) / 8), (unsigned)ns), 256, 0, st>>>(
             d_iq, iq_stride, (float2 *)b->dc_part.p, b->dc_stride, n_seg, s0);
@@ -448,11 +467,13 @@ static int enqueue(sdrb_bank *b, const uint8_t *d_iq, size_t iq_stride, int n_bl
                                                 b->dc_stride, (double2 *)b->dc_state.p, n_seg, s0);
         nl += 2;
     }
+    mark(b, st);                                            // class 1: ingest + main VFOs
     K1Params k1 = b->k1;
     k1.iq = d_iq; k1.iq_stride = iq_stride; k1.n_blocks = n_blocks; k1.stream0 = s0;
     const int k1_tiles = (h.block + K1_TILE - 1) / K1_TILE;
     k1_ingest_main<<<dim3((unsigned)ns, (unsigned)k1_tiles, (unsigned)n_blocks), K1_THREADS, 0, st>>>(k1);
     nl++;
+    mark(b, st);                                            // class 2: sub-VFO cascades
     for (const SubGroup &g : b->groups) {
         K2aParams kp;
         kp.subs = (const SubDev *)b->subdev.p + g.first;
@@ -469,24 +490,54 @@ static int enqueue(sdrb_bank *b, const uint8_t *d_iq, size_t iq_stride, int n_bl
         }
         nl++;
     }
+    mark(b, st);                                            // class 3: /late FIR
     if (b->n_late) {
         const int tiles = (n_blocks * b->max_late_samples + LATE_TILE - 1) / LATE_TILE;
         k2_late_fir<<<dim3((unsigned)ns, (unsigned)b->n_late, (unsigned)tiles), LATE_TILE, 0, st>>>(
             (const LateDev *)b->latedev.p, n_blocks, s0);
         nl++;
     }
+    mark(b, st);                                            // class 4: USB audio
     if (b->n_usb) {
         const int tiles = (n_blocks * b->max_usb_samples + USB_TILE - 1) / USB_TILE;
         k2b_usb_audio<<<dim3((unsigned)ns, (unsigned)b->n_usb, (unsigned)tiles), 256, 0, st>>>(
             (const UsbDev *)b->usbdev.p, n_blocks, s0, b->n_streams, h.pcm_per_block, d_pcm, d_tap);
         nl++;
     }
+    mark(b, st);                                            // class 5: carry
     k3_carry<<<dim3((unsigned)ns, (unsigned)(b->n_carry + 1)), 128, 0, st>>>(
         (const CarryItem *)b->carry.p, b->n_carry, n_blocks, d_iq, iq_stride, h.block, (uint8_t *)b->raw_tail.p,
         (long long *)b->blocks_done.p, s0);
     nl++;
+    mark(b, st);
     CU_TRY(cudaGetLastError());
     *launches += nl;
+    return SDRB_OK;
+}
+
+extern "C" int sdrb_bank_set_timing(sdrb_bank *b, int on) {
+    if (!b) { set_error("sdrb_bank_set_timing: NULL bank"); return SDRB_E_INVALID; }
+    b->timing = on != 0;
+    b->tev_used = 0;
+    for (int k = 0; k < SDRB_N_KERNEL_CLASSES; k++) { b->kernel_ms[k] = 0; b->kernel_calls[k] = 0; }
+    return SDRB_OK;
+}
+
+extern "C" int sdrb_bank_kernel_times(sdrb_bank *b, double *ms, long *calls) {
+    if (!b || !ms) { set_error("sdrb_bank_kernel_times: NULL argument"); return SDRB_E_INVALID; }
+    CU_TRY(cudaSetDevice(b->device));
+    CU_TRY(cudaDeviceSynchronize());
+    const size_t per = SDRB_N_KERNEL_CLASSES + 1;
+    for (size_t c = 0; c + per <= b->tev_used; c += per)
+        for (int k = 0; k < SDRB_N_KERNEL_CLASSES; k++) {
+            float t = 0.f;
+            if (cudaEventElapsedTime(&t, b->tev[c + (size_t)k], b->tev[c + (size_t)k + 1]) == cudaSuccess) {
+                b->kernel_ms[k] += t;
+                b->kernel_calls[k] += 1;
+            }
+        }
+    b->tev_used = 0;
+    for (int k = 0; k < SDRB_N_KERNEL_CLASSES; k++) { ms[k] = b->kernel_ms[k]; if (calls) calls[k] = b->kernel_calls[k]; }
     return SDRB_OK;
 }
 
