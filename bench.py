@@ -180,7 +180,7 @@ def reference_arm(args):
 def b200_arm(args):
     import torch
     import torch.distributed as dist
-    from sdrreceiver_b200 import binding as B
+    from sdrreceiver_b200 import binding as B, shard
 
     rank, local_rank, world = dist_env()
     if world > 1:
@@ -199,8 +199,7 @@ def b200_arm(args):
     base = base_streams(plan, n_base, NB * Bk)
     pin_in = B.PinnedBuffer(S * row)
     h_iq = pin_in.array.reshape(S, row)
-    for s in range(S):
-        g = rank + world * s
+    for s, g in enumerate(shard.stream_ids(rank, world, S)):
         h_iq[s] = np.roll(base[g % n_base], 2 * 977 * g)
     d_iq = torch.from_numpy(h_iq).to(dev)                      # resident copy for the kernel metric
     d_pcm = torch.empty((S, NB, plan.pcm_per_block), dtype=torch.int16, device=dev)
@@ -254,32 +253,19 @@ def b200_arm(args):
     sampler.stop_flag = True
     sampler.join(timeout=2)
 
-    # digest of the last result (correctness evidence gathered over NCCL with the timings)
-    pcm64 = d_pcm.to(torch.int64)
-    digest = [int(pcm64.sum().item()), int((pcm64 * pcm64).sum().item() % (1 << 62))]
-    stats = torch.tensor([dev_ms, e2e_ms if e2e_ms is not None else 0.0, float(samples_per_step)],
-                         dtype=torch.float64, device=dev)
-    if world > 1:
-        gathered = [torch.zeros_like(stats) for _ in range(world)]
-        dist.all_gather(gathered, stats)
-        dig_t = torch.tensor(digest, dtype=torch.int64, device=dev)
-        dig_all = [torch.zeros_like(dig_t) for _ in range(world)]
-        dist.all_gather(dig_all, dig_t)
-        digests = [[int(x) for x in t.tolist()] for t in dig_all]
-        stats_all = torch.stack(gathered).cpu().numpy()
-    else:
-        stats_all = stats.cpu().numpy()[None, :]
-        digests = [digest]
+    # timings + output digest of every rank, gathered over NCCL (the only collective in the job)
+    digest = shard.pcm_digest(d_pcm.cpu().numpy())
+    stats_all, digests = shard.gather([dev_ms, e2e_ms if e2e_ms is not None else 0.0, float(samples_per_step)],
+                                      digest, device=dev)
     if rank != 0:
         if world > 1:
             dist.destroy_process_group()
         return
 
-    max_dev_ms = float(stats_all[:, 0].max())
-    max_e2e_ms = float(stats_all[:, 1].max())
-    total_samples = float(stats_all[:, 2].sum()) * args.steps
-    value = total_samples / (max_dev_ms * 1e-3) / 1e6
-    e2e_value = total_samples / (max_e2e_ms * 1e-3) / 1e6 if e2e_ms is not None else None
+    agg = shard.aggregate(stats_all, args.steps)
+    max_dev_ms, max_e2e_ms, total_samples = agg["dev_ms"], agg["e2e_ms"], agg["total_samples"]
+    value = agg["value_msps"]
+    e2e_value = agg["e2e_msps"] if e2e_ms is not None else None
 
     # ---- roofline of the dominant kernel class (rank 0's events) ----
     fs = plan.fs

@@ -174,12 +174,6 @@ static int finish_plan(HostPlan &p) {
         const MainVfo &m = p.mains[(size_t)s.main_idx];
         s.fs = m.out_rate;
         s.block_in = m.out_rate / p.bufsplit;                           // mainwindow.cpp:223
-        if (s.block_in != m.block_out) {
-            // Reference quirk: a sub VFO that matched no main gets Fs = sample_rate but is
-            // fed main 0's decimated buffer and indexes past it (vfo.cpp:244). Undefined there.
-            set_error("plan: sub VFO '" + s.topic + "' is outside every main VFO's passband");
-            return SDRB_E_INVALID;
-        }
         if (s.decim < 0 || s.decim > 5 || (s.late != 0 && s.late != 5 && s.late != 6)) {
             set_error("plan: sub VFO '" + s.topic + "' needs 0..5 half-band stages and late in {0,5,6}");
             return SDRB_E_INVALID;
@@ -278,7 +272,7 @@ int plan_from_ini(const char *path, HostPlan &p) {
         if (out_rate <= 0) { set_error("sub VFO without data_rate/out_rate"); return SDRB_E_INVALID; }
         s.filter_bw = ini.num(k + "filter_bandwidth");
         int parent_mix = 0, parent_rate = p.fs;
-        s.main_idx = 0;
+        s.main_idx = -1;
         for (size_t a = 0; a < p.mains.size(); a++) {
             const int diff = std::abs((p.center - p.mains[a].mixer) - s.frequency);
             if (diff < p.mains[a].out_rate) {
@@ -287,6 +281,13 @@ int plan_from_ini(const char *path, HostPlan &p) {
                 parent_rate = p.mains[a].out_rate;
                 break;
             }
+        }
+        if (s.main_idx < 0) {
+            // Reference quirk (mainwindow.cpp:174-191): a sub VFO that matches no main keeps
+            // Fs = sample_rate but is fed main 0's decimated buffer and indexes past its end
+            // (vfo.cpp:244) -- undefined behaviour there, rejected here.
+            set_error("plan: sub VFO '" + ini.str(k + "topic") + "' is outside every main VFO's passband");
+            return SDRB_E_INVALID;
         }
         if (parent_rate / 48000 == 5) {
             s.decim = ilog2_floor_of_ratio(parent_rate, 5 * out_rate);

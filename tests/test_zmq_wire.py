@@ -1,0 +1,77 @@
+"""ZMQ wire format: the product's publisher (sdrb_publisher_*, libzmq loaded at run time) must
+put on the wire exactly what ZmqPublisher::publish does (zmqpublisher.cpp:82-96):
+[topic, 5 bytes][uint32 LE rate][int16 LE PCM], nothing for an empty payload. A pyzmq SUB
+socket plays JAERO. Host-only: no GPU needed."""
+import ctypes as C
+import time
+
+import numpy as np
+import pytest
+
+from conftest import plan_path
+from sdrreceiver_b200 import binding as B
+
+zmq = pytest.importorskip("zmq")
+
+
+def _open(addr, bind):
+    h = C.c_void_p()
+    rc = B.lib().sdrb_publisher_open(addr.encode(), int(bind), C.byref(h))
+    if rc == -5:
+        pytest.skip("libzmq not loadable here: " + B.lib().sdrb_last_error().decode())
+    assert rc == 0, B.lib().sdrb_last_error()
+    return h
+
+
+def test_three_frame_messages_reach_a_subscriber(tmp_path):
+    addr = "ipc://" + str(tmp_path / "sdrb.sock")
+    pub = _open(addr, True)
+    ctx = zmq.Context()
+    sub = ctx.socket(zmq.SUB)
+    sub.setsockopt(zmq.SUBSCRIBE, b"VFO")
+    sub.setsockopt(zmq.RCVTIMEO, 5000)
+    sub.connect(addr)
+    time.sleep(0.3)                                   # PUB/SUB slow joiner
+    L = B.lib()
+    pcm = (np.arange(3000, dtype=np.int16) - 1500)
+    assert L.sdrb_publisher_send(pub, b"VFO01", 12000, pcm.ctypes.data_as(C.c_void_p), pcm.nbytes) == 0
+    assert L.sdrb_publisher_send(pub, b"VFO02", 48000, pcm.ctypes.data_as(C.c_void_p), 0) == 0       # len 0: nothing sent
+    assert L.sdrb_publisher_send(pub, b"VFO123456", 24000, pcm.ctypes.data_as(C.c_void_p), 10) == 0   # topic cut to 5 bytes
+    m1 = sub.recv_multipart()
+    m2 = sub.recv_multipart()
+    assert [len(p) for p in m1] == [5, 4, 6000]
+    assert m1[0] == b"VFO01" and int.from_bytes(m1[1], "little") == 12000
+    assert np.array_equal(np.frombuffer(m1[2], dtype="<i2"), pcm)
+    assert m2[0] == b"VFO12" and int.from_bytes(m2[1], "little") == 24000 and len(m2[2]) == 10
+    L.sdrb_publisher_close(pub)
+    sub.close(0)
+    ctx.term()
+
+
+def test_send_block_emits_one_message_per_vfo_in_plan_order(tmp_path):
+    addr = "ipc://" + str(tmp_path / "sdrb2.sock")
+    pub = _open(addr, True)
+    ctx = zmq.Context()
+    sub = ctx.socket(zmq.SUB)
+    sub.setsockopt(zmq.SUBSCRIBE, b"")
+    sub.setsockopt(zmq.RCVTIMEO, 5000)
+    sub.connect(addr)
+    time.sleep(0.3)
+    plan = B.Plan(plan_path("54W_all"))
+    rec = np.arange(plan.pcm_per_block, dtype=np.int32).astype(np.int16)
+    assert B.lib().sdrb_publisher_send_block(pub, plan.h, rec.ctypes.data_as(C.c_void_p)) == 0
+    for s in plan.subs:
+        topic, rate, payload = sub.recv_multipart()
+        assert topic == s["topic"].encode()[:5].ljust(5, b"\0")
+        assert int.from_bytes(rate, "little") == s["out_rate"]
+        want = rec[s["pcm_offset"]:s["pcm_offset"] + s["samples_out"]]
+        assert np.array_equal(np.frombuffer(payload, dtype="<i2"), want)
+    B.lib().sdrb_publisher_close(pub)
+    sub.close(0)
+    ctx.term()
+
+
+def test_bad_address_is_an_error_code_not_a_crash():
+    h = C.c_void_p()
+    rc = B.lib().sdrb_publisher_open(b"notaproto://x", 1, C.byref(h))
+    assert rc == -5 and not h.value
