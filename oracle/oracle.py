@@ -55,6 +55,7 @@ def lib():
         L.orc_hilbert_points.restype = None; L.orc_hilbert_points.argtypes = [i, i, vp]
         L.orc_usb.restype = None; L.orc_usb.argtypes = [i, i, vp, l, vp]
         L.orc_low_pass.restype = i; L.orc_low_pass.argtypes = [d, d, d, d, vp, i]
+        L.orc_dc_trace.restype = None; L.orc_dc_trace.argtypes = [vp, l, i, vp]
         _lib = L
     return _lib
 
@@ -130,6 +131,15 @@ class Oracle:
             self.close()
         except Exception:
             pass
+
+
+def dc_trace(iq_u8, every=32):
+    """avept (sdrj.cpp:280) entering every `every`-th sample, complex64."""
+    iq = np.ascontiguousarray(iq_u8, dtype=np.uint8)
+    n = iq.size // 2
+    out = np.zeros(2 * (n // every), dtype=np.float32)
+    lib().orc_dc_trace(_p(iq), n, every, _p(out))
+    return out.view(np.complex64)
 
 
 def run_ref(ini_path, iq_u8, float_tap=False, main_tap=False, blocks=None):

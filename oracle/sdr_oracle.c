@@ -569,3 +569,17 @@ void orc_usb(int len, int Fs, const float *in_iq, long n, float *out) {
 int orc_low_pass(double gain, double fs, double cutoff, double tw, float *taps, int maxn) {
     return low_pass_hamming(gain, fs, cutoff, tw, taps, maxn);
 }
+
+/* DC-removal state trace -- sdrj.cpp:277-283. out[j] = avept entering sample j*every
+ * (i.e. after samples 0 .. j*every-1), for j = 0 .. n/every - 1. */
+void orc_dc_trace(const uint8_t *iq, long n, int every, float *out_iq) {
+    const float a = 1.0f - 0.000001f, c = 0.000001f;
+    cf32 avept;
+    long i;
+    avept.re = 0; avept.im = 0;
+    for (i = 0; i < n; ++i) {
+        if (i % every == 0) { out_iq[2 * (i / every)] = avept.re; out_iq[2 * (i / every) + 1] = avept.im; }
+        avept.re = avept.re * a + c * (float)((int)iq[2 * i] - 127);
+        avept.im = avept.im * a + c * (float)((int)iq[2 * i + 1] - 127);
+    }
+}

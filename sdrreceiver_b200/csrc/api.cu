@@ -153,8 +153,8 @@ struct sdrb_bank {
     // state
     DevBuf blocks_done, dc_state, raw_tail;
     // work
-    DevBuf dc_part, dc_start, main_out, zbuf, dbuf;
-    int dc_stride = 0;
+    DevBuf dc_anchor, dc_stats, dc_table, main_out, zbuf, dbuf;
+    int dc_stride = 0;                      // DC blocks (of 32 samples) per stream in dc_stats; table has DC_HALO_BLKS more
     // descriptors
     K1Params k1{};
     DevBuf subdev, latedev, usbdev, carry;
@@ -175,24 +175,10 @@ struct sdrb_bank {
     long kernel_calls[SDRB_N_KERNEL_CLASSES] = {0};
 };
 
-static int upload_dc_consts() {
-    DcConsts c;
-    const float a = 1.0f - 0.000001f;       // sdrj.cpp:281, evaluated in float like the reference
-    c.a = a;
-    c.c = 0.000001f;
-    const double ad = (double)a;
-    for (int j = 0; j <= 8; j++) c.apow[j] = (float)std::pow(ad, j);
-    for (int l = 0; l < 32; l++) { c.apow8[l] = (float)std::pow(ad, 8 * l); c.rpow8[l] = (float)std::pow(ad, 8 * (31 - l)); }
-    for (int d = 0; d < 5; d++) c.wscan[d] = (float)std::pow(ad, 8 * (1 << d));
-    c.a256 = std::pow(ad, 256);
-    CU_TRY(cudaMemcpyToSymbol(c_dc, &c, sizeof(c)));
-    return SDRB_OK;
-}
-
 extern "C" void sdrb_bank_destroy(sdrb_bank *b) {
     if (!b) return;
     cudaSetDevice(b->device);
-    DevBuf *all[] = {&b->luts, &b->taps, &b->blocks_done, &b->dc_state, &b->raw_tail, &b->dc_part, &b->dc_start,
+    DevBuf *all[] = {&b->luts, &b->taps, &b->blocks_done, &b->dc_state, &b->raw_tail, &b->dc_anchor, &b->dc_stats, &b->dc_table,
                      &b->main_out, &b->zbuf, &b->dbuf, &b->subdev, &b->latedev, &b->usbdev, &b->carry,
                      &b->d_iq, &b->d_pcm, &b->d_tap};
     for (DevBuf *d : all) d->release();
@@ -221,8 +207,7 @@ extern "C" int sdrb_bank_create(const sdrb_plan *plan, int device, int n_streams
     sdrb_bank *b = new (std::nothrow) sdrb_bank();
     if (!b) return SDRB_E_NOMEM;
     b->plan = plan; b->device = device; b->n_streams = n_streams; b->max_blocks = max_blocks;
-    int rc = upload_dc_consts();
-    if (rc != SDRB_OK) { sdrb_bank_destroy(b); return rc; }
+    int rc = SDRB_OK;
 
 #define BANK_TRY(x) do { rc = (x); if (rc != SDRB_OK) { sdrb_bank_destroy(b); return rc; } } while (0)
 #define BANK_CU(x) do { cudaError_t e_ = (x); if (e_ != cudaSuccess) { set_error(std::string(#x) + ": " + cudaGetErrorString(e_)); sdrb_bank_destroy(b); return SDRB_E_CUDA; } } while (0)
@@ -272,14 +257,14 @@ extern "C" int sdrb_bank_create(const sdrb_plan *plan, int device, int n_streams
 
     // ---- state ----
     BANK_TRY(b->blocks_done.alloc(sizeof(long long) * (size_t)n_streams));
-    BANK_TRY(b->dc_state.alloc(sizeof(double2) * 2 * (size_t)n_streams));
+    BANK_TRY(b->dc_state.alloc(sizeof(float2) * (size_t)n_streams));
     BANK_TRY(b->raw_tail.alloc((size_t)n_streams * 2 * RAW_TAIL));
 
     // ---- work buffers ----
-    const int n_seg_max = max_blocks * (h.block / DC_SEG);
-    b->dc_stride = n_seg_max + 2;
-    BANK_TRY(b->dc_part.alloc(sizeof(float2) * (size_t)n_streams * (size_t)b->dc_stride));
-    BANK_TRY(b->dc_start.alloc(sizeof(float2) * (size_t)n_streams * (size_t)b->dc_stride));
+    b->dc_stride = max_blocks * (h.block / DC_BLK);
+    BANK_TRY(b->dc_anchor.alloc(sizeof(DcAnchor) * 2 * (size_t)n_streams));
+    BANK_TRY(b->dc_stats.alloc(h.correct_dc ? sizeof(DcStats) * 2 * (size_t)n_streams * (size_t)b->dc_stride : 16));
+    BANK_TRY(b->dc_table.alloc(h.correct_dc ? sizeof(uint2) * 2 * (size_t)n_streams * (size_t)(b->dc_stride + DC_HALO_BLKS) : 16));
     {
         size_t at = 0;
         for (const MainVfo &m : h.mains) {
@@ -311,9 +296,10 @@ extern "C" int sdrb_bank_create(const sdrb_plan *plan, int device, int n_streams
     // ---- descriptors ----
     K1Params &k1 = b->k1;
     k1.tail = (const uint8_t *)b->raw_tail.p;
-    k1.dc_start = (const float2 *)b->dc_start.p;
+    k1.dc_table = (const uint2 *)b->dc_table.p;
+    k1.dc_anchor = (const DcAnchor *)b->dc_anchor.p;
     k1.blocks_done = (const long long *)b->blocks_done.p;
-    k1.dc_stride = b->dc_stride; k1.block = h.block; k1.correct_dc = h.correct_dc; k1.n_main = (int)h.mains.size();
+    k1.dc_stride = b->dc_stride + DC_HALO_BLKS; k1.block = h.block; k1.correct_dc = h.correct_dc; k1.n_main = (int)h.mains.size();
     for (size_t i = 0; i < h.mains.size(); i++) {
         MainDev &M = k1.mains[i];
         M.lut = (const float2 *)b->luts.p + main_lut_off[i];
@@ -420,7 +406,7 @@ extern "C" int sdrb_bank_reset(sdrb_bank *b, int stream) {
     CU_TRY(cudaSetDevice(b->device));
     const int s0 = stream < 0 ? 0 : stream, ns = stream < 0 ? b->n_streams : 1;
     CU_TRY(cudaMemset((long long *)b->blocks_done.p + s0, 0, sizeof(long long) * (size_t)ns));
-    CU_TRY(cudaMemset((double2 *)b->dc_state.p + 2 * (size_t)s0, 0, sizeof(double2) * 2 * (size_t)ns));
+    CU_TRY(cudaMemset((float2 *)b->dc_state.p + (size_t)s0, 0, sizeof(float2) * (size_t)ns));
     CU_TRY(cudaMemset((uint8_t *)b->raw_tail.p + (size_t)s0 * 2 * RAW_TAIL, 0, (size_t)ns * 2 * RAW_TAIL));
     // history regions: zero whole per-stream slices (cheap, and only done on reset)
     const size_t ms = b->main_stride * sizeof(float2);
@@ -458,14 +444,17 @@ static int enqueue(sdrb_bank *b, const uint8_t *d_iq, size_t iq_stride, int n_bl
                    int s0, int ns, cudaStream_t st, int *launches) {
     const HostPlan &h = b->plan->h;
     int nl = 0;
-    const int n_seg = n_blocks * (h.block / DC_SEG);
-    mark(b, st);                                            // class 0: DC scan
+    const int n_dcblk = n_blocks * (h.block / DC_BLK);
+    mark(b, st);                                            // class 0: DC recursion
     if (h.correct_dc) {
-        k0_dc_partial<<<dim3((unsigned)((n_seg + 7) / 8), (unsigned)ns), 256, 0, st>>>(
-            d_iq, iq_stride, (float2 *)b->dc_part.p, b->dc_stride, n_seg, s0);
-        k0_dc_scan<<<(unsigned)ns, 32, 0, st>>>((const float2 *)b->dc_part.p, b->dc_stride, (float2 *)b->dc_start.p,
-                                                b->dc_stride, (double2 *)b->dc_state.p, n_seg, s0);
-        nl += 2;
+        k0_dc_anchor<<<(unsigned)((2 * ns + 127) / 128), 128, 0, st>>>((const float2 *)b->dc_state.p,
+                                                                      (DcAnchor *)b->dc_anchor.p, ns, s0);
+        k0_dc_blocks<<<dim3((unsigned)((n_dcblk + 127) / 128), (unsigned)ns), 128, 0, st>>>(
+            d_iq, iq_stride, (const DcAnchor *)b->dc_anchor.p, (DcStats *)b->dc_stats.p, b->dc_stride, n_dcblk, s0);
+        k0_dc_walk<<<(unsigned)ns, 32, 0, st>>>(d_iq, iq_stride, (const DcStats *)b->dc_stats.p, b->dc_stride,
+                                                (const DcAnchor *)b->dc_anchor.p, (float2 *)b->dc_state.p,
+                                                (uint2 *)b->dc_table.p, b->dc_stride + DC_HALO_BLKS, n_dcblk, s0);
+        nl += 3;
     }
     mark(b, st);                                            // class 1: ingest + main VFOs
     K1Params k1 = b->k1;
@@ -507,7 +496,8 @@ static int enqueue(sdrb_bank *b, const uint8_t *d_iq, size_t iq_stride, int n_bl
     mark(b, st);                                            // class 5: carry
     k3_carry<<<dim3((unsigned)ns, (unsigned)(b->n_carry + 1)), 128, 0, st>>>(
         (const CarryItem *)b->carry.p, b->n_carry, n_blocks, d_iq, iq_stride, h.block, (uint8_t *)b->raw_tail.p,
-        (long long *)b->blocks_done.p, s0);
+        (long long *)b->blocks_done.p, h.correct_dc ? (uint2 *)b->dc_table.p : nullptr, b->dc_stride + DC_HALO_BLKS,
+        n_dcblk, s0);
     nl++;
     mark(b, st);
     CU_TRY(cudaGetLastError());
@@ -572,6 +562,18 @@ extern "C" int sdrb_bank_copy_main(sdrb_bank *b, int main_idx, int n_blocks, flo
     CU_TRY(cudaMemcpy2DAsync(d_out, row, (float2 *)b->main_out.p + b->main_off[(size_t)main_idx] + MAIN_HIST,
                              b->main_stride * sizeof(float2), row, (size_t)b->n_streams, cudaMemcpyDeviceToDevice,
                              (cudaStream_t)cuda_stream));
+    return SDRB_OK;
+}
+
+extern "C" int sdrb_bank_copy_dc_trace(sdrb_bank *b, int n_blocks, float *d_out, void *cuda_stream) {
+    if (!b || !d_out || n_blocks <= 0 || n_blocks > b->max_blocks || !b->plan->h.correct_dc) {
+        set_error("sdrb_bank_copy_dc_trace: bad argument or plan without correct_dc_bias"); return SDRB_E_INVALID;
+    }
+    CU_TRY(cudaSetDevice(b->device));
+    const int n = n_blocks * (b->plan->h.block / DC_BLK);
+    dc_trace_gather<<<dim3((unsigned)((n + 255) / 256), (unsigned)b->n_streams), 256, 0, (cudaStream_t)cuda_stream>>>(
+        (const uint2 *)b->dc_table.p, b->dc_stride + DC_HALO_BLKS, n, (float2 *)d_out);
+    CU_TRY(cudaGetLastError());
     return SDRB_OK;
 }
 

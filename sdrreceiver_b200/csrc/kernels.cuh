@@ -32,7 +32,7 @@ namespace sdrb {
 #define HB_P4 0.29332944952052842f
 #define HB_P5 0.5f
 
-constexpr int DC_SEG = 256;            // samples per DC scan segment (= one K1 warp)
+constexpr int DC_BLK = 32;             // samples per DC-recursion block (4 K1 lanes)
 constexpr int RAW_TAIL = 256;          // raw samples carried between calls (K1 halo warp)
 constexpr int K1_WARPS = 8;            // active warps per K1 CTA (+1 halo warp)
 constexpr int K1_THREADS = (K1_WARPS + 1) * 32;
@@ -45,16 +45,22 @@ constexpr int USB_TILE = 1024;         // audio samples per K2B CTA
 constexpr int LATE_TILE = 256;
 constexpr int MAX_FIR_TAPS = 512;
 
-struct DcConsts {
-    float a;            // 1.0f - 0.000001f
-    float c;            // 0.000001f
-    float apow[9];      // a^j, j = 0..8
-    float apow8[32];    // a^(8*lane)
-    float wscan[5];     // a^(8*2^d)
-    float rpow8[32];    // a^(8*(31-lane))
-    double a256;        // a^256
+constexpr int DC_HALO_BLKS = RAW_TAIL / DC_BLK;     // table entries kept from the previous call
+#define DC_A (1.0f - 0.000001f)         /* sdrj.cpp:281, evaluated in float like the reference */
+#define DC_C 0.000001f
+#define DC_MAGIC 12582912.0f            /* 1.5 * 2^23: (y + M) - M rounds y to nearest-even integer */
+
+// Per call and per (stream, arm): the float neighbourhood the DC state lives in.
+// Inside (lo, hi) the state keeps its sign and exponent and the rounded product
+// fl(s*a) equals s - r*ulp with r = r0 below the bit pattern T and r0 + 1 from T on.
+struct DcAnchor {
+    float sgn, inv_u;
+    int r0, ok;
+    unsigned T, lo, hi, pad;
 };
-__constant__ DcConsts c_dc;
+// Per 32-sample block and arm, in ulps of the anchor: D = sum(Q_k - r0); Amax = max prefix
+// (k < 32), Bmin = min of (prefix - k). Amax = 2^30 marks a block that must be stepped.
+struct DcStats { int D, Amax, Bmin; };
 
 struct MainDev {
     const float2 *lut;      // Oscillator table
@@ -67,7 +73,8 @@ struct K1Params {
     const uint8_t *iq;
     size_t iq_stride;
     const uint8_t *tail;            // [n_streams][2*RAW_TAIL]
-    const float2 *dc_start;         // [n_streams][dc_stride]; entry seg+1 = state entering seg
+    const uint2 *dc_table;          // [n_streams][dc_stride][2 arms]: {state bits at block start, mode}
+    const DcAnchor *dc_anchor;      // [n_streams][2 arms]
     const long long *blocks_done;   // [n_streams]
     int dc_stride, block, n_blocks, correct_dc, n_main, stream0;
     MainDev mains[SDRB_MAX_MAIN];
@@ -196,95 +203,186 @@ __device__ __forceinline__ void hb_publish(const float2 (&v)[R], float2 *__restr
 }
 
 // ------------------------------------------------------------------------------------
-// K0: DC-removal IIR  avept = avept*a + c*x  (sdrj.cpp:277-283) as a scan.
-// Pass 1: per 256-sample segment, P = sum_k a^(255-k) * c * x_k. One warp per segment.
+// K0: DC-removal IIR  avept = fl(fl(avept*a) + fl(c*x)),  a = 1 - 1e-6f  (sdrj.cpp:277-283).
+//
+// The recursion cannot be replaced by exact arithmetic: the rounded product fl(s*a) removes
+// an INTEGER number r = RN(17*M/2^24) of ulps per sample (M = 24-bit mantissa of s, r in 9..17),
+// so the state locks onto the nearest mantissa where r steps -- up to 6 % away from the ideal
+// low-pass value (0.4853 instead of 0.4934 for a DC of 0.5) -- and wanders there following the
+// data. That residual is audible in VFOs whose passband contains the DC line, so it is
+// reproduced bit for bit:
+//   k0_dc_anchor  per call: sign, ulp, r0 and the threshold T nearest to the carried state
+//   k0_dc_blocks  parallel: per 32-sample block the integer increments Q_k = RN(fl(c*x_k)/ulp)
+//                 and the block statistics that prove "no step of this block crosses T"
+//   k0_dc_walk    one warp per stream: block after block, either a pure translation
+//                 (W += D, exact in the integer-ulp domain) or 32 real float steps
+// K1 then re-derives every sample's avept from the block-start states.
 // ------------------------------------------------------------------------------------
-__global__ void __launch_bounds__(256) k0_dc_partial(const uint8_t *__restrict__ iq, size_t iq_stride,
-                                                      float2 *__restrict__ part, int part_stride,
-                                                      int n_seg, int stream0) {
-    const int stream = stream0 + blockIdx.y;
-    const int seg = blockIdx.x * 8 + (threadIdx.x >> 5);
-    const int lane = threadIdx.x & 31;
-    if (seg >= n_seg) return;
-    const uint4 raw = __ldg(reinterpret_cast<const uint4 *>(iq + (size_t)stream * iq_stride + (size_t)seg * (DC_SEG * 2)) + lane);
-    float2 x[8];
-    unpack8(raw, x);
-    const float a = c_dc.a, c = c_dc.c;
-    float2 acc = make_float2(c * x[0].x, c * x[0].y);
-#pragma unroll
-    for (int k = 1; k < 8; ++k) {
-        acc.x = fmaf(a, acc.x, c * x[k].x);
-        acc.y = fmaf(a, acc.y, c * x[k].y);
-    }
-    const float w = c_dc.rpow8[lane];
-    acc.x *= w;
-    acc.y *= w;
-#pragma unroll
-    for (int d = 16; d > 0; d >>= 1) {
-        acc.x += __shfl_xor_sync(0xffffffffu, acc.x, d);
-        acc.y += __shfl_xor_sync(0xffffffffu, acc.y, d);
-    }
-    if (lane == 0) part[(size_t)stream * part_stride + seg] = acc;
+__device__ __forceinline__ float dc_step(float s, float x) {
+    return __fadd_rn(__fmul_rn(s, DC_A), __fmul_rn(DC_C, x));
 }
 
-// Pass 2: one warp per stream walks the segment partials (double precision) and writes
-// the state entering every segment: start[0] = state entering the last segment of the
-// previous call (for K1's halo warp), start[1 + s] = state entering segment s.
-// dc_state[stream] = {A_next (entering sample 0 of the next call), A_prevseg}.
-__global__ void __launch_bounds__(32) k0_dc_scan(const float2 *__restrict__ part, int part_stride,
-                                                  float2 *__restrict__ start, int start_stride,
-                                                  double2 *__restrict__ dc_state, int n_seg, int stream0) {
-    const int stream = stream0 + blockIdx.x;
-    const int lane = threadIdx.x;
-    const int per = (n_seg + 31) / 32;
-    const int s_lo = min(lane * per, n_seg), s_hi = min(s_lo + per, n_seg);
-    const float2 *p = part + (size_t)stream * part_stride;
-    float2 *o = start + (size_t)stream * start_stride;
-    const double w = c_dc.a256;
-    // local composite: state_out = wl * state_in + sl
-    double wl = 1.0, sx = 0.0, sy = 0.0;
-    for (int s = s_lo; s < s_hi; ++s) {
-        const float2 v = p[s];
-        sx = sx * w + (double)v.x;
-        sy = sy * w + (double)v.y;
-        wl *= w;
-    }
-    // inclusive scan of composites over lanes
-    double cw = wl, cx = sx, cy = sy;
-#pragma unroll
-    for (int d = 1; d < 32; d <<= 1) {
-        const double pw = __shfl_up_sync(0xffffffffu, cw, d);
-        const double px = __shfl_up_sync(0xffffffffu, cx, d);
-        const double py = __shfl_up_sync(0xffffffffu, cy, d);
-        if (lane >= d) {
-            cx = cw * px + cx;
-            cy = cw * py + cy;
-            cw = cw * pw;
+// Q = RN_even(fl(c*x)/ulp) as an integer-valued float; tie = the real sum would be an exact
+// half-way case whose rounding depends on the state's parity (then the block is stepped).
+__device__ __forceinline__ float dc_incr(const DcAnchor &A, float x, bool &tie) {
+    const float y = __fmul_rn(__fmul_rn(DC_C, A.sgn * x), A.inv_u);
+    const float q = __fadd_rn(__fadd_rn(y, DC_MAGIC), -DC_MAGIC);
+    tie = fabsf(__fadd_rn(y, -q)) == 0.5f;
+    return q;
+}
+
+__global__ void __launch_bounds__(128) k0_dc_anchor(const float2 *__restrict__ dc_state, DcAnchor *__restrict__ anchors,
+                                                     int n_streams, int stream0) {
+    const int idx = blockIdx.x * 128 + threadIdx.x;
+    if (idx >= 2 * n_streams) return;
+    const int stream = stream0 + (idx >> 1), arm = idx & 1;
+    const float2 st = dc_state[stream];
+    const float s0 = arm ? st.y : st.x;
+    DcAnchor A;
+    A.sgn = s0 < 0.f ? -1.f : 1.f; A.inv_u = 0.f; A.r0 = 0; A.ok = 0; A.T = 0; A.lo = 0; A.hi = 0; A.pad = 0;
+    const float m = fabsf(s0);
+    const unsigned bits = __float_as_uint(m);
+    const unsigned ef = bits >> 23;
+    if (ef >= 40 && ef <= 200) {
+        const unsigned base = bits & 0xFF800000u;
+        const float u = __uint_as_float(base - (23u << 23));
+        A.inv_u = __uint_as_float((254u - (ef - 23u)) << 23);               // exactly 1/u
+        const float dec = __fadd_rn(m, -__fmul_rn(m, DC_A));                 // exact: r * u
+        const int r = __float2int_rn(__fmul_rn(dec, A.inv_u));
+        const double step = 16777216.0 / 17.0;                               // mantissa distance between steps of r
+        const double m_cur = (double)((bits & 0x7FFFFFu) + 0x800000u);
+        const double m_up = ceil((r + 0.5) * step), m_dn = ceil((r - 0.5) * step);
+        int r0; double m_t;
+        if (fabs(m_up - m_cur) <= fabs(m_cur - m_dn)) { r0 = r; m_t = m_up; } else { r0 = r - 1; m_t = m_dn; }
+        unsigned T;
+        if (m_t >= 16777216.0) T = base + 0x800000u;                         // never reached inside the window
+        else if (m_t < 8388608.0) T = base;                                  // always above: r = r0 + 1
+        else {
+            T = base + (unsigned)((long long)m_t - 8388608ll);
+            for (int it = 0; it < 6; ++it) {                                 // pin T with the real float product
+                const float a1 = __uint_as_float(T), a0 = __uint_as_float(T - 1);
+                const float d1 = __fmul_rn(__fadd_rn(a1, -__fmul_rn(a1, DC_A)), A.inv_u);
+                const float d0 = __fmul_rn(__fadd_rn(a0, -__fmul_rn(a0, DC_A)), A.inv_u);
+                if (d1 >= (float)(r0 + 1) && d0 <= (float)r0) break;
+                if (d1 < (float)(r0 + 1)) ++T; else --T;
+            }
+        }
+        // window: same binade, r in {r0, r0+1}, minus the largest excursion one block can make
+        double lo = 8388608.0 + 4096.0, hi = 16777216.0 - 65536.0;
+        lo = fmax(lo, ceil((r0 - 0.5) * step) + 2.0);
+        hi = fmin(hi, ceil((r0 + 1.5) * step) - 2.0);
+        const double qmax = ceil(128.0 * (double)DC_C * (double)A.inv_u) + 18.0;
+        const double margin = DC_BLK * qmax;
+        lo += margin; hi -= margin;
+        if (hi > lo && qmax < 1.0e6) {
+            A.lo = base + (unsigned)((long long)lo - 8388608ll);
+            A.hi = base + (unsigned)((long long)hi - 8388608ll);
+            A.r0 = r0; A.T = T; A.ok = 1;
+            (void)u;
         }
     }
-    // exclusive composite for this lane
-    double ew = __shfl_up_sync(0xffffffffu, cw, 1);
-    double ex = __shfl_up_sync(0xffffffffu, cx, 1);
-    double ey = __shfl_up_sync(0xffffffffu, cy, 1);
-    if (lane == 0) { ew = 1.0; ex = 0.0; ey = 0.0; }
-    const double2 st0 = dc_state[2 * (size_t)stream];        // entering sample 0
-    const double2 stp = dc_state[2 * (size_t)stream + 1];    // entering previous call's last segment
+    anchors[2 * stream + arm] = A;
+}
+
+__global__ void __launch_bounds__(128) k0_dc_blocks(const uint8_t *__restrict__ iq, size_t iq_stride,
+                                                     const DcAnchor *__restrict__ anchors, DcStats *__restrict__ stats,
+                                                     int stats_stride, int n_blk, int stream0) {
+    const int stream = stream0 + blockIdx.y;
+    const int blk = blockIdx.x * 128 + threadIdx.x;
+    if (blk >= n_blk) return;
+    const DcAnchor AI = anchors[2 * stream], AQ = anchors[2 * stream + 1];
+    DcStats *out = stats + ((size_t)stream * stats_stride + blk) * 2;
+    DcStats bad; bad.D = 0; bad.Amax = 1 << 30; bad.Bmin = -(1 << 30);
+    if (!AI.ok && !AQ.ok) { out[0] = bad; out[1] = bad; return; }
+    const uint4 *src = reinterpret_cast<const uint4 *>(iq + (size_t)stream * iq_stride + (size_t)blk * (2 * DC_BLK));
+    float uI = 0.f, uQ = 0.f, amaxI = -1e30f, amaxQ = -1e30f, bminI = 1e30f, bminQ = 1e30f;
+    bool badI = !AI.ok, badQ = !AQ.ok;
+    const float r0I = (float)AI.r0, r0Q = (float)AQ.r0;
+#pragma unroll
+    for (int v = 0; v < 4; ++v) {
+        float2 x[8];
+        unpack8(__ldg(src + v), x);
+#pragma unroll
+        for (int k = 0; k < 8; ++k) {
+            const float kk = (float)(8 * v + k);
+            amaxI = fmaxf(amaxI, uI); bminI = fminf(bminI, uI - kk);
+            amaxQ = fmaxf(amaxQ, uQ); bminQ = fminf(bminQ, uQ - kk);
+            bool t1, t2;
+            uI += dc_incr(AI, x[k].x, t1) - r0I;
+            uQ += dc_incr(AQ, x[k].y, t2) - r0Q;
+            badI |= t1; badQ |= t2;
+        }
+    }
+    DcStats sI, sQ;
+    sI.D = (int)uI; sI.Amax = (int)amaxI; sI.Bmin = (int)bminI;
+    sQ.D = (int)uQ; sQ.Amax = (int)amaxQ; sQ.Bmin = (int)bminQ;
+    out[0] = badI ? bad : sI;
+    out[1] = badQ ? bad : sQ;
+}
+
+// modes written to the table: 0 = translation below T, 1 = translation at/above T, 2 = stepped
+__global__ void __launch_bounds__(32) k0_dc_walk(const uint8_t *__restrict__ iq, size_t iq_stride,
+                                                  const DcStats *__restrict__ stats, int stats_stride,
+                                                  const DcAnchor *__restrict__ anchors, float2 *__restrict__ dc_state,
+                                                  uint2 *__restrict__ table, int table_stride, int n_blk, int stream0) {
+    __shared__ DcStats sst[2][32][2];
+    __shared__ uint4 sraw[2][32][4];
+    const int stream = stream0 + blockIdx.x;
+    const int lane = threadIdx.x, arm = lane & 1;
+    const DcAnchor A = anchors[2 * stream + arm];
+    const float2 st0 = dc_state[stream];
+    float s = arm ? st0.y : st0.x;
+    const DcStats *sp = stats + (size_t)stream * stats_stride * 2;
+    const uint4 *rp = reinterpret_cast<const uint4 *>(iq + (size_t)stream * iq_stride);
+    uint2 *tab = table + ((size_t)stream * table_stride + DC_HALO_BLKS) * 2;
+    const int n_batch = (n_blk + 31) / 32;
+
+    DcStats rs0, rs1; uint4 rr0, rr1, rr2, rr3;
+    auto fetch = [&](int batch) {
+        const int blk = min(batch * 32 + lane, n_blk - 1);
+        rs0 = sp[(size_t)blk * 2]; rs1 = sp[(size_t)blk * 2 + 1];
+        const uint4 *r = rp + (size_t)blk * 4;
+        rr0 = __ldg(r); rr1 = __ldg(r + 1); rr2 = __ldg(r + 2); rr3 = __ldg(r + 3);
+    };
+    auto stash = [&](int buf) {
+        sst[buf][lane][0] = rs0; sst[buf][lane][1] = rs1;
+        sraw[buf][lane][0] = rr0; sraw[buf][lane][1] = rr1; sraw[buf][lane][2] = rr2; sraw[buf][lane][3] = rr3;
+    };
+    fetch(0);
+    stash(0);
     __syncwarp();
-    double ax = ew * st0.x + ex, ay = ew * st0.y + ey;
-    if (lane == 0) o[0] = make_float2((float)stp.x, (float)stp.y);
-    double lx = ax, ly = ay;   // state entering the last processed segment
-    for (int s = s_lo; s < s_hi; ++s) {
-        o[1 + s] = make_float2((float)ax, (float)ay);
-        lx = ax; ly = ay;
-        const float2 v = p[s];
-        ax = ax * w + (double)v.x;
-        ay = ay * w + (double)v.y;
+    for (int batch = 0; batch < n_batch; ++batch) {
+        const int buf = batch & 1;
+        if (batch + 1 < n_batch) fetch(batch + 1);              // in flight while this batch is walked
+        if (lane < 2) {
+            const int nb = min(32, n_blk - batch * 32);
+            for (int j = 0; j < nb; ++j) {
+                const DcStats S = sst[buf][j][arm];
+                const unsigned W = __float_as_uint(fabsf(s));
+                const bool in_win = A.ok && (s * A.sgn > 0.f) && W > A.lo && W < A.hi && S.Amax < (1 << 29);
+                unsigned mode = 2u;
+                const unsigned before = __float_as_uint(s);
+                if (in_win && W < A.T && (long long)W + S.Amax < (long long)A.T) {
+                    s = A.sgn * __uint_as_float((unsigned)((int)W + S.D));
+                    mode = 0u;
+                } else if (in_win && W >= A.T && (long long)W + S.Bmin >= (long long)A.T) {
+                    s = A.sgn * __uint_as_float((unsigned)((int)W + S.D - DC_BLK));
+                    mode = 1u;
+                } else {
+                    const unsigned char *bytes = reinterpret_cast<const unsigned char *>(&sraw[buf][j][0]);
+#pragma unroll 8
+                    for (int k = 0; k < DC_BLK; ++k) s = dc_step(s, (float)((int)bytes[2 * k + arm] - 127));
+                }
+                tab[(size_t)(batch * 32 + j) * 2 + arm] = make_uint2(before, mode);
+            }
+        }
+        __syncwarp();
+        if (batch + 1 < n_batch) stash(buf ^ 1);
+        __syncwarp();
     }
-    // the lane that owns the last segment publishes the carry
-    if (s_hi == n_seg && s_lo < n_seg) {
-        dc_state[2 * (size_t)stream] = make_double2(ax, ay);
-        dc_state[2 * (size_t)stream + 1] = make_double2(lx, ly);
-    }
+    // carry: the state entering the next call
+    const float other = __shfl_xor_sync(0xffffffffu, s, 1);
+    if (lane == 0) dc_state[stream] = make_float2(s, other);
 }
 
 // ------------------------------------------------------------------------------------
@@ -321,36 +419,50 @@ __global__ void __launch_bounds__(K1_THREADS, 2) k1_ingest_main(const K1Params p
         const uint4 raw = __ldg(reinterpret_cast<const uint4 *>(src));
         unpack8(raw, x);
         if (p.correct_dc) {
-            const float a = c_dc.a, c = c_dc.c;
-            float2 L[8];
-            L[0] = make_float2(c * x[0].x, c * x[0].y);
-#pragma unroll
-            for (int k = 1; k < 8; ++k) {
-                L[k].x = fmaf(a, L[k - 1].x, c * x[k].x);
-                L[k].y = fmaf(a, L[k - 1].y, c * x[k].y);
-            }
-            // the whole warp exists or not together (256-aligned), so full-mask shuffles are safe
-            float2 inc = L[7];
-#pragma unroll
-            for (int d = 0; d < 5; ++d) {
-                const float vx = __shfl_up_sync(0xffffffffu, inc.x, 1 << d);
-                const float vy = __shfl_up_sync(0xffffffffu, inc.y, 1 << d);
-                if (lane >= (1 << d)) {
-                    inc.x = fmaf(c_dc.wscan[d], vx, inc.x);
-                    inc.y = fmaf(c_dc.wscan[d], vy, inc.y);
-                }
-            }
-            float px = __shfl_up_sync(0xffffffffu, inc.x, 1);
-            float py = __shfl_up_sync(0xffffffffu, inc.y, 1);
-            if (lane == 0) { px = 0.f; py = 0.f; }
-            const int seg = (b * B + i0 - 8 * lane) >> 8;      // -1: last segment of the previous call
-            const float2 aseg = __ldg(p.dc_start + (size_t)stream * p.dc_stride + (seg + 1));
-            const float sx = fmaf(c_dc.apow8[lane], aseg.x, px);
-            const float sy = fmaf(c_dc.apow8[lane], aseg.y, py);
+            // avept for each of this lane's 8 samples, bit-exact: start from the state the walk
+            // kernel left at the head of the 32-sample DC block (4 lanes), advance to this lane's
+            // chunk -- by translation in integer ulps when the block was a translation, by real
+            // float steps over the preceding samples otherwise -- then 8 real float steps.
+            const int dblk = ((b * B + i0) >> 5) + DC_HALO_BLKS;                // >= 0: halo entries in front
+            const int m = (i0 >> 3) & 3;                                          // chunk inside the DC block
+            const uint2 *te = p.dc_table + ((size_t)stream * p.dc_stride + dblk) * 2;
+            const uint2 eI = __ldg(te), eQ = __ldg(te + 1);
+            const DcAnchor AI = p.dc_anchor[2 * stream], AQ = p.dc_anchor[2 * stream + 1];
+            float dI = 0.f, dQ = 0.f;
 #pragma unroll
             for (int k = 0; k < 8; ++k) {
-                x[k].x -= fmaf(c_dc.apow[k + 1], sx, L[k].x);
-                x[k].y -= fmaf(c_dc.apow[k + 1], sy, L[k].y);
+                bool t;
+                dI += dc_incr(AI, x[k].x, t) - (float)AI.r0;
+                dQ += dc_incr(AQ, x[k].y, t) - (float)AQ.r0;
+            }
+            // exclusive prefix over the 4 lanes of the DC block
+            float pI = dI, pQ = dQ;
+#pragma unroll
+            for (int d = 1; d < 4; d <<= 1) {
+                const float vI = __shfl_up_sync(0xffffffffu, pI, d, 4), vQ = __shfl_up_sync(0xffffffffu, pQ, d, 4);
+                if (m >= d) { pI += vI; pQ += vQ; }
+            }
+            pI -= dI; pQ -= dQ;
+            float sI = __uint_as_float(eI.x), sQ = __uint_as_float(eQ.x);
+            if (eI.y < 2u) sI = AI.sgn * __uint_as_float((unsigned)((int)(eI.x & 0x7FFFFFFFu) + (int)pI - (eI.y ? 8 * m : 0)));
+            if (eQ.y < 2u) sQ = AQ.sgn * __uint_as_float((unsigned)((int)(eQ.x & 0x7FFFFFFFu) + (int)pQ - (eQ.y ? 8 * m : 0)));
+            if ((eI.y == 2u || eQ.y == 2u) && m > 0) {
+                for (int j = m; j > 0; --j) {                                     // preceding chunks of the block
+                    float2 y[8];
+                    unpack8(__ldg(reinterpret_cast<const uint4 *>(src) - j), y);
+#pragma unroll
+                    for (int k = 0; k < 8; ++k) {
+                        if (eI.y == 2u) sI = dc_step(sI, y[k].x);
+                        if (eQ.y == 2u) sQ = dc_step(sQ, y[k].y);
+                    }
+                }
+            }
+#pragma unroll
+            for (int k = 0; k < 8; ++k) {
+                sI = dc_step(sI, x[k].x);
+                sQ = dc_step(sQ, x[k].y);
+                x[k].x = __fadd_rn(x[k].x, -sI);
+                x[k].y = __fadd_rn(x[k].y, -sQ);
             }
         }
     }
@@ -718,6 +830,7 @@ __global__ void __launch_bounds__(256) k2b_usb_audio(const UsbDev *__restrict__ 
 __global__ void __launch_bounds__(128) k3_carry(const CarryItem *__restrict__ items, int n_items, int n_blocks,
                                                  const uint8_t *__restrict__ iq, size_t iq_stride, int block,
                                                  uint8_t *__restrict__ tail, long long *__restrict__ blocks_done,
+                                                 uint2 *__restrict__ dc_table, int dc_table_stride, int n_dcblk,
                                                  int stream0) {
     const int stream = stream0 + blockIdx.x;
     const int item = blockIdx.y;
@@ -732,7 +845,24 @@ __global__ void __launch_bounds__(128) k3_carry(const CarryItem *__restrict__ it
         uint4 *dst = reinterpret_cast<uint4 *>(tail + (size_t)stream * (2 * RAW_TAIL));
         for (int e = threadIdx.x; e < (2 * RAW_TAIL) / 16; e += 128) dst[e] = src[e];
         if (threadIdx.x == 0) blocks_done[stream] += n_blocks;
+        // DC table: the last DC_HALO_BLKS block-start states move to the front for the next call's
+        // halo warp; they become "stepped" entries because the next call has a new anchor.
+        if (dc_table && threadIdx.x < 2 * DC_HALO_BLKS) {
+            uint2 *t = dc_table + (size_t)stream * dc_table_stride * 2;
+            uint2 e = t[(size_t)n_dcblk * 2 + threadIdx.x];
+            e.y = 2u;
+            t[threadIdx.x] = e;
+        }
     }
+}
+
+// test/inspection helper: block-start DC states of the last call as float2 (I, Q)
+__global__ void __launch_bounds__(256) dc_trace_gather(const uint2 *__restrict__ table, int table_stride, int n,
+                                                        float2 *__restrict__ out) {
+    const int i = blockIdx.x * 256 + threadIdx.x;
+    if (i >= n) return;
+    const uint2 *t = table + ((size_t)blockIdx.y * table_stride + DC_HALO_BLKS + i) * 2;
+    out[(size_t)blockIdx.y * n + i] = make_float2(__uint_as_float(t[0].x), __uint_as_float(t[1].x));
 }
 
 }  // namespace sdrb
