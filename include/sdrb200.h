@@ -134,10 +134,12 @@ int sdrb_bank_process_device(sdrb_bank *bank, const uint8_t *d_iq, size_t iq_str
  * process call: cf32 [n_streams][n_blocks*block_out] on the device. */
 int sdrb_bank_copy_main(sdrb_bank *bank, int main_idx, int n_blocks, float *d_out_cf32, void *cuda_stream);
 
-/* Inspection: the DC-removal state (sdrj.cpp:280 `avept`) entering every 32nd sample of the
- * last process call, float2 (I,Q) [n_streams][n_blocks*block/32] on the device. The kernels
- * reproduce the reference's float recursion bit for bit; tests compare this trace exactly. */
-int sdrb_bank_copy_dc_trace(sdrb_bank *bank, int n_blocks, float *d_out, void *cuda_stream);
+/* Inspection: the DC-removal state (sdrj.cpp:280 `avept`) entering every 128th sample of the
+ * last process call, float2 (I,Q) [n_streams][n_blocks*block/128] on the device. The kernels
+ * reproduce the reference's float recursion bit for bit; tests compare this trace exactly.
+ * d_modes (optional, NULL = off): one byte per entry, low nibble I arm, high nibble Q arm:
+ * 0/1 = the 128 samples were advanced as one integer translation, 2 = stepped in float. */
+int sdrb_bank_copy_dc_trace(sdrb_bank *bank, int n_blocks, float *d_out, uint8_t *d_modes, void *cuda_stream);
 
 /*
  * Host-facing call: same work with HOST buffers (pinned from sdrb_host_alloc for full

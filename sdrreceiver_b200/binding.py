@@ -82,7 +82,7 @@ def lib():
         "sdrb_bank_blocks_done": (i, [vp, i, P(C.c_int64)]),
         "sdrb_bank_process_device": (i, [vp, vp, sz, i, vp, vp, vp]),
         "sdrb_bank_copy_main": (i, [vp, i, i, vp, vp]),
-        "sdrb_bank_copy_dc_trace": (i, [vp, i, vp, vp]),
+        "sdrb_bank_copy_dc_trace": (i, [vp, i, vp, vp, vp]),
         "sdrb_bank_process_host": (i, [vp, vp, sz, i, vp, vp]),
         "sdrb_bank_last_launches": (i, [vp]),
         "sdrb_bank_set_timing": (i, [vp, i]),
@@ -210,8 +210,9 @@ class Bank:
     def copy_main(self, main_idx, n_blocks, d_out_ptr, cuda_stream=None):
         _check(lib().sdrb_bank_copy_main(self.h, main_idx, n_blocks, d_out_ptr, cuda_stream), "sdrb_bank_copy_main")
 
-    def copy_dc_trace(self, n_blocks, d_out_ptr, cuda_stream=None):
-        _check(lib().sdrb_bank_copy_dc_trace(self.h, n_blocks, d_out_ptr, cuda_stream), "sdrb_bank_copy_dc_trace")
+    def copy_dc_trace(self, n_blocks, d_out_ptr, d_modes_ptr=None, cuda_stream=None):
+        _check(lib().sdrb_bank_copy_dc_trace(self.h, n_blocks, d_out_ptr, d_modes_ptr, cuda_stream),
+               "sdrb_bank_copy_dc_trace")
 
     def process_host(self, h_iq_ptr, iq_stride, n_blocks, h_pcm_ptr, h_tap_ptr=None):
         _check(lib().sdrb_bank_process_host(self.h, h_iq_ptr, iq_stride, n_blocks, h_pcm_ptr, h_tap_ptr),

@@ -167,6 +167,11 @@ struct sdrb_bank {
     DevBuf d_iq, d_pcm, d_tap;
     cudaStream_t s_copy_in = nullptr, s_compute = nullptr, s_copy_out = nullptr;
     std::vector<cudaEvent_t> ev_in, ev_done;
+    // DC recursion runs on side streams, one callback ahead of the ingest kernel
+    static constexpr int kSide = 8;
+    cudaStream_t s_dc[kSide] = {nullptr};
+    cudaEvent_t ev_entry[kSide] = {nullptr};
+    std::vector<cudaEvent_t> ev_dc[kSide];
     // optional per-kernel timing (bench.py roofline): event pairs around each kernel class
     bool timing = false;
     std::vector<cudaEvent_t> tev;           // 2 * SDRB_N_KERNEL_CLASSES * calls, recycled
@@ -185,6 +190,11 @@ extern "C" void sdrb_bank_destroy(sdrb_bank *b) {
     for (cudaEvent_t e : b->ev_in) cudaEventDestroy(e);
     for (cudaEvent_t e : b->ev_done) cudaEventDestroy(e);
     for (cudaEvent_t e : b->tev) cudaEventDestroy(e);
+    for (int k = 0; k < sdrb_bank::kSide; k++) {
+        if (b->s_dc[k]) cudaStreamDestroy(b->s_dc[k]);
+        if (b->ev_entry[k]) cudaEventDestroy(b->ev_entry[k]);
+        for (cudaEvent_t e : b->ev_dc[k]) cudaEventDestroy(e);
+    }
     if (b->s_copy_in) cudaStreamDestroy(b->s_copy_in);
     if (b->s_compute) cudaStreamDestroy(b->s_compute);
     if (b->s_copy_out) cudaStreamDestroy(b->s_copy_out);
@@ -263,7 +273,7 @@ extern "C" int sdrb_bank_create(const sdrb_plan *plan, int device, int n_streams
     // ---- work buffers ----
     b->dc_stride = max_blocks * (h.block / DC_BLK);
     BANK_TRY(b->dc_anchor.alloc(sizeof(DcAnchor) * 2 * (size_t)n_streams));
-    BANK_TRY(b->dc_stats.alloc(h.correct_dc ? sizeof(DcStats) * 2 * (size_t)n_streams * (size_t)b->dc_stride : 16));
+    BANK_TRY(b->dc_stats.alloc(h.correct_dc ? sizeof(DcStats) * 2 * (size_t)n_streams * (size_t)b->dc_stride + 1024 : 16));
     BANK_TRY(b->dc_table.alloc(h.correct_dc ? sizeof(uint2) * 2 * (size_t)n_streams * (size_t)(b->dc_stride + DC_HALO_BLKS) : 16));
     {
         size_t at = 0;
@@ -393,6 +403,16 @@ extern "C" int sdrb_bank_create(const sdrb_plan *plan, int device, int n_streams
     BANK_CU(cudaStreamCreateWithFlags(&b->s_copy_in, cudaStreamNonBlocking));
     BANK_CU(cudaStreamCreateWithFlags(&b->s_compute, cudaStreamNonBlocking));
     BANK_CU(cudaStreamCreateWithFlags(&b->s_copy_out, cudaStreamNonBlocking));
+    if (h.correct_dc)
+        for (int k = 0; k < sdrb_bank::kSide; k++) {
+            BANK_CU(cudaStreamCreateWithFlags(&b->s_dc[k], cudaStreamNonBlocking));
+            BANK_CU(cudaEventCreateWithFlags(&b->ev_entry[k], cudaEventDisableTiming));
+            for (int j = 0; j < max_blocks; j++) {
+                cudaEvent_t e;
+                BANK_CU(cudaEventCreateWithFlags(&e, cudaEventDisableTiming));
+                b->ev_dc[k].push_back(e);
+            }
+        }
 #undef BANK_TRY
 #undef BANK_CU
     rc = sdrb_bank_reset(b, -1);
@@ -441,27 +461,51 @@ static void mark(sdrb_bank *b, cudaStream_t st) {
 
 // Enqueue the whole pipeline for streams [s0, s0+ns) on `st`. Returns launches issued.
 static int enqueue(sdrb_bank *b, const uint8_t *d_iq, size_t iq_stride, int n_blocks, int16_t *d_pcm, float *d_tap,
-                   int s0, int ns, cudaStream_t st, int *launches) {
+                   int s0, int ns, cudaStream_t st, int slot, cudaEvent_t input_ready, int *launches) {
     const HostPlan &h = b->plan->h;
     int nl = 0;
-    const int n_dcblk = n_blocks * (h.block / DC_BLK);
-    mark(b, st);                                            // class 0: DC recursion
-    if (h.correct_dc) {
-        k0_dc_anchor<<<(unsigned)((2 * ns + 127) / 128), 128, 0, st>>>((const float2 *)b->dc_state.p,
-                                                                      (DcAnchor *)b->dc_anchor.p, ns, s0);
-        k0_dc_blocks<<<dim3((unsigned)((n_dcblk + 127) / 128), (unsigned)ns), 128, 0, st>>>(
-            d_iq, iq_stride, (const DcAnchor *)b->dc_anchor.p, (DcStats *)b->dc_stats.p, b->dc_stride, n_dcblk, s0);
-        k0_dc_walk<<<(unsigned)ns, 32, 0, st>>>(d_iq, iq_stride, (const DcStats *)b->dc_stats.p, b->dc_stride,
-                                                (const DcAnchor *)b->dc_anchor.p, (float2 *)b->dc_state.p,
-                                                (uint2 *)b->dc_table.p, b->dc_stride + DC_HALO_BLKS, n_dcblk, s0);
-        nl += 3;
-    }
-    mark(b, st);                                            // class 1: ingest + main VFOs
+    const int per_cb = h.block / DC_BLK, n_dcblk = n_blocks * per_cb;
     K1Params k1 = b->k1;
-    k1.iq = d_iq; k1.iq_stride = iq_stride; k1.n_blocks = n_blocks; k1.stream0 = s0;
+    k1.iq = d_iq; k1.iq_stride = iq_stride; k1.n_blocks = n_blocks; k1.stream0 = s0; k1.b0 = 0;
     const int k1_tiles = (h.block + K1_TILE - 1) / K1_TILE;
-    k1_ingest_main<<<dim3((unsigned)ns, (unsigned)k1_tiles, (unsigned)n_blocks), K1_THREADS, 0, st>>>(k1);
-    nl++;
+    mark(b, st);                                            // class 0: DC recursion (exposed part)
+    if (h.correct_dc) {
+        // Side stream: anchor, parallel block statistics, then the sequential walk one callback
+        // at a time; the ingest kernel of callback cb starts as soon as its walk is done, so only
+        // the first walk is exposed on the critical path.
+        cudaStream_t sd = b->s_dc[slot];
+        if (input_ready) {                                  // host path: wait for this group's H2D copy only
+            CU_TRY(cudaStreamWaitEvent(sd, input_ready, 0));
+        } else {                                            // device path: everything queued before this call
+            CU_TRY(cudaEventRecord(b->ev_entry[slot], st));
+            CU_TRY(cudaStreamWaitEvent(sd, b->ev_entry[slot], 0));
+        }
+        k0_dc_anchor<<<(unsigned)((2 * ns + 127) / 128), 128, 0, sd>>>((const float2 *)b->dc_state.p,
+                                                                      (DcAnchor *)b->dc_anchor.p, ns, s0);
+        k0_dc_blocks<<<dim3((unsigned)((n_dcblk + 127) / 128), (unsigned)ns), 128, 0, sd>>>(
+            d_iq, iq_stride, (const DcAnchor *)b->dc_anchor.p, (DcStats *)b->dc_stats.p, b->dc_stride, 0, n_dcblk, s0);
+        nl += 2;
+        for (int cb = 0; cb < n_blocks; cb++) {
+            k0_dc_walk<<<(unsigned)ns, 64, 0, sd>>>(d_iq, iq_stride, (const DcStats *)b->dc_stats.p, b->dc_stride,
+                                                    (const DcAnchor *)b->dc_anchor.p, (float2 *)b->dc_state.p,
+                                                    (uint2 *)b->dc_table.p, b->dc_stride + DC_HALO_BLKS, cb * per_cb,
+                                                    per_cb, s0);
+            CU_TRY(cudaEventRecord(b->ev_dc[slot][(size_t)cb], sd));
+            nl++;
+        }
+        CU_TRY(cudaStreamWaitEvent(st, b->ev_dc[slot][0], 0));
+        mark(b, st);                                        // class 1: ingest + main VFOs
+        for (int cb = 0; cb < n_blocks; cb++) {
+            if (cb) CU_TRY(cudaStreamWaitEvent(st, b->ev_dc[slot][(size_t)cb], 0));
+            k1.b0 = cb;
+            k1_ingest_main<<<dim3((unsigned)ns, (unsigned)k1_tiles, 1u), K1_THREADS, 0, st>>>(k1);
+            nl++;
+        }
+    } else {
+        mark(b, st);                                        // class 1: ingest + main VFOs
+        k1_ingest_main<<<dim3((unsigned)ns, (unsigned)k1_tiles, (unsigned)n_blocks), K1_THREADS, 0, st>>>(k1);
+        nl++;
+    }
     mark(b, st);                                            // class 2: sub-VFO cascades
     for (const SubGroup &g : b->groups) {
         K2aParams kp;
@@ -496,8 +540,8 @@ static int enqueue(sdrb_bank *b, const uint8_t *d_iq, size_t iq_stride, int n_bl
     mark(b, st);                                            // class 5: carry
     k3_carry<<<dim3((unsigned)ns, (unsigned)(b->n_carry + 1)), 128, 0, st>>>(
         (const CarryItem *)b->carry.p, b->n_carry, n_blocks, d_iq, iq_stride, h.block, (uint8_t *)b->raw_tail.p,
-        (long long *)b->blocks_done.p, h.correct_dc ? (uint2 *)b->dc_table.p : nullptr, b->dc_stride + DC_HALO_BLKS,
-        n_dcblk, s0);
+        (long long *)b->blocks_done.p, h.correct_dc ? (uint2 *)b->dc_table.p : nullptr, (const DcAnchor *)b->dc_anchor.p,
+        b->dc_stride + DC_HALO_BLKS, n_dcblk, s0);
     nl++;
     mark(b, st);
     CU_TRY(cudaGetLastError());
@@ -548,7 +592,8 @@ extern "C" int sdrb_bank_process_device(sdrb_bank *b, const uint8_t *d_iq, size_
     if (rc != SDRB_OK) return rc;
     CU_TRY(cudaSetDevice(b->device));
     b->last_launches = 0;
-    return enqueue(b, d_iq, iq_stride, n_blocks, d_pcm, d_tap, 0, b->n_streams, (cudaStream_t)cuda_stream, &b->last_launches);
+    return enqueue(b, d_iq, iq_stride, n_blocks, d_pcm, d_tap, 0, b->n_streams, (cudaStream_t)cuda_stream, 0,
+                   nullptr, &b->last_launches);
 }
 
 extern "C" int sdrb_bank_copy_main(sdrb_bank *b, int main_idx, int n_blocks, float *d_out, void *cuda_stream) {
@@ -565,14 +610,15 @@ extern "C" int sdrb_bank_copy_main(sdrb_bank *b, int main_idx, int n_blocks, flo
     return SDRB_OK;
 }
 
-extern "C" int sdrb_bank_copy_dc_trace(sdrb_bank *b, int n_blocks, float *d_out, void *cuda_stream) {
+extern "C" int sdrb_bank_copy_dc_trace(sdrb_bank *b, int n_blocks, float *d_out, uint8_t *d_modes, void *cuda_stream) {
     if (!b || !d_out || n_blocks <= 0 || n_blocks > b->max_blocks || !b->plan->h.correct_dc) {
         set_error("sdrb_bank_copy_dc_trace: bad argument or plan without correct_dc_bias"); return SDRB_E_INVALID;
     }
     CU_TRY(cudaSetDevice(b->device));
     const int n = n_blocks * (b->plan->h.block / DC_BLK);
     dc_trace_gather<<<dim3((unsigned)((n + 255) / 256), (unsigned)b->n_streams), 256, 0, (cudaStream_t)cuda_stream>>>(
-        (const uint2 *)b->dc_table.p, b->dc_stride + DC_HALO_BLKS, n, (float2 *)d_out);
+        (const uint2 *)b->dc_table.p, (const DcAnchor *)b->dc_anchor.p, b->dc_stride + DC_HALO_BLKS, n, (float2 *)d_out,
+        d_modes);
     CU_TRY(cudaGetLastError());
     return SDRB_OK;
 }
@@ -613,7 +659,8 @@ extern "C" int sdrb_bank_process_host(sdrb_bank *b, const uint8_t *h_iq, size_t 
         CU_TRY(cudaStreamWaitEvent(b->s_compute, b->ev_in[(size_t)g], 0));
         // kernels index streams absolutely: pass the bank-wide base pointers
         rc = enqueue(b, (const uint8_t *)b->d_iq.p, in_max, n_blocks, (int16_t *)b->d_pcm.p,
-                     h_tap ? (float *)b->d_tap.p : nullptr, s0, ns, b->s_compute, &b->last_launches);
+                     h_tap ? (float *)b->d_tap.p : nullptr, s0, ns, b->s_compute, g % sdrb_bank::kSide,
+                     b->ev_in[(size_t)g], &b->last_launches);
         if (rc != SDRB_OK) return rc;
         CU_TRY(cudaEventRecord(b->ev_done[(size_t)g], b->s_compute));
         CU_TRY(cudaStreamWaitEvent(b->s_copy_out, b->ev_done[(size_t)g], 0));

@@ -32,7 +32,7 @@ namespace sdrb {
 #define HB_P4 0.29332944952052842f
 #define HB_P5 0.5f
 
-constexpr int DC_BLK = 32;             // samples per DC-recursion block (4 K1 lanes)
+constexpr int DC_BLK = 128;            // samples per DC-recursion block (16 K1 lanes)
 constexpr int RAW_TAIL = 256;          // raw samples carried between calls (K1 halo warp)
 constexpr int K1_WARPS = 8;            // active warps per K1 CTA (+1 halo warp)
 constexpr int K1_THREADS = (K1_WARPS + 1) * 32;
@@ -58,9 +58,13 @@ struct DcAnchor {
     int r0, ok;
     unsigned T, lo, hi, pad;
 };
-// Per 32-sample block and arm, in ulps of the anchor: D = sum(Q_k - r0); Amax = max prefix
-// (k < 32), Bmin = min of (prefix - k). Amax = 2^30 marks a block that must be stepped.
-struct DcStats { int D, Amax, Bmin; };
+// Per DC block and arm, from the integer increments d_k = Q_k - r0 (ulps of the anchor,
+// U_k = their prefix sums, k < DC_BLK): D = U_DC_BLK and three bit-pattern thresholds relative
+// to lo + 1 (V = bits(|state|) - (lo + 1)):
+//   V < ta            =>  every state of the block stays below T    (translation by D)
+//   tb <= V < tb_hi   =>  every state stays in [T, hi)               (translation by D - DC_BLK)
+// ta = 0 / tb = 0xFFFFFFFF force real float stepping (ties, no anchor).
+struct DcStats { int D; unsigned ta, tb, tb_hi; };
 
 struct MainDev {
     const float2 *lut;      // Oscillator table
@@ -76,7 +80,7 @@ struct K1Params {
     const uint2 *dc_table;          // [n_streams][dc_stride][2 arms]: {state bits at block start, mode}
     const DcAnchor *dc_anchor;      // [n_streams][2 arms]
     const long long *blocks_done;   // [n_streams]
-    int dc_stride, block, n_blocks, correct_dc, n_main, stream0;
+    int dc_stride, block, n_blocks, correct_dc, n_main, stream0, b0;
     MainDev mains[SDRB_MAX_MAIN];
 };
 
@@ -271,10 +275,11 @@ __global__ void __launch_bounds__(128) k0_dc_anchor(const float2 *__restrict__ d
         double lo = 8388608.0 + 4096.0, hi = 16777216.0 - 65536.0;
         lo = fmax(lo, ceil((r0 - 0.5) * step) + 2.0);
         hi = fmin(hi, ceil((r0 + 1.5) * step) - 2.0);
+        // the low side keeps a margin for the largest dip one block can make below its start;
+        // the high side is checked exactly per block (DcStats::tb_hi)
         const double qmax = ceil(128.0 * (double)DC_C * (double)A.inv_u) + 18.0;
-        const double margin = DC_BLK * qmax;
-        lo += margin; hi -= margin;
-        if (hi > lo && qmax < 1.0e6) {
+        lo += DC_BLK * qmax;
+        if (hi > lo && qmax < 1.0e5) {
             A.lo = base + (unsigned)((long long)lo - 8388608ll);
             A.hi = base + (unsigned)((long long)hi - 8388608ll);
             A.r0 = r0; A.T = T; A.ok = 1;
@@ -286,103 +291,187 @@ __global__ void __launch_bounds__(128) k0_dc_anchor(const float2 *__restrict__ d
 
 __global__ void __launch_bounds__(128) k0_dc_blocks(const uint8_t *__restrict__ iq, size_t iq_stride,
                                                      const DcAnchor *__restrict__ anchors, DcStats *__restrict__ stats,
-                                                     int stats_stride, int n_blk, int stream0) {
+                                                     int stats_stride, int blk0, int n_blk, int stream0) {
     const int stream = stream0 + blockIdx.y;
-    const int blk = blockIdx.x * 128 + threadIdx.x;
-    if (blk >= n_blk) return;
+    const int blk = blk0 + blockIdx.x * 128 + threadIdx.x;
+    if (blk >= blk0 + n_blk) return;
     const DcAnchor AI = anchors[2 * stream], AQ = anchors[2 * stream + 1];
     DcStats *out = stats + ((size_t)stream * stats_stride + blk) * 2;
-    DcStats bad; bad.D = 0; bad.Amax = 1 << 30; bad.Bmin = -(1 << 30);
+    DcStats bad; bad.D = 0; bad.ta = 0u; bad.tb = 0xFFFFFFFFu; bad.tb_hi = 0u;
     if (!AI.ok && !AQ.ok) { out[0] = bad; out[1] = bad; return; }
     const uint4 *src = reinterpret_cast<const uint4 *>(iq + (size_t)stream * iq_stride + (size_t)blk * (2 * DC_BLK));
-    float uI = 0.f, uQ = 0.f, amaxI = -1e30f, amaxQ = -1e30f, bminI = 1e30f, bminQ = 1e30f;
+    float uI = 0.f, uQ = 0.f, amaxI = 0.f, amaxQ = 0.f, bminI = 0.f, bminQ = 0.f, bmaxI = 0.f, bmaxQ = 0.f;
     bool badI = !AI.ok, badQ = !AQ.ok;
     const float r0I = (float)AI.r0, r0Q = (float)AQ.r0;
-#pragma unroll
-    for (int v = 0; v < 4; ++v) {
+#pragma unroll 4
+    for (int v = 0; v < DC_BLK / 8; ++v) {
         float2 x[8];
         unpack8(__ldg(src + v), x);
 #pragma unroll
         for (int k = 0; k < 8; ++k) {
             const float kk = (float)(8 * v + k);
-            amaxI = fmaxf(amaxI, uI); bminI = fminf(bminI, uI - kk);
-            amaxQ = fmaxf(amaxQ, uQ); bminQ = fminf(bminQ, uQ - kk);
+            amaxI = fmaxf(amaxI, uI); bminI = fminf(bminI, uI - kk); bmaxI = fmaxf(bmaxI, uI - kk);
+            amaxQ = fmaxf(amaxQ, uQ); bminQ = fminf(bminQ, uQ - kk); bmaxQ = fmaxf(bmaxQ, uQ - kk);
             bool t1, t2;
             uI += dc_incr(AI, x[k].x, t1) - r0I;
             uQ += dc_incr(AQ, x[k].y, t2) - r0Q;
             badI |= t1; badQ |= t2;
         }
     }
+    // amax >= 0 >= bmin by construction (the k = 0 term), so ta <= T - lo1 <= tb
     DcStats sI, sQ;
-    sI.D = (int)uI; sI.Amax = (int)amaxI; sI.Bmin = (int)bminI;
-    sQ.D = (int)uQ; sQ.Amax = (int)amaxQ; sQ.Bmin = (int)bminQ;
+    long long t;
+    const long long lo1I = (long long)AI.lo + 1, lo1Q = (long long)AQ.lo + 1;
+    sI.D = (int)uI;
+    t = (long long)AI.T - (long long)amaxI - lo1I; sI.ta = t > 0 ? (unsigned)t : 0u;
+    t = (long long)AI.T - (long long)bminI - lo1I; sI.tb = t > 0 ? (unsigned)t : 0u;
+    t = (long long)AI.hi - (long long)bmaxI - lo1I; sI.tb_hi = t > 0 ? (unsigned)t : 0u;
+    sQ.D = (int)uQ;
+    t = (long long)AQ.T - (long long)amaxQ - lo1Q; sQ.ta = t > 0 ? (unsigned)t : 0u;
+    t = (long long)AQ.T - (long long)bminQ - lo1Q; sQ.tb = t > 0 ? (unsigned)t : 0u;
+    t = (long long)AQ.hi - (long long)bmaxQ - lo1Q; sQ.tb_hi = t > 0 ? (unsigned)t : 0u;
     out[0] = badI ? bad : sI;
     out[1] = badQ ? bad : sQ;
 }
 
-// modes written to the table: 0 = translation below T, 1 = translation at/above T, 2 = stepped
-__global__ void __launch_bounds__(32) k0_dc_walk(const uint8_t *__restrict__ iq, size_t iq_stride,
+// Sequential part: one CTA of two warps per stream, warp 0 walks the I arm, warp 1 the Q arm.
+// All 32 lanes of a warp keep a 3-deep cp.async ring of batches (8 blocks = 1024 samples:
+// statistics and raw bytes) flowing into shared memory and turn each landed batch into the
+// fl(c*x) products of its arm; lane 0 then walks the blocks. The loop-carried value is
+// V = bit pattern of |state| - (lo + 1): a translation block costs a compare and a select, a
+// stepped block DC_BLK dependent multiply-adds on the real float state.
+// Table entry per block and arm: {V, mode 0|1} for translations (below / at-or-above T),
+// {float bits of the state, 2} for stepped blocks.
+constexpr int DC_BATCH = 8;
+constexpr int DC_RING = 3;
+
+__device__ __forceinline__ void cp_async16(void *smem, const void *gmem) {
+    const unsigned sa = (unsigned)__cvta_generic_to_shared(smem);
+    asm volatile("cp.async.cg.shared.global [%0], [%1], 16;\n" ::"r"(sa), "l"(gmem));
+}
+__device__ __forceinline__ void cp_async_commit() { asm volatile("cp.async.commit_group;\n" ::); }
+template <int N> __device__ __forceinline__ void cp_async_wait() { asm volatile("cp.async.wait_group %0;\n" ::"n"(N)); }
+
+__global__ void __launch_bounds__(64) k0_dc_walk(const uint8_t *__restrict__ iq, size_t iq_stride,
                                                   const DcStats *__restrict__ stats, int stats_stride,
                                                   const DcAnchor *__restrict__ anchors, float2 *__restrict__ dc_state,
-                                                  uint2 *__restrict__ table, int table_stride, int n_blk, int stream0) {
-    __shared__ DcStats sst[2][32][2];
-    __shared__ uint4 sraw[2][32][4];
+                                                  uint2 *__restrict__ table, int table_stride, int blk0, int n_blk,
+                                                  int stream0) {
+    __shared__ __align__(16) DcStats sst[2][DC_RING][DC_BATCH * 2];        // [warp][slot][block][arm]
+    __shared__ __align__(16) uint4 sraw[2][DC_RING][4][32];                // [warp][slot][piece][lane]
+    __shared__ float sq[2][32 * 33];                                       // [warp][lane * 33 + i]: fl(c*x)
     const int stream = stream0 + blockIdx.x;
-    const int lane = threadIdx.x, arm = lane & 1;
-    const DcAnchor A = anchors[2 * stream + arm];
-    const float2 st0 = dc_state[stream];
-    float s = arm ? st0.y : st0.x;
-    const DcStats *sp = stats + (size_t)stream * stats_stride * 2;
-    const uint4 *rp = reinterpret_cast<const uint4 *>(iq + (size_t)stream * iq_stride);
-    uint2 *tab = table + ((size_t)stream * table_stride + DC_HALO_BLKS) * 2;
-    const int n_batch = (n_blk + 31) / 32;
+    const int arm = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    const DcStats *sp = stats + ((size_t)stream * stats_stride + blk0) * 2;
+    const uint4 *rp = reinterpret_cast<const uint4 *>(iq + (size_t)stream * iq_stride) + (size_t)blk0 * (DC_BLK / 8);
+    uint2 *tab = table + ((size_t)stream * table_stride + DC_HALO_BLKS + blk0) * 2 + arm;
+    const int n_batch = (n_blk + DC_BATCH - 1) / DC_BATCH;
+    const int n_q = n_blk * 4;                                             // 32-sample quarters in this launch
 
-    DcStats rs0, rs1; uint4 rr0, rr1, rr2, rr3;
-    auto fetch = [&](int batch) {
-        const int blk = min(batch * 32 + lane, n_blk - 1);
-        rs0 = sp[(size_t)blk * 2]; rs1 = sp[(size_t)blk * 2 + 1];
-        const uint4 *r = rp + (size_t)blk * 4;
-        rr0 = __ldg(r); rr1 = __ldg(r + 1); rr2 = __ldg(r + 2); rr3 = __ldg(r + 3);
-    };
-    auto stash = [&](int buf) {
-        sst[buf][lane][0] = rs0; sst[buf][lane][1] = rs1;
-        sraw[buf][lane][0] = rr0; sraw[buf][lane][1] = rr1; sraw[buf][lane][2] = rr2; sraw[buf][lane][3] = rr3;
-    };
-    fetch(0);
-    stash(0);
-    __syncwarp();
-    for (int batch = 0; batch < n_batch; ++batch) {
-        const int buf = batch & 1;
-        if (batch + 1 < n_batch) fetch(batch + 1);              // in flight while this batch is walked
-        if (lane < 2) {
-            const int nb = min(32, n_blk - batch * 32);
-            for (int j = 0; j < nb; ++j) {
-                const DcStats S = sst[buf][j][arm];
-                const unsigned W = __float_as_uint(fabsf(s));
-                const bool in_win = A.ok && (s * A.sgn > 0.f) && W > A.lo && W < A.hi && S.Amax < (1 << 29);
-                unsigned mode = 2u;
-                const unsigned before = __float_as_uint(s);
-                if (in_win && W < A.T && (long long)W + S.Amax < (long long)A.T) {
-                    s = A.sgn * __uint_as_float((unsigned)((int)W + S.D));
-                    mode = 0u;
-                } else if (in_win && W >= A.T && (long long)W + S.Bmin >= (long long)A.T) {
-                    s = A.sgn * __uint_as_float((unsigned)((int)W + S.D - DC_BLK));
-                    mode = 1u;
-                } else {
-                    const unsigned char *bytes = reinterpret_cast<const unsigned char *>(&sraw[buf][j][0]);
-#pragma unroll 8
-                    for (int k = 0; k < DC_BLK; ++k) s = dc_step(s, (float)((int)bytes[2 * k + arm] - 127));
-                }
-                tab[(size_t)(batch * 32 + j) * 2 + arm] = make_uint2(before, mode);
+    auto prefetch = [&](int batch) {
+        if (batch < n_batch) {
+            const int slot = batch % DC_RING;
+            if (lane < DC_BATCH * 2) {                                     // statistics: 16 entries of 16 bytes
+                const int e = min(batch * DC_BATCH * 2 + lane, n_blk * 2 - 1);
+                cp_async16(&sst[arm][slot][lane], sp + e);
             }
+            const int qtr = min(batch * 32 + lane, n_q - 1);               // tail: repeat the last quarter
+            const uint4 *r = rp + (size_t)qtr * 4;
+#pragma unroll
+            for (int v = 0; v < 4; ++v) cp_async16(&sraw[arm][slot][v][lane], r + v);
+        }
+        cp_async_commit();
+    };
+
+    const DcAnchor A = anchors[2 * stream + arm];
+    const unsigned lo1 = A.lo + 1u;
+    const unsigned sign_bit = A.sgn < 0.f ? 0x80000000u : 0u;
+    unsigned V = 0xFFFFFFFFu;                                     // invalid: forces stepping
+    float s = 0.f;
+    if (lane == 0) {
+        const float2 st0 = dc_state[stream];
+        s = arm ? st0.y : st0.x;
+        if (A.ok && s * A.sgn > 0.f) V = __float_as_uint(fabsf(s)) - lo1;
+    }
+    prefetch(0);
+    prefetch(1);
+    for (int batch = 0; batch < n_batch; ++batch) {
+        prefetch(batch + 2);
+        cp_async_wait<2>();                                       // this batch has landed
+        __syncwarp();
+        const int slot = batch % DC_RING;
+        // every lane: fl(c*x) of its 32-sample quarter for this arm (row stride 33: conflict free)
+#pragma unroll
+        for (int v = 0; v < 4; ++v) {
+            float2 x[8];
+            unpack8(sraw[arm][slot][v][lane], x);
+#pragma unroll
+            for (int k = 0; k < 8; ++k) sq[arm][lane * 33 + 8 * v + k] = __fmul_rn(DC_C, arm ? x[k].y : x[k].x);
         }
         __syncwarp();
-        if (batch + 1 < n_batch) stash(buf ^ 1);
-        __syncwarp();
+        if (lane == 0) {
+            const int nb = min(DC_BATCH, n_blk - batch * DC_BATCH);
+            uint2 *to = tab + (size_t)batch * DC_BATCH * 2;
+            // One block, careful version: decide, then translate or step through DC_BLK float updates.
+            auto walk_one = [&](int j) {
+                const DcStats S = sst[arm][slot][j * 2 + arm];
+                const bool fa = V < S.ta;
+                const bool fb = (V >= S.tb) & (V < S.tb_hi);
+                if (fa | fb) {
+                    to[(size_t)j * 2] = make_uint2(V, fb ? 1u : 0u);
+                    V = V + (unsigned)S.D - (fb ? (unsigned)DC_BLK : 0u);
+                } else {
+                    if (V != 0xFFFFFFFFu) s = __uint_as_float((V + lo1) | sign_bit);
+                    to[(size_t)j * 2] = make_uint2(__float_as_uint(s), 2u);
+#pragma unroll 1
+                    for (int c = 0; c < 4; ++c) {
+                        float q[32];
+#pragma unroll
+                        for (int k = 0; k < 32; ++k) q[k] = sq[arm][(4 * j + c) * 33 + k];
+#pragma unroll
+                        for (int k = 0; k < 32; ++k) s = __fadd_rn(__fmul_rn(s, DC_A), q[k]);
+                    }
+                    V = (A.ok && s * A.sgn > 0.f) ? __float_as_uint(fabsf(s)) - lo1 : 0xFFFFFFFFu;
+                }
+            };
+            // Four blocks per trip, speculatively as four translations: the loop-carried chain is
+            // compare -> select per block; validity and the table stores hang off it. Only when
+            // one of the four is not a provable translation is the group redone block by block.
+            int j0 = 0;
+            for (; j0 + 4 <= nb; j0 += 4) {
+                DcStats S4[4];
+#pragma unroll
+                for (int i = 0; i < 4; ++i) S4[i] = sst[arm][slot][(j0 + i) * 2 + arm];
+                unsigned Vs[5], up[4], bad = 0u;
+                Vs[0] = V;
+#pragma unroll
+                for (int i = 0; i < 4; ++i) {
+                    up[i] = Vs[i] >= S4[i].tb ? 1u : 0u;
+                    const unsigned ok = (Vs[i] < S4[i].ta ? 1u : 0u) | (up[i] & (Vs[i] < S4[i].tb_hi ? 1u : 0u));
+                    bad |= ok ^ 1u;
+                    Vs[i + 1] = Vs[i] + (unsigned)S4[i].D - up[i] * (unsigned)DC_BLK;
+                }
+                if (bad == 0u) {
+#pragma unroll
+                    for (int i = 0; i < 4; ++i) to[(size_t)(j0 + i) * 2] = make_uint2(Vs[i], up[i]);
+                    V = Vs[4];
+                } else {
+#pragma unroll 1
+                    for (int i = 0; i < 4; ++i) walk_one(j0 + i);
+                }
+            }
+#pragma unroll 1
+            for (; j0 < nb; ++j0) walk_one(j0);
+        }
+        __syncwarp();                                             // ring slot and sq may be refilled next iteration
     }
-    // carry: the state entering the next call
-    const float other = __shfl_xor_sync(0xffffffffu, s, 1);
-    if (lane == 0) dc_state[stream] = make_float2(s, other);
+    __shared__ float s_end[2];
+    if (lane == 0) {
+        if (V != 0xFFFFFFFFu) s = __uint_as_float((V + lo1) | sign_bit);
+        s_end[arm] = s;
+    }
+    __syncthreads();
+    if (threadIdx.x == 0) dc_state[stream] = make_float2(s_end[0], s_end[1]);
 }
 
 // ------------------------------------------------------------------------------------
@@ -399,7 +488,7 @@ __global__ void __launch_bounds__(K1_THREADS, 2) k1_ingest_main(const K1Params p
     __shared__ __align__(16) float2 sA2[(K1_THREADS + HB_PAD) * K1_A2_STR];
 
     const int stream = p.stream0 + blockIdx.x;
-    const int tile = blockIdx.y, b = blockIdx.z;
+    const int tile = blockIdx.y, b = p.b0 + blockIdx.z;
     const int t = threadIdx.x, lane = t & 31;
     const int B = p.block;
     const int i0 = tile * K1_TILE - 256 + t * 8;          // callback coordinate of the chunk
@@ -420,11 +509,11 @@ __global__ void __launch_bounds__(K1_THREADS, 2) k1_ingest_main(const K1Params p
         unpack8(raw, x);
         if (p.correct_dc) {
             // avept for each of this lane's 8 samples, bit-exact: start from the state the walk
-            // kernel left at the head of the 32-sample DC block (4 lanes), advance to this lane's
+            // kernel left at the head of the DC block (DC_BLK samples = 16 lanes), advance to this lane's
             // chunk -- by translation in integer ulps when the block was a translation, by real
             // float steps over the preceding samples otherwise -- then 8 real float steps.
-            const int dblk = ((b * B + i0) >> 5) + DC_HALO_BLKS;                // >= 0: halo entries in front
-            const int m = (i0 >> 3) & 3;                                          // chunk inside the DC block
+            const int dblk = (b * B + i0 + RAW_TAIL) / DC_BLK;                   // table index incl. halo entries
+            const int m = (i0 >> 3) & (DC_BLK / 8 - 1);                            // chunk inside the DC block
             const uint2 *te = p.dc_table + ((size_t)stream * p.dc_stride + dblk) * 2;
             const uint2 eI = __ldg(te), eQ = __ldg(te + 1);
             const DcAnchor AI = p.dc_anchor[2 * stream], AQ = p.dc_anchor[2 * stream + 1];
@@ -435,17 +524,18 @@ __global__ void __launch_bounds__(K1_THREADS, 2) k1_ingest_main(const K1Params p
                 dI += dc_incr(AI, x[k].x, t) - (float)AI.r0;
                 dQ += dc_incr(AQ, x[k].y, t) - (float)AQ.r0;
             }
-            // exclusive prefix over the 4 lanes of the DC block
+            // exclusive prefix over the 16 lanes of the DC block
             float pI = dI, pQ = dQ;
 #pragma unroll
-            for (int d = 1; d < 4; d <<= 1) {
-                const float vI = __shfl_up_sync(0xffffffffu, pI, d, 4), vQ = __shfl_up_sync(0xffffffffu, pQ, d, 4);
+            for (int d = 1; d < DC_BLK / 8; d <<= 1) {
+                const float vI = __shfl_up_sync(0xffffffffu, pI, d, DC_BLK / 8);
+                const float vQ = __shfl_up_sync(0xffffffffu, pQ, d, DC_BLK / 8);
                 if (m >= d) { pI += vI; pQ += vQ; }
             }
             pI -= dI; pQ -= dQ;
             float sI = __uint_as_float(eI.x), sQ = __uint_as_float(eQ.x);
-            if (eI.y < 2u) sI = AI.sgn * __uint_as_float((unsigned)((int)(eI.x & 0x7FFFFFFFu) + (int)pI - (eI.y ? 8 * m : 0)));
-            if (eQ.y < 2u) sQ = AQ.sgn * __uint_as_float((unsigned)((int)(eQ.x & 0x7FFFFFFFu) + (int)pQ - (eQ.y ? 8 * m : 0)));
+            if (eI.y < 2u) sI = AI.sgn * __uint_as_float(eI.x + AI.lo + 1u + (unsigned)((int)pI - (eI.y ? 8 * m : 0)));
+            if (eQ.y < 2u) sQ = AQ.sgn * __uint_as_float(eQ.x + AQ.lo + 1u + (unsigned)((int)pQ - (eQ.y ? 8 * m : 0)));
             if ((eI.y == 2u || eQ.y == 2u) && m > 0) {
                 for (int j = m; j > 0; --j) {                                     // preceding chunks of the block
                     float2 y[8];
@@ -830,8 +920,8 @@ __global__ void __launch_bounds__(256) k2b_usb_audio(const UsbDev *__restrict__ 
 __global__ void __launch_bounds__(128) k3_carry(const CarryItem *__restrict__ items, int n_items, int n_blocks,
                                                  const uint8_t *__restrict__ iq, size_t iq_stride, int block,
                                                  uint8_t *__restrict__ tail, long long *__restrict__ blocks_done,
-                                                 uint2 *__restrict__ dc_table, int dc_table_stride, int n_dcblk,
-                                                 int stream0) {
+                                                 uint2 *__restrict__ dc_table, const DcAnchor *__restrict__ dc_anchor,
+                                                 int dc_table_stride, int n_dcblk, int stream0) {
     const int stream = stream0 + blockIdx.x;
     const int item = blockIdx.y;
     if (item < n_items) {
@@ -850,6 +940,10 @@ __global__ void __launch_bounds__(128) k3_carry(const CarryItem *__restrict__ it
         if (dc_table && threadIdx.x < 2 * DC_HALO_BLKS) {
             uint2 *t = dc_table + (size_t)stream * dc_table_stride * 2;
             uint2 e = t[(size_t)n_dcblk * 2 + threadIdx.x];
+            if (e.y < 2u) {                                      // translation entry -> plain float bits
+                const DcAnchor A = dc_anchor[2 * stream + (threadIdx.x & 1)];
+                e.x = (e.x + A.lo + 1u) | (A.sgn < 0.f ? 0x80000000u : 0u);
+            }
             e.y = 2u;
             t[threadIdx.x] = e;
         }
@@ -857,12 +951,20 @@ __global__ void __launch_bounds__(128) k3_carry(const CarryItem *__restrict__ it
 }
 
 // test/inspection helper: block-start DC states of the last call as float2 (I, Q)
-__global__ void __launch_bounds__(256) dc_trace_gather(const uint2 *__restrict__ table, int table_stride, int n,
-                                                        float2 *__restrict__ out) {
+__global__ void __launch_bounds__(256) dc_trace_gather(const uint2 *__restrict__ table, const DcAnchor *__restrict__ anchors,
+                                                        int table_stride, int n, float2 *__restrict__ out,
+                                                        uint8_t *__restrict__ modes) {
     const int i = blockIdx.x * 256 + threadIdx.x;
     if (i >= n) return;
     const uint2 *t = table + ((size_t)blockIdx.y * table_stride + DC_HALO_BLKS + i) * 2;
-    out[(size_t)blockIdx.y * n + i] = make_float2(__uint_as_float(t[0].x), __uint_as_float(t[1].x));
+    float v[2];
+#pragma unroll
+    for (int a = 0; a < 2; ++a) {
+        const DcAnchor A = anchors[2 * blockIdx.y + a];
+        v[a] = t[a].y < 2u ? A.sgn * __uint_as_float(t[a].x + A.lo + 1u) : __uint_as_float(t[a].x);
+    }
+    out[(size_t)blockIdx.y * n + i] = make_float2(v[0], v[1]);
+    if (modes) modes[(size_t)blockIdx.y * n + i] = (uint8_t)(t[0].y | (t[1].y << 4));
 }
 
 }  // namespace sdrb

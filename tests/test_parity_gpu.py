@@ -224,7 +224,7 @@ def test_dc_state_is_bit_identical(dc, sigma, n_blocks, splits):
     iq = np.stack([synth.make_iq(op["Fs"], op["block"] * n_blocks, car, stream=s, sigma=sigma, dc=dc + 0.37 * s)
                    for s in range(2)])
     bank = B.Bank(plan, 2, max(splits))
-    row, per = plan.block * 2, plan.block // 32
+    row, per = plan.block * 2, plan.block // 128
     got, b0 = [], 0
     for nb in splits:
         bank.process_numpy(iq[:, b0 * row:(b0 + nb) * row], nb)
@@ -235,6 +235,6 @@ def test_dc_state_is_bit_identical(dc, sigma, n_blocks, splits):
         b0 += nb
     got = np.concatenate(got, axis=1)
     for s in range(2):
-        want = O.dc_trace(iq[s], 32).view(np.float32).reshape(-1, 2)
+        want = O.dc_trace(iq[s], 128).view(np.float32).reshape(-1, 2)
         assert np.array_equal(got[s].view(np.uint32), want.view(np.uint32)), (s, np.abs(got[s] - want).max())
     bank.close()
