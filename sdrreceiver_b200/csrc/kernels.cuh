@@ -664,26 +664,47 @@ __global__ void __launch_bounds__(K2A_THREADS, 2) k2a_sub_cascade(const K2aParam
     const float2 *inp = D.in + (size_t)stream * D.in_stride + MAIN_HIST + (size_t)b * B;
 
     // ---- phase 1: coalesced load + mix ----
-#pragma unroll 4
-    for (int j = 0; j < K2A_CHUNK / 2; ++j) {
-        const int g = j * (2 * K2A_THREADS) + 2 * t;      // CTA-relative sample (even)
-        const int i = r0 + g;
-        float4 m = make_float4(0.f, 0.f, 0.f, 0.f);
-        if (i < B && !(first_ever && i < 0)) {
-            const float4 xv = __ldg(reinterpret_cast<const float4 *>(inp + i));
-            int idx = lut_base + i;
-            if (idx < 0) idx += D.lut_len;
-            if (idx >= D.lut_len) idx -= D.lut_len;
-            float4 lv = __ldg(reinterpret_cast<const float4 *>(D.lut + idx));
-            if (first_ever && i == 0) {
-                const float2 last = __ldg(D.lut + (D.lut_len - 1));
-                lv.x = last.x; lv.y = last.y;
-            }
+    // Interior tiles (everything in range, table not wrapping inside the tile, not the very
+    // first callback) take a check-free path: fixed strides from one base pointer per operand.
+    const int lut_lo = lut_base + r0;
+    const bool interior = !first_ever && (r0 + K2A_THREADS * K2A_CHUNK <= B) &&
+                          ((lut_lo >= 0 && lut_lo + K2A_THREADS * K2A_CHUNK <= D.lut_len) ||
+                           (lut_lo < 0 && lut_lo + K2A_THREADS * K2A_CHUNK <= 0));
+    float4 *sdst = reinterpret_cast<float4 *>(sX + ((2 * t >> 5) + HB_PAD) * K2A_A0_STR + ((2 * t) & 31));
+    if (interior) {
+        const float4 *xp = reinterpret_cast<const float4 *>(inp + r0 + 2 * t);
+        const float4 *lp = reinterpret_cast<const float4 *>(D.lut + (lut_lo < 0 ? lut_lo + D.lut_len : lut_lo) + 2 * t);
+#pragma unroll 8
+        for (int j = 0; j < K2A_CHUNK / 2; ++j) {
+            const float4 xv = __ldg(xp + j * K2A_THREADS);
+            const float4 lv = __ldg(lp + j * K2A_THREADS);
             const float2 m0 = cmul(make_float2(lv.x, lv.y), make_float2(xv.x, xv.y));
             const float2 m1 = cmul(make_float2(lv.z, lv.w), make_float2(xv.z, xv.w));
-            m = make_float4(m0.x, m0.y, m1.x, m1.y);
+            // 512 samples = 16 chunks further on: 16 * K2A_A0_STR float2 = 8 * K2A_A0_STR float4
+            sdst[j * (8 * K2A_A0_STR)] = make_float4(m0.x, m0.y, m1.x, m1.y);
         }
-        *reinterpret_cast<float4 *>(sX + ((g >> 5) + HB_PAD) * K2A_A0_STR + (g & 31)) = m;
+    } else {
+#pragma unroll 2
+        for (int j = 0; j < K2A_CHUNK / 2; ++j) {
+            const int g = j * (2 * K2A_THREADS) + 2 * t;  // CTA-relative sample (even)
+            const int i = r0 + g;
+            float4 m = make_float4(0.f, 0.f, 0.f, 0.f);
+            if (i < B && !(first_ever && i < 0)) {
+                const float4 xv = __ldg(reinterpret_cast<const float4 *>(inp + i));
+                int idx = lut_base + i;
+                if (idx < 0) idx += D.lut_len;
+                if (idx >= D.lut_len) idx -= D.lut_len;
+                float4 lv = __ldg(reinterpret_cast<const float4 *>(D.lut + idx));
+                if (first_ever && i == 0) {
+                    const float2 last = __ldg(D.lut + (D.lut_len - 1));
+                    lv.x = last.x; lv.y = last.y;
+                }
+                const float2 m0 = cmul(make_float2(lv.x, lv.y), make_float2(xv.x, xv.y));
+                const float2 m1 = cmul(make_float2(lv.z, lv.w), make_float2(xv.z, xv.w));
+                m = make_float4(m0.x, m0.y, m1.x, m1.y);
+            }
+            sdst[j * (8 * K2A_A0_STR)] = m;
+        }
     }
     __syncthreads();
 
