@@ -149,6 +149,16 @@ int sdrb_bank_copy_dc_trace(sdrb_bank *bank, int n_blocks, float *d_out, uint8_t
  */
 int sdrb_bank_process_host(sdrb_bank *bank, const uint8_t *h_iq, size_t iq_stride, int n_blocks,
                            int16_t *h_pcm, float *h_tap);
+/* vfo::process entry (vfo.cpp:235-296): the caller supplies complex float samples (what
+ * sdrj::demodData hands to the main VFOs, i.e. already converted and DC-corrected by the
+ * caller); everything from the main-VFO mix on runs on the GPU. h_in: cf32, stream s at
+ * h_in + 2*s*stride_samples floats. State is shared with the uint8 entry points, do not mix
+ * the two kinds of calls on one bank without a reset. */
+int sdrb_bank_process_cf32_host(sdrb_bank *bank, const float *h_in_cf32, size_t stride_samples, int n_blocks,
+                                int16_t *h_pcm, float *h_tap);
+/* Main VFO outputs of the last call, to host: cf32 [n_streams][n_blocks*block_out]
+ * (vfo::decimate[decimateCount], vfo.h:39). */
+int sdrb_bank_read_main(sdrb_bank *bank, int main_idx, int n_blocks, float *h_out_cf32);
 /* Kernel launches issued by the last process_* call (for bench.py's gpu_launches). */
 int sdrb_bank_last_launches(const sdrb_bank *bank);
 /* Per-kernel-class device timing (CUDA events on the launching stream), for roofline
@@ -176,9 +186,13 @@ int sdrb_halfband11(const float *d_in_cf32, float *d_out_cf32, float *d_hist_cf3
                     void *cuda_stream);
 /* FIR::FIRUpdateAndProcess over a block (jonti/dsp.cpp:59-71): newest sample excluded;
  * d_hist = last ntaps inputs per channel (updated); decim >= 1 keeps every decim-th output
- * starting with the first (vfo::usb_decimdemod, vfo.cpp:334-387). */
+ * starting with the first (vfo::usb_decimdemod, vfo.cpp:334-387). Any block length n >= 1. */
 int sdrb_fir(const float *d_taps, int ntaps, const float *d_in, float *d_out, float *d_hist, int n_ch,
              int n, int decim, void *cuda_stream);
+/* Same with include_newest = 1: the FIRHilbert form y[m] = sum_i taps[i]*x[m - N + 1 + i]
+ * (jonti/dsp.cpp:218-231, ring of N with the newest sample included). Any n >= 1. */
+int sdrb_fir_ex(const float *d_taps, int ntaps, const float *d_in, float *d_out, float *d_hist, int n_ch,
+                int n, int decim, int include_newest, void *cuda_stream);
 /* delay(62)(re) - FIRHilbert125(im) (vfo.cpp:316-324; jonti/dsp.cpp:184-231); d_points = the
  * 125 FIRHilbert coefficients on the device (sdrb_hilbert_points), d_hist = last 124 complex
  * inputs per channel (updated). */

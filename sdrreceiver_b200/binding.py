@@ -84,6 +84,8 @@ def lib():
         "sdrb_bank_copy_main": (i, [vp, i, i, vp, vp]),
         "sdrb_bank_copy_dc_trace": (i, [vp, i, vp, vp, vp]),
         "sdrb_bank_process_host": (i, [vp, vp, sz, i, vp, vp]),
+        "sdrb_bank_process_cf32_host": (i, [vp, vp, sz, i, vp, vp]),
+        "sdrb_bank_read_main": (i, [vp, i, i, vp]),
         "sdrb_bank_last_launches": (i, [vp]),
         "sdrb_bank_set_timing": (i, [vp, i]),
         "sdrb_bank_kernel_times": (i, [vp, vp, vp]),
@@ -93,6 +95,7 @@ def lib():
         "sdrb_nco_mix": (i, [vp, i, C.c_int64, vp, vp, i, i, vp]),
         "sdrb_halfband11": (i, [vp, vp, vp, i, i, vp]),
         "sdrb_fir": (i, [vp, i, vp, vp, vp, i, i, i, vp]),
+        "sdrb_fir_ex": (i, [vp, i, vp, vp, vp, i, i, i, i, vp]),
         "sdrb_usb_demod": (i, [vp, vp, vp, vp, i, i, vp]),
         "sdrb_low_pass": (i, [d, d, d, d, vp, i]),
         "sdrb_hilbert_points": (i, [i, i, vp]),

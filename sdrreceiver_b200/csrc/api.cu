@@ -151,7 +151,7 @@ struct sdrb_bank {
     // tables
     DevBuf luts, taps;
     // state
-    DevBuf blocks_done, dc_state, raw_tail;
+    DevBuf blocks_done, dc_state, raw_tail, cf_tail;
     // work
     DevBuf dc_anchor, dc_stats, dc_table, main_out, zbuf, dbuf;
     int dc_stride = 0;                      // DC blocks (of 32 samples) per stream in dc_stats; table has DC_HALO_BLKS more
@@ -164,7 +164,7 @@ struct sdrb_bank {
     std::vector<size_t> main_off;           // per main: offset (float2 units) inside main_out per stream
     size_t main_stride = 0;                 // float2 per stream
     // host staging for process_host
-    DevBuf d_iq, d_pcm, d_tap;
+    DevBuf d_iq, d_pcm, d_tap, d_cf;
     cudaStream_t s_copy_in = nullptr, s_compute = nullptr, s_copy_out = nullptr;
     std::vector<cudaEvent_t> ev_in, ev_done;
     // DC recursion runs on side streams, one callback ahead of the ingest kernel
@@ -183,9 +183,9 @@ struct sdrb_bank {
 extern "C" void sdrb_bank_destroy(sdrb_bank *b) {
     if (!b) return;
     cudaSetDevice(b->device);
-    DevBuf *all[] = {&b->luts, &b->taps, &b->blocks_done, &b->dc_state, &b->raw_tail, &b->dc_anchor, &b->dc_stats, &b->dc_table,
+    DevBuf *all[] = {&b->luts, &b->taps, &b->blocks_done, &b->dc_state, &b->raw_tail, &b->cf_tail, &b->dc_anchor, &b->dc_stats, &b->dc_table,
                      &b->main_out, &b->zbuf, &b->dbuf, &b->subdev, &b->latedev, &b->usbdev, &b->carry,
-                     &b->d_iq, &b->d_pcm, &b->d_tap};
+                     &b->d_iq, &b->d_pcm, &b->d_tap, &b->d_cf};
     for (DevBuf *d : all) d->release();
     for (cudaEvent_t e : b->ev_in) cudaEventDestroy(e);
     for (cudaEvent_t e : b->ev_done) cudaEventDestroy(e);
@@ -269,6 +269,7 @@ extern "C" int sdrb_bank_create(const sdrb_plan *plan, int device, int n_streams
     BANK_TRY(b->blocks_done.alloc(sizeof(long long) * (size_t)n_streams));
     BANK_TRY(b->dc_state.alloc(sizeof(float2) * (size_t)n_streams));
     BANK_TRY(b->raw_tail.alloc((size_t)n_streams * 2 * RAW_TAIL));
+    BANK_TRY(b->cf_tail.alloc((size_t)n_streams * RAW_TAIL * sizeof(float2)));
 
     // ---- work buffers ----
     b->dc_stride = max_blocks * (h.block / DC_BLK);
@@ -306,6 +307,7 @@ extern "C" int sdrb_bank_create(const sdrb_plan *plan, int device, int n_streams
     // ---- descriptors ----
     K1Params &k1 = b->k1;
     k1.tail = (const uint8_t *)b->raw_tail.p;
+    k1.cf_in = nullptr; k1.cf_stride = 0; k1.cf_tail = (const float2 *)b->cf_tail.p;
     k1.dc_table = (const uint2 *)b->dc_table.p;
     k1.dc_anchor = (const DcAnchor *)b->dc_anchor.p;
     k1.blocks_done = (const long long *)b->blocks_done.p;
@@ -428,6 +430,7 @@ extern "C" int sdrb_bank_reset(sdrb_bank *b, int stream) {
     CU_TRY(cudaMemset((long long *)b->blocks_done.p + s0, 0, sizeof(long long) * (size_t)ns));
     CU_TRY(cudaMemset((float2 *)b->dc_state.p + (size_t)s0, 0, sizeof(float2) * (size_t)ns));
     CU_TRY(cudaMemset((uint8_t *)b->raw_tail.p + (size_t)s0 * 2 * RAW_TAIL, 0, (size_t)ns * 2 * RAW_TAIL));
+    CU_TRY(cudaMemset((float2 *)b->cf_tail.p + (size_t)s0 * RAW_TAIL, 0, (size_t)ns * RAW_TAIL * sizeof(float2)));
     // history regions: zero whole per-stream slices (cheap, and only done on reset)
     const size_t ms = b->main_stride * sizeof(float2);
     CU_TRY(cudaMemset((char *)b->main_out.p + ms * (size_t)s0, 0, ms * (size_t)ns));
@@ -461,7 +464,8 @@ static void mark(sdrb_bank *b, cudaStream_t st) {
 
 // Enqueue the whole pipeline for streams [s0, s0+ns) on `st`. Returns launches issued.
 static int enqueue(sdrb_bank *b, const uint8_t *d_iq, size_t iq_stride, int n_blocks, int16_t *d_pcm, float *d_tap,
-                   int s0, int ns, cudaStream_t st, int slot, cudaEvent_t input_ready, int *launches) {
+                   int s0, int ns, cudaStream_t st, int slot, cudaEvent_t input_ready, int *launches,
+                   const float2 *d_cf = nullptr, size_t cf_stride = 0) {
     const HostPlan &h = b->plan->h;
     int nl = 0;
     const int per_cb = h.block / DC_BLK, n_dcblk = n_blocks * per_cb;
@@ -469,7 +473,12 @@ static int enqueue(sdrb_bank *b, const uint8_t *d_iq, size_t iq_stride, int n_bl
     k1.iq = d_iq; k1.iq_stride = iq_stride; k1.n_blocks = n_blocks; k1.stream0 = s0; k1.b0 = 0;
     const int k1_tiles = (h.block + K1_TILE - 1) / K1_TILE;
     mark(b, st);                                            // class 0: DC recursion (exposed part)
-    if (h.correct_dc) {
+    k1.cf_in = d_cf; k1.cf_stride = cf_stride;
+    if (d_cf) {
+        mark(b, st);                                        // class 1: main VFOs on cf32 input, no DC stage
+        k1_ingest_main<false><<<dim3((unsigned)ns, (unsigned)k1_tiles, (unsigned)n_blocks), K1_THREADS, 0, st>>>(k1);
+        nl++;
+    } else if (h.correct_dc) {
         // Side stream: anchor, parallel block statistics, then the sequential walk one callback
         // at a time; the ingest kernel of callback cb starts as soon as its walk is done, so only
         // the first walk is exposed on the critical path.
@@ -498,12 +507,12 @@ static int enqueue(sdrb_bank *b, const uint8_t *d_iq, size_t iq_stride, int n_bl
         for (int cb = 0; cb < n_blocks; cb++) {
             if (cb) CU_TRY(cudaStreamWaitEvent(st, b->ev_dc[slot][(size_t)cb], 0));
             k1.b0 = cb;
-            k1_ingest_main<<<dim3((unsigned)ns, (unsigned)k1_tiles, 1u), K1_THREADS, 0, st>>>(k1);
+            k1_ingest_main<true><<<dim3((unsigned)ns, (unsigned)k1_tiles, 1u), K1_THREADS, 0, st>>>(k1);
             nl++;
         }
     } else {
         mark(b, st);                                        // class 1: ingest + main VFOs
-        k1_ingest_main<<<dim3((unsigned)ns, (unsigned)k1_tiles, (unsigned)n_blocks), K1_THREADS, 0, st>>>(k1);
+        k1_ingest_main<true><<<dim3((unsigned)ns, (unsigned)k1_tiles, (unsigned)n_blocks), K1_THREADS, 0, st>>>(k1);
         nl++;
     }
     mark(b, st);                                            // class 2: sub-VFO cascades
@@ -540,8 +549,8 @@ static int enqueue(sdrb_bank *b, const uint8_t *d_iq, size_t iq_stride, int n_bl
     mark(b, st);                                            // class 5: carry
     k3_carry<<<dim3((unsigned)ns, (unsigned)(b->n_carry + 1)), 128, 0, st>>>(
         (const CarryItem *)b->carry.p, b->n_carry, n_blocks, d_iq, iq_stride, h.block, (uint8_t *)b->raw_tail.p,
-        (long long *)b->blocks_done.p, h.correct_dc ? (uint2 *)b->dc_table.p : nullptr, (const DcAnchor *)b->dc_anchor.p,
-        b->dc_stride + DC_HALO_BLKS, n_dcblk, s0);
+        (long long *)b->blocks_done.p, (h.correct_dc && !d_cf) ? (uint2 *)b->dc_table.p : nullptr,
+        (const DcAnchor *)b->dc_anchor.p, b->dc_stride + DC_HALO_BLKS, n_dcblk, s0, d_cf, cf_stride, (float2 *)b->cf_tail.p);
     nl++;
     mark(b, st);
     CU_TRY(cudaGetLastError());
@@ -675,6 +684,49 @@ extern "C" int sdrb_bank_process_host(sdrb_bank *b, const uint8_t *h_iq, size_t 
     return SDRB_OK;
 }
 
+extern "C" int sdrb_bank_process_cf32_host(sdrb_bank *b, const float *h_in, size_t stride_samples, int n_blocks,
+                                           int16_t *h_pcm, float *h_tap) {
+    if (!b || !h_in || !h_pcm || n_blocks <= 0 || n_blocks > b->max_blocks ||
+        stride_samples < (size_t)n_blocks * (size_t)b->plan->h.block) {
+        set_error("sdrb_bank_process_cf32_host: bad argument"); return SDRB_E_INVALID;
+    }
+    CU_TRY(cudaSetDevice(b->device));
+    const HostPlan &h = b->plan->h;
+    const size_t row = (size_t)n_blocks * h.block, rec = (size_t)n_blocks * h.pcm_per_block;
+    const size_t cap = (size_t)b->max_blocks * h.block;
+    int rc;
+    if (!b->d_cf.p) { rc = b->d_cf.alloc(cap * sizeof(float2) * (size_t)b->n_streams); if (rc) return rc; }
+    if (!b->d_pcm.p) {
+        rc = b->d_pcm.alloc((size_t)b->max_blocks * h.pcm_per_block * sizeof(int16_t) * (size_t)b->n_streams); if (rc) return rc;
+    }
+    if (h_tap && !b->d_tap.p) {
+        rc = b->d_tap.alloc((size_t)b->max_blocks * h.pcm_per_block * sizeof(float) * (size_t)b->n_streams); if (rc) return rc;
+    }
+    cudaStream_t st = b->s_compute;
+    CU_TRY(cudaMemcpy2DAsync(b->d_cf.p, cap * sizeof(float2), h_in, stride_samples * sizeof(float2), row * sizeof(float2),
+                             (size_t)b->n_streams, cudaMemcpyHostToDevice, st));
+    b->last_launches = 0;
+    rc = enqueue(b, nullptr, 0, n_blocks, (int16_t *)b->d_pcm.p, h_tap ? (float *)b->d_tap.p : nullptr, 0, b->n_streams, st,
+                 0, nullptr, &b->last_launches, (const float2 *)b->d_cf.p, cap);
+    if (rc != SDRB_OK) return rc;
+    CU_TRY(cudaMemcpyAsync(h_pcm, b->d_pcm.p, rec * sizeof(int16_t) * (size_t)b->n_streams, cudaMemcpyDeviceToHost, st));
+    if (h_tap) CU_TRY(cudaMemcpyAsync(h_tap, b->d_tap.p, rec * sizeof(float) * (size_t)b->n_streams, cudaMemcpyDeviceToHost, st));
+    CU_TRY(cudaStreamSynchronize(st));
+    return SDRB_OK;
+}
+
+extern "C" int sdrb_bank_read_main(sdrb_bank *b, int main_idx, int n_blocks, float *h_out) {
+    if (!b || !h_out || main_idx < 0 || main_idx >= (int)b->plan->h.mains.size() || n_blocks <= 0 || n_blocks > b->max_blocks) {
+        set_error("sdrb_bank_read_main: bad argument"); return SDRB_E_INVALID;
+    }
+    CU_TRY(cudaSetDevice(b->device));
+    const MainVfo &m = b->plan->h.mains[(size_t)main_idx];
+    const size_t row = (size_t)n_blocks * m.block_out * sizeof(float2);
+    CU_TRY(cudaMemcpy2D(h_out, row, (float2 *)b->main_out.p + b->main_off[(size_t)main_idx] + MAIN_HIST,
+                        b->main_stride * sizeof(float2), row, (size_t)b->n_streams, cudaMemcpyDeviceToHost));
+    return SDRB_OK;
+}
+
 extern "C" int sdrb_bank_last_launches(const sdrb_bank *b) { return b ? b->last_launches : 0; }
 
 extern "C" void *sdrb_host_alloc(size_t bytes) {
@@ -743,28 +795,34 @@ extern "C" int sdrb_halfband11(const float *d_in, float *d_out, float *d_hist, i
     return SDRB_OK;
 }
 
-extern "C" int sdrb_fir(const float *d_taps, int ntaps, const float *d_in, float *d_out, float *d_hist, int n_ch,
-                        int n, int decim, void *cuda_stream) {
-    if (!d_taps || !d_in || !d_out || !d_hist || ntaps <= 0 || ntaps > 4096 || n_ch <= 0 || n < ntaps || decim < 1) {
-        set_error("sdrb_fir: bad argument (block must be at least ntaps long)"); return SDRB_E_INVALID;
+extern "C" int sdrb_fir_ex(const float *d_taps, int ntaps, const float *d_in, float *d_out, float *d_hist, int n_ch,
+                           int n, int decim, int include_newest, void *cuda_stream) {
+    if (!d_taps || !d_in || !d_out || !d_hist || ntaps <= 0 || ntaps > 4096 || n_ch <= 0 || n <= 0 || decim < 1) {
+        set_error("sdrb_fir: bad argument"); return SDRB_E_INVALID;
     }
     cudaStream_t st = (cudaStream_t)cuda_stream;
     const int n_out = (n + decim - 1) / decim;
-    prim_fir<<<dim3((unsigned)((n_out + 255) / 256), (unsigned)n_ch), 256, 0, st>>>(d_taps, ntaps, d_in, d_out, d_hist, n, decim, n_out);
-    prim_tail_carry<<<(unsigned)n_ch, 128, 0, st>>>(d_in, d_hist, n, ntaps, 1);
+    prim_fir<<<dim3((unsigned)((n_out + 255) / 256), (unsigned)n_ch), 256, 0, st>>>(d_taps, ntaps, d_in, d_out, d_hist, n,
+                                                                                 decim, n_out, include_newest ? 1 : 0);
+    prim_tail_carry<<<(unsigned)n_ch, 128, sizeof(float) * (size_t)ntaps, st>>>(d_in, d_hist, n, ntaps, 1);
     CU_TRY(cudaGetLastError());
     return SDRB_OK;
 }
 
+extern "C" int sdrb_fir(const float *d_taps, int ntaps, const float *d_in, float *d_out, float *d_hist, int n_ch,
+                        int n, int decim, void *cuda_stream) {
+    return sdrb_fir_ex(d_taps, ntaps, d_in, d_out, d_hist, n_ch, n, decim, 0, cuda_stream);
+}
+
 extern "C" int sdrb_usb_demod(const float *d_points, const float *d_in, float *d_out, float *d_hist, int n_ch, int n,
                               void *cuda_stream) {
-    if (!d_points || !d_in || !d_out || !d_hist || n_ch <= 0 || n < 124) {
-        set_error("sdrb_usb_demod: bad argument (block must be at least 124 long)"); return SDRB_E_INVALID;
+    if (!d_points || !d_in || !d_out || !d_hist || n_ch <= 0 || n <= 0) {
+        set_error("sdrb_usb_demod: bad argument"); return SDRB_E_INVALID;
     }
     cudaStream_t st = (cudaStream_t)cuda_stream;
     prim_usb<<<dim3((unsigned)((n + 255) / 256), (unsigned)n_ch), 256, 0, st>>>(
         d_points, (const float2 *)d_in, d_out, (const float2 *)d_hist, n);
-    prim_tail_carry<<<(unsigned)n_ch, 128, 0, st>>>(d_in, d_hist, n, 124, 2);
+    prim_tail_carry<<<(unsigned)n_ch, 128, sizeof(float) * 248, st>>>(d_in, d_hist, n, 124, 2);
     CU_TRY(cudaGetLastError());
     return SDRB_OK;
 }

@@ -77,6 +77,9 @@ struct K1Params {
     const uint8_t *iq;
     size_t iq_stride;
     const uint8_t *tail;            // [n_streams][2*RAW_TAIL]
+    const float2 *cf_in;            // cf32 input variant (vfo::process on already-converted samples)
+    const float2 *cf_tail;          // [n_streams][RAW_TAIL]
+    size_t cf_stride;
     const uint2 *dc_table;          // [n_streams][dc_stride][2 arms]: {state bits at block start, mode}
     const DcAnchor *dc_anchor;      // [n_streams][2 arms]
     const long long *blocks_done;   // [n_streams]
@@ -482,6 +485,7 @@ __global__ void __launch_bounds__(64) k0_dc_walk(const uint8_t *__restrict__ iq,
 // ------------------------------------------------------------------------------------
 constexpr int K1_A0_STR = 10, K1_A1_STR = 6, K1_A2_STR = 2;
 
+template <bool RAW>
 __global__ void __launch_bounds__(K1_THREADS, 2) k1_ingest_main(const K1Params p) {
     __shared__ __align__(16) float2 sA0[(K1_THREADS + HB_PAD) * K1_A0_STR];
     __shared__ __align__(16) float2 sA1[(K1_THREADS + HB_PAD) * K1_A1_STR];
@@ -501,7 +505,20 @@ __global__ void __launch_bounds__(K1_THREADS, 2) k1_ingest_main(const K1Params p
     float2 x[8];
 #pragma unroll
     for (int k = 0; k < 8; ++k) x[k] = make_float2(0.f, 0.f);
-    if (exists) {
+    if (exists && !RAW) {
+        // cf32 input (what vfo::process receives, vfo.cpp:235): no byte conversion, no DC removal
+        const float2 *csrc = (b == 0 && i0 < 0)
+            ? p.cf_tail + (size_t)stream * RAW_TAIL + (RAW_TAIL + i0)
+            : p.cf_in + (size_t)stream * p.cf_stride + ((size_t)b * B + i0);
+        const float4 *c4 = reinterpret_cast<const float4 *>(csrc);
+#pragma unroll
+        for (int k = 0; k < 4; ++k) {
+            const float4 v = __ldg(c4 + k);
+            x[2 * k] = make_float2(v.x, v.y);
+            x[2 * k + 1] = make_float2(v.z, v.w);
+        }
+    }
+    if (exists && RAW) {
         const uint8_t *src = (b == 0 && i0 < 0)
             ? p.tail + (size_t)stream * (2 * RAW_TAIL) + (2 * RAW_TAIL + 2 * i0)
             : p.iq + (size_t)stream * p.iq_stride + ((size_t)b * B + i0) * 2;
@@ -942,7 +959,9 @@ __global__ void __launch_bounds__(128) k3_carry(const CarryItem *__restrict__ it
                                                  const uint8_t *__restrict__ iq, size_t iq_stride, int block,
                                                  uint8_t *__restrict__ tail, long long *__restrict__ blocks_done,
                                                  uint2 *__restrict__ dc_table, const DcAnchor *__restrict__ dc_anchor,
-                                                 int dc_table_stride, int n_dcblk, int stream0) {
+                                                 int dc_table_stride, int n_dcblk, int stream0,
+                                                 const float2 *__restrict__ cf_in, size_t cf_stride,
+                                                 float2 *__restrict__ cf_tail) {
     const int stream = stream0 + blockIdx.x;
     const int item = blockIdx.y;
     if (item < n_items) {
@@ -952,9 +971,15 @@ __global__ void __launch_bounds__(128) k3_carry(const CarryItem *__restrict__ it
         uint4 *dst = reinterpret_cast<uint4 *>(base);
         for (int e = threadIdx.x; e < it.hist_bytes / 16; e += 128) dst[e] = src[e];
     } else {
-        const uint4 *src = reinterpret_cast<const uint4 *>(iq + (size_t)stream * iq_stride + ((size_t)n_blocks * block - RAW_TAIL) * 2);
-        uint4 *dst = reinterpret_cast<uint4 *>(tail + (size_t)stream * (2 * RAW_TAIL));
-        for (int e = threadIdx.x; e < (2 * RAW_TAIL) / 16; e += 128) dst[e] = src[e];
+        if (iq) {
+            const uint4 *src = reinterpret_cast<const uint4 *>(iq + (size_t)stream * iq_stride + ((size_t)n_blocks * block - RAW_TAIL) * 2);
+            uint4 *dst = reinterpret_cast<uint4 *>(tail + (size_t)stream * (2 * RAW_TAIL));
+            for (int e = threadIdx.x; e < (2 * RAW_TAIL) / 16; e += 128) dst[e] = src[e];
+        } else {
+            const float2 *src = cf_in + (size_t)stream * cf_stride + ((size_t)n_blocks * block - RAW_TAIL);
+            float2 *dst = cf_tail + (size_t)stream * RAW_TAIL;
+            for (int e = threadIdx.x; e < RAW_TAIL; e += 128) dst[e] = src[e];
+        }
         if (threadIdx.x == 0) blocks_done[stream] += n_blocks;
         // DC table: the last DC_HALO_BLKS block-start states move to the front for the next call's
         // halo warp; they become "stepped" entries because the next call has a new anchor.

@@ -40,15 +40,16 @@ __global__ void prim_halfband11_carry(const float2 *__restrict__ in, float2 *__r
     if (threadIdx.x < 11) hist[(size_t)blockIdx.x * 11 + threadIdx.x] = in[(size_t)blockIdx.x * n + (n - 12 + threadIdx.x)];
 }
 
-// FIR::FIRUpdateAndProcess (dsp.cpp:59-71): y[m] = sum_i taps[i] * x[decim*m - N + i]
+// FIR::FIRUpdateAndProcess (dsp.cpp:59-71): y[m] = sum_i taps[i] * x[decim*m - N + i]  (newest excluded),
+// or with inc = 1 the FIRHilbert form (dsp.cpp:218-231): y[m] = sum_i taps[i] * x[decim*m - N + 1 + i].
 __global__ void __launch_bounds__(256) prim_fir(const float *__restrict__ taps, int N, const float *__restrict__ in,
                                                  float *__restrict__ out, const float *__restrict__ hist, int n,
-                                                 int decim, int n_out) {
+                                                 int decim, int n_out, int inc) {
     const int m = blockIdx.x * 256 + threadIdx.x;
     if (m >= n_out) return;
     const float *x = in + (size_t)blockIdx.y * n;
     const float *h = hist + (size_t)blockIdx.y * N;
-    const int base = decim * m - N;
+    const int base = decim * m - N + inc;
     float acc = 0.f;
     for (int i = 0; i < N; ++i) {
         const int j = base + i;
@@ -57,11 +58,19 @@ __global__ void __launch_bounds__(256) prim_fir(const float *__restrict__ taps, 
     out[(size_t)blockIdx.y * n_out + m] = acc;
 }
 
-// keep the last `count` elements (of `width` floats) of every channel's block
+// History carry: the last `count` elements (of `width` floats) of [old history | block] become the
+// new history; blocks shorter than the history are allowed (per-sample facade calls).
 __global__ void prim_tail_carry(const float *__restrict__ in, float *__restrict__ hist, int n, int count, int width) {
-    const float *x = in + (size_t)blockIdx.x * n * width + (size_t)(n - count) * width;
+    extern __shared__ float stage[];
+    const float *x = in + (size_t)blockIdx.x * n * width;
     float *h = hist + (size_t)blockIdx.x * count * width;
-    for (int e = threadIdx.x; e < count * width; e += blockDim.x) h[e] = x[e];
+    const int total = count * width;
+    for (int e = threadIdx.x; e < total; e += blockDim.x) {
+        const int c = n * width + e;                      // position in [old history | block]
+        stage[e] = c < total ? h[c] : x[c - total];
+    }
+    __syncthreads();
+    for (int e = threadIdx.x; e < total; e += blockDim.x) h[e] = stage[e];
 }
 
 // usb = DelayThing(62)(re) - FIRHilbert125(im)  (vfo.cpp:316-324; dsp.cpp:218-231)
