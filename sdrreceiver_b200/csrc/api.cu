@@ -174,7 +174,8 @@ struct sdrb_bank {
     std::vector<cudaEvent_t> ev_dc[kSide];
     // optional per-kernel timing (bench.py roofline): event pairs around each kernel class
     bool timing = false;
-    std::vector<cudaEvent_t> tev;           // 2 * SDRB_N_KERNEL_CLASSES * calls, recycled
+    std::vector<cudaEvent_t> tev;           // start/end pairs, recycled
+    std::vector<int> tev_cls;               // class of each pair
     size_t tev_used = 0;
     double kernel_ms[SDRB_N_KERNEL_CLASSES] = {0};
     long kernel_calls[SDRB_N_KERNEL_CLASSES] = {0};
@@ -450,78 +451,78 @@ extern "C" int sdrb_bank_blocks_done(sdrb_bank *b, int stream, int64_t *blocks) 
     return SDRB_OK;
 }
 
-// Timing marks: when enabled, a cudaEvent pair brackets every kernel class on the launching
-// stream; sdrb_bank_kernel_times() folds them into per-class totals after a synchronize.
-static void mark(sdrb_bank *b, cudaStream_t st) {
-    if (!b->timing) return;
-    if (b->tev_used == b->tev.size()) {
-        cudaEvent_t e;
-        if (cudaEventCreate(&e) != cudaSuccess) return;
-        b->tev.push_back(e);
-    }
-    cudaEventRecord(b->tev[b->tev_used++], st);
-}
+// Per-kernel timing (bench.py roofline): when enabled, a cudaEvent pair brackets every launch
+// on its own stream; sdrb_bank_kernel_times() folds them into per-class totals after a
+// synchronize. Classes: 0 DC recursion, 1 ingest+main VFOs, 2 sub-VFO cascades, 3 /late FIR,
+// 4 USB audio, 5 carry.
+struct TimedScope {
+    sdrb_bank *b; cudaStream_t st; int cls; bool on;
+    TimedScope(sdrb_bank *b_, cudaStream_t st_, int cls_);
+    ~TimedScope();
+};
 
-// Enqueue the whole pipeline for streams [s0, s0+ns) on `st`. Returns launches issued.
-static int enqueue(sdrb_bank *b, const uint8_t *d_iq, size_t iq_stride, int n_blocks, int16_t *d_pcm, float *d_tap,
-                   int s0, int ns, cudaStream_t st, int slot, cudaEvent_t input_ready, int *launches,
-                   const float2 *d_cf = nullptr, size_t cf_stride = 0) {
+// One process call, as seen by the launch helpers.
+struct CallCtx {
+    const uint8_t *d_iq = nullptr; size_t iq_stride = 0;
+    const float2 *d_cf = nullptr; size_t cf_stride = 0;    // cf32 input variant (no DC stage)
+    int n_blocks = 0;
+    int16_t *d_pcm = nullptr; float *d_tap = nullptr;
+};
+
+// DC recursion of callback cb for streams [s0, s0+ns) on the side stream `sd`: (anchor once per
+// call,) parallel block statistics, sequential walk. `ready` (optional) = the input of this
+// callback has landed; `done` is recorded when the table of this callback is complete.
+static int enqueue_dc_cb(sdrb_bank *b, const CallCtx &c, int s0, int ns, cudaStream_t sd, int cb, cudaEvent_t ready,
+                         cudaEvent_t done, int *nl) {
     const HostPlan &h = b->plan->h;
-    int nl = 0;
-    const int per_cb = h.block / DC_BLK, n_dcblk = n_blocks * per_cb;
-    K1Params k1 = b->k1;
-    k1.iq = d_iq; k1.iq_stride = iq_stride; k1.n_blocks = n_blocks; k1.stream0 = s0; k1.b0 = 0;
-    const int k1_tiles = (h.block + K1_TILE - 1) / K1_TILE;
-    mark(b, st);                                            // class 0: DC recursion (exposed part)
-    k1.cf_in = d_cf; k1.cf_stride = cf_stride;
-    if (d_cf) {
-        mark(b, st);                                        // class 1: main VFOs on cf32 input, no DC stage
-        k1_ingest_main<false><<<dim3((unsigned)ns, (unsigned)k1_tiles, (unsigned)n_blocks), K1_THREADS, 0, st>>>(k1);
-        nl++;
-    } else if (h.correct_dc) {
-        // Side stream: anchor, parallel block statistics, then the sequential walk one callback
-        // at a time; the ingest kernel of callback cb starts as soon as its walk is done, so only
-        // the first walk is exposed on the critical path.
-        cudaStream_t sd = b->s_dc[slot];
-        if (input_ready) {                                  // host path: wait for this group's H2D copy only
-            CU_TRY(cudaStreamWaitEvent(sd, input_ready, 0));
-        } else {                                            // device path: everything queued before this call
-            CU_TRY(cudaEventRecord(b->ev_entry[slot], st));
-            CU_TRY(cudaStreamWaitEvent(sd, b->ev_entry[slot], 0));
-        }
+    const int per_cb = h.block / DC_BLK;
+    if (ready) CU_TRY(cudaStreamWaitEvent(sd, ready, 0));
+    if (cb == 0) {
+        TimedScope t(b, sd, 0);
         k0_dc_anchor<<<(unsigned)((2 * ns + 127) / 128), 128, 0, sd>>>((const float2 *)b->dc_state.p,
                                                                       (DcAnchor *)b->dc_anchor.p, ns, s0);
-        k0_dc_blocks<<<dim3((unsigned)((n_dcblk + 127) / 128), (unsigned)ns), 128, 0, sd>>>(
-            d_iq, iq_stride, (const DcAnchor *)b->dc_anchor.p, (DcStats *)b->dc_stats.p, b->dc_stride, 0, n_dcblk, s0);
-        nl += 2;
-        for (int cb = 0; cb < n_blocks; cb++) {
-            k0_dc_walk<<<(unsigned)ns, 64, 0, sd>>>(d_iq, iq_stride, (const DcStats *)b->dc_stats.p, b->dc_stride,
-                                                    (const DcAnchor *)b->dc_anchor.p, (float2 *)b->dc_state.p,
-                                                    (uint2 *)b->dc_table.p, b->dc_stride + DC_HALO_BLKS, cb * per_cb,
-                                                    per_cb, s0);
-            CU_TRY(cudaEventRecord(b->ev_dc[slot][(size_t)cb], sd));
-            nl++;
-        }
-        CU_TRY(cudaStreamWaitEvent(st, b->ev_dc[slot][0], 0));
-        mark(b, st);                                        // class 1: ingest + main VFOs
-        for (int cb = 0; cb < n_blocks; cb++) {
-            if (cb) CU_TRY(cudaStreamWaitEvent(st, b->ev_dc[slot][(size_t)cb], 0));
-            k1.b0 = cb;
-            k1_ingest_main<true><<<dim3((unsigned)ns, (unsigned)k1_tiles, 1u), K1_THREADS, 0, st>>>(k1);
-            nl++;
-        }
-    } else {
-        mark(b, st);                                        // class 1: ingest + main VFOs
-        k1_ingest_main<true><<<dim3((unsigned)ns, (unsigned)k1_tiles, (unsigned)n_blocks), K1_THREADS, 0, st>>>(k1);
-        nl++;
+        (*nl)++;
     }
-    mark(b, st);                                            // class 2: sub-VFO cascades
+    {
+        TimedScope t(b, sd, 0);
+        k0_dc_blocks<<<dim3((unsigned)((per_cb + 127) / 128), (unsigned)ns), 128, 0, sd>>>(
+            c.d_iq, c.iq_stride, (const DcAnchor *)b->dc_anchor.p, (DcStats *)b->dc_stats.p, b->dc_stride, cb * per_cb,
+            per_cb, s0);
+    }
+    {
+        TimedScope t(b, sd, 0);
+        k0_dc_walk<<<(unsigned)ns, 64, 0, sd>>>(c.d_iq, c.iq_stride, (const DcStats *)b->dc_stats.p, b->dc_stride,
+                                                (const DcAnchor *)b->dc_anchor.p, (float2 *)b->dc_state.p,
+                                                (uint2 *)b->dc_table.p, b->dc_stride + DC_HALO_BLKS, cb * per_cb, per_cb, s0);
+    }
+    (*nl) += 2;
+    CU_TRY(cudaEventRecord(done, sd));
+    return SDRB_OK;
+}
+
+// Everything after the DC stage for callback cb: ingest + main VFOs, sub-VFO cascades, /late FIR,
+// USB audio. `wait` (optional) gates the first kernel; `out_done` (optional) is recorded at the end.
+static int enqueue_main_cb(sdrb_bank *b, const CallCtx &c, int s0, int ns, cudaStream_t st, int cb, cudaEvent_t wait,
+                           cudaEvent_t out_done, int *nl) {
+    const HostPlan &h = b->plan->h;
+    if (wait) CU_TRY(cudaStreamWaitEvent(st, wait, 0));
+    K1Params k1 = b->k1;
+    k1.iq = c.d_iq; k1.iq_stride = c.iq_stride; k1.n_blocks = c.n_blocks; k1.stream0 = s0; k1.b0 = cb;
+    k1.cf_in = c.d_cf; k1.cf_stride = c.cf_stride;
+    const int k1_tiles = (h.block + K1_TILE - 1) / K1_TILE;
+    {
+        TimedScope t(b, st, 1);
+        if (c.d_cf) k1_ingest_main<false><<<dim3((unsigned)ns, (unsigned)k1_tiles, 1u), K1_THREADS, 0, st>>>(k1);
+        else k1_ingest_main<true><<<dim3((unsigned)ns, (unsigned)k1_tiles, 1u), K1_THREADS, 0, st>>>(k1);
+    }
+    (*nl)++;
     for (const SubGroup &g : b->groups) {
         K2aParams kp;
         kp.subs = (const SubDev *)b->subdev.p + g.first;
         kp.blocks_done = (const long long *)b->blocks_done.p;
-        kp.n_blocks = n_blocks; kp.tiles = g.tiles; kp.stream0 = s0;
-        const dim3 grid((unsigned)ns, (unsigned)g.count, (unsigned)(g.tiles * n_blocks));
+        kp.n_blocks = c.n_blocks; kp.tiles = g.tiles; kp.stream0 = s0; kp.b0 = cb;
+        const dim3 grid((unsigned)ns, (unsigned)g.count, (unsigned)g.tiles);
+        TimedScope t(b, st, 2);
         switch (g.decim) {
         case 0: k2a_mix_only<<<grid, 256, 0, st>>>(kp); break;
         case 1: k2a_sub_cascade<1><<<grid, K2A_THREADS, K2A_SMEM, st>>>(kp); break;
@@ -530,32 +531,77 @@ static int enqueue(sdrb_bank *b, const uint8_t *d_iq, size_t iq_stride, int n_bl
         case 4: k2a_sub_cascade<4><<<grid, K2A_THREADS, K2A_SMEM, st>>>(kp); break;
         default: k2a_sub_cascade<5><<<grid, K2A_THREADS, K2A_SMEM, st>>>(kp); break;
         }
-        nl++;
+        (*nl)++;
     }
-    mark(b, st);                                            // class 3: /late FIR
     if (b->n_late) {
-        const int tiles = (n_blocks * b->max_late_samples + LATE_TILE - 1) / LATE_TILE;
+        const int tiles = (b->max_late_samples + LATE_TILE - 1) / LATE_TILE;
+        TimedScope t(b, st, 3);
         k2_late_fir<<<dim3((unsigned)ns, (unsigned)b->n_late, (unsigned)tiles), LATE_TILE, 0, st>>>(
-            (const LateDev *)b->latedev.p, n_blocks, s0);
-        nl++;
+            (const LateDev *)b->latedev.p, cb, 1, s0);
+        (*nl)++;
     }
-    mark(b, st);                                            // class 4: USB audio
     if (b->n_usb) {
-        const int tiles = (n_blocks * b->max_usb_samples + USB_TILE - 1) / USB_TILE;
+        const int tiles = (b->max_usb_samples + USB_TILE - 1) / USB_TILE;
+        TimedScope t(b, st, 4);
         k2b_usb_audio<<<dim3((unsigned)ns, (unsigned)b->n_usb, (unsigned)tiles), 256, 0, st>>>(
-            (const UsbDev *)b->usbdev.p, n_blocks, s0, b->n_streams, h.pcm_per_block, d_pcm, d_tap);
-        nl++;
+            (const UsbDev *)b->usbdev.p, c.n_blocks, cb, 1, s0, h.pcm_per_block, c.d_pcm, c.d_tap);
+        (*nl)++;
     }
-    mark(b, st);                                            // class 5: carry
-    k3_carry<<<dim3((unsigned)ns, (unsigned)(b->n_carry + 1)), 128, 0, st>>>(
-        (const CarryItem *)b->carry.p, b->n_carry, n_blocks, d_iq, iq_stride, h.block, (uint8_t *)b->raw_tail.p,
-        (long long *)b->blocks_done.p, (h.correct_dc && !d_cf) ? (uint2 *)b->dc_table.p : nullptr,
-        (const DcAnchor *)b->dc_anchor.p, b->dc_stride + DC_HALO_BLKS, n_dcblk, s0, d_cf, cf_stride, (float2 *)b->cf_tail.p);
-    nl++;
-    mark(b, st);
-    CU_TRY(cudaGetLastError());
-    *launches += nl;
+    if (out_done) CU_TRY(cudaEventRecord(out_done, st));
     return SDRB_OK;
+}
+
+// End of a call: filter tails, raw tail and callback counters for the next call.
+static int enqueue_carry(sdrb_bank *b, const CallCtx &c, int s0, int ns, cudaStream_t st, int *nl) {
+    const HostPlan &h = b->plan->h;
+    const bool dc = h.correct_dc && !c.d_cf;
+    TimedScope t(b, st, 5);
+    k3_carry<<<dim3((unsigned)ns, (unsigned)(b->n_carry + 1)), 128, 0, st>>>(
+        (const CarryItem *)b->carry.p, b->n_carry, c.n_blocks, c.d_iq, c.iq_stride, h.block, (uint8_t *)b->raw_tail.p,
+        (long long *)b->blocks_done.p, dc ? (uint2 *)b->dc_table.p : nullptr, (const DcAnchor *)b->dc_anchor.p,
+        b->dc_stride + DC_HALO_BLKS, c.n_blocks * (h.block / DC_BLK), s0, c.d_cf, c.cf_stride, (float2 *)b->cf_tail.p);
+    (*nl)++;
+    CU_TRY(cudaGetLastError());
+    return SDRB_OK;
+}
+
+// Whole call for all streams of the bank on one stream (device-resident entry points): the DC walk
+// of callback cb+1 runs on the side stream while callback cb is filtered.
+static int enqueue_all(sdrb_bank *b, const CallCtx &c, cudaStream_t st, int *launches) {
+    const HostPlan &h = b->plan->h;
+    const bool dc = h.correct_dc && !c.d_cf;
+    const int ns = b->n_streams;
+    int rc;
+    if (dc) {
+        cudaStream_t sd = b->s_dc[0];
+        CU_TRY(cudaEventRecord(b->ev_entry[0], st));         // everything queued before this call
+        CU_TRY(cudaStreamWaitEvent(sd, b->ev_entry[0], 0));
+        for (int cb = 0; cb < c.n_blocks; cb++)
+            if ((rc = enqueue_dc_cb(b, c, 0, ns, sd, cb, nullptr, b->ev_dc[0][(size_t)cb], launches)) != SDRB_OK) return rc;
+    }
+    for (int cb = 0; cb < c.n_blocks; cb++)
+        if ((rc = enqueue_main_cb(b, c, 0, ns, st, cb, dc ? b->ev_dc[0][(size_t)cb] : nullptr, nullptr, launches)) != SDRB_OK)
+            return rc;
+    return enqueue_carry(b, c, 0, ns, st, launches);
+}
+
+TimedScope::TimedScope(sdrb_bank *b_, cudaStream_t st_, int cls_) : b(b_), st(st_), cls(cls_), on(b_->timing) {
+    if (!on) return;
+    if (b->tev_used + 2 > b->tev.size()) {
+        for (int k = 0; k < 2; k++) {
+            cudaEvent_t e;
+            if (cudaEventCreate(&e) != cudaSuccess) { on = false; return; }
+            b->tev.push_back(e);
+        }
+        b->tev_cls.resize(b->tev.size() / 2);
+    }
+    b->tev_cls[b->tev_used / 2] = cls;
+    cudaEventRecord(b->tev[b->tev_used], st);
+}
+TimedScope::~TimedScope() {
+    if (!on) return;
+    cudaEventRecord(b->tev[b->tev_used + 1], st);
+    b->tev_used += 2;
 }
 
 extern "C" int sdrb_bank_set_timing(sdrb_bank *b, int on) {
@@ -570,15 +616,14 @@ extern "C" int sdrb_bank_kernel_times(sdrb_bank *b, double *ms, long *calls) {
     if (!b || !ms) { set_error("sdrb_bank_kernel_times: NULL argument"); return SDRB_E_INVALID; }
     CU_TRY(cudaSetDevice(b->device));
     CU_TRY(cudaDeviceSynchronize());
-    const size_t per = SDRB_N_KERNEL_CLASSES + 1;
-    for (size_t c = 0; c + per <= b->tev_used; c += per)
-        for (int k = 0; k < SDRB_N_KERNEL_CLASSES; k++) {
-            float t = 0.f;
-            if (cudaEventElapsedTime(&t, b->tev[c + (size_t)k], b->tev[c + (size_t)k + 1]) == cudaSuccess) {
-                b->kernel_ms[k] += t;
-                b->kernel_calls[k] += 1;
-            }
+    for (size_t c = 0; c + 2 <= b->tev_used; c += 2) {
+        float t = 0.f;
+        const int k = b->tev_cls[c / 2];
+        if (cudaEventElapsedTime(&t, b->tev[c], b->tev[c + 1]) == cudaSuccess) {
+            b->kernel_ms[k] += t;
+            b->kernel_calls[k] += 1;
         }
+    }
     b->tev_used = 0;
     for (int k = 0; k < SDRB_N_KERNEL_CLASSES; k++) { ms[k] = b->kernel_ms[k]; if (calls) calls[k] = b->kernel_calls[k]; }
     return SDRB_OK;
@@ -601,8 +646,9 @@ extern "C" int sdrb_bank_process_device(sdrb_bank *b, const uint8_t *d_iq, size_
     if (rc != SDRB_OK) return rc;
     CU_TRY(cudaSetDevice(b->device));
     b->last_launches = 0;
-    return enqueue(b, d_iq, iq_stride, n_blocks, d_pcm, d_tap, 0, b->n_streams, (cudaStream_t)cuda_stream, 0,
-                   nullptr, &b->last_launches);
+    CallCtx c;
+    c.d_iq = d_iq; c.iq_stride = iq_stride; c.n_blocks = n_blocks; c.d_pcm = d_pcm; c.d_tap = d_tap;
+    return enqueue_all(b, c, (cudaStream_t)cuda_stream, &b->last_launches);
 }
 
 extern "C" int sdrb_bank_copy_main(sdrb_bank *b, int main_idx, int n_blocks, float *d_out, void *cuda_stream) {
@@ -648,9 +694,13 @@ extern "C" int sdrb_bank_process_host(sdrb_bank *b, const uint8_t *h_iq, size_t 
     if (h_tap && !b->d_tap.p) {
         rc = b->d_tap.alloc((size_t)b->max_blocks * h.pcm_per_block * sizeof(float) * (size_t)b->n_streams); if (rc) return rc;
     }
-    // stream groups: copy-in / compute / copy-out overlap across groups
-    const int n_groups = std::min(b->n_streams, 8);
-    while ((int)b->ev_in.size() < n_groups) {
+    // Chunks = (callback, stream group), callback-major: copy-in, kernels and copy-out of different
+    // chunks overlap on three streams (+ one DC side stream per group); a chunk's kernels start when
+    // its copy has landed. Callback-major order gives every group's sequential DC walk the time of
+    // the other groups' copies before its next callback arrives.
+    const int n_groups = std::min(b->n_streams, sdrb_bank::kSide);
+    const size_t need_ev = (size_t)n_groups * (size_t)b->max_blocks;
+    while (b->ev_in.size() < need_ev) {
         cudaEvent_t e1, e2;
         CU_TRY(cudaEventCreateWithFlags(&e1, cudaEventDisableTiming));
         CU_TRY(cudaEventCreateWithFlags(&e2, cudaEventDisableTiming));
@@ -658,27 +708,39 @@ extern "C" int sdrb_bank_process_host(sdrb_bank *b, const uint8_t *h_iq, size_t 
     }
     b->last_launches = 0;
     const int per = (b->n_streams + n_groups - 1) / n_groups;
-    for (int g = 0; g < n_groups; g++) {
-        const int s0 = g * per, ns = std::min(per, b->n_streams - s0);
-        if (ns <= 0) break;
-        uint8_t *din = (uint8_t *)b->d_iq.p + (size_t)s0 * in_max;
-        CU_TRY(cudaMemcpy2DAsync(din, in_max, h_iq + (size_t)s0 * iq_stride, iq_stride, in_row, (size_t)ns,
-                                 cudaMemcpyHostToDevice, b->s_copy_in));
-        CU_TRY(cudaEventRecord(b->ev_in[(size_t)g], b->s_copy_in));
-        CU_TRY(cudaStreamWaitEvent(b->s_compute, b->ev_in[(size_t)g], 0));
-        // kernels index streams absolutely: pass the bank-wide base pointers
-        rc = enqueue(b, (const uint8_t *)b->d_iq.p, in_max, n_blocks, (int16_t *)b->d_pcm.p,
-                     h_tap ? (float *)b->d_tap.p : nullptr, s0, ns, b->s_compute, g % sdrb_bank::kSide,
-                     b->ev_in[(size_t)g], &b->last_launches);
-        if (rc != SDRB_OK) return rc;
-        CU_TRY(cudaEventRecord(b->ev_done[(size_t)g], b->s_compute));
-        CU_TRY(cudaStreamWaitEvent(b->s_copy_out, b->ev_done[(size_t)g], 0));
-        CU_TRY(cudaMemcpyAsync(h_pcm + (size_t)s0 * rec, (int16_t *)b->d_pcm.p + (size_t)s0 * rec,
-                               rec * sizeof(int16_t) * (size_t)ns, cudaMemcpyDeviceToHost, b->s_copy_out));
-        if (h_tap)
-            CU_TRY(cudaMemcpyAsync(h_tap + (size_t)s0 * rec, (float *)b->d_tap.p + (size_t)s0 * rec,
-                                   rec * sizeof(float) * (size_t)ns, cudaMemcpyDeviceToHost, b->s_copy_out));
-    }
+    const size_t cb_in = (size_t)h.block * 2, cb_out = (size_t)h.pcm_per_block;
+    const bool dc = h.correct_dc != 0;
+    CallCtx c;
+    c.d_iq = (const uint8_t *)b->d_iq.p; c.iq_stride = in_max; c.n_blocks = n_blocks;   // kernels index streams absolutely
+    c.d_pcm = (int16_t *)b->d_pcm.p; c.d_tap = h_tap ? (float *)b->d_tap.p : nullptr;
+    for (int cb = 0; cb < n_blocks; cb++)
+        for (int g = 0; g < n_groups; g++) {
+            const int s0 = g * per, ns = std::min(per, b->n_streams - s0);
+            if (ns <= 0) break;
+            CU_TRY(cudaMemcpy2DAsync((uint8_t *)b->d_iq.p + (size_t)s0 * in_max + (size_t)cb * cb_in, in_max,
+                                     h_iq + (size_t)s0 * iq_stride + (size_t)cb * cb_in, iq_stride, cb_in, (size_t)ns,
+                                     cudaMemcpyHostToDevice, b->s_copy_in));
+            CU_TRY(cudaEventRecord(b->ev_in[(size_t)g * b->max_blocks + cb], b->s_copy_in));
+        }
+    for (int cb = 0; cb < n_blocks; cb++)
+        for (int g = 0; g < n_groups; g++) {
+            const int s0 = g * per, ns = std::min(per, b->n_streams - s0);
+            if (ns <= 0) break;
+            cudaEvent_t ein = b->ev_in[(size_t)g * b->max_blocks + cb], eout = b->ev_done[(size_t)g * b->max_blocks + cb];
+            if (dc && (rc = enqueue_dc_cb(b, c, s0, ns, b->s_dc[g], cb, ein, b->ev_dc[g][(size_t)cb], &b->last_launches)) != SDRB_OK)
+                return rc;
+            if ((rc = enqueue_main_cb(b, c, s0, ns, b->s_compute, cb, dc ? b->ev_dc[g][(size_t)cb] : ein, eout,
+                                      &b->last_launches)) != SDRB_OK)
+                return rc;
+            if (cb == n_blocks - 1 && (rc = enqueue_carry(b, c, s0, ns, b->s_compute, &b->last_launches)) != SDRB_OK) return rc;
+            CU_TRY(cudaStreamWaitEvent(b->s_copy_out, eout, 0));
+            const size_t off = (size_t)s0 * rec + (size_t)cb * cb_out;
+            CU_TRY(cudaMemcpy2DAsync(h_pcm + off, rec * sizeof(int16_t), (int16_t *)b->d_pcm.p + off, rec * sizeof(int16_t),
+                                     cb_out * sizeof(int16_t), (size_t)ns, cudaMemcpyDeviceToHost, b->s_copy_out));
+            if (h_tap)
+                CU_TRY(cudaMemcpy2DAsync(h_tap + off, rec * sizeof(float), (float *)b->d_tap.p + off, rec * sizeof(float),
+                                         cb_out * sizeof(float), (size_t)ns, cudaMemcpyDeviceToHost, b->s_copy_out));
+        }
     CU_TRY(cudaStreamSynchronize(b->s_copy_out));
     CU_TRY(cudaStreamSynchronize(b->s_compute));
     return SDRB_OK;
@@ -706,8 +768,10 @@ extern "C" int sdrb_bank_process_cf32_host(sdrb_bank *b, const float *h_in, size
     CU_TRY(cudaMemcpy2DAsync(b->d_cf.p, cap * sizeof(float2), h_in, stride_samples * sizeof(float2), row * sizeof(float2),
                              (size_t)b->n_streams, cudaMemcpyHostToDevice, st));
     b->last_launches = 0;
-    rc = enqueue(b, nullptr, 0, n_blocks, (int16_t *)b->d_pcm.p, h_tap ? (float *)b->d_tap.p : nullptr, 0, b->n_streams, st,
-                 0, nullptr, &b->last_launches, (const float2 *)b->d_cf.p, cap);
+    CallCtx c;
+    c.d_cf = (const float2 *)b->d_cf.p; c.cf_stride = cap; c.n_blocks = n_blocks;
+    c.d_pcm = (int16_t *)b->d_pcm.p; c.d_tap = h_tap ? (float *)b->d_tap.p : nullptr;
+    rc = enqueue_all(b, c, st, &b->last_launches);
     if (rc != SDRB_OK) return rc;
     CU_TRY(cudaMemcpyAsync(h_pcm, b->d_pcm.p, rec * sizeof(int16_t) * (size_t)b->n_streams, cudaMemcpyDeviceToHost, st));
     if (h_tap) CU_TRY(cudaMemcpyAsync(h_tap, b->d_tap.p, rec * sizeof(float) * (size_t)b->n_streams, cudaMemcpyDeviceToHost, st));

@@ -98,7 +98,7 @@ struct SubDev {
 struct K2aParams {
     const SubDev *subs;             // device array, this launch's group
     const long long *blocks_done;
-    int n_blocks, tiles, stream0;
+    int n_blocks, tiles, stream0, b0;     // this launch covers callbacks b0 .. b0 + gridDim.z/tiles - 1
 };
 
 struct LateDev {
@@ -130,6 +130,27 @@ struct CarryItem {
 __device__ __forceinline__ float2 cmul(float2 a, float2 b) {
     return make_float2(a.x * b.x - a.y * b.y, a.x * b.y + a.y * b.x);
 }
+
+// Blackwell packed FP32 pairs (FADD2 / FMUL2 / FFMA2): one issue slot for both arms of a complex
+// sample. Each element is rounded exactly like the scalar .rn instruction.
+__device__ __forceinline__ unsigned long long f2_bits(float2 v) { return *reinterpret_cast<unsigned long long *>(&v); }
+__device__ __forceinline__ float2 bits_f2(unsigned long long v) { return *reinterpret_cast<float2 *>(&v); }
+__device__ __forceinline__ float2 add2(float2 a, float2 b) {
+    unsigned long long r;
+    asm("add.rn.f32x2 %0, %1, %2;" : "=l"(r) : "l"(f2_bits(a)), "l"(f2_bits(b)));
+    return bits_f2(r);
+}
+__device__ __forceinline__ float2 mul2(float2 a, float2 b) {
+    unsigned long long r;
+    asm("mul.rn.f32x2 %0, %1, %2;" : "=l"(r) : "l"(f2_bits(a)), "l"(f2_bits(b)));
+    return bits_f2(r);
+}
+__device__ __forceinline__ float2 fma2(float2 a, float2 b, float2 c) {
+    unsigned long long r;
+    asm("fma.rn.f32x2 %0, %1, %2, %3;" : "=l"(r) : "l"(f2_bits(a)), "l"(f2_bits(b)), "l"(f2_bits(c)));
+    return bits_f2(r);
+}
+__device__ __forceinline__ float2 splat2(float v) { return make_float2(v, v); }
 
 // byte k of w -> (float)byte - 127  without the conversion pipe: splice the byte into the
 // mantissa of 2^23 and subtract 2^23 + 127.
@@ -188,8 +209,10 @@ __device__ __forceinline__ void hb_stage(const float2 (&in)[2 * R], float2 (&out
         (void)m;
         float2 w0, w2, w4, w5, w6, w8, w10;
         HB_TAP(w0, 0) HB_TAP(w2, 2) HB_TAP(w4, 4) HB_TAP(w5, 5) HB_TAP(w6, 6) HB_TAP(w8, 8) HB_TAP(w10, 10)
-        out[r].x = HB_P0 * (w0.x + w10.x) + HB_P2 * (w2.x + w8.x) + HB_P4 * (w4.x + w6.x) + HB_P5 * w5.x;
-        out[r].y = HB_P0 * (w0.y + w10.y) + HB_P2 * (w2.y + w8.y) + HB_P4 * (w4.y + w6.y) + HB_P5 * w5.y;
+        // both arms at once: 3 FADD2 + 1 FMUL2 + 3 FFMA2 per complex output
+        out[r] = fma2(splat2(HB_P5), w5,
+                      fma2(splat2(HB_P4), add2(w4, w6),
+                           fma2(splat2(HB_P2), add2(w2, w8), mul2(splat2(HB_P0), add2(w0, w10)))));
     }
 #undef HB_TAP
 }
@@ -534,13 +557,16 @@ __global__ void __launch_bounds__(K1_THREADS, 2) k1_ingest_main(const K1Params p
             const uint2 *te = p.dc_table + ((size_t)stream * p.dc_stride + dblk) * 2;
             const uint2 eI = __ldg(te), eQ = __ldg(te + 1);
             const DcAnchor AI = p.dc_anchor[2 * stream], AQ = p.dc_anchor[2 * stream + 1];
-            float dI = 0.f, dQ = 0.f;
+            // both arms packed (FMUL2/FADD2): q = fl(c*x) is shared by the increment and the step
+            const float2 sgn2 = make_float2(AI.sgn, AQ.sgn), invu2 = make_float2(AI.inv_u, AQ.inv_u);
+            float2 q[8], d2 = make_float2(0.f, 0.f);
 #pragma unroll
             for (int k = 0; k < 8; ++k) {
-                bool t;
-                dI += dc_incr(AI, x[k].x, t) - (float)AI.r0;
-                dQ += dc_incr(AQ, x[k].y, t) - (float)AQ.r0;
+                q[k] = mul2(splat2(DC_C), x[k]);
+                const float2 y = mul2(mul2(q[k], sgn2), invu2);                   // sign flip and 1/ulp are exact
+                d2 = add2(d2, add2(add2(y, splat2(DC_MAGIC)), splat2(-DC_MAGIC)));
             }
+            const float dI = d2.x - 8.f * (float)AI.r0, dQ = d2.y - 8.f * (float)AQ.r0;
             // exclusive prefix over the 16 lanes of the DC block
             float pI = dI, pQ = dQ;
 #pragma unroll
@@ -564,12 +590,11 @@ __global__ void __launch_bounds__(K1_THREADS, 2) k1_ingest_main(const K1Params p
                     }
                 }
             }
+            float2 s2 = make_float2(sI, sQ);
 #pragma unroll
             for (int k = 0; k < 8; ++k) {
-                sI = dc_step(sI, x[k].x);
-                sQ = dc_step(sQ, x[k].y);
-                x[k].x = __fadd_rn(x[k].x, -sI);
-                x[k].y = __fadd_rn(x[k].y, -sQ);
+                s2 = add2(mul2(s2, splat2(DC_A)), q[k]);                          // sdrj.cpp:281, both arms
+                x[k] = add2(x[k], make_float2(-s2.x, -s2.y));
             }
         }
     }
@@ -669,7 +694,7 @@ __global__ void __launch_bounds__(K2A_THREADS, 2) k2a_sub_cascade(const K2aParam
     constexpr int ADV = (K2A_THREADS - HT) * K2A_CHUNK;
     const SubDev &D = p.subs[blockIdx.y];
     const int stream = p.stream0 + blockIdx.x;
-    const int tile = blockIdx.z % p.tiles, b = blockIdx.z / p.tiles;
+    const int tile = blockIdx.z % p.tiles, b = p.b0 + blockIdx.z / p.tiles;
     const int t = threadIdx.x;
     const int B = D.block_in;
     const int r0 = tile * ADV - HT * K2A_CHUNK;           // callback coordinate of thread 0's chunk
@@ -792,7 +817,7 @@ __global__ void __launch_bounds__(K2A_THREADS, 2) k2a_sub_cascade(const K2aParam
 __global__ void __launch_bounds__(256) k2a_mix_only(const K2aParams p) {
     const SubDev &D = p.subs[blockIdx.y];
     const int stream = p.stream0 + blockIdx.x;
-    const int tile = blockIdx.z % p.tiles, b = blockIdx.z / p.tiles;
+    const int tile = blockIdx.z % p.tiles, b = p.b0 + blockIdx.z / p.tiles;
     const int B = D.block_in;
     const long long blk = p.blocks_done[stream] + b;
     const int lut_base = (int)((blk * (long long)B) % D.lut_len);
@@ -823,18 +848,18 @@ __global__ void __launch_bounds__(256) k2a_mix_only(const K2aParams p) {
 // (fir_decI/Q FIRUpdateAndProcess on the first sample of each group of `late`, FIRUpdate
 // on the others: vfo.cpp:346-384; newest sample excluded: dsp.cpp:59-71).
 // ------------------------------------------------------------------------------------
-__global__ void __launch_bounds__(LATE_TILE) k2_late_fir(const LateDev *__restrict__ devs, int n_blocks, int stream0) {
+__global__ void __launch_bounds__(LATE_TILE) k2_late_fir(const LateDev *__restrict__ devs, int cb0, int ncb, int stream0) {
     __shared__ float2 sz[LATE_TILE * 6 + MAX_FIR_TAPS];
     __shared__ float st[MAX_FIR_TAPS];
     const LateDev &D = devs[blockIdx.y];
     const int stream = stream0 + blockIdx.x;
-    const int n_total = n_blocks * D.samples_out;
-    const int m0 = blockIdx.z * LATE_TILE;
+    const int n_total = (cb0 + ncb) * D.samples_out;               // outputs exist up to here
+    const int m0 = cb0 * D.samples_out + blockIdx.z * LATE_TILE;
     if (m0 >= n_total) return;
     const int t = threadIdx.x;
     const int span = D.late * LATE_TILE + D.ntaps;
     const long long zlo = (long long)D.late * m0 - D.ntaps;       // may be negative: history
-    const long long zmax = (long long)n_blocks * D.block_z;
+    const long long zmax = (long long)(cb0 + ncb) * D.block_z;
     const float2 *zp = D.z + (size_t)stream * D.z_stride + D.z_hist;
     for (int e = t; e < span; e += LATE_TILE) {
         const long long zi = zlo + e;
@@ -880,8 +905,8 @@ __device__ __forceinline__ void fir4(const float *__restrict__ x, const float *_
 
 constexpr int USB_SPAN = USB_TILE + MAX_FIR_TAPS + 128;     // z samples a CTA may need
 
-__global__ void __launch_bounds__(256) k2b_usb_audio(const UsbDev *__restrict__ devs, int n_blocks, int stream0,
-                                                      int n_streams_total, int pcm_per_block,
+__global__ void __launch_bounds__(256) k2b_usb_audio(const UsbDev *__restrict__ devs, int n_blocks, int cb0, int ncb,
+                                                      int stream0, int pcm_per_block,
                                                       int16_t *__restrict__ pcm, float *__restrict__ tap) {
     __shared__ __align__(16) float sPlaneA[USB_SPAN / 2 + 8];    // im[zlo + 2j + 1]
     __shared__ __align__(16) float sPlaneB[USB_SPAN / 2 + 8];    // im[zlo + 2j + 2]
@@ -892,8 +917,8 @@ __global__ void __launch_bounds__(256) k2b_usb_audio(const UsbDev *__restrict__ 
 
     const UsbDev &D = devs[blockIdx.y];
     const int stream = stream0 + blockIdx.x;
-    const int n_total = n_blocks * D.samples_out;
-    const int n0 = blockIdx.z * USB_TILE;
+    const int n_total = (cb0 + ncb) * D.samples_out;               // samples that exist so far in this call
+    const int n0 = cb0 * D.samples_out + blockIdx.z * USB_TILE;
     if (n0 >= n_total) return;
     const int t = threadIdx.x;
     const int NP = D.np;
