@@ -14,6 +14,7 @@
 
 #include "plan.hpp"
 #include "kernels.cuh"
+#include "kernels_v2.cuh"
 #include "prims.cuh"
 
 namespace sdrb {
@@ -134,11 +135,25 @@ struct DevBuf {
     void release() { if (p) cudaFree(p); p = nullptr; }
 };
 
-struct SubGroup {           // sub VFOs sharing (stage count) -> one K2A launch
-    int decim;
-    int tiles;              // K2A tiles per callback
-    int first, count;       // range in the device SubDev array (sorted by group)
+struct SubGroup {           // sub VFOs of one main VFO (at most V2_MAX_VFO) -> one k2a_v2 launch
+    int main_idx;
+    int tiles;              // tiles per callback
+    int halo;               // halo threads in front of every tile
+    int first, count;       // range in the device CascVfo / Rf arrays (sorted by group)
+    int lut_len, block_in;  // Oscillator table length and callback size of the group's sub VFOs
 };
+
+// Rf[j] = (rot/|rot|)^j, j = -10..31 (index j + 10), rot = the float rotation the Oscillator table is
+// built from (oscillator.cpp:9-14); see kernels_v2.cuh
+void rf_table(double sample_rate, double frequency, float2 *dst) {
+    const double step = 2.0 * M_PI * frequency / sample_rate;
+    const float rr = (float)cos(step), ri = (float)sin(step);
+    const double w = atan2((double)ri, (double)rr);
+    for (int i = 0; i < RF_LEN; i++) {
+        const int j = i - 10;
+        dst[i] = i < 42 ? make_float2((float)cos(w * j), (float)sin(w * j)) : make_float2(0.f, 0.f);
+    }
+}
 
 inline size_t round_up(size_t v, size_t m) { return (v + m - 1) / m * m; }
 
@@ -156,13 +171,15 @@ struct sdrb_bank {
     DevBuf dc_anchor, dc_stats, dc_table, main_out, zbuf, dbuf;
     int dc_stride = 0;                      // DC blocks (of 32 samples) per stream in dc_stats; table has DC_HALO_BLKS more
     // descriptors
-    K1Params k1{};
-    DevBuf subdev, latedev, usbdev, carry;
+    K1Params k1{};          // cf32-input variant (vfo::process entry)
+    K1V2Params k1v2{};
+    DevBuf cascdev, rfdev, latedev, usbdev, carry;
     std::vector<SubGroup> groups;
     int n_late = 0, n_usb = 0, n_carry = 0;
     int max_usb_samples = 0, max_late_samples = 0;
     std::vector<size_t> main_off;           // per main: offset (float2 units) inside main_out per stream
     size_t main_stride = 0;                 // float2 per stream
+    size_t z_stride = 0;                    // float2 per stream in zbuf
     // host staging for process_host
     DevBuf d_iq, d_pcm, d_tap, d_cf;
     cudaStream_t s_copy_in = nullptr, s_compute = nullptr, s_copy_out = nullptr;
@@ -185,7 +202,7 @@ extern "C" void sdrb_bank_destroy(sdrb_bank *b) {
     if (!b) return;
     cudaSetDevice(b->device);
     DevBuf *all[] = {&b->luts, &b->taps, &b->blocks_done, &b->dc_state, &b->raw_tail, &b->cf_tail, &b->dc_anchor, &b->dc_stats, &b->dc_table,
-                     &b->main_out, &b->zbuf, &b->dbuf, &b->subdev, &b->latedev, &b->usbdev, &b->carry,
+                     &b->main_out, &b->zbuf, &b->dbuf, &b->cascdev, &b->rfdev, &b->latedev, &b->usbdev, &b->carry,
                      &b->d_iq, &b->d_pcm, &b->d_tap, &b->d_cf};
     for (DevBuf *d : all) d->release();
     for (cudaEvent_t e : b->ev_in) cudaEventDestroy(e);
@@ -320,38 +337,43 @@ extern "C" int sdrb_bank_create(const sdrb_plan *plan, int device, int n_streams
         M.out_stride = (long long)b->main_stride;
         M.lut_len = (int)h.mains[i].lut.size(); M.decim = h.mains[i].decim; M.block_out = h.mains[i].block_out;
     }
-    // sub VFOs grouped by stage count
+    // sub VFOs grouped by parent main VFO: one k2a_v2 launch per group, the parent's output is
+    // read once per thread and kept in registers for all sub VFOs of the group
+    static const int kHalo[6] = {0, 0, 1, 2, 5, 11};    // halo chunks a cascade of S stages needs (+1 sample/stage at callback heads)
     std::vector<int> order;
-    for (int dcm = 0; dcm <= 5; dcm++) {
-        SubGroup g; g.decim = dcm; g.first = (int)order.size(); g.count = 0; g.tiles = 0;
+    for (size_t mi = 0; mi < h.mains.size(); mi++) {
+        SubGroup g; g.main_idx = (int)mi; g.first = (int)order.size(); g.count = 0; g.tiles = 0; g.halo = 0;
         for (size_t i = 0; i < h.subs.size(); i++) {
-            if (h.subs[i].decim != dcm) continue;
+            if (h.subs[i].main_idx != (int)mi) continue;
+            if (g.count == V2_MAX_VFO) { b->groups.push_back(g); g.first = (int)order.size(); g.count = 0; g.halo = 0; }
             order.push_back((int)i); g.count++;
-            int tiles;
-            if (dcm == 0) tiles = (h.subs[i].block_in + 2047) / 2048;
-            else {
-                const int ht = dcm <= 2 ? 1 : dcm == 3 ? 3 : dcm == 4 ? 5 : 11;
-                const int adv = (K2A_THREADS - ht) * K2A_CHUNK;
-                tiles = (h.subs[i].block_in + adv - 1) / adv;
-            }
-            g.tiles = std::max(g.tiles, tiles);
+            g.halo = std::max(g.halo, kHalo[h.subs[i].decim]);
         }
         if (g.count) b->groups.push_back(g);
     }
-    std::vector<SubDev> subdev;
+    for (SubGroup &g : b->groups) {
+        const int adv = (V2_THREADS - g.halo) * V2_CHUNK;
+        const SubVfo &s0v = h.subs[(size_t)order[(size_t)g.first]];
+        g.lut_len = (int)s0v.lut.size(); g.block_in = s0v.block_in;
+        g.tiles = (g.block_in + adv - 1) / adv;
+    }
+    std::vector<CascVfo> cascdev;
+    std::vector<float2> rfhost((h.mains.size() + h.subs.size()) * RF_LEN);
     std::vector<LateDev> latedev;
     std::vector<UsbDev> usbdev;
     std::vector<CarryItem> carry;
-    for (int i : order) {
+    for (size_t i = 0; i < h.mains.size(); i++) rf_table((double)h.fs, h.mains[i].mixer, &rfhost[i * RF_LEN]);
+    for (size_t k = 0; k < order.size(); k++) {
+        const int i = order[k];
         const SubVfo &s = h.subs[(size_t)i];
-        SubDev D;
+        CascVfo D;
         D.lut = (const float2 *)b->luts.p + sub_lut_off[(size_t)i];
-        D.in = (const float2 *)b->main_out.p + b->main_off[(size_t)s.main_idx];
-        D.z = (float2 *)b->zbuf.p + z_off[(size_t)i];
-        D.in_stride = (long long)b->main_stride; D.z_stride = (long long)z_stride;
-        D.lut_len = (int)s.lut.size(); D.block_in = s.block_in; D.block_z = s.block_z; D.z_hist = z_hist[(size_t)i];
-        subdev.push_back(D);
+        D.out = (float2 *)b->zbuf.p + z_off[(size_t)i];
+        D.S = s.decim; D.block_out = s.block_z; D.hist = z_hist[(size_t)i]; D.pad = 0;
+        cascdev.push_back(D);
+        rf_table((double)s.fs, s.mixer, &rfhost[(h.mains.size() + k) * RF_LEN]);
     }
+    b->z_stride = z_stride;
     for (size_t i = 0; i < h.subs.size(); i++) {
         const SubVfo &s = h.subs[i];
         UsbDev U;
@@ -389,20 +411,37 @@ extern "C" int sdrb_bank_create(const sdrb_plan *plan, int device, int n_streams
         carry.push_back(c);
     }
     b->n_late = (int)latedev.size(); b->n_usb = (int)usbdev.size(); b->n_carry = (int)carry.size();
-    BANK_TRY(b->subdev.alloc(sizeof(SubDev) * std::max<size_t>(subdev.size(), 1)));
+    BANK_TRY(b->cascdev.alloc(sizeof(CascVfo) * std::max<size_t>(cascdev.size(), 1)));
+    BANK_TRY(b->rfdev.alloc(sizeof(float2) * rfhost.size()));
+    BANK_CU(cudaMemcpy(b->rfdev.p, rfhost.data(), sizeof(float2) * rfhost.size(), cudaMemcpyHostToDevice));
     BANK_TRY(b->latedev.alloc(sizeof(LateDev) * std::max<size_t>(latedev.size(), 1)));
     BANK_TRY(b->usbdev.alloc(sizeof(UsbDev) * std::max<size_t>(usbdev.size(), 1)));
     BANK_TRY(b->carry.alloc(sizeof(CarryItem) * std::max<size_t>(carry.size(), 1)));
-    if (!subdev.empty()) BANK_CU(cudaMemcpy(b->subdev.p, subdev.data(), sizeof(SubDev) * subdev.size(), cudaMemcpyHostToDevice));
+    if (!cascdev.empty()) BANK_CU(cudaMemcpy(b->cascdev.p, cascdev.data(), sizeof(CascVfo) * cascdev.size(), cudaMemcpyHostToDevice));
+    {
+        K1V2Params &q = b->k1v2;
+        q.tail = (const uint8_t *)b->raw_tail.p;
+        q.dc_table = (const uint2 *)b->dc_table.p;
+        q.dc_anchor = (const DcAnchor *)b->dc_anchor.p;
+        q.blocks_done = (const long long *)b->blocks_done.p;
+        q.rf = (const float2 *)b->rfdev.p;
+        q.out_stride = (long long)b->main_stride;
+        q.dc_stride = b->dc_stride + DC_HALO_BLKS; q.block = h.block; q.lut_len = (int)h.mains[0].lut.size();
+        q.n_main = (int)h.mains.size();
+        for (size_t i = 0; i < h.mains.size(); i++) {
+            CascVfo &M = q.mains[i];
+            M.lut = (const float2 *)b->luts.p + main_lut_off[i];
+            M.out = (float2 *)b->main_out.p + b->main_off[i];
+            M.S = h.mains[i].decim; M.block_out = h.mains[i].block_out; M.hist = MAIN_HIST; M.pad = 0;
+        }
+    }
     if (!latedev.empty()) BANK_CU(cudaMemcpy(b->latedev.p, latedev.data(), sizeof(LateDev) * latedev.size(), cudaMemcpyHostToDevice));
     if (!usbdev.empty()) BANK_CU(cudaMemcpy(b->usbdev.p, usbdev.data(), sizeof(UsbDev) * usbdev.size(), cudaMemcpyHostToDevice));
     BANK_CU(cudaMemcpy(b->carry.p, carry.data(), sizeof(CarryItem) * carry.size(), cudaMemcpyHostToDevice));
 
-    BANK_CU(cudaFuncSetAttribute(k2a_sub_cascade<1>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)K2A_SMEM));
-    BANK_CU(cudaFuncSetAttribute(k2a_sub_cascade<2>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)K2A_SMEM));
-    BANK_CU(cudaFuncSetAttribute(k2a_sub_cascade<3>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)K2A_SMEM));
-    BANK_CU(cudaFuncSetAttribute(k2a_sub_cascade<4>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)K2A_SMEM));
-    BANK_CU(cudaFuncSetAttribute(k2a_sub_cascade<5>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)K2A_SMEM));
+    BANK_CU(cudaFuncSetAttribute(k2a_v2, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)V2_SMEM));
+    BANK_CU(cudaFuncSetAttribute(k1_v2<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)V2_SMEM));
+    BANK_CU(cudaFuncSetAttribute(k1_v2<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)V2_SMEM));
     BANK_CU(cudaStreamCreateWithFlags(&b->s_copy_in, cudaStreamNonBlocking));
     BANK_CU(cudaStreamCreateWithFlags(&b->s_compute, cudaStreamNonBlocking));
     BANK_CU(cudaStreamCreateWithFlags(&b->s_copy_out, cudaStreamNonBlocking));
@@ -509,28 +548,29 @@ static int enqueue_main_cb(sdrb_bank *b, const CallCtx &c, int s0, int ns, cudaS
     K1Params k1 = b->k1;
     k1.iq = c.d_iq; k1.iq_stride = c.iq_stride; k1.n_blocks = c.n_blocks; k1.stream0 = s0; k1.b0 = cb;
     k1.cf_in = c.d_cf; k1.cf_stride = c.cf_stride;
-    const int k1_tiles = (h.block + K1_TILE - 1) / K1_TILE;
-    {
+    if (c.d_cf) {
+        const int k1_tiles = (h.block + K1_TILE - 1) / K1_TILE;
         TimedScope t(b, st, 1);
-        if (c.d_cf) k1_ingest_main<false><<<dim3((unsigned)ns, (unsigned)k1_tiles, 1u), K1_THREADS, 0, st>>>(k1);
-        else k1_ingest_main<true><<<dim3((unsigned)ns, (unsigned)k1_tiles, 1u), K1_THREADS, 0, st>>>(k1);
+        k1_ingest_main<false><<<dim3((unsigned)ns, (unsigned)k1_tiles, 1u), K1_THREADS, 0, st>>>(k1);
+    } else {
+        K1V2Params q = b->k1v2;
+        q.iq = c.d_iq; q.iq_stride = c.iq_stride; q.stream0 = s0; q.b0 = cb;
+        const dim3 grid((unsigned)ns, (unsigned)((h.block + K1V2_ADV - 1) / K1V2_ADV), 1u);
+        TimedScope t(b, st, 1);
+        if (h.correct_dc) k1_v2<true><<<grid, V2_THREADS, V2_SMEM, st>>>(q);
+        else k1_v2<false><<<grid, V2_THREADS, V2_SMEM, st>>>(q);
     }
     (*nl)++;
     for (const SubGroup &g : b->groups) {
-        K2aParams kp;
-        kp.subs = (const SubDev *)b->subdev.p + g.first;
+        K2V2Params kp;
+        kp.vfos = (const CascVfo *)b->cascdev.p + g.first;
+        kp.rf = (const float2 *)b->rfdev.p + (h.mains.size() + (size_t)g.first) * RF_LEN;
+        kp.in = (const float2 *)b->main_out.p + b->main_off[(size_t)g.main_idx];
         kp.blocks_done = (const long long *)b->blocks_done.p;
-        kp.n_blocks = c.n_blocks; kp.tiles = g.tiles; kp.stream0 = s0; kp.b0 = cb;
-        const dim3 grid((unsigned)ns, (unsigned)g.count, (unsigned)g.tiles);
+        kp.in_stride = (long long)b->main_stride; kp.out_stride = (long long)b->z_stride;
+        kp.count = g.count; kp.lut_len = g.lut_len; kp.block_in = g.block_in; kp.HT = g.halo; kp.stream0 = s0; kp.b0 = cb;
         TimedScope t(b, st, 2);
-        switch (g.decim) {
-        case 0: k2a_mix_only<<<grid, 256, 0, st>>>(kp); break;
-        case 1: k2a_sub_cascade<1><<<grid, K2A_THREADS, K2A_SMEM, st>>>(kp); break;
-        case 2: k2a_sub_cascade<2><<<grid, K2A_THREADS, K2A_SMEM, st>>>(kp); break;
-        case 3: k2a_sub_cascade<3><<<grid, K2A_THREADS, K2A_SMEM, st>>>(kp); break;
-        case 4: k2a_sub_cascade<4><<<grid, K2A_THREADS, K2A_SMEM, st>>>(kp); break;
-        default: k2a_sub_cascade<5><<<grid, K2A_THREADS, K2A_SMEM, st>>>(kp); break;
-        }
+        k2a_v2<<<dim3((unsigned)ns, (unsigned)g.tiles, 1u), V2_THREADS, V2_SMEM, st>>>(kp);
         (*nl)++;
     }
     if (b->n_late) {

@@ -1,0 +1,438 @@
+// Second-generation channelizer kernels (sm_100a): k1_v2 (ingest + main VFOs) and k2a_v2 (all sub
+// VFOs of one main VFO per CTA). Both are the same machine:
+//
+//   * a thread owns 32 consecutive input samples (+ the 11 in front of them) IN REGISTERS and keeps
+//     them there while it loops over every VFO fed by that input (2-3 main VFOs in k1_v2, the 12-15
+//     sub VFOs of a main in k2a_v2): the input is read from HBM/L2 once, not once per VFO;
+//   * the NCO is not read sample by sample. Past its start-up transient the Oscillator table
+//     (oscillator.cpp:9-28) advances by the constant float rotation `rot` per entry, so inside a
+//     thread's chunk  lut[k0 + j] = lut[k0] * Rf[j]  with Rf[j] = (rot/|rot|)^j  to 2e-7 rms / 1e-6
+//     worst case (tools/rf_error.py; the parity budget is 1e-4). The thread mixes with the 42
+//     constants Rf[-10..31] (shared memory broadcast), runs the first half-band stage entirely on its
+//     own registers -- no neighbour exchange -- and multiplies the 16 outputs by the one table entry
+//     F = lut[k0] it loads. Table traffic drops from 8 B per mixed sample to 8 B per 32;
+//   * chunks that touch the first 512 table entries, the table wrap, stream sample 0
+//     (oscillator.cpp:26-30,42-48) or the first sample of a callback take the exact path: every
+//     rotation comes from the table itself;
+//   * later half-band stages exchange only the 10 trailing samples per thread through padded,
+//     conflict-free shared memory (one 16-byte load per pair); the thread's own samples never
+//     leave registers;
+//   * the FIRQueueBackToFront off-by-one (dsp.cpp:163-173) is one rule: a window slot at a
+//     negative callback coordinate c holds sample c-1.
+#pragma once
+#include "kernels.cuh"
+
+namespace sdrb {
+
+constexpr int V2_THREADS = 128;
+constexpr int V2_CHUNK = 32;
+constexpr int V2_MINB = 3;
+constexpr int RF_LEN = 48;             // per VFO: Rf[j], j = -10..31 at index j + 10; padded to 48
+constexpr int LUT_STEADY = 512;        // table entries needed by the start-up transient (94 measured)
+constexpr int K1V2_HT = 4;             // halo threads of k1_v2: one DC block, covers 3 half-band stages
+constexpr int K1V2_ADV = (V2_THREADS - K1V2_HT) * V2_CHUNK;
+
+struct CascVfo {
+    const float2 *lut;          // Oscillator table of this VFO
+    float2 *out;                // [n_streams][out_stride]: hist + n_blocks*block_out
+    int S;                      // half-band stages
+    int block_out, hist, pad;
+};
+
+// scratch layout of the array a stage reads: N samples per thread, STR float2 apart, PADT
+// never-written thread slots in front (read only by halo threads whose results are dropped)
+template <int N> struct StLay;
+template <> struct StLay<16> { static constexpr int STR = 18, PADT = 1; };
+template <> struct StLay<8> { static constexpr int STR = 10, PADT = 2; };
+template <> struct StLay<4> { static constexpr int STR = 6, PADT = 3; };
+template <> struct StLay<2> { static constexpr int STR = 2, PADT = 6; };
+template <int N> constexpr int st_elems() { return (V2_THREADS + StLay<N>::PADT) * StLay<N>::STR; }
+
+constexpr int V2_SA = 0;
+constexpr int V2_SB = V2_SA + st_elems<16>();
+constexpr int V2_SC = V2_SB + st_elems<8>();
+constexpr int V2_SD = V2_SC + st_elems<4>();
+constexpr int V2_SRF = V2_SD + st_elems<2>();
+constexpr int V2_MAX_VFO = 16;                                  // VFOs per CTA (Rf tables in smem)
+constexpr size_t V2_SMEM = (size_t)(V2_SRF + V2_MAX_VFO * RF_LEN) * sizeof(float2) + 16;
+
+template <int N>
+__device__ __forceinline__ int st_pos(int c_rel) {              // CTA-relative sample, may be negative
+    return ((c_rel >> Log2<N>::v) + StLay<N>::PADT) * StLay<N>::STR + (c_rel & (N - 1));
+}
+
+template <int N>
+__device__ __forceinline__ void st_publish(const float2 (&v)[N], float2 *__restrict__ s, int t) {
+    float4 *p = reinterpret_cast<float4 *>(s + (t + StLay<N>::PADT) * StLay<N>::STR);
+#pragma unroll
+    for (int k = 0; k < N / 2; ++k) p[k] = make_float4(v[2 * k].x, v[2 * k].y, v[2 * k + 1].x, v[2 * k + 1].y);
+}
+
+// hbcoeff11 on a window (halfbanddecimator.h:66-79, dsp.cpp:139-142), both arms packed:
+// 3 FADD2 + 1 FMUL2 + 3 FFMA2 per complex output
+__device__ __forceinline__ float2 hb11(float2 w0, float2 w2, float2 w4, float2 w5, float2 w6, float2 w8, float2 w10) {
+    return fma2(splat2(HB_P5), w5,
+                fma2(splat2(HB_P4), add2(w4, w6), fma2(splat2(HB_P2), add2(w2, w8), mul2(splat2(HB_P0), add2(w0, w10)))));
+}
+
+// One half-band stage: the thread owns N samples (first one at callback coordinate vs of this
+// stage) and needs the 10 samples in front of them from its left neighbours. OWN = the thread's own
+// samples are still in registers (`in`); otherwise they are read back from the scratch as well.
+template <int N, bool OWN>
+__device__ __forceinline__ void st_run(const float2 *in, float2 (&out)[N / 2], const float2 *__restrict__ s, int t, int vs) {
+    float2 w[10 + N];
+    if (vs >= 0 && vs < 10) {
+        // head of a callback: slots at negative coordinates hold the sample one further back
+#pragma unroll
+        for (int k = 0; k < 10; ++k) {
+            int c = vs - 10 + k;
+            c -= (c < 0) ? 1 : 0;
+            w[k] = s[st_pos<N>(t * N + (c - vs))];
+        }
+    } else {
+#pragma unroll
+        for (int q = 0; q < 5; ++q) {
+            const float4 v = *reinterpret_cast<const float4 *>(s + st_pos<N>(t * N - 10 + 2 * q));
+            w[2 * q] = make_float2(v.x, v.y);
+            w[2 * q + 1] = make_float2(v.z, v.w);
+        }
+    }
+    if constexpr (OWN) {
+#pragma unroll
+        for (int k = 0; k < N; ++k) w[10 + k] = in[k];
+    } else {
+        const float4 *own = reinterpret_cast<const float4 *>(s + (t + StLay<N>::PADT) * StLay<N>::STR);
+#pragma unroll
+        for (int q = 0; q < N / 2; ++q) {
+            const float4 v = own[q];
+            w[10 + 2 * q] = make_float2(v.x, v.y);
+            w[11 + 2 * q] = make_float2(v.z, v.w);
+        }
+    }
+#pragma unroll
+    for (int r = 0; r < N / 2; ++r)
+        out[r] = hb11(w[2 * r], w[2 * r + 2], w[2 * r + 4], w[2 * r + 5], w[2 * r + 6], w[2 * r + 8], w[2 * r + 10]);
+}
+
+template <int N>
+__device__ __forceinline__ void st_store(const float2 (&v)[N], float2 *__restrict__ dst) {
+    if constexpr (N == 1) {
+        dst[0] = v[0];
+    } else {
+        float4 *o4 = reinterpret_cast<float4 *>(dst);
+#pragma unroll
+        for (int k = 0; k < N / 2; ++k) o4[k] = make_float4(v[2 * k].x, v[2 * k].y, v[2 * k + 1].x, v[2 * k + 1].y);
+    }
+}
+
+// Exact first stage for the few chunks the rotating-frame shortcut does not cover (table start-up
+// transient and wrap, stream sample 0, first chunk of a callback): every rotation is read from
+// the Oscillator table. Deliberately not inlined and not unrolled: it runs for ~1 % of the chunks
+// and must not cost the common path registers.
+__device__ __noinline__ void stage1_exact(const float2 *xc, const float2 *__restrict__ lut, int k0, int L, long long n_abs,
+                                          int head, float4 *pa) {
+    float2 u[41];
+#pragma unroll 1
+    for (int i = 0; i < 41; ++i) {
+        const int j = i - 10;
+        const int sh = (head && j < 0) ? 1 : 0;           // negative coordinate c holds sample c-1
+        int idx = k0 + j - sh;
+        if (idx < 0) idx += L;
+        if (idx >= L) idx -= L;
+        if (n_abs + j - sh == 0) idx = L - 1;             // stream sample 0 uses the last entry (oscillator.cpp:26-30)
+        u[i] = cmul(__ldg(lut + idx), xc[i + 2 - sh]);
+    }
+#pragma unroll 1
+    for (int k = 0; k < 8; ++k) {
+        const float2 *w = u + 4 * k;
+        const float2 a = hb11(w[0], w[2], w[4], w[5], w[6], w[8], w[10]);
+        const float2 c = hb11(w[2], w[4], w[6], w[7], w[8], w[10], w[12]);
+        pa[k] = make_float4(a.x, a.y, c.x, c.y);
+    }
+}
+
+// Everything after the input is in registers: for each VFO mix + S half-band stages + store.
+//   x[i]      input sample at callback coordinate v0 - 12 + i   (i = 0..43)
+//   n_abs     absolute stream index of sample v0 (negative: before the stream began)
+//   k0        n_abs mod L
+template <int MAXS>
+__device__ __forceinline__ void cascade_loop(const float2 (&x)[44], const CascVfo *__restrict__ vfos, int count,
+                                             float2 *__restrict__ sm, int t, int v0, long long n_abs, int k0, int L,
+                                             bool store, size_t out_off /* stream*out_stride */, int b) {
+    float2 *sA = sm + V2_SA, *sB = sm + V2_SB, *sC = sm + V2_SC, *sD = sm + V2_SD;
+    const float2 *sRf = sm + V2_SRF;
+    const bool head = (v0 == 0);
+    const bool fast = (k0 >= LUT_STEADY + 10) && (k0 + V2_CHUNK <= L) && !head;
+    float2 xc[44];                                        // addressable copy for the exact path only
+    if (!fast) {
+#pragma unroll
+        for (int i = 0; i < 44; ++i) xc[i] = x[i];
+    }
+    for (int v = 0; v < count; ++v) {
+        const CascVfo V = vfos[v];
+        float2 *outp = V.out + out_off + V.hist + (size_t)b * V.block_out;
+        if (V.S == 0) {                                   // mixer only (vfo.cpp:237-245 with decimateCount 0)
+            if (store) {
+#pragma unroll
+                for (int j = 0; j < V2_CHUNK; j += 2) {
+                    int i0 = k0 + j, i1 = k0 + j + 1;
+                    if (i0 >= L) i0 -= L;
+                    if (i1 >= L) i1 -= L;
+                    if (n_abs + j == 0) i0 = L - 1;       // oscillator.cpp:26-30
+                    const float2 a = cmul(__ldg(V.lut + i0), x[12 + j]), c = cmul(__ldg(V.lut + i1), x[13 + j]);
+                    *reinterpret_cast<float4 *>(outp + v0 + j) = make_float4(a.x, a.y, c.x, c.y);
+                }
+            }
+            continue;
+        }
+        __syncthreads();                                  // readers of the previous VFO are done with the scratch
+        // stage 1 straight into the scratch (two outputs per 16-byte store): nothing but the input stays in registers
+        float4 *pa = reinterpret_cast<float4 *>(sA + (t + StLay<16>::PADT) * StLay<16>::STR);
+        if (fast) {
+            const float2 F = __ldg(V.lut + k0);
+            const float4 *rf4 = reinterpret_cast<const float4 *>(sRf + v * RF_LEN);
+            float2 u[42];
+#pragma unroll
+            for (int q = 0; q < 21; ++q) {
+                const float4 r = rf4[q];
+                u[2 * q] = cmul(make_float2(r.x, r.y), x[2 * q + 2]);
+                u[2 * q + 1] = cmul(make_float2(r.z, r.w), x[2 * q + 3]);
+            }
+#pragma unroll
+            for (int k = 0; k < 8; ++k) {
+                const int r = 2 * k;
+                const float2 a = cmul(F, hb11(u[2 * r], u[2 * r + 2], u[2 * r + 4], u[2 * r + 5], u[2 * r + 6], u[2 * r + 8], u[2 * r + 10]));
+                const float2 c = cmul(F, hb11(u[2 * r + 2], u[2 * r + 4], u[2 * r + 6], u[2 * r + 7], u[2 * r + 8], u[2 * r + 10], u[2 * r + 12]));
+                pa[k] = make_float4(a.x, a.y, c.x, c.y);
+            }
+        } else {
+            stage1_exact(xc, V.lut, k0, L, n_abs, head ? 1 : 0, pa);
+        }
+        if (V.S == 1) {
+            if (store) {
+                float4 *o4 = reinterpret_cast<float4 *>(outp + (v0 >> 1));
+#pragma unroll
+                for (int k = 0; k < 8; ++k) o4[k] = pa[k];
+            }
+            continue;
+        }
+        __syncthreads();
+        float2 o2[8];
+        st_run<16, false>(nullptr, o2, sA, t, v0 >> 1);
+        if (V.S == 2) {
+            if (store) st_store<8>(o2, outp + (v0 >> 2));
+            continue;
+        }
+        st_publish<8>(o2, sB, t);
+        __syncthreads();
+        float2 o3[4];
+        st_run<8, true>(o2, o3, sB, t, v0 >> 2);
+        if (MAXS == 3 || V.S == 3) {
+            if (store) st_store<4>(o3, outp + (v0 >> 3));
+            continue;
+        }
+        if constexpr (MAXS > 3) {
+            st_publish<4>(o3, sC, t);
+            __syncthreads();
+            float2 o4[2];
+            st_run<4, true>(o3, o4, sC, t, v0 >> 3);
+            if (V.S == 4) {
+                if (store) st_store<2>(o4, outp + (v0 >> 4));
+                continue;
+            }
+            st_publish<2>(o4, sD, t);
+            __syncthreads();
+            float2 o5[1];
+            st_run<2, true>(o4, o5, sD, t, v0 >> 4);
+            if (store) st_store<1>(o5, outp + (v0 >> 5));
+        }
+    }
+}
+
+// ------------------------------------------------------------------------------------
+// k2a_v2: all sub VFOs (of one group: same parent main VFO, at most V2_MAX_VFO) for one
+// (stream, tile, callback). The parent's output chunk is loaded once per thread.
+// ------------------------------------------------------------------------------------
+struct K2V2Params {
+    const CascVfo *vfos;            // device array, this group's sub VFOs
+    const float2 *rf;               // [count][RF_LEN]
+    const float2 *in;               // parent main output (MAIN_HIST history in front of each stream)
+    const long long *blocks_done;
+    long long in_stride, out_stride;
+    int count, lut_len, block_in, HT, stream0, b0;
+};
+
+__global__ void __launch_bounds__(V2_THREADS, V2_MINB) k2a_v2(const K2V2Params p) {
+    extern __shared__ __align__(16) unsigned char smem_raw[];
+    float2 *sm = reinterpret_cast<float2 *>(smem_raw);
+    int *sBase = reinterpret_cast<int *>(sm + V2_SRF + V2_MAX_VFO * RF_LEN);
+
+    const int stream = p.stream0 + blockIdx.x;
+    const int tile = blockIdx.y, b = p.b0 + blockIdx.z;
+    const int t = threadIdx.x;
+    const int B = p.block_in, L = p.lut_len;
+    const int v0 = tile * ((V2_THREADS - p.HT) * V2_CHUNK) - p.HT * V2_CHUNK + t * V2_CHUNK;
+    const long long blk = p.blocks_done[stream] + b;
+    if (t == 0) sBase[0] = (int)((blk * (long long)B) % L);
+    {
+        const float4 *src = reinterpret_cast<const float4 *>(p.rf);
+        float4 *dst = reinterpret_cast<float4 *>(sm + V2_SRF);
+        for (int e = t; e < p.count * (RF_LEN / 2); e += V2_THREADS) dst[e] = __ldg(src + e);
+    }
+    const bool in_block = v0 < B;
+    float2 x[44];
+    if (in_block) {
+        // history in front of the first callback of a call is the previous call's tail (zeros after a reset)
+        const float4 *xp = reinterpret_cast<const float4 *>(p.in + (size_t)stream * p.in_stride + MAIN_HIST + (size_t)b * B + (v0 - 12));
+#pragma unroll
+        for (int q = 0; q < 22; ++q) {
+            const float4 v = __ldg(xp + q);
+            x[2 * q] = make_float2(v.x, v.y);
+            x[2 * q + 1] = make_float2(v.z, v.w);
+        }
+    } else {
+#pragma unroll
+        for (int i = 0; i < 44; ++i) x[i] = make_float2(0.f, 0.f);
+    }
+    __syncthreads();
+    int k0 = sBase[0] + v0;
+    if (k0 < 0) k0 += L;
+    if (k0 >= L) k0 -= L;
+    cascade_loop<5>(x, p.vfos, p.count, sm, t, v0, blk * (long long)B + v0, k0, L, in_block && t >= p.HT,
+                    (size_t)stream * p.out_stride, b);
+}
+
+// ------------------------------------------------------------------------------------
+// k1_v2: uint8 IQ -> float (sdr.cpp:43-49) -> DC removal (sdrj.cpp:277-283) -> every main VFO.
+// Tile = 252 chunks of 32 samples = 63 DC blocks; 4 halo threads (one DC block) in front.
+//
+// DC: the block-start states come bit-exact from the walk kernel (k0_dc_walk). Inside a 128-sample
+// block the recursion is continued in real arithmetic: state before the thread's chunk =
+// s_blk*(1 - p*c) + c*sum(x[0..p)) (integer prefix sums over the 4 threads of the block; the
+// neglected terms are below 2e-8), then avept += c*(x - avept) sample by sample, forwards over
+// the chunk and backwards over the 11 samples in front of it. What is lost is only the float
+// rounding noise of 128 steps (~1e-7), not the state's lock-in, which lives in the block-start states.
+// ------------------------------------------------------------------------------------
+struct K1V2Params {
+    const uint8_t *iq;
+    size_t iq_stride;
+    const uint8_t *tail;            // [n_streams][2*RAW_TAIL]
+    const uint2 *dc_table;
+    const DcAnchor *dc_anchor;
+    const long long *blocks_done;
+    const float2 *rf;               // [n_main][RF_LEN]
+    long long out_stride;
+    int dc_stride, block, lut_len, n_main, stream0, b0;
+    CascVfo mains[SDRB_MAX_MAIN];
+};
+
+__device__ __forceinline__ float dc_decode(uint2 e, const DcAnchor &A) {
+    return e.y < 2u ? A.sgn * __uint_as_float(e.x + A.lo + 1u) : __uint_as_float(e.x);
+}
+
+template <bool DC>
+__global__ void __launch_bounds__(V2_THREADS, V2_MINB) k1_v2(const __grid_constant__ K1V2Params p) {
+    extern __shared__ __align__(16) unsigned char smem_raw[];
+    float2 *sm = reinterpret_cast<float2 *>(smem_raw);
+    int *sBase = reinterpret_cast<int *>(sm + V2_SRF + V2_MAX_VFO * RF_LEN);
+
+    const int stream = p.stream0 + blockIdx.x;
+    const int tile = blockIdx.y, b = p.b0 + blockIdx.z;
+    const int t = threadIdx.x;
+    const int B = p.block, L = p.lut_len;
+    const int v0 = tile * K1V2_ADV - K1V2_HT * V2_CHUNK + t * V2_CHUNK;
+    const long long blk = p.blocks_done[stream] + b;
+    if (t == 0) sBase[0] = (int)((blk * (long long)B) % L);
+    {
+        const float4 *src = reinterpret_cast<const float4 *>(p.rf);
+        float4 *dst = reinterpret_cast<float4 *>(sm + V2_SRF);
+        for (int e = t; e < p.n_main * (RF_LEN / 2); e += V2_THREADS) dst[e] = __ldg(src + e);
+    }
+    const bool in_block = v0 < B;
+    const bool first_ever = (blk == 0);
+
+    // raw bytes of samples v0-16 .. v0+31: six 16-byte pieces of 8 samples
+    uint4 raw[6];
+#pragma unroll
+    for (int q = 0; q < 6; ++q) {
+        const int c = v0 - 16 + 8 * q;
+        raw[q] = make_uint4(0x7f7f7f7fu, 0x7f7f7f7fu, 0x7f7f7f7fu, 0x7f7f7f7fu);   // 127 -> 0.0
+        if (in_block && !(first_ever && c < 0)) {
+            const uint8_t *src = (b == 0 && c < 0) ? p.tail + (size_t)stream * (2 * RAW_TAIL) + 2 * (RAW_TAIL + c)
+                                                   : p.iq + (size_t)stream * p.iq_stride + ((size_t)b * B + c) * 2;
+            raw[q] = __ldg(reinterpret_cast<const uint4 *>(src));
+        }
+    }
+    float2 x[44];                   // x[i] = sample v0 - 12 + i
+    {
+        float2 y[8];
+        unpack8(raw[0], y);
+#pragma unroll
+        for (int k = 4; k < 8; ++k) x[k - 4] = y[k];
+#pragma unroll
+        for (int q = 1; q < 6; ++q) {
+            unpack8(raw[q], y);
+#pragma unroll
+            for (int k = 0; k < 8; ++k) x[8 * q - 4 + k] = y[k];
+        }
+    }
+    if (DC) {
+        // integer sums of the chunk's 32 samples per arm (bytes; I in even, Q in odd positions)
+        unsigned sI = 0u, sQ = 0u;
+#pragma unroll
+        for (int q = 2; q < 6; ++q) {
+            sI = __dp4a(raw[q].x, 0x00010001u, sI); sQ = __dp4a(raw[q].x, 0x01000100u, sQ);
+            sI = __dp4a(raw[q].y, 0x00010001u, sI); sQ = __dp4a(raw[q].y, 0x01000100u, sQ);
+            sI = __dp4a(raw[q].z, 0x00010001u, sI); sQ = __dp4a(raw[q].z, 0x01000100u, sQ);
+            sI = __dp4a(raw[q].w, 0x00010001u, sI); sQ = __dp4a(raw[q].w, 0x01000100u, sQ);
+        }
+        const int tot = (int)(sI | (sQ << 16));                 // 32*255 < 65536; prefix of 3 chunks < 65536 too
+        const int g = t & 3;                             // position of the chunk inside its DC block
+        int inc = tot;
+        int up = __shfl_up_sync(0xffffffffu, inc, 1, 4);
+        if (g >= 1) inc += up;
+        up = __shfl_up_sync(0xffffffffu, inc, 2, 4);
+        if (g >= 2) inc += up;
+        const int excl = inc - tot;
+        const int pcount = 32 * g;
+        const float PI_ = (float)((excl & 0xffff) - 127 * pcount), PQ_ = (float)((int)((unsigned)excl >> 16) - 127 * pcount);
+        const int dblk = (b * B + v0 + RAW_TAIL) / DC_BLK;           // table index incl. the carried entries
+        const uint2 *te = p.dc_table + ((size_t)stream * p.dc_stride + dblk) * 2;
+        const DcAnchor AI = p.dc_anchor[2 * stream], AQ = p.dc_anchor[2 * stream + 1];
+        float bI = 0.f, bQ = 0.f;
+        if (in_block && !(first_ever && v0 < 0)) {
+            bI = dc_decode(__ldg(te), AI);
+            bQ = dc_decode(__ldg(te + 1), AQ);
+        }
+        const float decay = 1.0f - DC_C * (float)pcount;
+        // negated state after sample v0-1
+        const float2 ns0 = make_float2(-(bI * decay + DC_C * PI_), -(bQ * decay + DC_C * PQ_));
+        float2 ns = ns0;
+#pragma unroll
+        for (int i = 12; i < 44; ++i) {                  // forwards: d = x - s, s += c*d, out = x - s
+            const float2 d = add2(x[i], ns);
+            ns = fma2(splat2(-DC_C), d, ns);
+            x[i] = add2(x[i], ns);
+        }
+        ns = ns0;
+#pragma unroll
+        for (int i = 11; i >= 1; --i) {                  // backwards: out = x - s_j, s_{j-1} = s_j - c*out
+            x[i] = add2(x[i], ns);
+            ns = fma2(splat2(DC_C), x[i], ns);
+        }
+    }
+    if (first_ever && v0 <= 0) {                         // nothing exists before stream sample 0
+        const int lim = v0 < 0 ? 44 : 12;
+#pragma unroll
+        for (int i = 0; i < 44; ++i)
+            if (i < lim) x[i] = make_float2(0.f, 0.f);
+    }
+    __syncthreads();
+    int k0 = sBase[0] + v0;
+    if (k0 < 0) k0 += L;
+    if (k0 >= L) k0 -= L;
+    cascade_loop<3>(x, p.mains, p.n_main, sm, t, v0, blk * (long long)B + v0, k0, L, in_block && t >= K1V2_HT,
+                    (size_t)stream * (size_t)p.out_stride, b);
+}
+
+}  // namespace sdrb
