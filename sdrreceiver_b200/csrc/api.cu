@@ -439,6 +439,7 @@ extern "C" int sdrb_bank_create(const sdrb_plan *plan, int device, int n_streams
     if (!usbdev.empty()) BANK_CU(cudaMemcpy(b->usbdev.p, usbdev.data(), sizeof(UsbDev) * usbdev.size(), cudaMemcpyHostToDevice));
     BANK_CU(cudaMemcpy(b->carry.p, carry.data(), sizeof(CarryItem) * carry.size(), cudaMemcpyHostToDevice));
 
+    BANK_CU(cudaFuncSetAttribute(k0_dc_walk, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)DCW_SMEM));
     BANK_CU(cudaFuncSetAttribute(k2a_v2, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)V2_SMEM));
     BANK_CU(cudaFuncSetAttribute(k1_v2<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)V2_SMEM));
     BANK_CU(cudaFuncSetAttribute(k1_v2<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)V2_SMEM));
@@ -530,7 +531,7 @@ static int enqueue_dc_cb(sdrb_bank *b, const CallCtx &c, int s0, int ns, cudaStr
     }
     {
         TimedScope t(b, sd, 0);
-        k0_dc_walk<<<(unsigned)ns, 64, 0, sd>>>(c.d_iq, c.iq_stride, (const DcStats *)b->dc_stats.p, b->dc_stride,
+        k0_dc_walk<<<(unsigned)ns, 64, DCW_SMEM, sd>>>(c.d_iq, c.iq_stride, (const DcStats *)b->dc_stats.p, b->dc_stride,
                                                 (const DcAnchor *)b->dc_anchor.p, (float2 *)b->dc_state.p,
                                                 (uint2 *)b->dc_table.p, b->dc_stride + DC_HALO_BLKS, cb * per_cb, per_cb, s0);
     }

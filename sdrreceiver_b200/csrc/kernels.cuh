@@ -159,6 +159,20 @@ __device__ __forceinline__ float u8_to_f(uint32_t w) {
     return __uint_as_float(__byte_perm(w, 0x4B000000u, 0x7540 | K)) - 8388735.0f;
 }
 
+// same, both arms of a sample in one FADD2: bytes 2k (I) and 2k+1 (Q) of w
+template <int K>
+__device__ __forceinline__ float2 u8_to_f2(uint32_t w) {
+    const float2 b = make_float2(__uint_as_float(__byte_perm(w, 0x4B000000u, 0x7540 | (2 * K))),
+                                 __uint_as_float(__byte_perm(w, 0x4B000000u, 0x7540 | (2 * K + 1))));
+    return add2(b, make_float2(-8388735.0f, -8388735.0f));
+}
+__device__ __forceinline__ void unpack8p(const uint4 raw, float2 (&x)[8]) {
+    x[0] = u8_to_f2<0>(raw.x); x[1] = u8_to_f2<1>(raw.x);
+    x[2] = u8_to_f2<0>(raw.y); x[3] = u8_to_f2<1>(raw.y);
+    x[4] = u8_to_f2<0>(raw.z); x[5] = u8_to_f2<1>(raw.z);
+    x[6] = u8_to_f2<0>(raw.w); x[7] = u8_to_f2<1>(raw.w);
+}
+
 __device__ __forceinline__ void unpack8(const uint4 raw, float2 (&x)[8]) {
     x[0] = make_float2(u8_to_f<0>(raw.x), u8_to_f<1>(raw.x));
     x[1] = make_float2(u8_to_f<2>(raw.x), u8_to_f<3>(raw.x));
@@ -361,15 +375,28 @@ __global__ void __launch_bounds__(128) k0_dc_blocks(const uint8_t *__restrict__ 
 }
 
 // Sequential part: one CTA of two warps per stream, warp 0 walks the I arm, warp 1 the Q arm.
-// All 32 lanes of a warp keep a 3-deep cp.async ring of batches (8 blocks = 1024 samples:
-// statistics and raw bytes) flowing into shared memory and turn each landed batch into the
-// fl(c*x) products of its arm; lane 0 then walks the blocks. The loop-carried value is
-// V = bit pattern of |state| - (lo + 1): a translation block costs a compare and a select, a
-// stepped block DC_BLK dependent multiply-adds on the real float state.
-// Table entry per block and arm: {V, mode 0|1} for translations (below / at-or-above T),
-// {float bits of the state, 2} for stepped blocks.
-constexpr int DC_BATCH = 8;
-constexpr int DC_RING = 3;
+// The loop-carried value is V = bit pattern of |state| - (lo + 1), identical in all 32 lanes.
+//
+//  * 32 blocks at a time, one per lane: a warp prefix sum of the block totals D gives every lane
+//    the state its block would start from if all blocks before it were translations ("all below
+//    T" and "all at or above T" are both tried); each lane checks its own block's thresholds and
+//    a ballot finds the longest provable run. A run of 32 translations costs one scan, not 32
+//    dependent steps.
+//  * the block that ends a run is retried on its own; if its states really straddle T it is
+//    solved by the whole warp in the integer-ulp domain: 4 samples per lane, V_k = V + U_k - C_k
+//    with U the prefix sums of the increments and C_k = #{i < k : V_i >= T}, i.e.
+//    C_{i+1} = C_i + [C_i <= V + U_i - T]; the lanes iterate their four indicators against the
+//    ballot-counted indicators of the lanes before them until nothing changes (the sequential
+//    solution is the unique fixed point; 2-3 rounds in practice, at most 33).
+//  * blocks with a rounding tie, or states outside the anchor's window, fall back to 128 real
+//    float steps on lane 0.
+// Raw bytes are only needed for straddling blocks; they flow through a cp.async ring anyway so
+// that a straddling block never waits for HBM.
+// Table entry per block and arm: {V, 0|1} (translations / integer solve), {float bits, 2} (stepped).
+constexpr int DCW_BATCH = 32;
+constexpr int DCW_RING = 4;
+constexpr int DCW_SLOT16 = DCW_BATCH * (2 * DC_BLK / 16);                    // uint4 per ring slot
+constexpr size_t DCW_SMEM = (size_t)2 * DCW_RING * DCW_SLOT16 * 16 + 2 * DC_BLK * sizeof(float);
 
 __device__ __forceinline__ void cp_async16(void *smem, const void *gmem) {
     const unsigned sa = (unsigned)__cvta_generic_to_shared(smem);
@@ -383,113 +410,183 @@ __global__ void __launch_bounds__(64) k0_dc_walk(const uint8_t *__restrict__ iq,
                                                   const DcAnchor *__restrict__ anchors, float2 *__restrict__ dc_state,
                                                   uint2 *__restrict__ table, int table_stride, int blk0, int n_blk,
                                                   int stream0) {
-    __shared__ __align__(16) DcStats sst[2][DC_RING][DC_BATCH * 2];        // [warp][slot][block][arm]
-    __shared__ __align__(16) uint4 sraw[2][DC_RING][4][32];                // [warp][slot][piece][lane]
-    __shared__ float sq[2][32 * 33];                                       // [warp][lane * 33 + i]: fl(c*x)
+    extern __shared__ __align__(16) unsigned char dcw_smem[];
     const int stream = stream0 + blockIdx.x;
     const int arm = threadIdx.x >> 5, lane = threadIdx.x & 31;
-    const DcStats *sp = stats + ((size_t)stream * stats_stride + blk0) * 2;
-    const uint4 *rp = reinterpret_cast<const uint4 *>(iq + (size_t)stream * iq_stride) + (size_t)blk0 * (DC_BLK / 8);
+    uint4 *ring = reinterpret_cast<uint4 *>(dcw_smem) + (size_t)arm * DCW_RING * DCW_SLOT16;
+    float *sq = reinterpret_cast<float *>(dcw_smem + (size_t)2 * DCW_RING * DCW_SLOT16 * 16) + arm * DC_BLK;
+    const DcStats *sp = stats + ((size_t)stream * stats_stride + blk0) * 2 + arm;
+    const uint4 *rp = reinterpret_cast<const uint4 *>(iq + (size_t)stream * iq_stride) + (size_t)blk0 * (2 * DC_BLK / 16);
     uint2 *tab = table + ((size_t)stream * table_stride + DC_HALO_BLKS + blk0) * 2 + arm;
-    const int n_batch = (n_blk + DC_BATCH - 1) / DC_BATCH;
-    const int n_q = n_blk * 4;                                             // 32-sample quarters in this launch
+    const int n_batch = (n_blk + DCW_BATCH - 1) / DCW_BATCH;
+    const unsigned lt_mask = (1u << lane) - 1u;
 
     auto prefetch = [&](int batch) {
         if (batch < n_batch) {
-            const int slot = batch % DC_RING;
-            if (lane < DC_BATCH * 2) {                                     // statistics: 16 entries of 16 bytes
-                const int e = min(batch * DC_BATCH * 2 + lane, n_blk * 2 - 1);
-                cp_async16(&sst[arm][slot][lane], sp + e);
-            }
-            const int qtr = min(batch * 32 + lane, n_q - 1);               // tail: repeat the last quarter
-            const uint4 *r = rp + (size_t)qtr * 4;
+            uint4 *dst = ring + (size_t)(batch % DCW_RING) * DCW_SLOT16;
+            const uint4 *src = rp + (size_t)batch * DCW_SLOT16;
+            const int n_valid = min(DCW_BATCH, n_blk - batch * DCW_BATCH) * (2 * DC_BLK / 16);
 #pragma unroll
-            for (int v = 0; v < 4; ++v) cp_async16(&sraw[arm][slot][v][lane], r + v);
+            for (int i = 0; i < DCW_SLOT16 / 32; ++i) {
+                const int e = i * 32 + lane;
+                if (e < n_valid) cp_async16(dst + e, src + e);
+            }
         }
         cp_async_commit();
+    };
+    auto load_stats = [&](int batch) {
+        DcStats S; S.D = 0; S.ta = 0xFFFFFFFFu; S.tb = 0u; S.tb_hi = 0xFFFFFFFFu;          // neutral: passes both ways
+        const int j = batch * DCW_BATCH + lane;
+        if (j < n_blk) S = sp[(size_t)j * 2];
+        return S;
     };
 
     const DcAnchor A = anchors[2 * stream + arm];
     const unsigned lo1 = A.lo + 1u;
     const unsigned sign_bit = A.sgn < 0.f ? 0x80000000u : 0u;
-    unsigned V = 0xFFFFFFFFu;                                     // invalid: forces stepping
-    float s = 0.f;
-    if (lane == 0) {
+    const unsigned win = A.ok ? A.hi - lo1 : 0u;                    // V in [0, win): the integer model holds
+    const int Tv = (int)(A.T - lo1);
+    const float r0f = (float)A.r0;
+    unsigned V = 0xFFFFFFFFu;                                       // invalid: forces float stepping
+    float s;
+    {
         const float2 st0 = dc_state[stream];
         s = arm ? st0.y : st0.x;
         if (A.ok && s * A.sgn > 0.f) V = __float_as_uint(fabsf(s)) - lo1;
     }
     prefetch(0);
     prefetch(1);
+    prefetch(2);
+    DcStats Snext = load_stats(0);
     for (int batch = 0; batch < n_batch; ++batch) {
-        prefetch(batch + 2);
-        cp_async_wait<2>();                                       // this batch has landed
+        cp_async_wait<3>();                                         // the slot about to be refilled has landed (and been consumed)
         __syncwarp();
-        const int slot = batch % DC_RING;
-        // every lane: fl(c*x) of its 32-sample quarter for this arm (row stride 33: conflict free)
+        prefetch(batch + 3);
+        const DcStats S = Snext;
+        if (batch + 1 < n_batch) Snext = load_stats(batch + 1);
+        const int nb = min(DCW_BATCH, n_blk - batch * DCW_BATCH);
+        const uint4 *slot = ring + (size_t)(batch % DCW_RING) * DCW_SLOT16;
+        uint2 *to = tab + (size_t)batch * DCW_BATCH * 2;
+        bool raw_ready = false;
+        int j0 = 0;
+        while (j0 < nb) {
+            int n = j0;                                             // block to be handled on its own
+            if (V < win) {
+                // ---- speculative run of translations from block j0 ----
+                const unsigned d = lane >= j0 ? (unsigned)S.D : 0u;
+                unsigned inc = d;
 #pragma unroll
-        for (int v = 0; v < 4; ++v) {
-            float2 x[8];
-            unpack8(sraw[arm][slot][v][lane], x);
+                for (int o = 1; o < 32; o <<= 1) {
+                    const unsigned v = __shfl_up_sync(0xffffffffu, inc, o);
+                    if (lane >= o) inc += v;
+                }
+                const unsigned V0 = V + (inc - d);
+                const unsigned V1 = V0 - (unsigned)DC_BLK * (unsigned)(lane - j0);
+                const bool ok0 = lane < j0 || V0 < S.ta;
+                const bool ok1 = lane < j0 || (V1 >= S.tb && V1 < S.tb_hi);
+                const unsigned m0 = __ballot_sync(0xffffffffu, ok0), m1 = __ballot_sync(0xffffffffu, ok1);
+                const int n0 = m0 == 0xFFFFFFFFu ? 32 : __ffs(~m0) - 1;
+                const int n1 = m1 == 0xFFFFFFFFu ? 32 : __ffs(~m1) - 1;
+                const bool up = n1 > n0;
+                n = up ? n1 : n0;
+                const unsigned Vsel = up ? V1 : V0;
+                if (lane >= j0 && lane < n && lane < nb) to[(size_t)lane * 2] = make_uint2(Vsel, up ? 1u : 0u);
+                if (n >= nb) {                                      // every remaining block translated
+                    const unsigned E = Vsel + (unsigned)S.D - (up ? (unsigned)DC_BLK : 0u);
+                    V = __shfl_sync(0xffffffffu, E, nb - 1);
+                    break;
+                }
+                V = __shfl_sync(0xffffffffu, Vsel, n);              // state at the start of block n
+            }
+            // ---- block n on its own ----
+            const int Dn = __shfl_sync(0xffffffffu, S.D, n);
+            const unsigned tan = __shfl_sync(0xffffffffu, S.ta, n), tbn = __shfl_sync(0xffffffffu, S.tb, n);
+            const unsigned tbhn = __shfl_sync(0xffffffffu, S.tb_hi, n);
+            const bool fa = V < win && V < tan, fb = V < win && V >= tbn && V < tbhn;
+            if (fa | fb) {
+                if (lane == 0) to[(size_t)n * 2] = make_uint2(V, fb ? 1u : 0u);
+                V = V + (unsigned)Dn - (fb ? (unsigned)DC_BLK : 0u);
+                j0 = n + 1;
+                continue;
+            }
+            if (!raw_ready) {
+                cp_async_wait<3>();                                 // this batch's bytes have landed
+                __syncwarp();
+                raw_ready = true;
+            }
+            // the lane's 4 samples of this arm
+            const uint2 rw = *reinterpret_cast<const uint2 *>(reinterpret_cast<const unsigned char *>(slot + (size_t)n * (2 * DC_BLK / 16)) + lane * 8);
+            const unsigned w0 = arm ? rw.x >> 8 : rw.x, w1 = arm ? rw.y >> 8 : rw.y;
+            const float x0 = u8_to_f<0>(w0), x1 = u8_to_f<2>(w0), x2 = u8_to_f<0>(w1), x3 = u8_to_f<2>(w1);
+            bool solved = false;
+            if (V < win) {
+                bool t0, t1, t2, t3;
+                const int d0 = (int)(dc_incr(A, x0, t0) - r0f), d1 = (int)(dc_incr(A, x1, t1) - r0f);
+                const int d2 = (int)(dc_incr(A, x2, t2) - r0f), d3 = (int)(dc_incr(A, x3, t3) - r0f);
+                const int p1 = d0, p2 = p1 + d1, p3 = p2 + d2, tot = p3 + d3;
+                int inc = tot;
 #pragma unroll
-            for (int k = 0; k < 8; ++k) sq[arm][lane * 33 + 8 * v + k] = __fmul_rn(DC_C, arm ? x[k].y : x[k].x);
-        }
-        __syncwarp();
-        if (lane == 0) {
-            const int nb = min(DC_BATCH, n_blk - batch * DC_BATCH);
-            uint2 *to = tab + (size_t)batch * DC_BATCH * 2;
-            // One block, careful version: decide, then translate or step through DC_BLK float updates.
-            auto walk_one = [&](int j) {
-                const DcStats S = sst[arm][slot][j * 2 + arm];
-                const bool fa = V < S.ta;
-                const bool fb = (V >= S.tb) & (V < S.tb_hi);
-                if (fa | fb) {
-                    to[(size_t)j * 2] = make_uint2(V, fb ? 1u : 0u);
-                    V = V + (unsigned)S.D - (fb ? (unsigned)DC_BLK : 0u);
-                } else {
-                    if (V != 0xFFFFFFFFu) s = __uint_as_float((V + lo1) | sign_bit);
-                    to[(size_t)j * 2] = make_uint2(__float_as_uint(s), 2u);
+                for (int o = 1; o < 32; o <<= 1) {
+                    const int v = __shfl_up_sync(0xffffffffu, inc, o);
+                    if (lane >= o) inc += v;
+                }
+                const int base = (int)V + (inc - tot);              // V + U at the lane's first sample
+                const int W0 = base - Tv, W1 = W0 + p1, W2 = W0 + p2, W3 = W0 + p3;
+                int cin = 0, c0 = 0, c1 = 0, c2 = 0, c3 = 0;
+                unsigned b0 = 0, b1 = 0, b2 = 0, b3 = 0;
+                for (int it = 0; it < 34; ++it) {
+                    c0 = cin;
+                    const int i0 = c0 <= W0; c1 = c0 + i0;
+                    const int i1 = c1 <= W1; c2 = c1 + i1;
+                    const int i2 = c2 <= W2; c3 = c2 + i2;
+                    const int i3 = c3 <= W3;
+                    b0 = __ballot_sync(0xffffffffu, i0); b1 = __ballot_sync(0xffffffffu, i1);
+                    b2 = __ballot_sync(0xffffffffu, i2); b3 = __ballot_sync(0xffffffffu, i3);
+                    const int nc = __popc(b0 & lt_mask) + __popc(b1 & lt_mask) + __popc(b2 & lt_mask) + __popc(b3 & lt_mask);
+                    const bool changed = nc != cin;
+                    cin = nc;
+                    if (!__any_sync(0xffffffffu, changed)) break;
+                }
+                // every state of the block must stay inside the window (the low side has a one-block
+                // margin built into the anchor) and no increment may be a rounding tie
+                const int hiw = (int)win;
+                const bool inside = (base - c0 < hiw) && (base + p1 - c1 < hiw) && (base + p2 - c2 < hiw) && (base + p3 - c3 < hiw);
+                const bool fine = inside && !(t0 | t1 | t2 | t3);
+                const int total = __shfl_sync(0xffffffffu, inc, 31);
+                const int ctot = __popc(b0) + __popc(b1) + __popc(b2) + __popc(b3);
+                const int vend = (int)V + total - ctot;
+                if (__all_sync(0xffffffffu, fine) && vend >= 0 && vend < hiw) {
+                    if (lane == 0) to[(size_t)n * 2] = make_uint2(V, 0u);
+                    V = (unsigned)vend;
+                    solved = true;
+                }
+            }
+            if (!solved) {
+                // real float steps (sdrj.cpp:281) on lane 0; the other lanes only provide fl(c*x)
+                if (V != 0xFFFFFFFFu) s = __uint_as_float((V + lo1) | sign_bit);
+                __syncwarp();
+                *reinterpret_cast<float4 *>(sq + 4 * lane) = make_float4(__fmul_rn(DC_C, x0), __fmul_rn(DC_C, x1), __fmul_rn(DC_C, x2), __fmul_rn(DC_C, x3));
+                __syncwarp();
+                if (lane == 0) {
+                    to[(size_t)n * 2] = make_uint2(__float_as_uint(s), 2u);
 #pragma unroll 1
-                    for (int c = 0; c < 4; ++c) {
+                    for (int c = 0; c < DC_BLK / 32; ++c) {
                         float q[32];
 #pragma unroll
-                        for (int k = 0; k < 32; ++k) q[k] = sq[arm][(4 * j + c) * 33 + k];
+                        for (int k = 0; k < 8; ++k) {
+                            const float4 v = *reinterpret_cast<const float4 *>(sq + 32 * c + 4 * k);
+                            q[4 * k] = v.x; q[4 * k + 1] = v.y; q[4 * k + 2] = v.z; q[4 * k + 3] = v.w;
+                        }
 #pragma unroll
                         for (int k = 0; k < 32; ++k) s = __fadd_rn(__fmul_rn(s, DC_A), q[k]);
                     }
-                    V = (A.ok && s * A.sgn > 0.f) ? __float_as_uint(fabsf(s)) - lo1 : 0xFFFFFFFFu;
                 }
-            };
-            // Four blocks per trip, speculatively as four translations: the loop-carried chain is
-            // compare -> select per block; validity and the table stores hang off it. Only when
-            // one of the four is not a provable translation is the group redone block by block.
-            int j0 = 0;
-            for (; j0 + 4 <= nb; j0 += 4) {
-                DcStats S4[4];
-#pragma unroll
-                for (int i = 0; i < 4; ++i) S4[i] = sst[arm][slot][(j0 + i) * 2 + arm];
-                unsigned Vs[5], up[4], bad = 0u;
-                Vs[0] = V;
-#pragma unroll
-                for (int i = 0; i < 4; ++i) {
-                    up[i] = Vs[i] >= S4[i].tb ? 1u : 0u;
-                    const unsigned ok = (Vs[i] < S4[i].ta ? 1u : 0u) | (up[i] & (Vs[i] < S4[i].tb_hi ? 1u : 0u));
-                    bad |= ok ^ 1u;
-                    Vs[i + 1] = Vs[i] + (unsigned)S4[i].D - up[i] * (unsigned)DC_BLK;
-                }
-                if (bad == 0u) {
-#pragma unroll
-                    for (int i = 0; i < 4; ++i) to[(size_t)(j0 + i) * 2] = make_uint2(Vs[i], up[i]);
-                    V = Vs[4];
-                } else {
-#pragma unroll 1
-                    for (int i = 0; i < 4; ++i) walk_one(j0 + i);
-                }
+                s = __shfl_sync(0xffffffffu, s, 0);
+                V = (A.ok && s * A.sgn > 0.f) ? __float_as_uint(fabsf(s)) - lo1 : 0xFFFFFFFFu;
             }
-#pragma unroll 1
-            for (; j0 < nb; ++j0) walk_one(j0);
+            j0 = n + 1;
         }
-        __syncwarp();                                             // ring slot and sq may be refilled next iteration
+        __syncwarp();
     }
     __shared__ float s_end[2];
     if (lane == 0) {

@@ -54,7 +54,8 @@ constexpr int V2_SC = V2_SB + st_elems<8>();
 constexpr int V2_SD = V2_SC + st_elems<4>();
 constexpr int V2_SRF = V2_SD + st_elems<2>();
 constexpr int V2_MAX_VFO = 16;                                  // VFOs per CTA (Rf tables in smem)
-constexpr size_t V2_SMEM = (size_t)(V2_SRF + V2_MAX_VFO * RF_LEN) * sizeof(float2) + 16;
+constexpr int V2_SDESC = V2_SRF + V2_MAX_VFO * RF_LEN;         // CascVfo descriptors (4 float2 each), then 16 bytes of misc
+constexpr size_t V2_SMEM = (size_t)(V2_SDESC + V2_MAX_VFO * 4) * sizeof(float2) + 16;
 
 template <int N>
 __device__ __forceinline__ int st_pos(int c_rel) {              // CTA-relative sample, may be negative
@@ -131,22 +132,25 @@ __device__ __forceinline__ void st_store(const float2 (&v)[N], float2 *__restric
 // and must not cost the common path registers.
 __device__ __noinline__ void stage1_exact(const float2 *xc, const float2 *__restrict__ lut, int k0, int L, long long n_abs,
                                           int head, float4 *pa) {
-    float2 u[41];
-#pragma unroll 1
-    for (int i = 0; i < 41; ++i) {
+    float2 rot[41];
+#pragma unroll
+    for (int i = 0; i < 41; ++i) {                        // all table reads in flight together
         const int j = i - 10;
-        const int sh = (head && j < 0) ? 1 : 0;           // negative coordinate c holds sample c-1
+        const int sh = (j < 0) ? head : 0;                // negative coordinate c holds sample c-1
         int idx = k0 + j - sh;
         if (idx < 0) idx += L;
         if (idx >= L) idx -= L;
         if (n_abs + j - sh == 0) idx = L - 1;             // stream sample 0 uses the last entry (oscillator.cpp:26-30)
-        u[i] = cmul(__ldg(lut + idx), xc[i + 2 - sh]);
+        rot[i] = __ldg(lut + idx);
     }
-#pragma unroll 1
+    float2 u[41];
+#pragma unroll
+    for (int i = 0; i < 41; ++i) u[i] = cmul(rot[i], xc[i + 2 - (i < 10 ? head : 0)]);
+#pragma unroll
     for (int k = 0; k < 8; ++k) {
-        const float2 *w = u + 4 * k;
-        const float2 a = hb11(w[0], w[2], w[4], w[5], w[6], w[8], w[10]);
-        const float2 c = hb11(w[2], w[4], w[6], w[7], w[8], w[10], w[12]);
+        const int r = 2 * k;
+        const float2 a = hb11(u[2 * r], u[2 * r + 2], u[2 * r + 4], u[2 * r + 5], u[2 * r + 6], u[2 * r + 8], u[2 * r + 10]);
+        const float2 c = hb11(u[2 * r + 2], u[2 * r + 4], u[2 * r + 6], u[2 * r + 7], u[2 * r + 8], u[2 * r + 10], u[2 * r + 12]);
         pa[k] = make_float4(a.x, a.y, c.x, c.y);
     }
 }
@@ -168,8 +172,12 @@ __device__ __forceinline__ void cascade_loop(const float2 (&x)[44], const CascVf
 #pragma unroll
         for (int i = 0; i < 44; ++i) xc[i] = x[i];
     }
+    float2 Fnext = make_float2(1.f, 0.f);
+    if (fast) Fnext = __ldg(vfos[0].lut + k0);
     for (int v = 0; v < count; ++v) {
         const CascVfo V = vfos[v];
+        const float2 F = Fnext;
+        if (fast && v + 1 < count) Fnext = __ldg(vfos[v + 1].lut + k0);   // one VFO ahead: never waited for
         float2 *outp = V.out + out_off + V.hist + (size_t)b * V.block_out;
         if (V.S == 0) {                                   // mixer only (vfo.cpp:237-245 with decimateCount 0)
             if (store) {
@@ -189,7 +197,6 @@ __device__ __forceinline__ void cascade_loop(const float2 (&x)[44], const CascVf
         // stage 1 straight into the scratch (two outputs per 16-byte store): nothing but the input stays in registers
         float4 *pa = reinterpret_cast<float4 *>(sA + (t + StLay<16>::PADT) * StLay<16>::STR);
         if (fast) {
-            const float2 F = __ldg(V.lut + k0);
             const float4 *rf4 = reinterpret_cast<const float4 *>(sRf + v * RF_LEN);
             float2 u[42];
 #pragma unroll
@@ -265,7 +272,7 @@ struct K2V2Params {
 __global__ void __launch_bounds__(V2_THREADS, V2_MINB) k2a_v2(const K2V2Params p) {
     extern __shared__ __align__(16) unsigned char smem_raw[];
     float2 *sm = reinterpret_cast<float2 *>(smem_raw);
-    int *sBase = reinterpret_cast<int *>(sm + V2_SRF + V2_MAX_VFO * RF_LEN);
+    int *sBase = reinterpret_cast<int *>(sm + V2_SDESC + V2_MAX_VFO * 4);
 
     const int stream = p.stream0 + blockIdx.x;
     const int tile = blockIdx.y, b = p.b0 + blockIdx.z;
@@ -278,6 +285,10 @@ __global__ void __launch_bounds__(V2_THREADS, V2_MINB) k2a_v2(const K2V2Params p
         const float4 *src = reinterpret_cast<const float4 *>(p.rf);
         float4 *dst = reinterpret_cast<float4 *>(sm + V2_SRF);
         for (int e = t; e < p.count * (RF_LEN / 2); e += V2_THREADS) dst[e] = __ldg(src + e);
+        static_assert(sizeof(CascVfo) == 32, "descriptor copy assumes 32 bytes");
+        const float4 *dsrc = reinterpret_cast<const float4 *>(p.vfos);
+        float4 *ddst = reinterpret_cast<float4 *>(sm + V2_SDESC);
+        for (int e = t; e < p.count * 2; e += V2_THREADS) ddst[e] = __ldg(dsrc + e);
     }
     const bool in_block = v0 < B;
     float2 x[44];
@@ -298,7 +309,7 @@ __global__ void __launch_bounds__(V2_THREADS, V2_MINB) k2a_v2(const K2V2Params p
     int k0 = sBase[0] + v0;
     if (k0 < 0) k0 += L;
     if (k0 >= L) k0 -= L;
-    cascade_loop<5>(x, p.vfos, p.count, sm, t, v0, blk * (long long)B + v0, k0, L, in_block && t >= p.HT,
+    cascade_loop<5>(x, reinterpret_cast<const CascVfo *>(sm + V2_SDESC), p.count, sm, t, v0, blk * (long long)B + v0, k0, L, in_block && t >= p.HT,
                     (size_t)stream * p.out_stride, b);
 }
 
@@ -334,7 +345,7 @@ template <bool DC>
 __global__ void __launch_bounds__(V2_THREADS, V2_MINB) k1_v2(const __grid_constant__ K1V2Params p) {
     extern __shared__ __align__(16) unsigned char smem_raw[];
     float2 *sm = reinterpret_cast<float2 *>(smem_raw);
-    int *sBase = reinterpret_cast<int *>(sm + V2_SRF + V2_MAX_VFO * RF_LEN);
+    int *sBase = reinterpret_cast<int *>(sm + V2_SDESC + V2_MAX_VFO * 4);
 
     const int stream = p.stream0 + blockIdx.x;
     const int tile = blockIdx.y, b = p.b0 + blockIdx.z;
@@ -366,12 +377,12 @@ __global__ void __launch_bounds__(V2_THREADS, V2_MINB) k1_v2(const __grid_consta
     float2 x[44];                   // x[i] = sample v0 - 12 + i
     {
         float2 y[8];
-        unpack8(raw[0], y);
+        unpack8p(raw[0], y);
 #pragma unroll
         for (int k = 4; k < 8; ++k) x[k - 4] = y[k];
 #pragma unroll
         for (int q = 1; q < 6; ++q) {
-            unpack8(raw[q], y);
+            unpack8p(raw[q], y);
 #pragma unroll
             for (int k = 0; k < 8; ++k) x[8 * q - 4 + k] = y[k];
         }
