@@ -177,6 +177,8 @@ struct sdrb_bank {
     std::vector<SubGroup> groups;
     int n_late = 0, n_usb = 0, n_carry = 0;
     int max_usb_samples = 0, max_late_samples = 0;
+    int uv_np_max = 0, uv_eo_rows = 0, uv_warp_floats = 0, uv_tiles = 0;   // k2b_v2 launch geometry
+    size_t uv_smem = 0;
     std::vector<size_t> main_off;           // per main: offset (float2 units) inside main_out per stream
     size_t main_stride = 0;                 // float2 per stream
     size_t z_stride = 0;                    // float2 per stream in zbuf
@@ -267,7 +269,7 @@ extern "C" int sdrb_bank_create(const sdrb_plan *plan, int device, int n_streams
         hil_off.push_back(taps_host.size());
         taps_host.push_back(0.f); taps_host.push_back(0.f);
         for (int j = 0; j < 62; j++) taps_host.push_back(s.hilbert[(size_t)(2 * j + 1)]);
-        const int n = (int)s.lpf_taps.size(), np = (int)round_up((size_t)n, 4);
+        const int n = (int)s.lpf_taps.size(), np = (int)round_up((size_t)n, 16);   // k2b_v2 works in blocks of 16 taps
         if (np > MAX_FIR_TAPS || (int)s.dec_taps.size() > MAX_FIR_TAPS) {
             set_error("bank: filter longer than 512 taps"); sdrb_bank_destroy(b); return SDRB_E_INVALID;
         }
@@ -400,6 +402,8 @@ extern "C" int sdrb_bank_create(const sdrb_plan *plan, int device, int n_streams
         U.gain = s.gain;
         usbdev.push_back(U);
         b->max_usb_samples = std::max(b->max_usb_samples, s.samples_out);
+        b->uv_np_max = std::max(b->uv_np_max, U.np);
+        b->uv_tiles = std::max(b->uv_tiles, (s.samples_out + (UV_USB - U.np) - 1) / (UV_USB - U.np));
         CarryItem c; c.base = (float2 *)b->zbuf.p + z_off[i]; c.stride = (long long)(z_stride * sizeof(float2));
         c.hist_bytes = z_hist[i] * (int)sizeof(float2); c.block_bytes = s.block_z * (int)sizeof(float2);
         carry.push_back(c);
@@ -439,6 +443,10 @@ extern "C" int sdrb_bank_create(const sdrb_plan *plan, int device, int n_streams
     if (!usbdev.empty()) BANK_CU(cudaMemcpy(b->usbdev.p, usbdev.data(), sizeof(UsbDev) * usbdev.size(), cudaMemcpyHostToDevice));
     BANK_CU(cudaMemcpy(b->carry.p, carry.data(), sizeof(CarryItem) * carry.size(), cudaMemcpyHostToDevice));
 
+    b->uv_eo_rows = 34 + b->uv_np_max / 32;
+    b->uv_warp_floats = std::max(UV_IN_FLOATS, 2 * b->uv_eo_rows * UV_ROW);
+    b->uv_smem = sizeof(float) * (2 * (size_t)(64 + b->uv_np_max) + (size_t)UV_WARPS * b->uv_warp_floats);
+    BANK_CU(cudaFuncSetAttribute(k2b_v2, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)b->uv_smem));
     BANK_CU(cudaFuncSetAttribute(k0_dc_walk, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)DCW_SMEM));
     BANK_CU(cudaFuncSetAttribute(k2a_v2, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)V2_SMEM));
     BANK_CU(cudaFuncSetAttribute(k1_v2<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)V2_SMEM));
@@ -446,9 +454,13 @@ extern "C" int sdrb_bank_create(const sdrb_plan *plan, int device, int n_streams
     BANK_CU(cudaStreamCreateWithFlags(&b->s_copy_in, cudaStreamNonBlocking));
     BANK_CU(cudaStreamCreateWithFlags(&b->s_compute, cudaStreamNonBlocking));
     BANK_CU(cudaStreamCreateWithFlags(&b->s_copy_out, cudaStreamNonBlocking));
-    if (h.correct_dc)
+    if (h.correct_dc) {
+        // The DC walk is a long dependent chain on few warps: give its side streams the highest priority so its
+        // CTAs take the first registers/shared memory the filter kernels free instead of queueing behind their grids.
+        int prio_least = 0, prio_greatest = 0;
+        BANK_CU(cudaDeviceGetStreamPriorityRange(&prio_least, &prio_greatest));
         for (int k = 0; k < sdrb_bank::kSide; k++) {
-            BANK_CU(cudaStreamCreateWithFlags(&b->s_dc[k], cudaStreamNonBlocking));
+            BANK_CU(cudaStreamCreateWithPriority(&b->s_dc[k], cudaStreamNonBlocking, prio_greatest));
             BANK_CU(cudaEventCreateWithFlags(&b->ev_entry[k], cudaEventDisableTiming));
             for (int j = 0; j < max_blocks; j++) {
                 cudaEvent_t e;
@@ -456,6 +468,7 @@ extern "C" int sdrb_bank_create(const sdrb_plan *plan, int device, int n_streams
                 b->ev_dc[k].push_back(e);
             }
         }
+    }
 #undef BANK_TRY
 #undef BANK_CU
     rc = sdrb_bank_reset(b, -1);
@@ -582,10 +595,14 @@ static int enqueue_main_cb(sdrb_bank *b, const CallCtx &c, int s0, int ns, cudaS
         (*nl)++;
     }
     if (b->n_usb) {
-        const int tiles = (b->max_usb_samples + USB_TILE - 1) / USB_TILE;
+        K2bV2Params up;
+        up.devs = (const UsbDev *)b->usbdev.p; up.pcm = c.d_pcm; up.tap = c.d_tap;
+        up.n_blocks = c.n_blocks; up.cb0 = cb; up.ncb = 1; up.stream0 = s0; up.stream_end = s0 + ns;
+        up.pcm_per_block = h.pcm_per_block; up.warp_floats = b->uv_warp_floats; up.eo_rows = b->uv_eo_rows;
+        up.np_max = b->uv_np_max;
         TimedScope t(b, st, 4);
-        k2b_usb_audio<<<dim3((unsigned)ns, (unsigned)b->n_usb, (unsigned)tiles), 256, 0, st>>>(
-            (const UsbDev *)b->usbdev.p, c.n_blocks, cb, 1, s0, h.pcm_per_block, c.d_pcm, c.d_tap);
+        k2b_v2<<<dim3((unsigned)((ns + UV_WARPS - 1) / UV_WARPS), (unsigned)b->n_usb, (unsigned)b->uv_tiles), UV_WARPS * 32,
+                 b->uv_smem, st>>>(up);
         (*nl)++;
     }
     if (out_done) CU_TRY(cudaEventRecord(out_done, st));

@@ -447,3 +447,202 @@ __global__ void __launch_bounds__(V2_THREADS, V2_MINB) k1_v2(const __grid_consta
 }
 
 }  // namespace sdrb
+
+namespace sdrb {
+
+// ------------------------------------------------------------------------------------
+// k2b_v2: USB demodulation + optional low-pass + gain + int16, one WARP per tile, no CTA barrier.
+//   usb[n] = re[n-62] - sum_{i odd} points[i]*im[n-124+i]      (vfo.cpp:316-324, dsp.cpp:218-231)
+//   out[n] = sum_{t<N} lpf[t]*usb[n-N+t]                        (dsp.cpp:59-71: newest sample excluded)
+//   pcm    = (short)(out*gain*32768.0)                          (vfo.cpp:328)
+// A tile is 1024 usb values (1024 - NP outputs; the first NP are the low-pass history). A lane owns
+// 32 consecutive values = 16 packed pairs and keeps 16 FP32x2 accumulators:
+//   * Hilbert: only odd taps are non-zero, so usb[2w] and usb[2w+1] use the same 62 coefficients on
+//     im[2w-123+2m] and im[2w-122+2m]: the pair (im[2v+1], im[2v+2]) IS the packed operand -- one
+//     FFMA2 per tap and output pair, operands straight out of 16-byte shared loads;
+//   * low-pass: the pair (out[k], out[k+1]) needs (usb[k+t], usb[k+t+1]): even t from the natural
+//     pairs E, odd t from a copy O shifted by one sample;
+//   * shared arrays are rows of 32 floats + 4 pad: a lane's row starts 36 words after its
+//     neighbour's, so every 16-byte access of a warp is conflict free; E/O overlay the input rows.
+// Work per 16 taps: 16 LDS.128 + 256 FFMA2 per lane.
+// ------------------------------------------------------------------------------------
+constexpr int UV_USB = 1024;                 // usb values per tile
+constexpr int UV_ROW = 36;                   // floats per padded row
+constexpr int UV_WARPS = 4;                  // warps (= streams) per CTA
+constexpr int UV_RE_ROWS = 32, UV_IM_ROWS = 36;
+constexpr int UV_IN_FLOATS = (UV_RE_ROWS + UV_IM_ROWS) * UV_ROW;
+
+struct K2bV2Params {
+    const UsbDev *devs;
+    int16_t *pcm;
+    float *tap;
+    int n_blocks, cb0, ncb, stream0, stream_end, pcm_per_block;
+    int warp_floats;                        // shared floats per warp: max(input rows, 2 * E/O rows)
+    int eo_rows;                            // rows of each of E and O
+    int np_max;                             // longest (padded) low-pass of the plan
+};
+
+__device__ __forceinline__ constexpr int uv_off(int x) { return (x >> 4) * UV_ROW + (x & 15) * 2; }   // pair index -> float offset
+
+// acc[r] += sum_{s<STEPS} coef[s*CSTR] * W[X0 + r + s],  r = 0..15; W = packed pairs of the lane's rows
+template <int STEPS, int CSTR, int X0>
+__device__ __forceinline__ void uv_fir_block(float2 (&acc)[16], const float *__restrict__ row, const float2 *__restrict__ coef2) {
+    constexpr int NCH = (16 + STEPS) / 2;                    // 16-byte chunks = 2 pairs each (one pair more than needed)
+    float2 W[2 * NCH];
+#pragma unroll
+    for (int c = 0; c < NCH; ++c) {
+        const float4 v = *reinterpret_cast<const float4 *>(row + uv_off(X0 + 2 * c));
+        W[2 * c] = make_float2(v.x, v.y);
+        W[2 * c + 1] = make_float2(v.z, v.w);
+    }
+#pragma unroll
+    for (int s = 0; s < STEPS; ++s) {
+        const float2 c2 = coef2[s * CSTR];
+#pragma unroll
+        for (int r = 0; r < 16; ++r) acc[r] = fma2(c2, W[r + s], acc[r]);
+    }
+}
+
+__global__ void __launch_bounds__(UV_WARPS * 32, 4) k2b_v2(const K2bV2Params p) {
+    extern __shared__ __align__(16) float uv_smem[];
+    const UsbDev &D = p.devs[blockIdx.y];
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    const int NP = D.np;                                    // multiple of 16 (leading zeros)
+    const int tile_out = UV_USB - NP;
+    const int n_lo = p.cb0 * D.samples_out, n_total = (p.cb0 + p.ncb) * D.samples_out;
+    const int n0 = n_lo + blockIdx.z * tile_out;
+    if (n0 >= n_total) return;
+    // coefficient pairs (h, h), shared by the CTA's warps
+    float2 *sHil2 = reinterpret_cast<float2 *>(uv_smem);
+    float2 *sLpf2 = sHil2 + 64;
+    float *wbase = uv_smem + 2 * (64 + p.np_max) + (size_t)warp * p.warp_floats;
+    for (int e = threadIdx.x; e < 64; e += UV_WARPS * 32) { const float h = D.hil[e]; sHil2[e] = make_float2(h, h); }
+    for (int e = threadIdx.x; e < NP; e += UV_WARPS * 32) { const float c = D.lpf[e]; sLpf2[e] = make_float2(c, c); }
+    __syncthreads();                                        // the only CTA-wide barrier
+    const int stream = p.stream0 + blockIdx.x * UV_WARPS + warp;
+    if (stream >= p.stream_end) return;
+
+    // ---- input rows: re (z-local 66..1089) and im (z-local 1..1152) ----
+    float *sRe = wbase, *sIm = wbase + UV_RE_ROWS * UV_ROW;
+    const long long zlo = (long long)n0 - NP - 128;
+    const float2 *zp = D.src + (size_t)stream * D.src_stride + D.src_hist;
+    {
+        // all 37 loads of the lane in flight before the first store: one HBM/L2 latency per tile, not nine
+        constexpr int NIT = (UV_USB + 128 + 1 + 31) / 32;
+        float2 v[NIT];
+#pragma unroll
+        for (int it = 0; it < NIT; ++it) {
+            const int q = it * 32 + lane;
+            const long long zi = zlo + q;
+            v[it] = make_float2(0.f, 0.f);
+            if (q <= UV_USB + 128 && zi < n_total) v[it] = __ldg(zp + zi);
+        }
+#pragma unroll
+        for (int it = 0; it < NIT; ++it) {
+            const int q = it * 32 + lane;
+            const int u = q - 66, k = q - 1;
+            if (u >= 0 && u < UV_USB) sRe[(u >> 5) * UV_ROW + (u & 31)] = v[it].x;
+            if (k >= 0 && k < UV_USB + 128) sIm[(k >> 5) * UV_ROW + (k & 31)] = v[it].y;
+        }
+    }
+    __syncwarp();
+
+    // ---- Hilbert: pair (usb[32 lane + 2r], usb[.. + 2r + 1]) = re - sum_j hil[j] * P[16 lane + r + j] ----
+    float2 acc[16];
+#pragma unroll
+    for (int r = 0; r < 16; ++r) acc[r] = make_float2(0.f, 0.f);
+    const float *imrow = sIm + lane * UV_ROW;
+    uv_fir_block<16, 1, 0>(acc, imrow, sHil2);
+    uv_fir_block<16, 1, 16>(acc, imrow, sHil2 + 16);
+    uv_fir_block<16, 1, 32>(acc, imrow, sHil2 + 32);
+    uv_fir_block<16, 1, 48>(acc, imrow, sHil2 + 48);
+    {
+        const float4 *re4 = reinterpret_cast<const float4 *>(sRe + lane * UV_ROW);
+#pragma unroll
+        for (int c = 0; c < 8; ++c) {
+            const float4 v = re4[c];
+            acc[2 * c] = make_float2(v.x - acc[2 * c].x, v.y - acc[2 * c].y);
+            acc[2 * c + 1] = make_float2(v.z - acc[2 * c + 1].x, v.w - acc[2 * c + 1].y);
+        }
+    }
+    if (NP > 0) {
+        // ---- E/O rows over the (now dead) input rows, then the low-pass ----
+        const float nxt = __shfl_down_sync(0xffffffffu, acc[0].x, 1);   // first usb value of the next lane
+        __syncwarp();
+        float *sE = wbase, *sO = wbase + p.eo_rows * UV_ROW;
+        float4 *e4 = reinterpret_cast<float4 *>(sE + lane * UV_ROW), *o4 = reinterpret_cast<float4 *>(sO + lane * UV_ROW);
+#pragma unroll
+        for (int c = 0; c < 8; ++c) {
+            e4[c] = make_float4(acc[2 * c].x, acc[2 * c].y, acc[2 * c + 1].x, acc[2 * c + 1].y);
+            const float last = c < 7 ? acc[c < 7 ? 2 * c + 2 : 0].x : nxt;
+            o4[c] = make_float4(acc[2 * c].y, acc[2 * c + 1].x, acc[2 * c + 1].y, last);
+        }
+        __syncwarp();
+#pragma unroll
+        for (int r = 0; r < 16; ++r) acc[r] = make_float2(0.f, 0.f);
+        const float *erow = sE + lane * UV_ROW, *orow = sO + lane * UV_ROW;
+        const int nb16 = NP >> 4;                             // blocks of 16 taps = 8 pair steps on E and on O
+        int b = 0;
+        for (; b + 2 <= nb16; b += 2) {
+            const float *er = erow + (b >> 1) * UV_ROW, *orr = orow + (b >> 1) * UV_ROW;
+            const float2 *cf = sLpf2 + 16 * b;
+            uv_fir_block<8, 2, 0>(acc, er, cf);
+            uv_fir_block<8, 2, 0>(acc, orr, cf + 1);
+            uv_fir_block<8, 2, 8>(acc, er, cf + 16);
+            uv_fir_block<8, 2, 8>(acc, orr, cf + 17);
+        }
+        if (b < nb16) {
+            const float *er = erow + (b >> 1) * UV_ROW, *orr = orow + (b >> 1) * UV_ROW;
+            const float2 *cf = sLpf2 + 16 * b;
+            uv_fir_block<8, 2, 0>(acc, er, cf);
+            uv_fir_block<8, 2, 0>(acc, orr, cf + 1);
+        }
+    }
+    // ---- gain, quantise, store: 32 consecutive outputs per lane ----
+    const int k0 = 32 * lane;
+    if (k0 >= tile_out) return;
+    const int n = n0 + k0;
+    if (n >= n_total) return;
+    const int blk = n / D.samples_out, i = n - blk * D.samples_out;
+    const size_t at = ((size_t)stream * p.n_blocks + blk) * p.pcm_per_block + D.pcm_offset + i;
+    const float g = D.gain;
+    const bool whole = (k0 + 32 <= tile_out) && (i + 32 <= D.samples_out) && ((at & 7) == 0);
+    if (whole) {
+        uint4 *dst = reinterpret_cast<uint4 *>(p.pcm + at);
+#pragma unroll
+        for (int c = 0; c < 4; ++c) {
+            unsigned w[4];
+#pragma unroll
+            for (int h = 0; h < 4; ++h) {
+                const float2 v = acc[4 * c + h];
+                const int lo = __float2int_rz((v.x * g) * 32768.0f), hi = __float2int_rz((v.y * g) * 32768.0f);
+                w[h] = ((unsigned)lo & 0xffffu) | ((unsigned)hi << 16);
+            }
+            dst[c] = make_uint4(w[0], w[1], w[2], w[3]);
+        }
+        if (p.tap) {
+            float4 *t4 = reinterpret_cast<float4 *>(p.tap + at);
+#pragma unroll
+            for (int c = 0; c < 8; ++c)
+                t4[c] = make_float4((acc[2 * c].x * g) * 32768.0f, (acc[2 * c].y * g) * 32768.0f,
+                                    (acc[2 * c + 1].x * g) * 32768.0f, (acc[2 * c + 1].y * g) * 32768.0f);
+        }
+    } else {
+#pragma unroll
+        for (int r = 0; r < 16; ++r) {
+#pragma unroll
+            for (int h = 0; h < 2; ++h) {
+                const int kk = k0 + 2 * r + h, nn = n0 + kk;
+                if (kk < tile_out && nn < n_total) {
+                    const int bl = nn / D.samples_out, ii = nn - bl * D.samples_out;
+                    const size_t a2 = ((size_t)stream * p.n_blocks + bl) * p.pcm_per_block + D.pcm_offset + ii;
+                    const float v = ((h ? acc[r].y : acc[r].x) * g) * 32768.0f;
+                    p.pcm[a2] = (int16_t)__float2int_rz(v);
+                    if (p.tap) p.tap[a2] = v;
+                }
+            }
+        }
+    }
+}
+
+}  // namespace sdrb
