@@ -173,6 +173,7 @@ struct sdrb_bank {
     // descriptors
     K1Params k1{};          // cf32-input variant (vfo::process entry)
     K1V2Params k1v2{};
+    std::vector<K2V2Params> k2v2;                 // one prebuilt parameter block per sub-VFO group
     DevBuf cascdev, rfdev, latedev, usbdev, carry;
     std::vector<SubGroup> groups;
     int n_late = 0, n_usb = 0, n_carry = 0;
@@ -428,16 +429,29 @@ extern "C" int sdrb_bank_create(const sdrb_plan *plan, int device, int n_streams
         q.dc_table = (const uint2 *)b->dc_table.p;
         q.dc_anchor = (const DcAnchor *)b->dc_anchor.p;
         q.blocks_done = (const long long *)b->blocks_done.p;
-        q.rf = (const float2 *)b->rfdev.p;
+        for (size_t i = 0; i < h.mains.size(); i++) memcpy(q.rf[i].q, &rfhost[i * RF_LEN], sizeof(RfTab));
         q.out_stride = (long long)b->main_stride;
         q.dc_stride = b->dc_stride + DC_HALO_BLKS; q.block = h.block; q.lut_len = (int)h.mains[0].lut.size();
         q.n_main = (int)h.mains.size();
         for (size_t i = 0; i < h.mains.size(); i++) {
-            CascVfo &M = q.mains[i];
+            CascVfo &M = q.vfos[i];
             M.lut = (const float2 *)b->luts.p + main_lut_off[i];
             M.out = (float2 *)b->main_out.p + b->main_off[i];
             M.S = h.mains[i].decim; M.block_out = h.mains[i].block_out; M.hist = MAIN_HIST; M.pad = 0;
         }
+    }
+    b->k2v2.assign(b->groups.size(), K2V2Params{});
+    for (size_t gi = 0; gi < b->groups.size(); gi++) {
+        const SubGroup &g = b->groups[gi];
+        K2V2Params &kp = b->k2v2[gi];
+        for (int v = 0; v < g.count; v++) {
+            kp.vfos[v] = cascdev[(size_t)(g.first + v)];
+            memcpy(kp.rf[v].q, &rfhost[(h.mains.size() + (size_t)(g.first + v)) * RF_LEN], sizeof(RfTab));
+        }
+        kp.in = (const float2 *)b->main_out.p + b->main_off[(size_t)g.main_idx];
+        kp.blocks_done = (const long long *)b->blocks_done.p;
+        kp.in_stride = (long long)b->main_stride; kp.out_stride = (long long)b->z_stride;
+        kp.count = g.count; kp.lut_len = g.lut_len; kp.block_in = g.block_in; kp.HT = g.halo;
     }
     if (!latedev.empty()) BANK_CU(cudaMemcpy(b->latedev.p, latedev.data(), sizeof(LateDev) * latedev.size(), cudaMemcpyHostToDevice));
     if (!usbdev.empty()) BANK_CU(cudaMemcpy(b->usbdev.p, usbdev.data(), sizeof(UsbDev) * usbdev.size(), cudaMemcpyHostToDevice));
@@ -576,13 +590,8 @@ static int enqueue_main_cb(sdrb_bank *b, const CallCtx &c, int s0, int ns, cudaS
     }
     (*nl)++;
     for (const SubGroup &g : b->groups) {
-        K2V2Params kp;
-        kp.vfos = (const CascVfo *)b->cascdev.p + g.first;
-        kp.rf = (const float2 *)b->rfdev.p + (h.mains.size() + (size_t)g.first) * RF_LEN;
-        kp.in = (const float2 *)b->main_out.p + b->main_off[(size_t)g.main_idx];
-        kp.blocks_done = (const long long *)b->blocks_done.p;
-        kp.in_stride = (long long)b->main_stride; kp.out_stride = (long long)b->z_stride;
-        kp.count = g.count; kp.lut_len = g.lut_len; kp.block_in = g.block_in; kp.HT = g.halo; kp.stream0 = s0; kp.b0 = cb;
+        K2V2Params &kp = b->k2v2[(size_t)(&g - b->groups.data())];
+        kp.stream0 = s0; kp.b0 = cb;
         TimedScope t(b, st, 2);
         k2a_v2<<<dim3((unsigned)ns, (unsigned)g.tiles, 1u), V2_THREADS, V2_SMEM, st>>>(kp);
         (*nl)++;

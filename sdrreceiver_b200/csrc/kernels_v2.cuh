@@ -28,6 +28,7 @@ constexpr int V2_THREADS = 128;
 constexpr int V2_CHUNK = 32;
 constexpr int V2_MINB = 3;
 constexpr int RF_LEN = 48;             // per VFO: Rf[j], j = -10..31 at index j + 10; padded to 48
+constexpr int V2_MAX_VFO = 16;         // VFOs per launch (descriptors + Rf tables in the kernel parameters)
 constexpr int LUT_STEADY = 512;        // table entries needed by the start-up transient (94 measured)
 constexpr int K1V2_HT = 4;             // halo threads of k1_v2: one DC block, covers 3 half-band stages
 constexpr int K1V2_ADV = (V2_THREADS - K1V2_HT) * V2_CHUNK;
@@ -38,6 +39,11 @@ struct CascVfo {
     int S;                      // half-band stages
     int block_out, hist, pad;
 };
+// Rf[j], j = -10..31 at pair index (j + 10) / 2. The tables and the VFO descriptors travel in the
+// kernel parameters (constant bank): the VFO index is uniform across the CTA, so the rotation
+// operands come through the uniform/constant path and cost the shared-memory pipe nothing
+// (they were 21 broadcast LDS.128 per VFO and thread; ncu had k2a at 79 % L1/shared throughput).
+struct RfTab { float4 q[RF_LEN / 2]; };
 
 // scratch layout of the array a stage reads: N samples per thread, STR float2 apart, PADT
 // never-written thread slots in front (read only by halo threads whose results are dropped)
@@ -52,10 +58,8 @@ constexpr int V2_SA = 0;
 constexpr int V2_SB = V2_SA + st_elems<16>();
 constexpr int V2_SC = V2_SB + st_elems<8>();
 constexpr int V2_SD = V2_SC + st_elems<4>();
-constexpr int V2_SRF = V2_SD + st_elems<2>();
-constexpr int V2_MAX_VFO = 16;                                  // VFOs per CTA (Rf tables in smem)
-constexpr int V2_SDESC = V2_SRF + V2_MAX_VFO * RF_LEN;         // CascVfo descriptors (4 float2 each), then 16 bytes of misc
-constexpr size_t V2_SMEM = (size_t)(V2_SDESC + V2_MAX_VFO * 4) * sizeof(float2) + 16;
+constexpr int V2_SEND = V2_SD + st_elems<2>();                  // then 16 bytes of misc
+constexpr size_t V2_SMEM = (size_t)V2_SEND * sizeof(float2) + 16;
 
 template <int N>
 __device__ __forceinline__ int st_pos(int c_rel) {              // CTA-relative sample, may be negative
@@ -159,12 +163,12 @@ __device__ __noinline__ void stage1_exact(const float2 *xc, const float2 *__rest
 //   x[i]      input sample at callback coordinate v0 - 12 + i   (i = 0..43)
 //   n_abs     absolute stream index of sample v0 (negative: before the stream began)
 //   k0        n_abs mod L
-template <int MAXS>
-__device__ __forceinline__ void cascade_loop(const float2 (&x)[44], const CascVfo *__restrict__ vfos, int count,
+//   P         the kernel's parameter struct (__grid_constant__): P::vfos[], P::rf[]
+template <int MAXS, class P>
+__device__ __forceinline__ void cascade_loop(const float2 (&x)[44], const P &p, int count,
                                              float2 *__restrict__ sm, int t, int v0, long long n_abs, int k0, int L,
                                              bool store, size_t out_off /* stream*out_stride */, int b) {
     float2 *sA = sm + V2_SA, *sB = sm + V2_SB, *sC = sm + V2_SC, *sD = sm + V2_SD;
-    const float2 *sRf = sm + V2_SRF;
     const bool head = (v0 == 0);
     const bool fast = (k0 >= LUT_STEADY + 10) && (k0 + V2_CHUNK <= L) && !head;
     float2 xc[44];                                        // addressable copy for the exact path only
@@ -173,11 +177,11 @@ __device__ __forceinline__ void cascade_loop(const float2 (&x)[44], const CascVf
         for (int i = 0; i < 44; ++i) xc[i] = x[i];
     }
     float2 Fnext = make_float2(1.f, 0.f);
-    if (fast) Fnext = __ldg(vfos[0].lut + k0);
+    if (fast) Fnext = __ldg(p.vfos[0].lut + k0);
     for (int v = 0; v < count; ++v) {
-        const CascVfo V = vfos[v];
+        const CascVfo V = p.vfos[v];
         const float2 F = Fnext;
-        if (fast && v + 1 < count) Fnext = __ldg(vfos[v + 1].lut + k0);   // one VFO ahead: never waited for
+        if (fast && v + 1 < count) Fnext = __ldg(p.vfos[v + 1].lut + k0);   // one VFO ahead: never waited for
         float2 *outp = V.out + out_off + V.hist + (size_t)b * V.block_out;
         if (V.S == 0) {                                   // mixer only (vfo.cpp:237-245 with decimateCount 0)
             if (store) {
@@ -197,11 +201,10 @@ __device__ __forceinline__ void cascade_loop(const float2 (&x)[44], const CascVf
         // stage 1 straight into the scratch (two outputs per 16-byte store): nothing but the input stays in registers
         float4 *pa = reinterpret_cast<float4 *>(sA + (t + StLay<16>::PADT) * StLay<16>::STR);
         if (fast) {
-            const float4 *rf4 = reinterpret_cast<const float4 *>(sRf + v * RF_LEN);
             float2 u[42];
 #pragma unroll
             for (int q = 0; q < 21; ++q) {
-                const float4 r = rf4[q];
+                const float4 r = p.rf[v].q[q];
                 u[2 * q] = cmul(make_float2(r.x, r.y), x[2 * q + 2]);
                 u[2 * q + 1] = cmul(make_float2(r.z, r.w), x[2 * q + 3]);
             }
@@ -261,18 +264,18 @@ __device__ __forceinline__ void cascade_loop(const float2 (&x)[44], const CascVf
 // (stream, tile, callback). The parent's output chunk is loaded once per thread.
 // ------------------------------------------------------------------------------------
 struct K2V2Params {
-    const CascVfo *vfos;            // device array, this group's sub VFOs
-    const float2 *rf;               // [count][RF_LEN]
+    CascVfo vfos[V2_MAX_VFO];       // this group's sub VFOs
+    RfTab rf[V2_MAX_VFO];
     const float2 *in;               // parent main output (MAIN_HIST history in front of each stream)
     const long long *blocks_done;
     long long in_stride, out_stride;
     int count, lut_len, block_in, HT, stream0, b0;
 };
 
-__global__ void __launch_bounds__(V2_THREADS, V2_MINB) k2a_v2(const K2V2Params p) {
+__global__ void __launch_bounds__(V2_THREADS, V2_MINB) k2a_v2(const __grid_constant__ K2V2Params p) {
     extern __shared__ __align__(16) unsigned char smem_raw[];
     float2 *sm = reinterpret_cast<float2 *>(smem_raw);
-    int *sBase = reinterpret_cast<int *>(sm + V2_SDESC + V2_MAX_VFO * 4);
+    int *sBase = reinterpret_cast<int *>(sm + V2_SEND);
 
     const int stream = p.stream0 + blockIdx.x;
     const int tile = blockIdx.y, b = p.b0 + blockIdx.z;
@@ -281,15 +284,6 @@ __global__ void __launch_bounds__(V2_THREADS, V2_MINB) k2a_v2(const K2V2Params p
     const int v0 = tile * ((V2_THREADS - p.HT) * V2_CHUNK) - p.HT * V2_CHUNK + t * V2_CHUNK;
     const long long blk = p.blocks_done[stream] + b;
     if (t == 0) sBase[0] = (int)((blk * (long long)B) % L);
-    {
-        const float4 *src = reinterpret_cast<const float4 *>(p.rf);
-        float4 *dst = reinterpret_cast<float4 *>(sm + V2_SRF);
-        for (int e = t; e < p.count * (RF_LEN / 2); e += V2_THREADS) dst[e] = __ldg(src + e);
-        static_assert(sizeof(CascVfo) == 32, "descriptor copy assumes 32 bytes");
-        const float4 *dsrc = reinterpret_cast<const float4 *>(p.vfos);
-        float4 *ddst = reinterpret_cast<float4 *>(sm + V2_SDESC);
-        for (int e = t; e < p.count * 2; e += V2_THREADS) ddst[e] = __ldg(dsrc + e);
-    }
     const bool in_block = v0 < B;
     float2 x[44];
     if (in_block) {
@@ -309,7 +303,7 @@ __global__ void __launch_bounds__(V2_THREADS, V2_MINB) k2a_v2(const K2V2Params p
     int k0 = sBase[0] + v0;
     if (k0 < 0) k0 += L;
     if (k0 >= L) k0 -= L;
-    cascade_loop<5>(x, reinterpret_cast<const CascVfo *>(sm + V2_SDESC), p.count, sm, t, v0, blk * (long long)B + v0, k0, L, in_block && t >= p.HT,
+    cascade_loop<5>(x, p, p.count, sm, t, v0, blk * (long long)B + v0, k0, L, in_block && t >= p.HT,
                     (size_t)stream * p.out_stride, b);
 }
 
@@ -331,10 +325,10 @@ struct K1V2Params {
     const uint2 *dc_table;
     const DcAnchor *dc_anchor;
     const long long *blocks_done;
-    const float2 *rf;               // [n_main][RF_LEN]
     long long out_stride;
     int dc_stride, block, lut_len, n_main, stream0, b0;
-    CascVfo mains[SDRB_MAX_MAIN];
+    CascVfo vfos[SDRB_MAX_MAIN];    // the main VFOs
+    RfTab rf[SDRB_MAX_MAIN];
 };
 
 __device__ __forceinline__ float dc_decode(uint2 e, const DcAnchor &A) {
@@ -345,7 +339,7 @@ template <bool DC>
 __global__ void __launch_bounds__(V2_THREADS, V2_MINB) k1_v2(const __grid_constant__ K1V2Params p) {
     extern __shared__ __align__(16) unsigned char smem_raw[];
     float2 *sm = reinterpret_cast<float2 *>(smem_raw);
-    int *sBase = reinterpret_cast<int *>(sm + V2_SDESC + V2_MAX_VFO * 4);
+    int *sBase = reinterpret_cast<int *>(sm + V2_SEND);
 
     const int stream = p.stream0 + blockIdx.x;
     const int tile = blockIdx.y, b = p.b0 + blockIdx.z;
@@ -354,11 +348,6 @@ __global__ void __launch_bounds__(V2_THREADS, V2_MINB) k1_v2(const __grid_consta
     const int v0 = tile * K1V2_ADV - K1V2_HT * V2_CHUNK + t * V2_CHUNK;
     const long long blk = p.blocks_done[stream] + b;
     if (t == 0) sBase[0] = (int)((blk * (long long)B) % L);
-    {
-        const float4 *src = reinterpret_cast<const float4 *>(p.rf);
-        float4 *dst = reinterpret_cast<float4 *>(sm + V2_SRF);
-        for (int e = t; e < p.n_main * (RF_LEN / 2); e += V2_THREADS) dst[e] = __ldg(src + e);
-    }
     const bool in_block = v0 < B;
     const bool first_ever = (blk == 0);
 
@@ -442,7 +431,7 @@ __global__ void __launch_bounds__(V2_THREADS, V2_MINB) k1_v2(const __grid_consta
     int k0 = sBase[0] + v0;
     if (k0 < 0) k0 += L;
     if (k0 >= L) k0 -= L;
-    cascade_loop<3>(x, p.mains, p.n_main, sm, t, v0, blk * (long long)B + v0, k0, L, in_block && t >= K1V2_HT,
+    cascade_loop<3>(x, p, p.n_main, sm, t, v0, blk * (long long)B + v0, k0, L, in_block && t >= K1V2_HT,
                     (size_t)stream * (size_t)p.out_stride, b);
 }
 
@@ -484,14 +473,19 @@ struct K2bV2Params {
 
 __device__ __forceinline__ constexpr int uv_off(int x) { return (x >> 4) * UV_ROW + (x & 15) * 2; }   // pair index -> float offset
 
-// acc[r] += sum_{s<STEPS} coef[s*CSTR] * W[X0 + r + s],  r = 0..15; W = packed pairs of the lane's rows
-template <int STEPS, int CSTR, int X0>
-__device__ __forceinline__ void uv_fir_block(float2 (&acc)[16], const float *__restrict__ row, const float2 *__restrict__ coef2) {
+// acc[r] += sum_{s<STEPS} coef[s*CSTR] * W[p0 + r + s],  r = 0..15; W = packed pairs of the lane's rows.
+// p0 (even) is a run-time value: the callers loop over tap blocks WITHOUT unrolling, so the hot code
+// of the kernel is two bodies of 256 FFMA2 (~10 KB). The fully unrolled version was 103 KB of SASS and
+// the warps of a CTA, which run independently here, stalled on instruction fetch ("no instruction"
+// 2.9 stalls per issue in ncu) -- see profiles/r01_k2b_icache.md.
+template <int STEPS, int CSTR>
+__device__ __forceinline__ void uv_fir_block(float2 (&acc)[16], const float *__restrict__ row, int p0, const float2 *__restrict__ coef2) {
     constexpr int NCH = (16 + STEPS) / 2;                    // 16-byte chunks = 2 pairs each (one pair more than needed)
     float2 W[2 * NCH];
 #pragma unroll
     for (int c = 0; c < NCH; ++c) {
-        const float4 v = *reinterpret_cast<const float4 *>(row + uv_off(X0 + 2 * c));
+        const int p = p0 + 2 * c;                            // pair p lives at float 2p + 4*(p/16) of the padded rows
+        const float4 v = *reinterpret_cast<const float4 *>(row + 2 * p + 4 * (p >> 4));
         W[2 * c] = make_float2(v.x, v.y);
         W[2 * c + 1] = make_float2(v.z, v.w);
     }
@@ -500,6 +494,23 @@ __device__ __forceinline__ void uv_fir_block(float2 (&acc)[16], const float *__r
         const float2 c2 = coef2[s * CSTR];
 #pragma unroll
         for (int r = 0; r < 16; ++r) acc[r] = fma2(c2, W[r + s], acc[r]);
+    }
+}
+
+// Ragged end of a tile / callback / call (not taken for the sample plans, whose sizes are multiples
+// of 8): element-wise stores. Out of line and rolled so that it costs the hot path nothing.
+__device__ __noinline__ void uv_store_ragged(const float *v, int k0, int tile_out, int n0, int n_total, int samples_out, int stream,
+                                             int n_blocks, int pcm_per_block, int pcm_offset, int16_t *pcm, float *tap) {
+    int nn = n0 + k0;
+    int bl = nn / samples_out, ii = nn - bl * samples_out;
+#pragma unroll 1
+    for (int e = 0; e < 32; ++e, ++nn) {
+        if (k0 + e < tile_out && nn < n_total) {
+            const size_t a2 = ((size_t)stream * n_blocks + bl) * pcm_per_block + pcm_offset + ii;
+            pcm[a2] = (int16_t)__float2int_rz(v[e]);
+            if (tap) tap[a2] = v[e];
+        }
+        if (++ii == samples_out) { ii = 0; ++bl; }
     }
 }
 
@@ -552,10 +563,8 @@ __global__ void __launch_bounds__(UV_WARPS * 32, 4) k2b_v2(const K2bV2Params p) 
 #pragma unroll
     for (int r = 0; r < 16; ++r) acc[r] = make_float2(0.f, 0.f);
     const float *imrow = sIm + lane * UV_ROW;
-    uv_fir_block<16, 1, 0>(acc, imrow, sHil2);
-    uv_fir_block<16, 1, 16>(acc, imrow, sHil2 + 16);
-    uv_fir_block<16, 1, 32>(acc, imrow, sHil2 + 32);
-    uv_fir_block<16, 1, 48>(acc, imrow, sHil2 + 48);
+#pragma unroll 1
+    for (int s = 0; s < 4; ++s) uv_fir_block<16, 1>(acc, imrow, 16 * s, sHil2 + 16 * s);
     {
         const float4 *re4 = reinterpret_cast<const float4 *>(sRe + lane * UV_ROW);
 #pragma unroll
@@ -582,20 +591,11 @@ __global__ void __launch_bounds__(UV_WARPS * 32, 4) k2b_v2(const K2bV2Params p) 
         for (int r = 0; r < 16; ++r) acc[r] = make_float2(0.f, 0.f);
         const float *erow = sE + lane * UV_ROW, *orow = sO + lane * UV_ROW;
         const int nb16 = NP >> 4;                             // blocks of 16 taps = 8 pair steps on E and on O
-        int b = 0;
-        for (; b + 2 <= nb16; b += 2) {
-            const float *er = erow + (b >> 1) * UV_ROW, *orr = orow + (b >> 1) * UV_ROW;
+#pragma unroll 1
+        for (int b = 0; b < nb16; ++b) {
             const float2 *cf = sLpf2 + 16 * b;
-            uv_fir_block<8, 2, 0>(acc, er, cf);
-            uv_fir_block<8, 2, 0>(acc, orr, cf + 1);
-            uv_fir_block<8, 2, 8>(acc, er, cf + 16);
-            uv_fir_block<8, 2, 8>(acc, orr, cf + 17);
-        }
-        if (b < nb16) {
-            const float *er = erow + (b >> 1) * UV_ROW, *orr = orow + (b >> 1) * UV_ROW;
-            const float2 *cf = sLpf2 + 16 * b;
-            uv_fir_block<8, 2, 0>(acc, er, cf);
-            uv_fir_block<8, 2, 0>(acc, orr, cf + 1);
+            uv_fir_block<8, 2>(acc, erow, 8 * b, cf);
+            uv_fir_block<8, 2>(acc, orow, 8 * b, cf + 1);
         }
     }
     // ---- gain, quantise, store: 32 consecutive outputs per lane ----
@@ -606,11 +606,12 @@ __global__ void __launch_bounds__(UV_WARPS * 32, 4) k2b_v2(const K2bV2Params p) 
     const int blk = n / D.samples_out, i = n - blk * D.samples_out;
     const size_t at = ((size_t)stream * p.n_blocks + blk) * p.pcm_per_block + D.pcm_offset + i;
     const float g = D.gain;
-    const bool whole = (k0 + 32 <= tile_out) && (i + 32 <= D.samples_out) && ((at & 7) == 0);
-    if (whole) {
+    const int nv = min(32, min(tile_out - k0, n_total - n));      // outputs this lane owns
+    if ((nv & 7) == 0 && (i + nv <= D.samples_out) && ((at & 7) == 0)) {   // whole 16-byte groups inside one callback record
         uint4 *dst = reinterpret_cast<uint4 *>(p.pcm + at);
 #pragma unroll
         for (int c = 0; c < 4; ++c) {
+            if (8 * c >= nv) break;
             unsigned w[4];
 #pragma unroll
             for (int h = 0; h < 4; ++h) {
@@ -624,24 +625,18 @@ __global__ void __launch_bounds__(UV_WARPS * 32, 4) k2b_v2(const K2bV2Params p) 
             float4 *t4 = reinterpret_cast<float4 *>(p.tap + at);
 #pragma unroll
             for (int c = 0; c < 8; ++c)
-                t4[c] = make_float4((acc[2 * c].x * g) * 32768.0f, (acc[2 * c].y * g) * 32768.0f,
-                                    (acc[2 * c + 1].x * g) * 32768.0f, (acc[2 * c + 1].y * g) * 32768.0f);
+                if (4 * c < nv)
+                    t4[c] = make_float4((acc[2 * c].x * g) * 32768.0f, (acc[2 * c].y * g) * 32768.0f,
+                                        (acc[2 * c + 1].x * g) * 32768.0f, (acc[2 * c + 1].y * g) * 32768.0f);
         }
     } else {
+        float v[32];
 #pragma unroll
         for (int r = 0; r < 16; ++r) {
-#pragma unroll
-            for (int h = 0; h < 2; ++h) {
-                const int kk = k0 + 2 * r + h, nn = n0 + kk;
-                if (kk < tile_out && nn < n_total) {
-                    const int bl = nn / D.samples_out, ii = nn - bl * D.samples_out;
-                    const size_t a2 = ((size_t)stream * p.n_blocks + bl) * p.pcm_per_block + D.pcm_offset + ii;
-                    const float v = ((h ? acc[r].y : acc[r].x) * g) * 32768.0f;
-                    p.pcm[a2] = (int16_t)__float2int_rz(v);
-                    if (p.tap) p.tap[a2] = v;
-                }
-            }
+            v[2 * r] = (acc[r].x * g) * 32768.0f;
+            v[2 * r + 1] = (acc[r].y * g) * 32768.0f;
         }
+        uv_store_ragged(v, k0, tile_out, n0, n_total, D.samples_out, stream, p.n_blocks, p.pcm_per_block, D.pcm_offset, p.pcm, p.tap);
     }
 }
 
