@@ -208,8 +208,15 @@ def b200_arm(args):
     bank = B.Bank(plan, S, NB, device=local_rank)
     stream = torch.cuda.Stream(device=dev)
 
+    # the input is resident before the timed region: tell the library so with an event (a streaming
+    # caller would record it after the copy that fills its next input buffer)
+    torch.cuda.synchronize()
+    in_ready = torch.cuda.Event()
+    in_ready.record(stream)
+    in_ready.synchronize()
+
     def step_device():
-        bank.process_device(d_iq.data_ptr(), row, NB, d_pcm.data_ptr(), None, stream.cuda_stream)
+        bank.process_device(d_iq.data_ptr(), row, NB, d_pcm.data_ptr(), None, stream.cuda_stream, in_ready.cuda_event)
 
     def step_host():
         bank.process_host(pin_in.ptr, row, NB, pin_out.ptr, None)

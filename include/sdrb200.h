@@ -130,6 +130,14 @@ int sdrb_bank_blocks_done(sdrb_bank *bank, int stream, int64_t *blocks);
  */
 int sdrb_bank_process_device(sdrb_bank *bank, const uint8_t *d_iq, size_t iq_stride, int n_blocks,
                              int16_t *d_pcm, float *d_tap, void *cuda_stream);
+/* Same call for a streaming caller that double-buffers its input: `input_ready_event` is a
+ * cudaEvent_t (NULL = behave like sdrb_bank_process_device) that fires when d_iq is valid. The
+ * DC-removal pre-pass (a sequential recursion, sdrj.cpp:277-283, run on an internal side stream)
+ * then waits only for that event, not for the work queued on `stream` before this call, and
+ * overlaps the filters of the previous call. Everything the caller observes (d_pcm, d_tap, state)
+ * is still ordered on `stream`. */
+int sdrb_bank_process_device_ex(sdrb_bank *bank, const uint8_t *d_iq, size_t iq_stride, int n_blocks,
+                                int16_t *d_pcm, float *d_tap, void *cuda_stream, void *input_ready_event);
 /* Copy out the main VFO outputs (vfo::decimate[decimateCount], vfo.h:39) of the last
  * process call: cf32 [n_streams][n_blocks*block_out] on the device. */
 int sdrb_bank_copy_main(sdrb_bank *bank, int main_idx, int n_blocks, float *d_out_cf32, void *cuda_stream);

@@ -81,6 +81,7 @@ def lib():
         "sdrb_bank_reset": (i, [vp, i]),
         "sdrb_bank_blocks_done": (i, [vp, i, P(C.c_int64)]),
         "sdrb_bank_process_device": (i, [vp, vp, sz, i, vp, vp, vp]),
+        "sdrb_bank_process_device_ex": (i, [vp, vp, sz, i, vp, vp, vp, vp]),
         "sdrb_bank_copy_main": (i, [vp, i, i, vp, vp]),
         "sdrb_bank_copy_dc_trace": (i, [vp, i, vp, vp, vp]),
         "sdrb_bank_process_host": (i, [vp, vp, sz, i, vp, vp]),
@@ -206,9 +207,12 @@ class Bank:
         _check(lib().sdrb_bank_blocks_done(self.h, stream, C.byref(v)), "sdrb_bank_blocks_done")
         return v.value
 
-    def process_device(self, d_iq_ptr, iq_stride, n_blocks, d_pcm_ptr, d_tap_ptr=None, cuda_stream=None):
-        _check(lib().sdrb_bank_process_device(self.h, d_iq_ptr, iq_stride, n_blocks, d_pcm_ptr, d_tap_ptr,
-                                              cuda_stream), "sdrb_bank_process_device")
+    def process_device(self, d_iq_ptr, iq_stride, n_blocks, d_pcm_ptr, d_tap_ptr=None, cuda_stream=None,
+                       input_ready_event=None):
+        """input_ready_event: raw cudaEvent_t (int) after which d_iq is valid; lets the DC pre-pass of this
+        call overlap the previous call (sdrb_bank_process_device_ex)."""
+        _check(lib().sdrb_bank_process_device_ex(self.h, d_iq_ptr, iq_stride, n_blocks, d_pcm_ptr, d_tap_ptr,
+                                                 cuda_stream, input_ready_event), "sdrb_bank_process_device_ex")
 
     def copy_main(self, main_idx, n_blocks, d_out_ptr, cuda_stream=None):
         _check(lib().sdrb_bank_copy_main(self.h, main_idx, n_blocks, d_out_ptr, cuda_stream), "sdrb_bank_copy_main")

@@ -170,6 +170,13 @@ struct sdrb_bank {
     // work
     DevBuf dc_anchor, dc_stats, dc_table, main_out, zbuf, dbuf;
     int dc_stride = 0;                      // DC blocks (of 32 samples) per stream in dc_stats; table has DC_HALO_BLKS more
+    // dc_anchor and dc_table exist twice and alternate from call to call: the DC pre-pass of call
+    // n+1 (side stream) may then run while the filters of call n still read call n's table.
+    int dc_par = 0;                         // buffer the NEXT call writes
+    cudaEvent_t ev_end[2] = {nullptr, nullptr};   // end of the last call that used buffer 0 / 1
+    bool ev_end_valid[2] = {false, false};
+    DcAnchor *anchor_buf(int par) const { return (DcAnchor *)dc_anchor.p + (size_t)par * 2 * (size_t)n_streams; }
+    uint2 *table_buf(int par) const { return (uint2 *)dc_table.p + (size_t)par * 2 * (size_t)n_streams * (size_t)(dc_stride + DC_HALO_BLKS); }
     // descriptors
     K1Params k1{};          // cf32-input variant (vfo::process entry)
     K1V2Params k1v2{};
@@ -214,6 +221,7 @@ extern "C" void sdrb_bank_destroy(sdrb_bank *b) {
     for (int k = 0; k < sdrb_bank::kSide; k++) {
         if (b->s_dc[k]) cudaStreamDestroy(b->s_dc[k]);
         if (b->ev_entry[k]) cudaEventDestroy(b->ev_entry[k]);
+        if (k < 2 && b->ev_end[k]) cudaEventDestroy(b->ev_end[k]);
         for (cudaEvent_t e : b->ev_dc[k]) cudaEventDestroy(e);
     }
     if (b->s_copy_in) cudaStreamDestroy(b->s_copy_in);
@@ -294,9 +302,9 @@ extern "C" int sdrb_bank_create(const sdrb_plan *plan, int device, int n_streams
 
     // ---- work buffers ----
     b->dc_stride = max_blocks * (h.block / DC_BLK);
-    BANK_TRY(b->dc_anchor.alloc(sizeof(DcAnchor) * 2 * (size_t)n_streams));
+    BANK_TRY(b->dc_anchor.alloc(2 * sizeof(DcAnchor) * 2 * (size_t)n_streams));
     BANK_TRY(b->dc_stats.alloc(h.correct_dc ? sizeof(DcStats) * 2 * (size_t)n_streams * (size_t)b->dc_stride + 1024 : 16));
-    BANK_TRY(b->dc_table.alloc(h.correct_dc ? sizeof(uint2) * 2 * (size_t)n_streams * (size_t)(b->dc_stride + DC_HALO_BLKS) : 16));
+    BANK_TRY(b->dc_table.alloc(h.correct_dc ? 2 * sizeof(uint2) * 2 * (size_t)n_streams * (size_t)(b->dc_stride + DC_HALO_BLKS) : 64));
     {
         size_t at = 0;
         for (const MainVfo &m : h.mains) {
@@ -476,6 +484,7 @@ extern "C" int sdrb_bank_create(const sdrb_plan *plan, int device, int n_streams
         for (int k = 0; k < sdrb_bank::kSide; k++) {
             BANK_CU(cudaStreamCreateWithPriority(&b->s_dc[k], cudaStreamNonBlocking, prio_greatest));
             BANK_CU(cudaEventCreateWithFlags(&b->ev_entry[k], cudaEventDisableTiming));
+            if (k < 2) BANK_CU(cudaEventCreateWithFlags(&b->ev_end[k], cudaEventDisableTiming));
             for (int j = 0; j < max_blocks; j++) {
                 cudaEvent_t e;
                 BANK_CU(cudaEventCreateWithFlags(&e, cudaEventDisableTiming));
@@ -495,6 +504,7 @@ extern "C" int sdrb_bank_reset(sdrb_bank *b, int stream) {
     if (!b || stream < -1 || stream >= b->n_streams) { set_error("sdrb_bank_reset: bad argument"); return SDRB_E_INVALID; }
     CU_TRY(cudaSetDevice(b->device));
     const int s0 = stream < 0 ? 0 : stream, ns = stream < 0 ? b->n_streams : 1;
+    CU_TRY(cudaDeviceSynchronize());                     // nothing of an earlier call may still be in flight
     CU_TRY(cudaMemset((long long *)b->blocks_done.p + s0, 0, sizeof(long long) * (size_t)ns));
     CU_TRY(cudaMemset((float2 *)b->dc_state.p + (size_t)s0, 0, sizeof(float2) * (size_t)ns));
     CU_TRY(cudaMemset((uint8_t *)b->raw_tail.p + (size_t)s0 * 2 * RAW_TAIL, 0, (size_t)ns * 2 * RAW_TAIL));
@@ -534,6 +544,7 @@ struct CallCtx {
     const float2 *d_cf = nullptr; size_t cf_stride = 0;    // cf32 input variant (no DC stage)
     int n_blocks = 0;
     int16_t *d_pcm = nullptr; float *d_tap = nullptr;
+    int par = 0;                                            // which dc_anchor / dc_table buffer this call owns
 };
 
 // DC recursion of callback cb for streams [s0, s0+ns) on the side stream `sd`: (anchor once per
@@ -547,20 +558,20 @@ static int enqueue_dc_cb(sdrb_bank *b, const CallCtx &c, int s0, int ns, cudaStr
     if (cb == 0) {
         TimedScope t(b, sd, 0);
         k0_dc_anchor<<<(unsigned)((2 * ns + 127) / 128), 128, 0, sd>>>((const float2 *)b->dc_state.p,
-                                                                      (DcAnchor *)b->dc_anchor.p, ns, s0);
+                                                                      b->anchor_buf(c.par), ns, s0);
         (*nl)++;
     }
     {
         TimedScope t(b, sd, 0);
         k0_dc_blocks<<<dim3((unsigned)((per_cb + 127) / 128), (unsigned)ns), 128, 0, sd>>>(
-            c.d_iq, c.iq_stride, (const DcAnchor *)b->dc_anchor.p, (DcStats *)b->dc_stats.p, b->dc_stride, cb * per_cb,
+            c.d_iq, c.iq_stride, b->anchor_buf(c.par), (DcStats *)b->dc_stats.p, b->dc_stride, cb * per_cb,
             per_cb, s0);
     }
     {
         TimedScope t(b, sd, 0);
         k0_dc_walk<<<(unsigned)ns, 64, DCW_SMEM, sd>>>(c.d_iq, c.iq_stride, (const DcStats *)b->dc_stats.p, b->dc_stride,
-                                                (const DcAnchor *)b->dc_anchor.p, (float2 *)b->dc_state.p,
-                                                (uint2 *)b->dc_table.p, b->dc_stride + DC_HALO_BLKS, cb * per_cb, per_cb, s0);
+                                                b->anchor_buf(c.par), (float2 *)b->dc_state.p,
+                                                b->table_buf(c.par), b->dc_stride + DC_HALO_BLKS, cb * per_cb, per_cb, s0);
     }
     (*nl) += 2;
     CU_TRY(cudaEventRecord(done, sd));
@@ -576,6 +587,7 @@ static int enqueue_main_cb(sdrb_bank *b, const CallCtx &c, int s0, int ns, cudaS
     K1Params k1 = b->k1;
     k1.iq = c.d_iq; k1.iq_stride = c.iq_stride; k1.n_blocks = c.n_blocks; k1.stream0 = s0; k1.b0 = cb;
     k1.cf_in = c.d_cf; k1.cf_stride = c.cf_stride;
+    k1.dc_table = b->table_buf(c.par); k1.dc_anchor = b->anchor_buf(c.par);
     if (c.d_cf) {
         const int k1_tiles = (h.block + K1_TILE - 1) / K1_TILE;
         TimedScope t(b, st, 1);
@@ -583,6 +595,7 @@ static int enqueue_main_cb(sdrb_bank *b, const CallCtx &c, int s0, int ns, cudaS
     } else {
         K1V2Params q = b->k1v2;
         q.iq = c.d_iq; q.iq_stride = c.iq_stride; q.stream0 = s0; q.b0 = cb;
+        q.dc_table = b->table_buf(c.par); q.dc_anchor = b->anchor_buf(c.par);
         const dim3 grid((unsigned)ns, (unsigned)((h.block + K1V2_ADV - 1) / K1V2_ADV), 1u);
         TimedScope t(b, st, 1);
         if (h.correct_dc) k1_v2<true><<<grid, V2_THREADS, V2_SMEM, st>>>(q);
@@ -625,7 +638,7 @@ static int enqueue_carry(sdrb_bank *b, const CallCtx &c, int s0, int ns, cudaStr
     TimedScope t(b, st, 5);
     k3_carry<<<dim3((unsigned)ns, (unsigned)(b->n_carry + 1)), 128, 0, st>>>(
         (const CarryItem *)b->carry.p, b->n_carry, c.n_blocks, c.d_iq, c.iq_stride, h.block, (uint8_t *)b->raw_tail.p,
-        (long long *)b->blocks_done.p, dc ? (uint2 *)b->dc_table.p : nullptr, (const DcAnchor *)b->dc_anchor.p,
+        (long long *)b->blocks_done.p, dc ? b->table_buf(c.par) : nullptr, b->table_buf(c.par ^ 1), b->anchor_buf(c.par),
         b->dc_stride + DC_HALO_BLKS, c.n_blocks * (h.block / DC_BLK), s0, c.d_cf, c.cf_stride, (float2 *)b->cf_tail.p);
     (*nl)++;
     CU_TRY(cudaGetLastError());
@@ -634,22 +647,37 @@ static int enqueue_carry(sdrb_bank *b, const CallCtx &c, int s0, int ns, cudaStr
 
 // Whole call for all streams of the bank on one stream (device-resident entry points): the DC walk
 // of callback cb+1 runs on the side stream while callback cb is filtered.
-static int enqueue_all(sdrb_bank *b, const CallCtx &c, cudaStream_t st, int *launches) {
+// `input_ready` (optional cudaEvent_t): the input of this call is valid once that event has fired.
+// The DC pre-pass then waits only for it (and for the call before the previous one, whose table
+// buffer it reuses) instead of for everything queued on `st` -- it overlaps the previous call.
+static int enqueue_all(sdrb_bank *b, CallCtx &c, cudaStream_t st, int *launches, cudaEvent_t input_ready = nullptr) {
     const HostPlan &h = b->plan->h;
     const bool dc = h.correct_dc && !c.d_cf;
     const int ns = b->n_streams;
     int rc;
+    c.par = b->dc_par;
     if (dc) {
         cudaStream_t sd = b->s_dc[0];
-        CU_TRY(cudaEventRecord(b->ev_entry[0], st));         // everything queued before this call
-        CU_TRY(cudaStreamWaitEvent(sd, b->ev_entry[0], 0));
+        if (input_ready) {
+            CU_TRY(cudaStreamWaitEvent(sd, input_ready, 0));
+            if (b->ev_end_valid[c.par]) CU_TRY(cudaStreamWaitEvent(sd, b->ev_end[c.par], 0));
+        } else {
+            CU_TRY(cudaEventRecord(b->ev_entry[0], st));         // everything queued before this call
+            CU_TRY(cudaStreamWaitEvent(sd, b->ev_entry[0], 0));
+        }
         for (int cb = 0; cb < c.n_blocks; cb++)
             if ((rc = enqueue_dc_cb(b, c, 0, ns, sd, cb, nullptr, b->ev_dc[0][(size_t)cb], launches)) != SDRB_OK) return rc;
     }
     for (int cb = 0; cb < c.n_blocks; cb++)
         if ((rc = enqueue_main_cb(b, c, 0, ns, st, cb, dc ? b->ev_dc[0][(size_t)cb] : nullptr, nullptr, launches)) != SDRB_OK)
             return rc;
-    return enqueue_carry(b, c, 0, ns, st, launches);
+    if ((rc = enqueue_carry(b, c, 0, ns, st, launches)) != SDRB_OK) return rc;
+    if (dc) {
+        CU_TRY(cudaEventRecord(b->ev_end[c.par], st));
+        b->ev_end_valid[c.par] = true;
+    }
+    b->dc_par ^= 1;
+    return SDRB_OK;
 }
 
 TimedScope::TimedScope(sdrb_bank *b_, cudaStream_t st_, int cls_) : b(b_), st(st_), cls(cls_), on(b_->timing) {
@@ -707,15 +735,20 @@ static int check_process_args(sdrb_bank *b, const void *iq, size_t iq_stride, in
     return SDRB_OK;
 }
 
-extern "C" int sdrb_bank_process_device(sdrb_bank *b, const uint8_t *d_iq, size_t iq_stride, int n_blocks,
-                                        int16_t *d_pcm, float *d_tap, void *cuda_stream) {
+extern "C" int sdrb_bank_process_device_ex(sdrb_bank *b, const uint8_t *d_iq, size_t iq_stride, int n_blocks,
+                                           int16_t *d_pcm, float *d_tap, void *cuda_stream, void *input_ready_event) {
     int rc = check_process_args(b, d_iq, iq_stride, n_blocks, d_pcm);
     if (rc != SDRB_OK) return rc;
     CU_TRY(cudaSetDevice(b->device));
     b->last_launches = 0;
     CallCtx c;
     c.d_iq = d_iq; c.iq_stride = iq_stride; c.n_blocks = n_blocks; c.d_pcm = d_pcm; c.d_tap = d_tap;
-    return enqueue_all(b, c, (cudaStream_t)cuda_stream, &b->last_launches);
+    return enqueue_all(b, c, (cudaStream_t)cuda_stream, &b->last_launches, (cudaEvent_t)input_ready_event);
+}
+
+extern "C" int sdrb_bank_process_device(sdrb_bank *b, const uint8_t *d_iq, size_t iq_stride, int n_blocks,
+                                        int16_t *d_pcm, float *d_tap, void *cuda_stream) {
+    return sdrb_bank_process_device_ex(b, d_iq, iq_stride, n_blocks, d_pcm, d_tap, cuda_stream, nullptr);
 }
 
 extern "C" int sdrb_bank_copy_main(sdrb_bank *b, int main_idx, int n_blocks, float *d_out, void *cuda_stream) {
@@ -739,7 +772,7 @@ extern "C" int sdrb_bank_copy_dc_trace(sdrb_bank *b, int n_blocks, float *d_out,
     CU_TRY(cudaSetDevice(b->device));
     const int n = n_blocks * (b->plan->h.block / DC_BLK);
     dc_trace_gather<<<dim3((unsigned)((n + 255) / 256), (unsigned)b->n_streams), 256, 0, (cudaStream_t)cuda_stream>>>(
-        (const uint2 *)b->dc_table.p, (const DcAnchor *)b->dc_anchor.p, b->dc_stride + DC_HALO_BLKS, n, (float2 *)d_out,
+        b->table_buf(b->dc_par ^ 1), b->anchor_buf(b->dc_par ^ 1), b->dc_stride + DC_HALO_BLKS, n, (float2 *)d_out,
         d_modes);
     CU_TRY(cudaGetLastError());
     return SDRB_OK;
@@ -780,6 +813,9 @@ extern "C" int sdrb_bank_process_host(sdrb_bank *b, const uint8_t *h_iq, size_t 
     CallCtx c;
     c.d_iq = (const uint8_t *)b->d_iq.p; c.iq_stride = in_max; c.n_blocks = n_blocks;   // kernels index streams absolutely
     c.d_pcm = (int16_t *)b->d_pcm.p; c.d_tap = h_tap ? (float *)b->d_tap.p : nullptr;
+    c.par = b->dc_par;
+    b->dc_par ^= 1;                                       // the call is synchronous: no event bookkeeping needed
+    b->ev_end_valid[0] = b->ev_end_valid[1] = false;
     for (int cb = 0; cb < n_blocks; cb++)
         for (int g = 0; g < n_groups; g++) {
             const int s0 = g * per, ns = std::min(per, b->n_streams - s0);

@@ -1080,7 +1080,8 @@ __global__ void __launch_bounds__(256) k2b_usb_audio(const UsbDev *__restrict__ 
 __global__ void __launch_bounds__(128) k3_carry(const CarryItem *__restrict__ items, int n_items, int n_blocks,
                                                  const uint8_t *__restrict__ iq, size_t iq_stride, int block,
                                                  uint8_t *__restrict__ tail, long long *__restrict__ blocks_done,
-                                                 uint2 *__restrict__ dc_table, const DcAnchor *__restrict__ dc_anchor,
+                                                 const uint2 *__restrict__ dc_table, uint2 *__restrict__ dc_table_next,
+                                                 const DcAnchor *__restrict__ dc_anchor,
                                                  int dc_table_stride, int n_dcblk, int stream0,
                                                  const float2 *__restrict__ cf_in, size_t cf_stride,
                                                  float2 *__restrict__ cf_tail) {
@@ -1106,14 +1107,14 @@ __global__ void __launch_bounds__(128) k3_carry(const CarryItem *__restrict__ it
         // DC table: the last DC_HALO_BLKS block-start states move to the front for the next call's
         // halo warp; they become "stepped" entries because the next call has a new anchor.
         if (dc_table && threadIdx.x < 2 * DC_HALO_BLKS) {
-            uint2 *t = dc_table + (size_t)stream * dc_table_stride * 2;
+            const uint2 *t = dc_table + (size_t)stream * dc_table_stride * 2;
             uint2 e = t[(size_t)n_dcblk * 2 + threadIdx.x];
             if (e.y < 2u) {                                      // translation entry -> plain float bits
                 const DcAnchor A = dc_anchor[2 * stream + (threadIdx.x & 1)];
                 e.x = (e.x + A.lo + 1u) | (A.sgn < 0.f ? 0x80000000u : 0u);
             }
             e.y = 2u;
-            t[threadIdx.x] = e;
+            dc_table_next[(size_t)stream * dc_table_stride * 2 + threadIdx.x] = e;   // the next call owns the other buffer
         }
     }
 }

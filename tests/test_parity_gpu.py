@@ -135,6 +135,44 @@ def test_device_entry_point_equals_host_entry_point():
     bank.close()
 
 
+def test_overlapped_device_calls_with_input_ready_event():
+    """sdrb_bank_process_device_ex: six back-to-back calls on a DC-removing plan, each handed an
+    'input ready' event so that its DC pre-pass runs while the previous call is still filtering
+    (double-buffered anchor/table). Must be bit-identical to the serialised calls, DC trace included."""
+    import torch
+    op = OP.build_plan(plan_path("25E")); plan = B.Plan(plan_path("25E"))
+    n_streams, calls, nb = 3, 6, 2
+    iq = np.stack([make_input(op, calls * nb, stream=s) for s in range(n_streams)])
+    row = plan.block * 2 * nb
+    d_iq = [torch.from_numpy(np.ascontiguousarray(iq[:, k * row:(k + 1) * row])).cuda() for k in range(calls)]
+    n_dc = nb * plan.block // 128
+
+    def run(overlap):
+        bank = B.Bank(plan, n_streams, nb)
+        st = torch.cuda.Stream()
+        ready = torch.cuda.Event()
+        ready.record(st)
+        ready.synchronize()
+        pcm = [torch.zeros((n_streams, nb, plan.pcm_per_block), dtype=torch.int16, device="cuda") for _ in range(calls)]
+        trace = torch.zeros((n_streams, n_dc, 2), dtype=torch.float32, device="cuda")
+        for k in range(calls):
+            bank.process_device(d_iq[k].data_ptr(), row, nb, pcm[k].data_ptr(), None, st.cuda_stream,
+                                ready.cuda_event if overlap else None)
+        bank.copy_dc_trace(nb, trace.data_ptr(), None, st.cuda_stream)     # DC states of the last call
+        st.synchronize()
+        torch.cuda.synchronize()
+        out = np.concatenate([p.cpu().numpy() for p in pcm], axis=1), trace.cpu().numpy()
+        bank.close()
+        return out
+
+    pcm_a, tr_a = run(False)
+    pcm_b, tr_b = run(True)
+    assert np.array_equal(pcm_a, pcm_b)
+    assert np.array_equal(tr_a.view(np.uint32), tr_b.view(np.uint32))
+    pcm_h, _, _ = run_gpu(plan, iq, [nb] * calls)
+    assert np.array_equal(pcm_a, pcm_h)
+
+
 def test_argument_errors():
     plan = B.Plan(plan_path("54W_288K"))
     bank = B.Bank(plan, 1, 2)
