@@ -45,6 +45,12 @@ typedef struct sdrb_bank sdrb_bank;   /* n_streams receivers of one plan on one 
 typedef struct {
     double mixer_hz;        /* center_frequency - frequency          (mainwindow.cpp:131) */
     int32_t decim;          /* half-band stages                      (mainwindow.cpp:130) */
+    /* IQ forwarder (vfo::compress, vfo.cpp:389-424): a main VFO WITHOUT sub VFOs re-publishes its
+     * decimated IQ as bytes when it has a topic (mainwindow.cpp:109-126). */
+    char topic[8];          /* zmq_topic, "" = nothing is published  (mainwindow.cpp:110) */
+    int32_t compress_scale; /* compress_scale, <= 0 means 1          (mainwindow.cpp:112-118, vfo.cpp:24) */
+    int32_t compress_style; /* vfo::cstyle: 1 = two 4-bit arms per byte (what MainWindow always sets,
+                               mainwindow.cpp:133), anything else = int8 I,Q pairs; 0 here means 1 */
 } sdrb_main_desc;
 
 typedef struct {
@@ -80,6 +86,12 @@ typedef struct {
     double mixer_hz;
     int32_t frequency;            /* absolute Hz (ini plans), else 0 */
     int32_t decim, out_rate, block_out;   /* block_out = block >> decim */
+    int32_t n_subs;               /* sub VFOs fed by this main VFO */
+    int32_t forward;              /* 1: no sub VFOs and a topic -> publishes compressed IQ */
+    int32_t compress_scale, compress_style;
+    int32_t fwd_bytes_per_block;  /* ZMQ payload of one callback: block_out (style 1) or 2*block_out */
+    char topic[8];
+    char zmq_address[128];        /* the address this main VFO connects to (mainwindow.cpp:109) */
 } sdrb_main_info;
 
 typedef struct {
@@ -141,6 +153,14 @@ int sdrb_bank_process_device_ex(sdrb_bank *bank, const uint8_t *d_iq, size_t iq_
 /* Copy out the main VFO outputs (vfo::decimate[decimateCount], vfo.h:39) of the last
  * process call: cf32 [n_streams][n_blocks*block_out] on the device. */
 int sdrb_bank_copy_main(sdrb_bank *bank, int main_idx, int n_blocks, float *d_out_cf32, void *cuda_stream);
+
+/* IQ forwarder output of the last process call (vfo::compress, vfo.cpp:389-424, followed by
+ * vfo::transmitData, vfo.cpp:439-451): for main VFO `main_idx` the packed bytes of every stream,
+ * uint8 [n_streams][n_blocks*fwd_bytes_per_block]; each fwd_bytes_per_block slice is one ZMQ
+ * payload (rate frame = the main VFO's out_rate). Computed on demand from the main VFO output,
+ * valid for any main VFO (the reference runs compress() only where there are no sub VFOs). */
+int sdrb_bank_copy_forward(sdrb_bank *bank, int main_idx, int n_blocks, uint8_t *d_out, void *cuda_stream);
+int sdrb_bank_read_forward(sdrb_bank *bank, int main_idx, int n_blocks, uint8_t *h_out);
 
 /* Inspection: the DC-removal state (sdrj.cpp:280 `avept`) entering every 128th sample of the
  * last process call, float2 (I,Q) [n_streams][n_blocks*block/128] on the device. The kernels
@@ -206,6 +226,12 @@ int sdrb_fir_ex(const float *d_taps, int ntaps, const float *d_in, float *d_out,
  * inputs per channel (updated). */
 int sdrb_usb_demod(const float *d_points, const float *d_in_cf32, float *d_out, float *d_hist_cf32,
                    int n_ch, int n, void *cuda_stream);
+/* vfo::compress (vfo.cpp:389-424) on n complex samples per channel. style 1: out[i] =
+ * ((signed char)((re/scale)*128) & 0xF0) | (((signed char)((im/scale)*128) & 0xF0) >> 4), n bytes
+ * per channel; otherwise out[2i] = (signed char)(re*128), out[2i+1] = (signed char)(im*128), 2n
+ * bytes. Conversions truncate toward zero and keep the low 8 bits (what the reference's x86 build
+ * does; it is undefined behaviour in C++ outside -128..127). */
+int sdrb_compress_iq(const float *d_in_cf32, uint8_t *d_out, int n_ch, int n, int scale, int style, void *cuda_stream);
 /* gnuradio firdes low_pass, Hamming (gnuradio/firfilter.cpp:64-108). Returns ntaps or
  * SDRB_E_INVALID where the reference throws std::out_of_range. Host only. */
 int sdrb_low_pass(double gain, double fs, double cutoff, double tw, float *taps, int max_taps);
@@ -215,6 +241,28 @@ int sdrb_hilbert_points(int len, int fs, float *points);
 /* ---- spectrum path: Hann window + 8192-point FFT (mainwindow.cpp:411-455, kiss_fft) ---- */
 int sdrb_spectrum_fft(const float *d_in_cf32, float *d_out_cf32, int n_batch, int nfft, int apply_hann,
                       void *cuda_stream);
+
+/* The spectrum display MainWindow keeps (fftHandlerSlot, mainwindow.cpp:411-455; state
+ * mainwindow.h:54-72), for n_displays independent displays (e.g. one per receiver of a bank):
+ *   inr[a] = data[a]*hann[a] for a < min(nfft, len) -- samples beyond `len` keep their previous
+ *            value, as in the reference when a sub VFO's short buffer is shown (cpp:418-425);
+ *   X = FFT(inr);  pwr[b] = 0.95*pwr[b] + 0.05*10*log10(max(1e5*|X[i]|/nfft, 1)), b = i + nfft/2 mod nfft;
+ *   smooth[i] = mean(pwr[i..i+4]), i < nfft-10;  stats = {maxval, aveval} as used for the y axis.
+ * pwr/smooth/stats are double like the reference's QVector<double>. reset = what selecting
+ * another VFO in the combo box does (mainwindow.cpp:539-551): pwr and inr to zero. */
+typedef struct sdrb_spectrum sdrb_spectrum;
+int sdrb_spectrum_create(int device, int n_displays, int nfft, sdrb_spectrum **out);
+void sdrb_spectrum_destroy(sdrb_spectrum *sp);
+int sdrb_spectrum_reset(sdrb_spectrum *sp, int display /* -1 = all */);
+/* One fftHandlerSlot per display. d_in_cf32: display k reads complex samples at
+ * d_in + 2*k*in_stride floats; len = data.size() of the reference's signal (any length >= 0).
+ * d_fft_out (optional): the complex spectrum X, cf32 [n_displays][nfft]. Only enqueues. */
+int sdrb_spectrum_feed_device(sdrb_spectrum *sp, const float *d_in_cf32, size_t in_stride, int len, float *d_fft_out,
+                              void *cuda_stream);
+int sdrb_spectrum_feed_host(sdrb_spectrum *sp, const float *h_in_cf32, size_t in_stride, int len);
+/* Host copies (any pointer may be NULL): smooth double [n][nfft-10], pwr double [n][nfft],
+ * stats double [n][2] = {maxval, aveval}. Synchronises the device. */
+int sdrb_spectrum_read(sdrb_spectrum *sp, double *h_smooth, double *h_pwr, double *h_stats);
 
 /* ---- ZMQ output (zmqpublisher.cpp:15-96), libzmq loaded at run time ---- */
 typedef struct sdrb_publisher sdrb_publisher;

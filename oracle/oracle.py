@@ -56,6 +56,7 @@ def lib():
         L.orc_usb.restype = None; L.orc_usb.argtypes = [i, i, vp, l, vp]
         L.orc_low_pass.restype = i; L.orc_low_pass.argtypes = [d, d, d, d, vp, i]
         L.orc_dc_trace.restype = None; L.orc_dc_trace.argtypes = [vp, l, i, vp]
+        L.orc_compress.restype = None; L.orc_compress.argtypes = [vp, l, i, i, vp]
         _lib = L
     return _lib
 
@@ -72,8 +73,40 @@ def ref_prims():
         L.ref_usb.restype = None; L.ref_usb.argtypes = [i, i, vp, l, vp]
         L.ref_low_pass.restype = i; L.ref_low_pass.argtypes = [d, d, d, d, vp, i]
         L.ref_kiss_fft.restype = None; L.ref_kiss_fft.argtypes = [i, vp, vp]
+        L.ref_spectrum_new.restype = vp; L.ref_spectrum_new.argtypes = [i]
+        L.ref_spectrum_free.restype = None; L.ref_spectrum_free.argtypes = [vp]
+        L.ref_spectrum_reset.restype = None; L.ref_spectrum_reset.argtypes = [vp]
+        L.ref_spectrum_feed.restype = None; L.ref_spectrum_feed.argtypes = [vp, vp, i]
+        L.ref_spectrum_get.restype = None; L.ref_spectrum_get.argtypes = [vp, vp, vp, vp, vp]
         _prims = L
     return _prims
+
+
+class RefSpectrum:
+    """MainWindow's spectrum state driven headless (oracle/ref_prims.cpp): the reference's FFTWrapper and
+    kiss_fft, fftHandlerSlot's arithmetic restated (mainwindow.cpp:411-455)."""
+
+    def __init__(self, nfft=8192):
+        self.nfft = nfft
+        self.h = ref_prims().ref_spectrum_new(nfft)
+
+    def reset(self):
+        ref_prims().ref_spectrum_reset(self.h)
+
+    def feed(self, x):
+        x = np.ascontiguousarray(x, dtype=np.complex64)
+        ref_prims().ref_spectrum_feed(self.h, _p(x.view(np.float32)), x.size)
+
+    def get(self):
+        smooth, pwr = np.zeros(self.nfft - 10), np.zeros(self.nfft)
+        out, stats = np.zeros(2 * self.nfft, np.float32), np.zeros(2)
+        ref_prims().ref_spectrum_get(self.h, _p(smooth), _p(pwr), _p(out), _p(stats))
+        return smooth, pwr, out.view(np.complex64), stats
+
+    def close(self):
+        if self.h:
+            ref_prims().ref_spectrum_free(self.h)
+            self.h = None
 
 
 def _p(a):
@@ -131,6 +164,14 @@ class Oracle:
             self.close()
         except Exception:
             pass
+
+
+def compress(cf, scalecomp=1, cstyle=1):
+    """vfo::compress (vfo.cpp:389-424) of complex64 samples: uint8 payload."""
+    x = np.ascontiguousarray(cf, dtype=np.complex64)
+    out = np.zeros(x.size * (1 if cstyle == 1 else 2), dtype=np.uint8)
+    lib().orc_compress(_p(x.view(np.float32)), x.size, int(scalecomp), int(cstyle), _p(out))
+    return out
 
 
 def dc_trace(iq_u8, every=32):

@@ -78,9 +78,14 @@ def build_plan(path):
         freq = _to_int(g(p + "frequency"))
         out_rate = _to_int(g(p + "out_rate"))
         decim = 0 if Fs // out_rate == 1 else int(math.log2(Fs // out_rate))
+        scalecomp = _to_int(g(p + "compress_scale"))    # mainwindow.cpp:112-118; vfo.cpp:24 default 1
+        addr, topic = g(p + "zmq_address"), g(p + "zmq_topic")
+        if not (addr and topic):                        # mainwindow.cpp:120-126: both or neither
+            addr, topic = "", ""
         plan["mains"].append({
             "freq": freq, "mixer": float(center - freq), "decim": decim,
             "out_rate": int(Fs / (2 ** decim)), "samples_per_buffer": buflen // 2,
+            "topic": topic, "zmq_address": addr, "scalecomp": scalecomp if scalecomp > 0 else 1,
         })
     for i in range(_to_int(g("vfos/size"))):            # mainwindow.cpp:141-235
         p = "vfos/%d/" % (i + 1)

@@ -7,9 +7,24 @@
 #include "oscillator.h"
 #include "halfbanddecimator.h"
 #include "gnuradio/firfilter.h"
+#include <cmath>
+#include "jonti/fftwrapper.h"
 extern "C" {
 #include "kiss_fft130/kiss_fft.h"
 }
+
+// The spectrum display state of MainWindow (mainwindow.h:54-72), without the widget. MainWindow
+// itself is GUI-bound and cannot be linked headless, so fftHandlerSlot's arithmetic
+// (mainwindow.cpp:411-455) is restated below as C++ with the same expression types; the FFT is
+// the reference's own FFTWrapper<float> over its vendored kiss_fft.
+struct RefSpectrum {
+    int nFFT;
+    FFTWrapper<float> *fft;
+    QVector<cpx_typef> out, inr;
+    QVector<float> hann_window;
+    QVector<double> pwr, smooth_pwr;
+    double maxval, aveval;
+};
 
 extern "C" {
 
@@ -83,6 +98,69 @@ void ref_kiss_fft(int n, const float *in_iq, float *out_iq) {
     kiss_fft_cfg cfg = kiss_fft_alloc(n, 0, 0, 0);
     kiss_fft(cfg, (const kiss_fft_cpx *)in_iq, (kiss_fft_cpx *)out_iq);
     free(cfg);
+}
+
+
+// MainWindow::MainWindow, spectrum part (mainwindow.cpp:243-252, 284-288)
+void *ref_spectrum_new(int nFFT) {
+    RefSpectrum *sp = new RefSpectrum();
+    sp->nFFT = nFFT;
+    sp->fft = new FFTWrapper<float>(nFFT, false);
+    sp->out.resize(nFFT);
+    sp->inr.resize(nFFT);
+    sp->pwr.resize(nFFT);
+    sp->smooth_pwr.resize(nFFT - 10);
+    sp->hann_window.resize(nFFT);
+    for (int i = 0; i < sp->hann_window.size(); i++) sp->hann_window[i] = 0.5 * (1.0 - cos(2 * M_PI * ((float)i) / (nFFT - 1.0)));
+    sp->maxval = sp->aveval = 0;
+    return sp;
+}
+void ref_spectrum_free(void *h) {
+    RefSpectrum *sp = (RefSpectrum *)h;
+    delete sp->fft;
+    delete sp;
+}
+// on_comboVFO_currentIndexChanged (mainwindow.cpp:539-551)
+void ref_spectrum_reset(void *h) {
+    RefSpectrum *sp = (RefSpectrum *)h;
+    for (int i = 0; i < sp->pwr.size(); i++) sp->pwr[i] = 0;
+    for (int a = 0; a < sp->nFFT; a++) sp->inr[a] = 0;
+}
+// fftHandlerSlot (mainwindow.cpp:411-455): `lenth` complex samples arrive
+void ref_spectrum_feed(void *h, const float *data_iq, int lenth) {
+    RefSpectrum *sp = (RefSpectrum *)h;
+    const cpx_typef *data = (const cpx_typef *)data_iq;
+    double maxval = 0;
+    double aveval = 0;
+    for (int a = 0; a < sp->nFFT; a++) {
+        if (a < lenth) sp->inr[a] = data[a] * sp->hann_window[a];
+    }
+    sp->fft->transform(sp->inr, sp->out);
+    QVector<cpx_typef> &out = sp->out;
+    QVector<double> &pwr = sp->pwr;
+    const int nFFT = sp->nFFT;
+    for (int i = 0; i < pwr.size(); i++) {
+        int b = i + pwr.size() / 2;
+        if (b >= pwr.size()) b = b - pwr.size();
+        double val = 0;
+        val = sqrt(out[i].imag() * out[i].imag() + out[i].real() * out[i].real());
+        pwr[b] = pwr[b] * 0.95 + 0.05 * 10 * log10(fmax(100000.0 * abs((1.0 / nFFT) * val), 1));
+        if (pwr[b] > maxval) maxval = pwr[b];
+        aveval += pwr[b];
+    }
+    for (int i = 0; i < sp->smooth_pwr.size(); i++)
+        sp->smooth_pwr[i] = (pwr[i + 4] + pwr[i + 3] + pwr[i + 2] + pwr[i + 1] + pwr[i]) / 5;
+    aveval /= pwr.size();
+    if ((maxval - aveval) < 10) maxval = aveval + 10.0;
+    sp->maxval = maxval;
+    sp->aveval = aveval;
+}
+void ref_spectrum_get(void *h, double *smooth, double *pwr, float *fft_out_iq, double *stats) {
+    RefSpectrum *sp = (RefSpectrum *)h;
+    if (smooth) memcpy(smooth, sp->smooth_pwr.data(), sizeof(double) * sp->smooth_pwr.size());
+    if (pwr) memcpy(pwr, sp->pwr.data(), sizeof(double) * sp->pwr.size());
+    if (fft_out_iq) memcpy(fft_out_iq, sp->out.data(), sizeof(cpx_typef) * sp->out.size());
+    if (stats) { stats[0] = sp->maxval; stats[1] = sp->aveval; }
 }
 
 }

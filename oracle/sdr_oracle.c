@@ -572,6 +572,29 @@ int orc_low_pass(double gain, double fs, double cutoff, double tw, float *taps, 
 
 /* DC-removal state trace -- sdrj.cpp:277-283. out[j] = avept entering sample j*every
  * (i.e. after samples 0 .. j*every-1), for j = 0 .. n/every - 1. */
+/* vfo::compress -- vfo.cpp:389-424. The IQ forwarder of a VFO that has no sub VFOs and is not a
+ * USB demodulator: cstyle 1 packs the upper 4 bits of each arm into one byte, anything else
+ * sends int8 I,Q pairs. `scalecomp` is an int (vfo.h:114): re/scalecomp is a float division.
+ * The reference converts float -> signed char directly (undefined outside -128..127); its x86
+ * build truncates to a 32-bit int and keeps the low byte, which is what is written here.
+ * Pinned against the unmodified reference through oracle/_ref on plans/FWD_test.ini. */
+static signed char to_s8(float v) { return (signed char)(int)v; }
+void orc_compress(const float *in_iq, long n, int scalecomp, int cstyle, unsigned char *out) {
+    long i;
+    if (cstyle == 1) {
+        for (i = 0; i < n; i++) {
+            signed char real = to_s8((in_iq[2 * i] / scalecomp) * 128);
+            signed char imag = to_s8((in_iq[2 * i + 1] / scalecomp) * 128);
+            out[i] = (unsigned char)((real & 0xF0) | (imag & 0xF0) >> 4);
+        }
+    } else {
+        for (i = 0; i < n; i++) {
+            out[2 * i] = (unsigned char)to_s8(in_iq[2 * i] * 128);
+            out[2 * i + 1] = (unsigned char)to_s8(in_iq[2 * i + 1] * 128);
+        }
+    }
+}
+
 void orc_dc_trace(const uint8_t *iq, long n, int every, float *out_iq) {
     const float a = 1.0f - 0.000001f, c = 0.000001f;
     cf32 avept;

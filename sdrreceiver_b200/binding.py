@@ -20,7 +20,8 @@ class SdrbError(RuntimeError):
 
 
 class MainDesc(C.Structure):
-    _fields_ = [("mixer_hz", C.c_double), ("decim", C.c_int32)]
+    _fields_ = [("mixer_hz", C.c_double), ("decim", C.c_int32), ("topic", C.c_char * 8),
+                ("compress_scale", C.c_int32), ("compress_style", C.c_int32)]
 
 
 class SubDesc(C.Structure):
@@ -44,7 +45,9 @@ class PlanInfo(C.Structure):
 
 class MainInfo(C.Structure):
     _fields_ = [("mixer_hz", C.c_double), ("frequency", C.c_int32), ("decim", C.c_int32),
-                ("out_rate", C.c_int32), ("block_out", C.c_int32)]
+                ("out_rate", C.c_int32), ("block_out", C.c_int32), ("n_subs", C.c_int32), ("forward", C.c_int32),
+                ("compress_scale", C.c_int32), ("compress_style", C.c_int32), ("fwd_bytes_per_block", C.c_int32),
+                ("topic", C.c_char * 8), ("zmq_address", C.c_char * 128)]
 
 
 class SubInfo(C.Structure):
@@ -84,6 +87,9 @@ def lib():
         "sdrb_bank_process_device_ex": (i, [vp, vp, sz, i, vp, vp, vp, vp]),
         "sdrb_bank_copy_main": (i, [vp, i, i, vp, vp]),
         "sdrb_bank_copy_dc_trace": (i, [vp, i, vp, vp, vp]),
+        "sdrb_bank_copy_forward": (i, [vp, i, i, vp, vp]),
+        "sdrb_bank_read_forward": (i, [vp, i, i, vp]),
+        "sdrb_compress_iq": (i, [vp, vp, i, i, i, i, vp]),
         "sdrb_bank_process_host": (i, [vp, vp, sz, i, vp, vp]),
         "sdrb_bank_process_cf32_host": (i, [vp, vp, sz, i, vp, vp]),
         "sdrb_bank_read_main": (i, [vp, i, i, vp]),
@@ -101,6 +107,12 @@ def lib():
         "sdrb_low_pass": (i, [d, d, d, d, vp, i]),
         "sdrb_hilbert_points": (i, [i, i, vp]),
         "sdrb_spectrum_fft": (i, [vp, vp, i, i, i, vp]),
+        "sdrb_spectrum_create": (i, [i, i, i, P(vp)]),
+        "sdrb_spectrum_destroy": (None, [vp]),
+        "sdrb_spectrum_reset": (i, [vp, i]),
+        "sdrb_spectrum_feed_device": (i, [vp, vp, sz, i, vp, vp]),
+        "sdrb_spectrum_feed_host": (i, [vp, vp, sz, i]),
+        "sdrb_spectrum_read": (i, [vp, vp, vp, vp]),
         "sdrb_publisher_open": (i, [C.c_char_p, i, P(vp)]),
         "sdrb_publisher_send": (i, [vp, C.c_char_p, C.c_uint32, vp, C.c_uint32]),
         "sdrb_publisher_send_block": (i, [vp, vp, vp]),
@@ -144,7 +156,10 @@ class Plan:
             m = MainInfo()
             _check(L.sdrb_plan_get_main(h, k, C.byref(m)), "sdrb_plan_get_main")
             self.mains.append({"mixer": m.mixer_hz, "freq": m.frequency, "decim": m.decim,
-                               "out_rate": m.out_rate, "block_out": m.block_out})
+                               "out_rate": m.out_rate, "block_out": m.block_out, "n_subs": m.n_subs,
+                               "forward": bool(m.forward), "scalecomp": m.compress_scale, "cstyle": m.compress_style,
+                               "fwd_bytes": m.fwd_bytes_per_block, "topic": m.topic.decode(),
+                               "zmq_address": m.zmq_address.decode()})
         for k in range(info.n_sub):
             s = SubInfo()
             _check(L.sdrb_plan_get_sub(h, k, C.byref(s)), "sdrb_plan_get_sub")
@@ -161,6 +176,8 @@ class Plan:
         d.n_main, d.n_sub = len(mains), len(subs)
         for k, m in enumerate(mains):
             d.mains[k].mixer_hz, d.mains[k].decim = m["mixer"], m["decim"]
+            d.mains[k].topic = m.get("topic", "").encode()[:7]
+            d.mains[k].compress_scale, d.mains[k].compress_style = m.get("scalecomp", 1), m.get("cstyle", 1)
         for k, s in enumerate(subs):
             d.subs[k].topic = s.get("topic", "VFO%02d" % k).encode()[:7]
             d.subs[k].main_idx, d.subs[k].mixer_hz = s["main"], s["mixer"]
@@ -221,6 +238,16 @@ class Bank:
         _check(lib().sdrb_bank_copy_dc_trace(self.h, n_blocks, d_out_ptr, d_modes_ptr, cuda_stream),
                "sdrb_bank_copy_dc_trace")
 
+    def copy_forward(self, main_idx, n_blocks, d_out_ptr, cuda_stream=None):
+        _check(lib().sdrb_bank_copy_forward(self.h, main_idx, n_blocks, d_out_ptr, cuda_stream), "sdrb_bank_copy_forward")
+
+    def read_forward(self, main_idx, n_blocks):
+        """vfo::compress payloads of the last call: uint8 [n_streams, n_blocks, fwd_bytes]."""
+        out = np.zeros((self.n_streams, n_blocks, self.plan.mains[main_idx]["fwd_bytes"]), dtype=np.uint8)
+        _check(lib().sdrb_bank_read_forward(self.h, main_idx, n_blocks, out.ctypes.data_as(C.c_void_p)),
+               "sdrb_bank_read_forward")
+        return out
+
     def process_host(self, h_iq_ptr, iq_stride, n_blocks, h_pcm_ptr, h_tap_ptr=None):
         _check(lib().sdrb_bank_process_host(self.h, h_iq_ptr, iq_stride, n_blocks, h_pcm_ptr, h_tap_ptr),
                "sdrb_bank_process_host")
@@ -256,6 +283,47 @@ class Bank:
     def close(self):
         if getattr(self, "h", None):
             lib().sdrb_bank_destroy(self.h)
+            self.h = None
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass
+
+
+class Spectrum:
+    """MainWindow's spectrum display state for n independent displays (fftHandlerSlot)."""
+    NFFT = 8192
+
+    def __init__(self, n_displays, device=0):
+        self.n = n_displays
+        h = C.c_void_p()
+        _check(lib().sdrb_spectrum_create(device, n_displays, self.NFFT, C.byref(h)), "sdrb_spectrum_create")
+        self.h = h
+
+    def reset(self, display=-1):
+        _check(lib().sdrb_spectrum_reset(self.h, display), "sdrb_spectrum_reset")
+
+    def feed_device(self, d_in_ptr, in_stride, length, d_fft_out_ptr=None, cuda_stream=None):
+        _check(lib().sdrb_spectrum_feed_device(self.h, d_in_ptr, in_stride, length, d_fft_out_ptr, cuda_stream),
+               "sdrb_spectrum_feed_device")
+
+    def feed_numpy(self, x):
+        """x: complex64 [n_displays, len]."""
+        x = np.ascontiguousarray(x, dtype=np.complex64).reshape(self.n, -1)
+        _check(lib().sdrb_spectrum_feed_host(self.h, x.ctypes.data_as(C.c_void_p), x.shape[1], x.shape[1]),
+               "sdrb_spectrum_feed_host")
+
+    def read(self):
+        smooth = np.zeros((self.n, self.NFFT - 10)); pwr = np.zeros((self.n, self.NFFT)); stats = np.zeros((self.n, 2))
+        _check(lib().sdrb_spectrum_read(self.h, smooth.ctypes.data_as(C.c_void_p), pwr.ctypes.data_as(C.c_void_p),
+                                        stats.ctypes.data_as(C.c_void_p)), "sdrb_spectrum_read")
+        return smooth, pwr, stats
+
+    def close(self):
+        if getattr(self, "h", None):
+            lib().sdrb_spectrum_destroy(self.h)
             self.h = None
 
     def __del__(self):

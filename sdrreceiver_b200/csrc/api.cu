@@ -81,6 +81,13 @@ extern "C" int sdrb_plan_get_main(const sdrb_plan *plan, int idx, sdrb_main_info
     const MainVfo &m = plan->h.mains[(size_t)idx];
     info->mixer_hz = m.mixer; info->frequency = m.frequency; info->decim = m.decim;
     info->out_rate = m.out_rate; info->block_out = m.block_out;
+    info->n_subs = m.n_subs; info->forward = (m.n_subs == 0 && !m.topic.empty()) ? 1 : 0;
+    info->compress_scale = m.compress_scale; info->compress_style = m.compress_style;
+    info->fwd_bytes_per_block = m.fwd_bytes;
+    memset(info->topic, 0, sizeof(info->topic));
+    strncpy(info->topic, m.topic.c_str(), sizeof(info->topic) - 1);
+    memset(info->zmq_address, 0, sizeof(info->zmq_address));
+    strncpy(info->zmq_address, m.zmq_address.c_str(), sizeof(info->zmq_address) - 1);
     return SDRB_OK;
 }
 
@@ -191,7 +198,7 @@ struct sdrb_bank {
     size_t main_stride = 0;                 // float2 per stream
     size_t z_stride = 0;                    // float2 per stream in zbuf
     // host staging for process_host
-    DevBuf d_iq, d_pcm, d_tap, d_cf;
+    DevBuf d_iq, d_pcm, d_tap, d_cf, d_fwd;
     cudaStream_t s_copy_in = nullptr, s_compute = nullptr, s_copy_out = nullptr;
     std::vector<cudaEvent_t> ev_in, ev_done;
     // DC recursion runs on side streams, one callback ahead of the ingest kernel
@@ -213,7 +220,7 @@ extern "C" void sdrb_bank_destroy(sdrb_bank *b) {
     cudaSetDevice(b->device);
     DevBuf *all[] = {&b->luts, &b->taps, &b->blocks_done, &b->dc_state, &b->raw_tail, &b->cf_tail, &b->dc_anchor, &b->dc_stats, &b->dc_table,
                      &b->main_out, &b->zbuf, &b->dbuf, &b->cascdev, &b->rfdev, &b->latedev, &b->usbdev, &b->carry,
-                     &b->d_iq, &b->d_pcm, &b->d_tap, &b->d_cf};
+                     &b->d_iq, &b->d_pcm, &b->d_tap, &b->d_cf, &b->d_fwd};
     for (DevBuf *d : all) d->release();
     for (cudaEvent_t e : b->ev_in) cudaEventDestroy(e);
     for (cudaEvent_t e : b->ev_done) cudaEventDestroy(e);
@@ -765,6 +772,55 @@ extern "C" int sdrb_bank_copy_main(sdrb_bank *b, int main_idx, int n_blocks, flo
     return SDRB_OK;
 }
 
+// vfo::compress (vfo.cpp:389-424) of a main VFO's output of the last call, straight from main_out.
+static int forward_launch(sdrb_bank *b, int main_idx, int n_blocks, uint8_t *d_out, cudaStream_t st) {
+    const MainVfo &m = b->plan->h.mains[(size_t)main_idx];
+    const int n = n_blocks * m.block_out;
+    const int per = m.compress_style == 1 ? 1 : 2;
+    k_compress<<<dim3((unsigned)(((n + 3) / 4 + 255) / 256), (unsigned)b->n_streams), 256, 0, st>>>(
+        (const float2 *)b->main_out.p + b->main_off[(size_t)main_idx] + MAIN_HIST, (long long)b->main_stride, d_out,
+        (long long)n * per, n, (float)m.compress_scale, m.compress_style);
+    CU_TRY(cudaGetLastError());
+    return SDRB_OK;
+}
+
+extern "C" int sdrb_bank_copy_forward(sdrb_bank *b, int main_idx, int n_blocks, uint8_t *d_out, void *cuda_stream) {
+    if (!b || !d_out || main_idx < 0 || main_idx >= (int)b->plan->h.mains.size() || n_blocks <= 0 || n_blocks > b->max_blocks) {
+        set_error("sdrb_bank_copy_forward: bad argument"); return SDRB_E_INVALID;
+    }
+    CU_TRY(cudaSetDevice(b->device));
+    return forward_launch(b, main_idx, n_blocks, d_out, (cudaStream_t)cuda_stream);
+}
+
+extern "C" int sdrb_bank_read_forward(sdrb_bank *b, int main_idx, int n_blocks, uint8_t *h_out) {
+    if (!b || !h_out || main_idx < 0 || main_idx >= (int)b->plan->h.mains.size() || n_blocks <= 0 || n_blocks > b->max_blocks) {
+        set_error("sdrb_bank_read_forward: bad argument"); return SDRB_E_INVALID;
+    }
+    CU_TRY(cudaSetDevice(b->device));
+    const MainVfo &m = b->plan->h.mains[(size_t)main_idx];
+    const size_t bytes = (size_t)b->n_streams * (size_t)n_blocks * (size_t)m.fwd_bytes;
+    if (b->d_fwd.bytes < bytes) {
+        b->d_fwd.release(); b->d_fwd.bytes = 0;
+        int rc = b->d_fwd.alloc((size_t)b->n_streams * (size_t)b->max_blocks * (size_t)m.fwd_bytes); if (rc) return rc;
+    }
+    cudaStream_t st = b->s_compute;
+    int rc = forward_launch(b, main_idx, n_blocks, (uint8_t *)b->d_fwd.p, st);
+    if (rc != SDRB_OK) return rc;
+    CU_TRY(cudaMemcpyAsync(h_out, b->d_fwd.p, bytes, cudaMemcpyDeviceToHost, st));
+    CU_TRY(cudaStreamSynchronize(st));
+    return SDRB_OK;
+}
+
+extern "C" int sdrb_compress_iq(const float *d_in, uint8_t *d_out, int n_ch, int n, int scale, int style, void *cuda_stream) {
+    if (!d_in || !d_out || n_ch <= 0 || n <= 0) { set_error("sdrb_compress_iq: bad argument"); return SDRB_E_INVALID; }
+    if (scale <= 0) scale = 1;
+    const int per = style == 1 ? 1 : 2;
+    k_compress<<<dim3((unsigned)(((n + 3) / 4 + 255) / 256), (unsigned)n_ch), 256, 0, (cudaStream_t)cuda_stream>>>(
+        (const float2 *)d_in, (long long)n, d_out, (long long)n * per, n, (float)scale, style);
+    CU_TRY(cudaGetLastError());
+    return SDRB_OK;
+}
+
 extern "C" int sdrb_bank_copy_dc_trace(sdrb_bank *b, int n_blocks, float *d_out, uint8_t *d_modes, void *cuda_stream) {
     if (!b || !d_out || n_blocks <= 0 || n_blocks > b->max_blocks || !b->plan->h.correct_dc) {
         set_error("sdrb_bank_copy_dc_trace: bad argument or plan without correct_dc_bias"); return SDRB_E_INVALID;
@@ -1006,5 +1062,95 @@ extern "C" int sdrb_spectrum_fft(const float *d_in, float *d_out, int n_batch, i
     prim_fft8192<<<(unsigned)n_batch, 512, 8192 * sizeof(float2), (cudaStream_t)cuda_stream>>>(
         (const float2 *)d_in, (float2 *)d_out, apply_hann);
     CU_TRY(cudaGetLastError());
+    return SDRB_OK;
+}
+
+// ---- spectrum display state (MainWindow::fftHandlerSlot, mainwindow.cpp:411-455) ----
+struct sdrb_spectrum {
+    int device = 0, n = 0;
+    DevBuf inr, pwr, smooth, stats;
+};
+
+extern "C" void sdrb_spectrum_destroy(sdrb_spectrum *sp) {
+    if (!sp) return;
+    cudaSetDevice(sp->device);
+    sp->inr.release(); sp->pwr.release(); sp->smooth.release(); sp->stats.release();
+    delete sp;
+}
+
+extern "C" int sdrb_spectrum_reset(sdrb_spectrum *sp, int display) {
+    if (!sp || display < -1 || display >= sp->n) { set_error("sdrb_spectrum_reset: bad argument"); return SDRB_E_INVALID; }
+    CU_TRY(cudaSetDevice(sp->device));
+    const size_t d0 = display < 0 ? 0 : (size_t)display, nd = display < 0 ? (size_t)sp->n : 1;
+    CU_TRY(cudaDeviceSynchronize());
+    CU_TRY(cudaMemset((float2 *)sp->inr.p + d0 * FFT_N, 0, nd * FFT_N * sizeof(float2)));     // mainwindow.cpp:547-550
+    CU_TRY(cudaMemset((double *)sp->pwr.p + d0 * FFT_N, 0, nd * FFT_N * sizeof(double)));     // mainwindow.cpp:542-545
+    CU_TRY(cudaMemset((double *)sp->smooth.p + d0 * (FFT_N - 10), 0, nd * (FFT_N - 10) * sizeof(double)));
+    CU_TRY(cudaMemset((double *)sp->stats.p + d0 * 2, 0, nd * 2 * sizeof(double)));
+    CU_TRY(cudaDeviceSynchronize());
+    return SDRB_OK;
+}
+
+extern "C" int sdrb_spectrum_create(int device, int n_displays, int nfft, sdrb_spectrum **out) {
+    if (!out || n_displays <= 0 || nfft != FFT_N) {
+        set_error("sdrb_spectrum_create: nfft must be 8192 (mainwindow.cpp:243)"); return SDRB_E_INVALID;
+    }
+    *out = nullptr;
+    CU_TRY(cudaSetDevice(device));
+    sdrb_spectrum *sp = new (std::nothrow) sdrb_spectrum();
+    if (!sp) { set_error("out of memory"); return SDRB_E_NOMEM; }
+    sp->device = device; sp->n = n_displays;
+    int rc;
+    if ((rc = sp->inr.alloc((size_t)n_displays * FFT_N * sizeof(float2))) || (rc = sp->pwr.alloc((size_t)n_displays * FFT_N * sizeof(double))) ||
+        (rc = sp->smooth.alloc((size_t)n_displays * (FFT_N - 10) * sizeof(double))) || (rc = sp->stats.alloc((size_t)n_displays * 2 * sizeof(double)))) {
+        sdrb_spectrum_destroy(sp); return rc;
+    }
+    if (cudaFuncSetAttribute(k_spectrum_feed, cudaFuncAttributeMaxDynamicSharedMemorySize, FFT_N * (int)sizeof(float2)) != cudaSuccess) {
+        set_error("sdrb_spectrum_create: cannot reserve 64 KB of shared memory"); sdrb_spectrum_destroy(sp); return SDRB_E_CUDA;
+    }
+    rc = sdrb_spectrum_reset(sp, -1);
+    if (rc != SDRB_OK) { sdrb_spectrum_destroy(sp); return rc; }
+    *out = sp;
+    return SDRB_OK;
+}
+
+extern "C" int sdrb_spectrum_feed_device(sdrb_spectrum *sp, const float *d_in, size_t in_stride, int len, float *d_fft_out,
+                                         void *cuda_stream) {
+    if (!sp || !d_in || len < 0 || (sp->n > 1 && in_stride < (size_t)std::min(len, FFT_N))) {
+        set_error("sdrb_spectrum_feed_device: bad argument"); return SDRB_E_INVALID;
+    }
+    CU_TRY(cudaSetDevice(sp->device));
+    k_spectrum_feed<<<(unsigned)sp->n, FFT_THREADS, FFT_N * sizeof(float2), (cudaStream_t)cuda_stream>>>(
+        (const float2 *)d_in, (long long)in_stride, len, (float2 *)sp->inr.p, (double *)sp->pwr.p, (double *)sp->smooth.p,
+        (double *)sp->stats.p, (float2 *)d_fft_out);
+    CU_TRY(cudaGetLastError());
+    return SDRB_OK;
+}
+
+extern "C" int sdrb_spectrum_feed_host(sdrb_spectrum *sp, const float *h_in, size_t in_stride, int len) {
+    if (!sp || !h_in || len < 0) { set_error("sdrb_spectrum_feed_host: bad argument"); return SDRB_E_INVALID; }
+    CU_TRY(cudaSetDevice(sp->device));
+    const int use = std::min(len, FFT_N);                       // only the first nFFT samples are looked at
+    float2 *stage = nullptr;
+    CU_TRY(cudaMalloc(&stage, (size_t)sp->n * FFT_N * sizeof(float2)));
+    cudaError_t e = cudaSuccess;
+    if (use > 0)
+        e = cudaMemcpy2D(stage, FFT_N * sizeof(float2), h_in, in_stride * sizeof(float2), (size_t)use * sizeof(float2), (size_t)sp->n,
+                         cudaMemcpyHostToDevice);
+    int rc = SDRB_OK;
+    if (e != cudaSuccess) { set_error(std::string("sdrb_spectrum_feed_host: ") + cudaGetErrorString(e)); rc = SDRB_E_CUDA; }
+    if (rc == SDRB_OK) rc = sdrb_spectrum_feed_device(sp, (const float *)stage, FFT_N, len, nullptr, nullptr);
+    cudaDeviceSynchronize();
+    cudaFree(stage);
+    return rc;
+}
+
+extern "C" int sdrb_spectrum_read(sdrb_spectrum *sp, double *h_smooth, double *h_pwr, double *h_stats) {
+    if (!sp) { set_error("sdrb_spectrum_read: NULL"); return SDRB_E_INVALID; }
+    CU_TRY(cudaSetDevice(sp->device));
+    CU_TRY(cudaDeviceSynchronize());
+    if (h_smooth) CU_TRY(cudaMemcpy(h_smooth, sp->smooth.p, (size_t)sp->n * (FFT_N - 10) * sizeof(double), cudaMemcpyDeviceToHost));
+    if (h_pwr) CU_TRY(cudaMemcpy(h_pwr, sp->pwr.p, (size_t)sp->n * FFT_N * sizeof(double), cudaMemcpyDeviceToHost));
+    if (h_stats) CU_TRY(cudaMemcpy(h_stats, sp->stats.p, (size_t)sp->n * 2 * sizeof(double), cudaMemcpyDeviceToHost));
     return SDRB_OK;
 }

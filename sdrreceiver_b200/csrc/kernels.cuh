@@ -1119,6 +1119,64 @@ __global__ void __launch_bounds__(128) k3_carry(const CarryItem *__restrict__ it
     }
 }
 
+// ------------------------------------------------------------------------------------
+// k_compress: vfo::compress (vfo.cpp:389-424), the IQ forwarder of a main VFO without sub VFOs.
+//   style 1:  byte = ((signed char)((re/scale)*128) & 0xF0) | (((signed char)((im/scale)*128) & 0xF0) >> 4)
+//   else:     bytes = (signed char)(re*128), (signed char)(im*128)
+// float -> signed char as the reference's x86 build does it: truncate toward zero to int, keep
+// the low 8 bits. Pure streaming: 8 B read + 1 (2) B written per sample, a thread owns 4
+// consecutive samples (two 16-byte loads, one 4- or 8-byte store), grid.y = stream.
+// ------------------------------------------------------------------------------------
+__device__ __forceinline__ unsigned comp_s8(float v) { return (unsigned)__float2int_rz(v) & 0xffu; }
+__device__ __forceinline__ unsigned comp_pack(float2 v, float scale) {
+    const unsigned re = comp_s8((v.x / scale) * 128.0f), im = comp_s8((v.y / scale) * 128.0f);
+    return (re & 0xF0u) | ((im & 0xF0u) >> 4);
+}
+
+__global__ void __launch_bounds__(256) k_compress(const float2 *__restrict__ in, long long in_stride, uint8_t *__restrict__ out,
+                                                  long long out_stride, int n, float scale, int style) {
+    const int i0 = (blockIdx.x * 256 + threadIdx.x) * 4;
+    if (i0 >= n) return;
+    const float2 *src = in + (size_t)blockIdx.y * in_stride + i0;
+    uint8_t *dst = out + (size_t)blockIdx.y * out_stride;
+    const bool vec = (i0 + 4 <= n) && ((reinterpret_cast<uintptr_t>(src) & 15) == 0);
+    float2 v[4];
+    if (vec) {
+        const float4 a = __ldg(reinterpret_cast<const float4 *>(src)), c = __ldg(reinterpret_cast<const float4 *>(src) + 1);
+        v[0] = make_float2(a.x, a.y); v[1] = make_float2(a.z, a.w); v[2] = make_float2(c.x, c.y); v[3] = make_float2(c.z, c.w);
+    } else {
+#pragma unroll
+        for (int k = 0; k < 4; ++k) v[k] = (i0 + k < n) ? __ldg(src + k) : make_float2(0.f, 0.f);
+    }
+    if (style == 1) {
+        const unsigned w = comp_pack(v[0], scale) | (comp_pack(v[1], scale) << 8) | (comp_pack(v[2], scale) << 16) |
+                           (comp_pack(v[3], scale) << 24);
+        if (vec && ((reinterpret_cast<uintptr_t>(dst + i0) & 3) == 0)) {
+            *reinterpret_cast<unsigned *>(dst + i0) = w;
+        } else {
+#pragma unroll
+            for (int k = 0; k < 4; ++k)
+                if (i0 + k < n) dst[i0 + k] = (uint8_t)(w >> (8 * k));
+        }
+    } else {
+        unsigned w[2];
+#pragma unroll
+        for (int h = 0; h < 2; ++h)
+            w[h] = comp_s8(v[2 * h].x * 128.0f) | (comp_s8(v[2 * h].y * 128.0f) << 8) | (comp_s8(v[2 * h + 1].x * 128.0f) << 16) |
+                   (comp_s8(v[2 * h + 1].y * 128.0f) << 24);
+        if (vec && ((reinterpret_cast<uintptr_t>(dst + 2 * (size_t)i0) & 7) == 0)) {
+            *reinterpret_cast<uint2 *>(dst + 2 * (size_t)i0) = make_uint2(w[0], w[1]);
+        } else {
+#pragma unroll
+            for (int k = 0; k < 4; ++k)
+                if (i0 + k < n) {
+                    dst[2 * (size_t)(i0 + k)] = (uint8_t)(w[k >> 1] >> (16 * (k & 1)));
+                    dst[2 * (size_t)(i0 + k) + 1] = (uint8_t)(w[k >> 1] >> (16 * (k & 1) + 8));
+                }
+        }
+    }
+}
+
 // test/inspection helper: block-start DC states of the last call as float2 (I, Q)
 __global__ void __launch_bounds__(256) dc_trace_gather(const uint2 *__restrict__ table, const DcAnchor *__restrict__ anchors,
                                                         int table_stride, int n, float2 *__restrict__ out,

@@ -18,6 +18,12 @@ struct MainVfo {
     int out_rate = 0;
     int block_out = 0;          // samples per callback after the cascade
     std::vector<cf32> lut;      // Oscillator table, (int)Fs entries
+    // IQ forwarder (vfo::compress): ini keys zmq_address / zmq_topic / compress_scale of [main_vfos]
+    std::string topic, zmq_address;
+    int compress_scale = 1;     // vfo::scalecomp, 1 unless compress_scale > 0 (vfo.cpp:24, mainwindow.cpp:112-118)
+    int compress_style = 1;     // vfo::cstyle as MainWindow sets it (mainwindow.cpp:133)
+    int n_subs = 0;
+    int fwd_bytes = 0;          // payload bytes per callback
 };
 
 struct SubVfo {

@@ -163,6 +163,10 @@ static int finish_plan(HostPlan &p) {
         m.out_rate = (int)(p.fs / std::pow(2, m.decim));               // vfo::getOutRate
         m.block_out = p.block >> m.decim;
         m.lut = nco_table(p.fs, m.mixer);
+        if (m.compress_scale <= 0) m.compress_scale = 1;
+        if (m.compress_style == 0) m.compress_style = 1;
+        m.fwd_bytes = m.compress_style == 1 ? m.block_out : 2 * m.block_out;   // vfo.cpp:143-150
+        m.n_subs = 0;
     }
     int off = 0;
     double out_rates = 0, flops = 0;
@@ -171,7 +175,8 @@ static int finish_plan(HostPlan &p) {
             set_error("plan: sub VFO refers to a main VFO that does not exist");
             return SDRB_E_INVALID;
         }
-        const MainVfo &m = p.mains[(size_t)s.main_idx];
+        MainVfo &m = p.mains[(size_t)s.main_idx];
+        m.n_subs++;
         s.fs = m.out_rate;
         s.block_in = m.out_rate / p.bufsplit;                           // mainwindow.cpp:223
         if (s.decim < 0 || s.decim > 5 || (s.late != 0 && s.late != 5 && s.late != 6)) {
@@ -258,6 +263,10 @@ int plan_from_ini(const char *path, HostPlan &p) {
         m.decim = (p.fs / want == 1) ? 0 : ilog2_floor_of_ratio(p.fs, want);
         m.mixer = p.center - m.frequency;
         m.out_rate = (int)(p.fs / std::pow(2, m.decim));
+        const int compscale = ini.num(k + "compress_scale");            // mainwindow.cpp:112-118
+        if (compscale > 0) m.compress_scale = compscale;
+        const std::string addr = ini.str(k + "zmq_address"), topic = ini.str(k + "zmq_topic");
+        if (!addr.empty() && !topic.empty()) { m.zmq_address = addr; m.topic = topic; }   // mainwindow.cpp:120-126
         p.mains.push_back(m);
     }
     const int n_sub = ini.num("vfos/size");                             // mainwindow.cpp:141-235
@@ -320,6 +329,9 @@ int plan_from_desc(const sdrb_plan_desc &d, HostPlan &p) {
         MainVfo m;
         m.mixer = d.mains[i].mixer_hz;
         m.decim = d.mains[i].decim;
+        m.topic.assign(d.mains[i].topic, strnlen(d.mains[i].topic, sizeof(d.mains[i].topic)));
+        m.compress_scale = d.mains[i].compress_scale;
+        m.compress_style = d.mains[i].compress_style;
         p.mains.push_back(m);
     }
     for (int i = 0; i < d.n_sub; i++) {

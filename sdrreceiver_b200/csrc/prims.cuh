@@ -89,25 +89,20 @@ __global__ void __launch_bounds__(256) prim_usb(const float *__restrict__ pts, c
     out[(size_t)blockIdx.y * n + i] = at(i - 62).x - acc;
 }
 
-// Spectrum path: optional Hann window (mainwindow.cpp:284-288, 416-423) and an 8192-point
-// forward complex FFT, unscaled like kiss_fft (kiss_fft.c:339-388). One CTA per transform,
-// whole transform in shared memory: bit-reversed load, 13 radix-2 stages.
-__global__ void __launch_bounds__(512) prim_fft8192(const float2 *__restrict__ in, float2 *__restrict__ out, int hann) {
-    extern __shared__ float2 s[];
-    constexpr int N = 8192, LOGN = 13;
-    const float2 *x = in + (size_t)blockIdx.x * N;
-    for (int i = threadIdx.x; i < N; i += 512) {
-        float2 v = x[i];
-        if (hann) {
-            const float w = (float)(0.5 * (1.0 - cos(2.0 * 3.14159265358979323846 * (double)(float)i / (N - 1.0))));
-            v.x *= w; v.y *= w;
-        }
-        s[__brev((unsigned)i) >> (32 - LOGN)] = v;
-    }
-    __syncthreads();
-    for (int st = 0; st < LOGN; ++st) {
+// Spectrum path: Hann window (mainwindow.cpp:284-288, 416-423) and an 8192-point forward complex
+// FFT, unscaled like kiss_fft (kiss_fft.c:339-388). One CTA per transform, whole transform in
+// shared memory: bit-reversed load, 13 radix-2 stages.
+constexpr int FFT_N = 8192, FFT_LOGN = 13, FFT_THREADS = 512;
+
+__device__ __forceinline__ float hann8192(int i) {         // float(0.5*(1 - cos(2*pi*float(i)/(N-1)))), mainwindow.cpp:287
+    return (float)(0.5 * (1.0 - cos(2.0 * 3.14159265358979323846 * (double)(float)i / (FFT_N - 1.0))));
+}
+
+// s[] holds the input in bit-reversed order on entry (and a __syncthreads has been passed)
+__device__ __forceinline__ void fft8192_stages(float2 *s) {
+    for (int st = 0; st < FFT_LOGN; ++st) {
         const int half = 1 << st;
-        for (int bfly = threadIdx.x; bfly < N / 2; bfly += 512) {
+        for (int bfly = threadIdx.x; bfly < FFT_N / 2; bfly += FFT_THREADS) {
             const int k = bfly & (half - 1);
             const int i0 = ((bfly >> st) << (st + 1)) + k, i1 = i0 + half;
             float sn, cs;
@@ -119,8 +114,82 @@ __global__ void __launch_bounds__(512) prim_fft8192(const float2 *__restrict__ i
         }
         __syncthreads();
     }
-    float2 *y = out + (size_t)blockIdx.x * N;
-    for (int i = threadIdx.x; i < N; i += 512) y[i] = s[i];
+}
+
+__global__ void __launch_bounds__(FFT_THREADS) prim_fft8192(const float2 *__restrict__ in, float2 *__restrict__ out, int hann) {
+    extern __shared__ float2 s[];
+    const float2 *x = in + (size_t)blockIdx.x * FFT_N;
+    for (int i = threadIdx.x; i < FFT_N; i += FFT_THREADS) {
+        float2 v = x[i];
+        if (hann) {
+            const float w = hann8192(i);
+            v.x *= w; v.y *= w;
+        }
+        s[__brev((unsigned)i) >> (32 - FFT_LOGN)] = v;
+    }
+    __syncthreads();
+    fft8192_stages(s);
+    float2 *y = out + (size_t)blockIdx.x * FFT_N;
+    for (int i = threadIdx.x; i < FFT_N; i += FFT_THREADS) y[i] = s[i];
+}
+
+// MainWindow::fftHandlerSlot (mainwindow.cpp:411-455) for a batch of independent spectrum displays,
+// one CTA each. State per display in HBM: inr[N] (the windowed input; entries beyond `len` keep
+// their previous content, mainwindow.cpp:418-425) and pwr[N] (double, the 0.95/0.05 dB average).
+//   inr[a]  = data[a]*hann[a], a < min(N, len)
+//   X       = FFT(inr)                                         (kiss_fft, unscaled)
+//   pwr[b]  = pwr[b]*0.95 + 0.05*10*log10(max(1e5*|X[i]|/N, 1)),  b = (i + N/2) mod N
+//   smooth[i] = (pwr[i] + ... + pwr[i+4])/5, i < N-10;  stats = {max(pwr) (at least avg+10), avg(pwr)}
+__global__ void __launch_bounds__(FFT_THREADS) k_spectrum_feed(const float2 *__restrict__ data, long long data_stride, int len,
+                                                               float2 *__restrict__ inr, double *__restrict__ pwr,
+                                                               double *__restrict__ smooth, double *__restrict__ stats,
+                                                               float2 *__restrict__ fft_out) {
+    extern __shared__ float2 s[];
+    __shared__ double red_max[FFT_THREADS / 32], red_sum[FFT_THREADS / 32];
+    const int d = blockIdx.x;
+    const float2 *x = data + (size_t)d * data_stride;
+    float2 *keep = inr + (size_t)d * FFT_N;
+    double *P = pwr + (size_t)d * FFT_N;
+    for (int i = threadIdx.x; i < FFT_N; i += FFT_THREADS) {
+        float2 v;
+        if (i < len) {
+            const float w = hann8192(i);
+            v = x[i];
+            v.x *= w; v.y *= w;
+            keep[i] = v;
+        } else {
+            v = keep[i];
+        }
+        s[__brev((unsigned)i) >> (32 - FFT_LOGN)] = v;
+    }
+    __syncthreads();
+    fft8192_stages(s);
+    double mx = 0.0, sum = 0.0;
+    for (int i = threadIdx.x; i < FFT_N; i += FFT_THREADS) {
+        const float2 X = s[i];
+        if (fft_out) fft_out[(size_t)d * FFT_N + i] = X;
+        const int b = (i + FFT_N / 2) & (FFT_N - 1);
+        const double val = (double)sqrtf(X.y * X.y + X.x * X.x);
+        const double p = P[b] * 0.95 + 0.05 * 10 * log10(fmax(100000.0 * fabs((1.0 / FFT_N) * val), 1.0));
+        P[b] = p;
+        mx = fmax(mx, p);
+        sum += p;
+    }
+    for (int o = 16; o > 0; o >>= 1) {
+        mx = fmax(mx, __shfl_xor_sync(0xffffffffu, mx, o));
+        sum += __shfl_xor_sync(0xffffffffu, sum, o);
+    }
+    if ((threadIdx.x & 31) == 0) { red_max[threadIdx.x >> 5] = mx; red_sum[threadIdx.x >> 5] = sum; }
+    __syncthreads();                                           // also orders the pwr[] stores before the smoothing reads
+    for (int i = threadIdx.x; i < FFT_N - 10; i += FFT_THREADS)
+        smooth[(size_t)d * (FFT_N - 10) + i] = (P[i + 4] + P[i + 3] + P[i + 2] + P[i + 1] + P[i]) / 5;
+    if (threadIdx.x == 0) {
+        for (int w = 1; w < FFT_THREADS / 32; ++w) { mx = fmax(mx, red_max[w]); sum += red_sum[w]; }
+        const double ave = sum / FFT_N;
+        if (mx - ave < 10) mx = ave + 10.0;
+        stats[2 * d] = mx;
+        stats[2 * d + 1] = ave;
+    }
 }
 
 }  // namespace sdrb

@@ -3,6 +3,7 @@
 // demodulated goes through an sdrb_* entry point, i.e. through a CUDA kernel.
 #include <cuda_runtime.h>
 
+#include <algorithm>
 #include <cmath>
 #include <cstring>
 
@@ -263,6 +264,7 @@ void vfo::init(int spb, bool bind, int late) {
     if (demodUSB && late > 0) { targetRate /= late; samplesOut /= late; }
     outputRate = (uint32_t)targetRate;
     transmit_usb.assign((size_t)samplesOut, 0);
+    transmit_iq.assign((size_t)(cstyle == 1 ? samplesOut : 2 * samplesOut), 0);          // vfo.cpp:143-150
     decimate[0].resize((size_t)spb);
     for (int a = 1; a < decimateCount + 1; a++) decimate[a].resize(decimate[a - 1].size() / 2);
     if (!vfo::bind_publisher.connected && bind) {
@@ -284,14 +286,21 @@ static void fill_sub_desc(sdrb_sub_desc &d, const std::string &topic, int main_i
     d.main_idx = main_idx; d.mixer_hz = mixer; d.decim = decim; d.late = late; d.filter_bw = filterbw; d.gain = gain;
 }
 
+static void fill_main_desc(sdrb_main_desc &d, double mixer, int decim, const std::string &topic, int scalecomp, int cstyle) {
+    memset(&d, 0, sizeof(d));
+    d.mixer_hz = mixer; d.decim = decim;
+    strncpy(d.topic, topic.c_str(), sizeof(d.topic) - 1);
+    d.compress_scale = scalecomp;
+    d.compress_style = cstyle == 1 ? 1 : 2;                  // vfo.cpp:393: 1 = 4-bit arms, anything else int8 pairs
+}
+
 void vfo::compile_tree() {
-    if (!mpVFOs || mpVFOs->empty())
-        throw Error("vfo::process: a VFO without children would publish compressed IQ (vfo::compress), which is not built");
     sdrb_plan_desc *d = new sdrb_plan_desc();
     memset(d, 0, sizeof(*d));
     d->sample_rate = Fs; d->block = samplesPerBuffer; d->bufsplit = Fs / samplesPerBuffer; d->correct_dc = 0;
-    d->n_main = 1; d->mains[0].mixer_hz = mixer_freq; d->mains[0].decim = decimateCount;
-    d->n_sub = (int)mpVFOs->size();
+    d->n_main = 1;
+    fill_main_desc(d->mains[0], mixer_freq, decimateCount, zmqTopic, scalecomp, cstyle);
+    d->n_sub = mpVFOs ? (int)mpVFOs->size() : 0;
     if (d->n_sub > SDRB_MAX_SUB) { delete d; throw Error("vfo: too many sub VFOs"); }
     for (int i = 0; i < d->n_sub; i++) {
         const vfo *c = (*mpVFOs)[(size_t)i];
@@ -303,18 +312,22 @@ void vfo::compile_tree() {
     check(sdrb_bank_create(plan, 0, 1, 1, &bank), "sdrb_bank_create");
     sdrb_plan_info info;
     sdrb_plan_get_info(plan, &info);
-    pcm_record.assign((size_t)info.pcm_per_block, 0);
+    pcm_record.assign((size_t)std::max(info.pcm_per_block, 1), 0);
 }
 
 void vfo::process(const std::vector<cpx_typef> &samples) {
-    if (!mpVFOs || mpVFOs->empty())
+    if (demodUSB)
         throw Error("vfo::process on a leaf VFO: leaves are driven by their parent (vfo.cpp:253-266)");
     if ((int)samples.size() != samplesPerBuffer) throw Error("vfo::process: samples.size() must equal samplesPerBuffer");
     if (!bank) compile_tree();
     check(sdrb_bank_process_cf32_host(bank, reinterpret_cast<const float *>(samples.data()), samples.size(), 1,
                                       pcm_record.data(), nullptr), "sdrb_bank_process_cf32_host");
     check(sdrb_bank_read_main(bank, 0, 1, reinterpret_cast<float *>(decimate[decimateCount].data())), "sdrb_bank_read_main");
-    for (size_t i = 0; i < mpVFOs->size(); i++) {
+    if (!mpVFOs || mpVFOs->empty()) {                        // vfo.cpp:268-286: compress() + transmitData()
+        check(sdrb_bank_read_forward(bank, 0, 1, reinterpret_cast<uint8_t *>(transmit_iq.data())), "sdrb_bank_read_forward");
+        transmitData();
+    }
+    for (size_t i = 0; mpVFOs && i < mpVFOs->size(); i++) {
         vfo *c = (*mpVFOs)[i];
         sdrb_sub_info si;
         sdrb_plan_get_sub(plan, (int)i, &si);
@@ -324,9 +337,13 @@ void vfo::process(const std::vector<cpx_typef> &samples) {
     if (emitFFT && fftData) fftData(decimate[decimateCount]);
 }
 
-void vfo::transmitData() {                                   // vfo.cpp:426-437 (USB branch)
-    if (!demodUSB) return;
+void vfo::transmitData() {                                   // vfo.cpp:426-453
     ZmqPublisher &p = zmqBind ? vfo::bind_publisher : connect_publisher;
+    if (!demodUSB) {
+        if (zmqTopic.length() > 0)
+            p.publish(reinterpret_cast<unsigned char *>(transmit_iq.data()), (uint32_t)transmit_iq.size(), zmqTopic, outputRate);
+        return;
+    }
     p.publish(reinterpret_cast<unsigned char *>(transmit_usb.data()), (uint32_t)(transmit_usb.size() * sizeof(short)),
               zmqTopic, outputRate);
 }
@@ -357,7 +374,7 @@ void sdrj::compile_tree(int block) {
     leaves.clear();
     for (int m = 0; m < d->n_main; m++) {
         const vfo *mv = (*mpVFOs)[(size_t)m];
-        d->mains[m].mixer_hz = mv->mixer_freq; d->mains[m].decim = mv->decimateCount;
+        fill_main_desc(d->mains[m], mv->mixer_freq, mv->decimateCount, mv->zmqTopic, mv->scalecomp, mv->cstyle);
         if (!mv->mpVFOs) continue;
         for (vfo *c : *mv->mpVFOs) {
             if (d->n_sub >= SDRB_MAX_SUB) { delete d; throw Error("sdrj: too many sub VFOs"); }
@@ -372,7 +389,7 @@ void sdrj::compile_tree(int block) {
     check(sdrb_bank_create(plan, 0, 1, 1, &bank), "sdrb_bank_create");
     sdrb_plan_info info;
     sdrb_plan_get_info(plan, &info);
-    pcm_record.assign((size_t)info.pcm_per_block, 0);
+    pcm_record.assign((size_t)std::max(info.pcm_per_block, 1), 0);
     staging.assign(((size_t)block * 2 + 15) / 16 * 16, 127);
 }
 
@@ -391,6 +408,12 @@ void sdrj::run(const unsigned char *bytes, uint32_t len) {
         sdrb_plan_get_sub(plan, (int)i, &si);
         c->transmit_usb.assign(pcm_record.begin() + si.pcm_offset, pcm_record.begin() + si.pcm_offset + si.samples_out);
         if (publishEnabled) c->transmitData();
+    }
+    for (size_t m = 0; m < mpVFOs->size(); m++) {             // childless main VFOs forward packed IQ (vfo.cpp:268-286)
+        vfo *mv = (*mpVFOs)[m];
+        if (mv->mpVFOs && !mv->mpVFOs->empty()) continue;
+        check(sdrb_bank_read_forward(bank, (int)m, 1, reinterpret_cast<uint8_t *>(mv->transmit_iq.data())), "sdrb_bank_read_forward");
+        if (publishEnabled) mv->transmitData();
     }
     // sdrj.cpp:296-303: every 4th buffer goes to the spectrum display when "Main" is selected
     if (count == 4 && emitFFT && fftData) {

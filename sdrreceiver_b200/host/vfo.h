@@ -6,7 +6,9 @@
 // plan on first use (sdrb_plan_create) and from then on every call runs the whole subtree on
 // the device: mix + half-band cascade, then per child mix, cascade, /late FIR, USB demod,
 // low-pass, gain, int16 and the ZMQ publish. Calling process() on a child throws: the
-// reference only ever reaches children through their parent (vfo.cpp:253-266).
+// reference only ever reaches children through their parent (vfo.cpp:253-266). A root without
+// children is the reference's IQ forwarder: mix + cascade, vfo::compress (vfo.cpp:389-424) and,
+// when it has a topic, one ZMQ message of packed IQ bytes per callback.
 #ifndef VFO_H
 #define VFO_H
 #include <cstdint>
@@ -51,6 +53,8 @@ public:
 
     // what the last callback produced for this (leaf) VFO: the ZMQ payload
     const std::vector<short> &lastAudio() const { return transmit_usb; }
+    // ... and for a childless root: the vfo::compress payload (transmit_iq, vfo.h:69)
+    const std::vector<signed char> &lastForward() const { return transmit_iq; }
     uint32_t getOutputRate() const { return outputRate; }
     const std::string &getZmqTopic() const { return zmqTopic; }
 
@@ -62,6 +66,7 @@ private:
     static ZmqPublisher bind_publisher;
     ZmqPublisher connect_publisher;
     std::vector<short> transmit_usb;
+    std::vector<signed char> transmit_iq;
     int decimateCount;
     uint32_t outputRate;
     float gain;

@@ -5,7 +5,7 @@
 // and the facade headers: no CUDA headers, no Qt.
 //
 //   facade_check tree  PLAN.ini IQ.u8 OUTDIR N_BLOCKS     sdrj path (uint8 in, DC, all VFOs)
-//   facade_check vfo   PLAN.ini IQ.u8 OUTDIR N_BLOCKS     vfo::process on main VFO 0 (cf32 in)
+//   facade_check vfo   PLAN.ini IQ.u8 OUTDIR N_BLOCKS [K]  vfo::process on main VFO K (default 0; cf32 in)
 //   facade_check prims OUTDIR                             per-class known answers
 #include <cstdio>
 #include <cstdlib>
@@ -51,6 +51,8 @@ static void build_tree(const char *ini, sdrb_plan_info &info) {
         pVFO->setMixerFreq(m.mixer_hz);
         pVFO->setDemodUSB(false);
         pVFO->setCompressonStyle(1);
+        if (m.compress_scale > 0) pVFO->setScaleComp(m.compress_scale);     // mainwindow.cpp:112-118
+        if (m.topic[0]) { pVFO->setZmqAddress(""); pVFO->setZmqTopic(m.topic); }   // no socket in the test
         pVFO->init(info.block, false);
         pVFO->setVFOs(&VFOsub[i]);
         VFOmain.push_back(pVFO);
@@ -95,9 +97,12 @@ static int run_tree(int argc, char **argv) {
         } else {
             radio->rtlsdr_callback(src, (uint32_t)len);
         }
-        for (int m = 0; m < (int)VFOmain.size(); m++)
+        for (int m = 0; m < (int)VFOmain.size(); m++) {
             for (vfo *leaf : VFOsub[m])
                 append(out + "/" + leaf->getZmqTopic() + ".pcm", leaf->lastAudio().data(), leaf->lastAudio().size());
+            if (VFOsub[m].empty() && !VFOmain[m]->getZmqTopic().empty())    // IQ forwarder (vfo::compress)
+                append(out + "/" + VFOmain[m]->getZmqTopic() + ".iq8", VFOmain[m]->lastForward().data(), VFOmain[m]->lastForward().size());
+        }
     }
     delete radio;                                    // deletes the whole tree, like sdrj::~sdrj
     return 0;
@@ -110,7 +115,8 @@ static int run_vfo(int argc, char **argv) {
     std::vector<unsigned char> iq = slurp(argv[3]);
     const std::string out = argv[4];
     const int n_blocks = atoi(argv[5]);
-    vfo *root = VFOmain[0];
+    const int K = argc > 6 ? atoi(argv[6]) : 0;
+    vfo *root = VFOmain[(size_t)K];
     std::vector<cpx_typef> samples((size_t)info.block);
     for (int b = 0; b < n_blocks; b++) {
         const unsigned char *src = iq.data() + (size_t)b * info.block * 2;
@@ -118,9 +124,10 @@ static int run_vfo(int argc, char **argv) {
             samples[(size_t)i] = cpx_typef((float)((int)src[2 * i] - 127), (float)((int)src[2 * i + 1] - 127));
         root->process(samples);
         const std::vector<cpx_typef> &tap = root->decimate[(int)lround(log2((double)info.sample_rate / root->getOutRate()))];
-        append(out + "/main0.cf32", tap.data(), tap.size());
-        for (vfo *leaf : VFOsub[0])
+        append(out + "/main" + std::to_string(K) + ".cf32", tap.data(), tap.size());
+        for (vfo *leaf : VFOsub[K])
             append(out + "/" + leaf->getZmqTopic() + ".pcm", leaf->lastAudio().data(), leaf->lastAudio().size());
+        if (VFOsub[K].empty()) append(out + "/" + root->getZmqTopic() + ".iq8", root->lastForward().data(), root->lastForward().size());
     }
     bool threw = false;
     try { VFOsub[0][0]->process(samples); } catch (const sdrb_host::Error &) { threw = true; }

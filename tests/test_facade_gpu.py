@@ -62,6 +62,47 @@ def test_vfo_process_on_a_main_vfo(tmp_path):
     orc.close()
 
 
+def _nibbles_close(got, want):
+    """vfo::compress bytes from main-VFO outputs that agree to ~1e-6: a nibble may differ by one step
+    (mod 16) where a sample sits on a quantisation step, in a tiny fraction of the bytes."""
+    assert got.size == want.size
+    dre = ((got >> 4).astype(np.int32) - (want >> 4).astype(np.int32)) % 16
+    dim = ((got & 15).astype(np.int32) - (want & 15).astype(np.int32)) % 16
+    assert np.isin(dre, (0, 1, 15)).all() and np.isin(dim, (0, 1, 15)).all()
+    assert np.mean(got != want) < 2e-3
+
+
+def test_iq_forwarder_through_sdrj_and_vfo(tmp_path):
+    """Main VFOs without sub VFOs publish vfo::compress bytes (vfo.cpp:268-286, 389-424)."""
+    name, n_blocks = "FWD_test", 3
+    op = OP.build_plan(plan_path(name))
+    iq = synth.make_iq(op["Fs"], op["block"] * n_blocks, synth.carriers_for_plan(op["center"], op["subs"]))
+    iq.tofile(tmp_path / "iq.u8")
+    (tmp_path / "tree").mkdir(); (tmp_path / "vfo").mkdir()
+    run("tree", plan_path(name), tmp_path / "iq.u8", tmp_path / "tree", n_blocks)
+    orc = O.Oracle(op, main_tap=True)
+    orc.process(iq)
+    for k in (1, 2):
+        m = op["mains"][k]
+        got = np.fromfile(tmp_path / "tree" / (m["topic"] + ".iq8"), dtype=np.uint8)
+        _nibbles_close(got, O.compress(orc.main_tap(k), m["scalecomp"], 1))
+    for k, s in enumerate(op["subs"]):
+        got = np.fromfile(tmp_path / "tree" / (s["topic"] + ".pcm"), dtype=np.int16)
+        assert np.abs(got.astype(np.int32) - orc.pcm(k).astype(np.int32)).max() <= 1
+    orc.close()
+    # vfo::process on the childless root itself (cf32 in, no DC stage, a plan with zero sub VFOs)
+    run("vfo", plan_path(name), tmp_path / "iq.u8", tmp_path / "vfo", n_blocks, 1)
+    solo = dict(op, dc=False, mains=[op["mains"][1]], subs=[])
+    orc = O.Oracle(solo, main_tap=True)
+    orc.process(iq)
+    tap = np.fromfile(tmp_path / "vfo" / "main1.cf32", dtype=np.complex64)
+    assert np.linalg.norm(tap - orc.main_tap(0)) / np.linalg.norm(orc.main_tap(0)) <= 1e-5
+    got = np.fromfile(tmp_path / "vfo" / "IQ002.iq8", dtype=np.uint8)
+    assert np.array_equal(got, O.compress(tap, 16, 1))
+    _nibbles_close(got, O.compress(orc.main_tap(0), 16, 1))
+    orc.close()
+
+
 def test_class_facades(tmp_path):
     out = run("prims", tmp_path)
     assert out == {"hb23_throws": "1", "lowpass_throws": "1"}
