@@ -154,6 +154,18 @@ int sdrb_bank_process_device_ex(sdrb_bank *bank, const uint8_t *d_iq, size_t iq_
  * process call: cf32 [n_streams][n_blocks*block_out] on the device. */
 int sdrb_bank_copy_main(sdrb_bank *bank, int main_idx, int n_blocks, float *d_out_cf32, void *cuda_stream);
 
+/* Spectrum sources of the last process call, as the reference emits them through fftData:
+ *   input: the `samples` vector of sdrj::demodData (sdrj.cpp:271-294; shown when "Main" is selected,
+ *          sdrj.cpp:296-303): converted and, with correct_dc_bias, DC-corrected input of callback
+ *          `cb`, first n samples (n a multiple of 128, <= block): cf32 [n_streams][n]. Bit-identical
+ *          to the reference. For the device entry points the d_iq of that call must still be valid.
+ *   sub:   vfo::decimate[decimateCount] of sub VFO sub_idx (vfo.cpp:290-293; shown when that VFO is
+ *          selected): cf32 [n_streams][n_blocks*block_z], block_z = (in_rate/bufsplit) >> decim. */
+int sdrb_bank_copy_input(sdrb_bank *bank, int cb, int n, float *d_out_cf32, void *cuda_stream);
+int sdrb_bank_read_input(sdrb_bank *bank, int cb, int n, float *h_out_cf32);
+int sdrb_bank_copy_sub(sdrb_bank *bank, int sub_idx, int n_blocks, float *d_out_cf32, void *cuda_stream);
+int sdrb_bank_read_sub(sdrb_bank *bank, int sub_idx, int n_blocks, float *h_out_cf32);
+
 /* IQ forwarder output of the last process call (vfo::compress, vfo.cpp:389-424, followed by
  * vfo::transmitData, vfo.cpp:439-451): for main VFO `main_idx` the packed bytes of every stream,
  * uint8 [n_streams][n_blocks*fwd_bytes_per_block]; each fwd_bytes_per_block slice is one ZMQ
@@ -260,6 +272,12 @@ int sdrb_spectrum_reset(sdrb_spectrum *sp, int display /* -1 = all */);
 int sdrb_spectrum_feed_device(sdrb_spectrum *sp, const float *d_in_cf32, size_t in_stride, int len, float *d_fft_out,
                               void *cuda_stream);
 int sdrb_spectrum_feed_host(sdrb_spectrum *sp, const float *h_in_cf32, size_t in_stride, int len);
+/* The batched form: one fftHandlerSlot per receiver of `bank` (sp must have n_streams displays on
+ * the same device) straight from the bank's device buffers, callback `cb` of the last process
+ * call. source -1 = "Main": the DC-corrected input samples, emitted by the reference on every
+ * 4th callback (sdrj.cpp:296-303); source k >= 0 = sub VFO k's decimate[decimateCount], emitted
+ * on every callback while that VFO is selected (vfo.cpp:290-293). Only enqueues. */
+int sdrb_bank_spectrum_feed(sdrb_bank *bank, sdrb_spectrum *sp, int source, int cb, float *d_fft_out, void *cuda_stream);
 /* Host copies (any pointer may be NULL): smooth double [n][nfft-10], pwr double [n][nfft],
  * stats double [n][2] = {maxval, aveval}. Synchronises the device. */
 int sdrb_spectrum_read(sdrb_spectrum *sp, double *h_smooth, double *h_pwr, double *h_stats);

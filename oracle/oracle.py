@@ -57,6 +57,7 @@ def lib():
         L.orc_low_pass.restype = i; L.orc_low_pass.argtypes = [d, d, d, d, vp, i]
         L.orc_dc_trace.restype = None; L.orc_dc_trace.argtypes = [vp, l, i, vp]
         L.orc_compress.restype = None; L.orc_compress.argtypes = [vp, l, i, i, vp]
+        L.orc_input_samples.restype = None; L.orc_input_samples.argtypes = [vp, l, i, vp]
         _lib = L
     return _lib
 
@@ -174,6 +175,15 @@ def compress(cf, scalecomp=1, cstyle=1):
     return out
 
 
+def input_samples(iq_u8, correct_dc):
+    """The `samples` vector of sdrj::demodData for the whole stream (sdrj.cpp:271-294): complex64."""
+    iq = np.ascontiguousarray(iq_u8, dtype=np.uint8)
+    n = iq.size // 2
+    out = np.zeros(2 * n, dtype=np.float32)
+    lib().orc_input_samples(_p(iq), n, int(bool(correct_dc)), _p(out))
+    return out.view(np.complex64)
+
+
 def dc_trace(iq_u8, every=32):
     """avept (sdrj.cpp:280) entering every `every`-th sample, complex64."""
     iq = np.ascontiguousarray(iq_u8, dtype=np.uint8)
@@ -183,10 +193,12 @@ def dc_trace(iq_u8, every=32):
     return out.view(np.complex64)
 
 
-def run_ref(ini_path, iq_u8, float_tap=False, main_tap=False, blocks=None):
+def run_ref(ini_path, iq_u8, float_tap=False, main_tap=False, blocks=None, fft=None):
     """Run the unmodified reference on `iq_u8`. Returns (outputs, frames, mains):
     outputs[topic] = int16 (or float32) array, frames = list of (topic_bytes, rate,
-    payload_bytes, parts), mains[k] = complex64 decimate[decimateCount] of main k."""
+    payload_bytes, parts), mains[k] = complex64 decimate[decimateCount] of main k.
+    fft="Main" or a sub VFO topic: the combo-box selection; a 4th value is returned, the list of
+    (callback, "sdrj"|"vfo", complex64 buffer) the reference emitted through its fftData signals."""
     exe = os.path.join(REF_DIR, "sdr_ref_f32" if float_tap else "sdr_ref_i16")
     with tempfile.TemporaryDirectory() as d:
         inp = os.path.join(d, "iq.u8")
@@ -196,6 +208,8 @@ def run_ref(ini_path, iq_u8, float_tap=False, main_tap=False, blocks=None):
             cmd.append("--main-tap")
         if blocks is not None:
             cmd += ["--blocks", str(blocks)]
+        if fft is not None:
+            cmd += ["--fft", fft]
         subprocess.run(cmd, check=True)
         outs, frames, mains = {}, [], {}
         for fn in sorted(os.listdir(d)):
@@ -207,6 +221,14 @@ def run_ref(ini_path, iq_u8, float_tap=False, main_tap=False, blocks=None):
             for line in f:
                 t, rate, nb, parts = line.split()
                 frames.append((bytes.fromhex(t), int(rate), int(nb), int(parts)))
+        if fft is not None:
+            emits, data, at = [], np.fromfile(os.path.join(d, "fft.cf32"), dtype=np.complex64), 0
+            with open(os.path.join(d, "fft.txt")) as f:
+                for line in f:
+                    cb, who, n = line.split()
+                    emits.append((int(cb), who, data[at:at + int(n)].copy()))
+                    at += int(n)
+            return outs, frames, mains, emits
     return outs, frames, mains
 
 

@@ -21,6 +21,9 @@
 //   DIR/main<k>.cf32  (--main-tap) decimate[decimateCount] of main VFO k, every block
 //   --time            no files; prints "samples seconds" for the demodData loop only
 //   --skip N          (with --time) first N callbacks run untimed (warm-up)
+//   --fft SEL         what MainWindow's VFO combo box does (mainwindow.cpp:539-541): SEL = "Main" or
+//                     a sub VFO topic is sent to sdrj::fftVFOSlot and every sub VFO's fftVFOSlot
+//                     (mainwindow.cpp:228,261); the emitted buffers go to DIR/fft.cf32 / fft.txt
 #include <chrono>
 #include <cstdio>
 #include <fstream>
@@ -31,8 +34,17 @@
 #include "sdrj.h"
 
 // ---- moc stand-ins (signals are plain functions once Q_OBJECT is empty) ----
-void vfo::fftData(const std::vector<cpx_typef> &) {}
-void sdrj::fftData(const std::vector<cpx_typef> &) {}
+// With --fft SEL the two fftData signals write what they carry (the spectrum display's input,
+// mainwindow.cpp:227,259) to DIR/fft.cf32 and one line "callback source length" to DIR/fft.txt.
+static FILE *g_fft_out = 0, *g_fft_log = 0;
+static long g_callback = 0;
+static void fft_emit(const char *who, const std::vector<cpx_typef> &v) {
+    if (!g_fft_out) return;
+    fwrite(v.data(), sizeof(cpx_typef), v.size(), g_fft_out);
+    fprintf(g_fft_log, "%ld %s %zu\n", g_callback, who, v.size());
+}
+void vfo::fftData(const std::vector<cpx_typef> &v) { fft_emit("vfo", v); }
+void sdrj::fftData(const std::vector<cpx_typef> &v) { fft_emit("sdrj", v); }
 void sdr::audio_signal_out(const float *, int) {}
 
 // ---- librtlsdr: no device ----
@@ -113,6 +125,7 @@ int main(int argc, char **argv) {
     const char *ini_path = 0, *in_path = 0, *out_dir = 0;
     long max_blocks = -1, skip_blocks = 0;
     bool main_tap = false, timing = false;
+    const char *fft_sel = 0;
     for (int i = 1; i < argc; i++) {
         std::string a = argv[i];
         if (a == "--ini" && i + 1 < argc) ini_path = argv[++i];
@@ -122,6 +135,7 @@ int main(int argc, char **argv) {
         else if (a == "--main-tap") main_tap = true;
         else if (a == "--time") timing = true;
         else if (a == "--skip" && i + 1 < argc) skip_blocks = atol(argv[++i]);
+        else if (a == "--fft" && i + 1 < argc) fft_sel = argv[++i];
         else { fprintf(stderr, "unknown argument %s\n", argv[i]); return 2; }
     }
     if (!ini_path || !in_path || (!out_dir && !timing)) {
@@ -218,6 +232,11 @@ int main(int argc, char **argv) {
     radio->setVFOs(&VFOmain);
     radio->setDCCorrection(dc);
     radio->fftVFOSlot("none");   // sdrj::emitFFT is otherwise uninitialised (sdrj.cpp:4-18)
+    if (fft_sel) {
+        radio->fftVFOSlot(fft_sel);
+        for (int m = 0; m < 3; m++)
+            for (int a = 0; a < VFOsub[m].length(); a++) VFOsub[m].at(a)->fftVFOSlot(fft_sel);
+    }
 
     // ---- input ----
     FILE *fi = fopen(in_path, "rb");
@@ -243,11 +262,16 @@ int main(int argc, char **argv) {
                 mtap.push_back(fopen((d + "/main" + std::to_string(k) + ".cf32").c_str(), "wb"));
     }
     g_capture = !timing;
+    if (fft_sel && !timing) {
+        g_fft_out = fopen((std::string(out_dir) + "/fft.cf32").c_str(), "wb");
+        g_fft_log = fopen((std::string(out_dir) + "/fft.txt").c_str(), "w");
+    }
 
     std::vector<float> fl(buflen);
     double seconds = 0;
     for (long b = 0; b < nblocks; b++) {
         const unsigned char *src = iq.data() + b * (long)buflen;
+        g_callback = b;
         auto t0 = std::chrono::steady_clock::now();
         for (int i = 0; i < buflen; i++) fl[i] = radio->floats.at(src[i]);   // sdr.cpp:122-129
         radio->demodData(fl.data(), buflen);
@@ -281,6 +305,7 @@ int main(int argc, char **argv) {
     }
     for (auto &kv : pcm) if (kv.second) fclose(kv.second);
     for (FILE *f : mtap) if (f) fclose(f);
+    if (g_fft_out) { fclose(g_fft_out); fclose(g_fft_log); }
     fclose(frames);
     return 0;
 }

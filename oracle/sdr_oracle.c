@@ -595,6 +595,30 @@ void orc_compress(const float *in_iq, long n, int scalecomp, int cstyle, unsigne
     }
 }
 
+/* The `samples` vector of sdrj::demodData (sdrj.cpp:271-294) for a whole stream from its start:
+ * byte -> float (jonti/sdr.cpp:43-49) and, if correct_dc, the running-mean removal. It is what
+ * the "Main" spectrum is computed from (sdrj.cpp:296-303). Pinned to the unmodified reference
+ * through the fftData signal (oracle/ref_harness.cpp --fft Main). */
+void orc_input_samples(const uint8_t *iq, long n, int correct_dc, float *out_iq) {
+    const float a = 1.0f - 0.000001f, c = 0.000001f;
+    cf32 avept;
+    long i;
+    avept.re = 0; avept.im = 0;
+    for (i = 0; i < n; ++i) {
+        cf32 curr;
+        curr.re = (float)((int)iq[2 * i] - 127);
+        curr.im = (float)((int)iq[2 * i + 1] - 127);
+        if (correct_dc) {
+            avept.re = avept.re * a + c * curr.re;
+            avept.im = avept.im * a + c * curr.im;
+            curr.re -= avept.re;
+            curr.im -= avept.im;
+        }
+        out_iq[2 * i] = curr.re;
+        out_iq[2 * i + 1] = curr.im;
+    }
+}
+
 void orc_dc_trace(const uint8_t *iq, long n, int every, float *out_iq) {
     const float a = 1.0f - 0.000001f, c = 0.000001f;
     cf32 avept;

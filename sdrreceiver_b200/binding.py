@@ -113,6 +113,11 @@ def lib():
         "sdrb_spectrum_feed_device": (i, [vp, vp, sz, i, vp, vp]),
         "sdrb_spectrum_feed_host": (i, [vp, vp, sz, i]),
         "sdrb_spectrum_read": (i, [vp, vp, vp, vp]),
+        "sdrb_bank_spectrum_feed": (i, [vp, vp, i, i, vp, vp]),
+        "sdrb_bank_copy_input": (i, [vp, i, i, vp, vp]),
+        "sdrb_bank_read_input": (i, [vp, i, i, vp]),
+        "sdrb_bank_copy_sub": (i, [vp, i, i, vp, vp]),
+        "sdrb_bank_read_sub": (i, [vp, i, i, vp]),
         "sdrb_publisher_open": (i, [C.c_char_p, i, P(vp)]),
         "sdrb_publisher_send": (i, [vp, C.c_char_p, C.c_uint32, vp, C.c_uint32]),
         "sdrb_publisher_send_block": (i, [vp, vp, vp]),
@@ -237,6 +242,24 @@ class Bank:
     def copy_dc_trace(self, n_blocks, d_out_ptr, d_modes_ptr=None, cuda_stream=None):
         _check(lib().sdrb_bank_copy_dc_trace(self.h, n_blocks, d_out_ptr, d_modes_ptr, cuda_stream),
                "sdrb_bank_copy_dc_trace")
+
+    def read_input(self, cb, n):
+        """sdrj::demodData's `samples` of callback cb of the last call: complex64 [n_streams, n]."""
+        out = np.zeros((self.n_streams, n), dtype=np.complex64)
+        _check(lib().sdrb_bank_read_input(self.h, cb, n, out.ctypes.data_as(C.c_void_p)), "sdrb_bank_read_input")
+        return out
+
+    def read_sub(self, sub_idx, n_blocks):
+        """vfo::decimate[decimateCount] of a sub VFO for the last call: complex64 [n_streams, n_blocks*block_z]."""
+        s = self.plan.subs[sub_idx]
+        block_z = s["samples_out"] * (s["late"] or 1)
+        out = np.zeros((self.n_streams, n_blocks * block_z), dtype=np.complex64)
+        _check(lib().sdrb_bank_read_sub(self.h, sub_idx, n_blocks, out.ctypes.data_as(C.c_void_p)), "sdrb_bank_read_sub")
+        return out
+
+    def spectrum_feed(self, spectrum, source, cb, d_fft_out_ptr=None, cuda_stream=None):
+        _check(lib().sdrb_bank_spectrum_feed(self.h, spectrum.h, source, cb, d_fft_out_ptr, cuda_stream),
+               "sdrb_bank_spectrum_feed")
 
     def copy_forward(self, main_idx, n_blocks, d_out_ptr, cuda_stream=None):
         _check(lib().sdrb_bank_copy_forward(self.h, main_idx, n_blocks, d_out_ptr, cuda_stream), "sdrb_bank_copy_forward")

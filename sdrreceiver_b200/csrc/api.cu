@@ -7,6 +7,7 @@
 #include <cmath>
 #include <cstdio>
 #include <cstring>
+#include <functional>
 #include <map>
 #include <new>
 #include <string>
@@ -197,6 +198,12 @@ struct sdrb_bank {
     std::vector<size_t> main_off;           // per main: offset (float2 units) inside main_out per stream
     size_t main_stride = 0;                 // float2 per stream
     size_t z_stride = 0;                    // float2 per stream in zbuf
+    std::vector<size_t> sub_z_off;          // per sub VFO: offset of its slice inside a stream's zbuf row
+    std::vector<int> sub_z_hist;            // ... and the history samples in front of the body
+    // what the last process call consumed (inspection entry points: spectrum of the raw input)
+    const uint8_t *last_iq = nullptr; size_t last_iq_stride = 0;
+    const float2 *last_cf = nullptr; size_t last_cf_stride = 0;
+    int last_blocks = 0, last_par = 0;
     // host staging for process_host
     DevBuf d_iq, d_pcm, d_tap, d_cf, d_fwd;
     cudaStream_t s_copy_in = nullptr, s_compute = nullptr, s_copy_out = nullptr;
@@ -392,6 +399,7 @@ extern "C" int sdrb_bank_create(const sdrb_plan *plan, int device, int n_streams
         rf_table((double)s.fs, s.mixer, &rfhost[(h.mains.size() + k) * RF_LEN]);
     }
     b->z_stride = z_stride;
+    b->sub_z_off = z_off; b->sub_z_hist = z_hist;
     for (size_t i = 0; i < h.subs.size(); i++) {
         const SubVfo &s = h.subs[i];
         UsbDev U;
@@ -663,6 +671,8 @@ static int enqueue_all(sdrb_bank *b, CallCtx &c, cudaStream_t st, int *launches,
     const int ns = b->n_streams;
     int rc;
     c.par = b->dc_par;
+    b->last_iq = c.d_iq; b->last_iq_stride = c.iq_stride; b->last_cf = c.d_cf; b->last_cf_stride = c.cf_stride;
+    b->last_blocks = c.n_blocks; b->last_par = c.par;
     if (dc) {
         cudaStream_t sd = b->s_dc[0];
         if (input_ready) {
@@ -821,6 +831,80 @@ extern "C" int sdrb_compress_iq(const float *d_in, uint8_t *d_out, int n_ch, int
     return SDRB_OK;
 }
 
+// sdrj::demodData's `samples` (sdrj.cpp:271-294) of callback cb of the last call, first n samples.
+static int input_launch(sdrb_bank *b, int cb, int n, float2 *d_out, cudaStream_t st) {
+    const HostPlan &h = b->plan->h;
+    if (b->last_cf) {
+        CU_TRY(cudaMemcpy2DAsync(d_out, (size_t)n * sizeof(float2), b->last_cf + (size_t)cb * h.block, b->last_cf_stride * sizeof(float2),
+                                 (size_t)n * sizeof(float2), (size_t)b->n_streams, cudaMemcpyDeviceToDevice, st));
+        return SDRB_OK;
+    }
+    const bool dc = h.correct_dc != 0;
+    k_input_samples<<<dim3((unsigned)((n / DC_BLK + 63) / 64), (unsigned)b->n_streams), 64, 0, st>>>(
+        b->last_iq, b->last_iq_stride, (size_t)cb * h.block, n, dc ? b->table_buf(b->last_par) : nullptr, b->anchor_buf(b->last_par),
+        b->dc_stride + DC_HALO_BLKS, cb * (h.block / DC_BLK), d_out);
+    CU_TRY(cudaGetLastError());
+    return SDRB_OK;
+}
+
+static int check_input_args(sdrb_bank *b, int cb, int n, const void *out, const char *who) {
+    if (!b || !out || !(b->last_iq || b->last_cf) || cb < 0 || cb >= b->last_blocks || n <= 0 || n > b->plan->h.block || n % DC_BLK != 0) {
+        set_error(std::string(who) + ": needs a previous process call, 0 <= cb < its n_blocks and n a multiple of 128 up to the callback size");
+        return SDRB_E_INVALID;
+    }
+    return SDRB_OK;
+}
+
+extern "C" int sdrb_bank_copy_input(sdrb_bank *b, int cb, int n, float *d_out, void *cuda_stream) {
+    int rc = check_input_args(b, cb, n, d_out, "sdrb_bank_copy_input");
+    if (rc != SDRB_OK) return rc;
+    CU_TRY(cudaSetDevice(b->device));
+    return input_launch(b, cb, n, (float2 *)d_out, (cudaStream_t)cuda_stream);
+}
+
+extern "C" int sdrb_bank_copy_sub(sdrb_bank *b, int sub_idx, int n_blocks, float *d_out, void *cuda_stream) {
+    if (!b || !d_out || sub_idx < 0 || sub_idx >= (int)b->plan->h.subs.size() || n_blocks <= 0 || n_blocks > b->max_blocks) {
+        set_error("sdrb_bank_copy_sub: bad argument"); return SDRB_E_INVALID;
+    }
+    CU_TRY(cudaSetDevice(b->device));
+    const SubVfo &s = b->plan->h.subs[(size_t)sub_idx];
+    const size_t row = (size_t)n_blocks * s.block_z * sizeof(float2);
+    CU_TRY(cudaMemcpy2DAsync(d_out, row, (float2 *)b->zbuf.p + b->sub_z_off[(size_t)sub_idx] + b->sub_z_hist[(size_t)sub_idx],
+                             b->z_stride * sizeof(float2), row, (size_t)b->n_streams, cudaMemcpyDeviceToDevice,
+                             (cudaStream_t)cuda_stream));
+    return SDRB_OK;
+}
+
+// Host variants for the C++ facades: device scratch, copy, synchronise.
+static int read_back(sdrb_bank *b, size_t bytes, void *h_out, const std::function<int(void *, cudaStream_t)> &fill) {
+    void *tmp = nullptr;
+    CU_TRY(cudaMalloc(&tmp, bytes ? bytes : 16));
+    int rc = fill(tmp, b->s_compute);
+    cudaError_t e = cudaSuccess;
+    if (rc == SDRB_OK) e = cudaMemcpyAsync(h_out, tmp, bytes, cudaMemcpyDeviceToHost, b->s_compute);
+    cudaStreamSynchronize(b->s_compute);
+    cudaFree(tmp);
+    if (rc == SDRB_OK && e != cudaSuccess) { set_error(std::string("read back: ") + cudaGetErrorString(e)); rc = SDRB_E_CUDA; }
+    return rc;
+}
+
+extern "C" int sdrb_bank_read_input(sdrb_bank *b, int cb, int n, float *h_out) {
+    int rc = check_input_args(b, cb, n, h_out, "sdrb_bank_read_input");
+    if (rc != SDRB_OK) return rc;
+    CU_TRY(cudaSetDevice(b->device));
+    return read_back(b, (size_t)b->n_streams * (size_t)n * sizeof(float2), h_out,
+                     [&](void *d, cudaStream_t st) { return input_launch(b, cb, n, (float2 *)d, st); });
+}
+
+extern "C" int sdrb_bank_read_sub(sdrb_bank *b, int sub_idx, int n_blocks, float *h_out) {
+    if (!b || !h_out || sub_idx < 0 || sub_idx >= (int)b->plan->h.subs.size() || n_blocks <= 0 || n_blocks > b->max_blocks) {
+        set_error("sdrb_bank_read_sub: bad argument"); return SDRB_E_INVALID;
+    }
+    CU_TRY(cudaSetDevice(b->device));
+    const size_t bytes = (size_t)b->n_streams * (size_t)n_blocks * (size_t)b->plan->h.subs[(size_t)sub_idx].block_z * sizeof(float2);
+    return read_back(b, bytes, h_out, [&](void *d, cudaStream_t st) { return sdrb_bank_copy_sub(b, sub_idx, n_blocks, (float *)d, st); });
+}
+
 extern "C" int sdrb_bank_copy_dc_trace(sdrb_bank *b, int n_blocks, float *d_out, uint8_t *d_modes, void *cuda_stream) {
     if (!b || !d_out || n_blocks <= 0 || n_blocks > b->max_blocks || !b->plan->h.correct_dc) {
         set_error("sdrb_bank_copy_dc_trace: bad argument or plan without correct_dc_bias"); return SDRB_E_INVALID;
@@ -870,6 +954,8 @@ extern "C" int sdrb_bank_process_host(sdrb_bank *b, const uint8_t *h_iq, size_t 
     c.d_iq = (const uint8_t *)b->d_iq.p; c.iq_stride = in_max; c.n_blocks = n_blocks;   // kernels index streams absolutely
     c.d_pcm = (int16_t *)b->d_pcm.p; c.d_tap = h_tap ? (float *)b->d_tap.p : nullptr;
     c.par = b->dc_par;
+    b->last_iq = c.d_iq; b->last_iq_stride = c.iq_stride; b->last_cf = nullptr; b->last_cf_stride = 0;
+    b->last_blocks = n_blocks; b->last_par = c.par;
     b->dc_par ^= 1;                                       // the call is synchronous: no event bookkeeping needed
     b->ev_end_valid[0] = b->ev_end_valid[1] = false;
     for (int cb = 0; cb < n_blocks; cb++)
@@ -1068,13 +1154,13 @@ extern "C" int sdrb_spectrum_fft(const float *d_in, float *d_out, int n_batch, i
 // ---- spectrum display state (MainWindow::fftHandlerSlot, mainwindow.cpp:411-455) ----
 struct sdrb_spectrum {
     int device = 0, n = 0;
-    DevBuf inr, pwr, smooth, stats;
+    DevBuf inr, pwr, smooth, stats, scratch;
 };
 
 extern "C" void sdrb_spectrum_destroy(sdrb_spectrum *sp) {
     if (!sp) return;
     cudaSetDevice(sp->device);
-    sp->inr.release(); sp->pwr.release(); sp->smooth.release(); sp->stats.release();
+    sp->inr.release(); sp->pwr.release(); sp->smooth.release(); sp->stats.release(); sp->scratch.release();
     delete sp;
 }
 
@@ -1125,6 +1211,30 @@ extern "C" int sdrb_spectrum_feed_device(sdrb_spectrum *sp, const float *d_in, s
         (double *)sp->stats.p, (float2 *)d_fft_out);
     CU_TRY(cudaGetLastError());
     return SDRB_OK;
+}
+
+// fftHandlerSlot for every receiver of a bank at once, straight from the bank's device buffers:
+// source -1 = "Main" (sdrj.cpp:296-303: the DC-corrected input samples), k >= 0 = sub VFO k
+// (vfo.cpp:290-293: its decimate[decimateCount]); callback cb of the last process call.
+extern "C" int sdrb_bank_spectrum_feed(sdrb_bank *b, sdrb_spectrum *sp, int source, int cb, float *d_fft_out, void *cuda_stream) {
+    if (!b || !sp || sp->n != b->n_streams || sp->device != b->device || source < -1 || source >= (int)b->plan->h.subs.size() ||
+        cb < 0 || cb >= b->last_blocks) {
+        set_error("sdrb_bank_spectrum_feed: needs one display per stream of the bank, a valid source and a callback of the last call");
+        return SDRB_E_INVALID;
+    }
+    CU_TRY(cudaSetDevice(b->device));
+    cudaStream_t st = (cudaStream_t)cuda_stream;
+    if (source < 0) {
+        const int n = std::min(b->plan->h.block, FFT_N) / DC_BLK * DC_BLK;
+        if (!sp->scratch.p) { int rc = sp->scratch.alloc((size_t)sp->n * FFT_N * sizeof(float2)); if (rc) return rc; }
+        int rc = input_launch(b, cb, n, (float2 *)sp->scratch.p, st);
+        if (rc != SDRB_OK) return rc;
+        // a callback shorter than the FFT (none of the supported rates) would leave the tail stale, like the reference
+        return sdrb_spectrum_feed_device(sp, (const float *)sp->scratch.p, (size_t)n, n, d_fft_out, cuda_stream);
+    }
+    const SubVfo &s = b->plan->h.subs[(size_t)source];
+    const float2 *z = (const float2 *)b->zbuf.p + b->sub_z_off[(size_t)source] + b->sub_z_hist[(size_t)source] + (size_t)cb * s.block_z;
+    return sdrb_spectrum_feed_device(sp, (const float *)z, b->z_stride, s.block_z, d_fft_out, cuda_stream);
 }
 
 extern "C" int sdrb_spectrum_feed_host(sdrb_spectrum *sp, const float *h_in, size_t in_stride, int len) {

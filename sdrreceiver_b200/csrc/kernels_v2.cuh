@@ -335,6 +335,43 @@ __device__ __forceinline__ float dc_decode(uint2 e, const DcAnchor &A) {
     return e.y < 2u ? A.sgn * __uint_as_float(e.x + A.lo + 1u) : __uint_as_float(e.x);
 }
 
+// Inspection: the `samples` vector of sdrj::demodData (sdrj.cpp:271-294) -- converted and, with
+// correct_dc_bias, DC-corrected input -- for the first n samples of one callback. It is what the
+// "Main" spectrum shows (sdrj.cpp:296-303). One thread per 128-sample DC block: it starts from the
+// block-start state of the walk (bit-exact) and repeats the reference's float steps (no FMA), so
+// the result is bit-identical to the reference. table == nullptr: conversion only.
+__global__ void __launch_bounds__(64) k_input_samples(const uint8_t *__restrict__ iq, size_t iq_stride, size_t first, int n,
+                                                      const uint2 *__restrict__ table, const DcAnchor *__restrict__ anchor,
+                                                      int table_stride, int blk0, float2 *__restrict__ out) {
+    const int j = blockIdx.x * 64 + threadIdx.x;                 // DC block inside the request
+    if (j * DC_BLK >= n) return;
+    const int stream = blockIdx.y;
+    const uint8_t *src = iq + (size_t)stream * iq_stride + (first + (size_t)j * DC_BLK) * 2;
+    float2 *dst = out + (size_t)stream * n + (size_t)j * DC_BLK;
+    float sI = 0.f, sQ = 0.f;
+    if (table) {
+        const uint2 *te = table + ((size_t)stream * table_stride + DC_HALO_BLKS + blk0 + j) * 2;
+        sI = dc_decode(__ldg(te), anchor[2 * stream]);
+        sQ = dc_decode(__ldg(te + 1), anchor[2 * stream + 1]);
+    }
+    for (int q = 0; q < DC_BLK / 8; ++q) {
+        const uint4 raw = __ldg(reinterpret_cast<const uint4 *>(src) + q);
+        const unsigned w[4] = {raw.x, raw.y, raw.z, raw.w};
+#pragma unroll
+        for (int k = 0; k < 8; ++k) {
+            const unsigned pr = w[k >> 1] >> (16 * (k & 1));
+            float xI = (float)((int)(pr & 0xffu) - 127), xQ = (float)((int)((pr >> 8) & 0xffu) - 127);   // sdr.cpp:48
+            if (table) {                                         // sdrj.cpp:281-282, float ops as written
+                sI = __fadd_rn(__fmul_rn(sI, DC_A), __fmul_rn(DC_C, xI));
+                sQ = __fadd_rn(__fmul_rn(sQ, DC_A), __fmul_rn(DC_C, xQ));
+                xI = __fsub_rn(xI, sI);
+                xQ = __fsub_rn(xQ, sQ);
+            }
+            dst[q * 8 + k] = make_float2(xI, xQ);
+        }
+    }
+}
+
 template <bool DC>
 __global__ void __launch_bounds__(V2_THREADS, V2_MINB) k1_v2(const __grid_constant__ K1V2Params p) {
     extern __shared__ __align__(16) unsigned char smem_raw[];

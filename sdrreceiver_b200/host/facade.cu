@@ -333,8 +333,17 @@ void vfo::process(const std::vector<cpx_typef> &samples) {
         sdrb_plan_get_sub(plan, (int)i, &si);
         c->transmit_usb.assign(pcm_record.begin() + si.pcm_offset, pcm_record.begin() + si.pcm_offset + si.samples_out);
         c->transmitData();
+        c->emit_selected(bank, (int)i);
     }
     if (emitFFT && fftData) fftData(decimate[decimateCount]);
+}
+
+// vfo.cpp:290-293: a leaf selected in the spectrum combo box emits its decimate[decimateCount]
+void vfo::emit_selected(sdrb_bank *root_bank, int sub_idx) {
+    if (!emitFFT || !fftData) return;
+    std::vector<cpx_typef> &z = decimate[decimateCount];
+    check(sdrb_bank_read_sub(root_bank, sub_idx, 1, reinterpret_cast<float *>(z.data())), "sdrb_bank_read_sub");
+    fftData(z);
 }
 
 void vfo::transmitData() {                                   // vfo.cpp:426-453
@@ -408,6 +417,7 @@ void sdrj::run(const unsigned char *bytes, uint32_t len) {
         sdrb_plan_get_sub(plan, (int)i, &si);
         c->transmit_usb.assign(pcm_record.begin() + si.pcm_offset, pcm_record.begin() + si.pcm_offset + si.samples_out);
         if (publishEnabled) c->transmitData();
+        c->emit_selected(bank, (int)i);
     }
     for (size_t m = 0; m < mpVFOs->size(); m++) {             // childless main VFOs forward packed IQ (vfo.cpp:268-286)
         vfo *mv = (*mpVFOs)[m];
@@ -416,11 +426,12 @@ void sdrj::run(const unsigned char *bytes, uint32_t len) {
         if (publishEnabled) mv->transmitData();
     }
     // sdrj.cpp:296-303: every 4th buffer goes to the spectrum display when "Main" is selected
-    if (count == 4 && emitFFT && fftData) {
-        samples.resize((size_t)block);
-        for (int i = 0; i < block; i++)
-            samples[(size_t)i] = cpx_typef(floats[staging[2 * (size_t)i]], floats[staging[2 * (size_t)i + 1]]);
-        fftData(samples);
+    if (count == 4 && emitFFT) {
+        if (fftData) {
+            samples.resize((size_t)block);                    // the DC-corrected `samples` of sdrj.cpp:271-294, bit-exact
+            check(sdrb_bank_read_input(bank, 0, block, reinterpret_cast<float *>(samples.data())), "sdrb_bank_read_input");
+            fftData(samples);
+        }
         count = 0;
     }
     count++;

@@ -76,6 +76,7 @@ private:
     int samplesPerBuffer, lateDecimate;
     bool emitFFT;
     void transmitData();
+    void emit_selected(sdrb_bank *root_bank, int sub_idx);
     // GPU side (roots only)
     sdrb_plan *plan;
     sdrb_bank *bank;

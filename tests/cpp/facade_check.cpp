@@ -4,7 +4,8 @@
 // tests/test_facade_gpu.py can compare it with the oracle. Links only against libsdrb200.so
 // and the facade headers: no CUDA headers, no Qt.
 //
-//   facade_check tree  PLAN.ini IQ.u8 OUTDIR N_BLOCKS     sdrj path (uint8 in, DC, all VFOs)
+//   facade_check tree  PLAN.ini IQ.u8 OUTDIR N_BLOCKS [SEL]  sdrj path (uint8 in, DC, all VFOs); SEL = spectrum
+//                                                          selection ("Main" or a topic): fftData buffers -> fft.cf32/fft.txt
 //   facade_check vfo   PLAN.ini IQ.u8 OUTDIR N_BLOCKS [K]  vfo::process on main VFO K (default 0; cf32 in)
 //   facade_check prims OUTDIR                             per-class known answers
 #include <cstdio>
@@ -87,9 +88,26 @@ static int run_tree(int argc, char **argv) {
     radio->setDCCorrection(info.correct_dc != 0);
     radio->fftVFOSlot("none");
     radio->publishEnabled = false;
+    static long callback = 0;
+    if (argc > 6) {                                  // the combo box (mainwindow.cpp:228,261,539-541)
+        const std::string sel = argv[6];
+        auto sink = [out](const char *who) {
+            return [out, who](const std::vector<cpx_typef> &v) {
+                append(out + "/fft.cf32", v.data(), v.size());
+                FILE *f = fopen((out + "/fft.txt").c_str(), "a");
+                fprintf(f, "%ld %s %zu\n", callback, who, v.size());
+                fclose(f);
+            };
+        };
+        radio->fftData = sink("sdrj");
+        radio->fftVFOSlot(sel);
+        for (int m = 0; m < (int)VFOmain.size(); m++)
+            for (vfo *leaf : VFOsub[m]) { leaf->fftData = sink("vfo"); leaf->fftVFOSlot(sel); }
+    }
     const size_t len = (size_t)info.block * 2;
     std::vector<float> fl(len);
     for (int b = 0; b < n_blocks; b++) {
+        callback = b;
         unsigned char *src = iq.data() + (size_t)b * len;
         if (b & 1) {                                 // odd callbacks through the float entry, like rtl_tcp (sdrj.cpp:155-162)
             for (size_t i = 0; i < len; i++) fl[i] = radio->floats.at(src[i]);

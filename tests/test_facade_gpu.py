@@ -103,6 +103,38 @@ def test_iq_forwarder_through_sdrj_and_vfo(tmp_path):
     orc.close()
 
 
+def _read_emits(d):
+    data, at, out = np.fromfile(d / "fft.cf32", dtype=np.complex64), 0, []
+    for line in open(d / "fft.txt"):
+        cb, who, n = line.split()
+        out.append((int(cb), who, data[at:at + int(n)]))
+        at += int(n)
+    return out
+
+
+@pytest.mark.skipif(not O.have_ref(), reason="needs oracle/_ref (the reference's own fftData emissions)")
+def test_spectrum_signals_like_the_reference(tmp_path):
+    """The fftData signals (what MainWindow::fftHandlerSlot receives): 'Main' -> sdrj emits its DC-corrected
+    samples on callbacks 4, 8, ... (sdrj.cpp:296-303), a sub VFO topic -> that VFO emits
+    decimate[decimateCount] on every callback (vfo.cpp:290-293)."""
+    name, n_blocks = "CBAND_143E", 9
+    op = OP.build_plan(plan_path(name))
+    iq = synth.make_iq(op["Fs"], op["block"] * n_blocks, synth.carriers_for_plan(op["center"], op["subs"]), level=level_for(op))
+    iq.tofile(tmp_path / "iq.u8")
+    for sel in ("Main", op["subs"][3]["topic"]):
+        d = tmp_path / sel
+        d.mkdir()
+        run("tree", plan_path(name), tmp_path / "iq.u8", d, n_blocks, sel)
+        got = _read_emits(d)
+        want = O.run_ref(plan_path(name), iq, fft=sel)[3]
+        assert [(cb, who, x.size) for cb, who, x in got] == [(cb, who, x.size) for cb, who, x in want]
+        for (_, _, g), (_, _, w) in zip(got, want):
+            if sel == "Main":
+                assert np.array_equal(g.view(np.uint32), w.view(np.uint32))        # DC-corrected input: bit-identical
+            else:
+                assert np.linalg.norm(g - w) / np.linalg.norm(w) <= 1e-5
+
+
 def test_class_facades(tmp_path):
     out = run("prims", tmp_path)
     assert out == {"hb23_throws": "1", "lowpass_throws": "1"}

@@ -89,6 +89,48 @@ def test_spectrum_display_matches_reference():
 
 
 @pytest.mark.gpu
+@needs_ref
+def test_bank_spectrum_sources_match_the_reference():
+    """BASELINE config 4: CBAND_143E with the spectrum path on -- 'Main' (every 4th callback, DC-corrected
+    input) and a selected sub VFO (every callback), batched over the receivers of a bank, against the
+    buffers the unmodified reference emits through fftData and its own FFT."""
+    import os
+    from conftest import plan_path
+    from oracle import plan as OP
+    from sdrreceiver_b200 import synth
+    name, n_blocks, sub = "CBAND_143E", 5, 3
+    op = OP.build_plan(plan_path(name)); plan = B.Plan(plan_path(name))
+    iq = np.stack([synth.make_iq(op["Fs"], op["block"] * n_blocks, synth.carriers_for_plan(op["center"], op["subs"]), stream=s)
+                   for s in range(2)])
+    bank = B.Bank(plan, 2, n_blocks)
+    bank.process_numpy(iq, n_blocks)
+    sp_main, sp_sub = B.Spectrum(2), B.Spectrum(2)
+    bank.spectrum_feed(sp_main, -1, 4)                              # the reference's first "Main" emission is callback 4
+    for cb in range(n_blocks):
+        bank.spectrum_feed(sp_sub, sub, cb)
+    got_in = bank.read_input(4, 8192)
+    got_z = bank.read_sub(sub, n_blocks)
+    for s in range(2):
+        e_main = O.run_ref(plan_path(name), iq[s], fft="Main")[3]
+        e_sub = O.run_ref(plan_path(name), iq[s], fft=op["subs"][sub]["topic"])[3]
+        assert [cb for cb, _, _ in e_main] == [4] and [cb for cb, _, _ in e_sub] == list(range(n_blocks))
+        assert np.array_equal(got_in[s].view(np.uint32), e_main[0][2][:8192].view(np.uint32))
+        z_ref = np.concatenate([x for _, _, x in e_sub])
+        assert np.linalg.norm(got_z[s] - z_ref) / np.linalg.norm(z_ref) <= 1e-5
+        r_main, r_sub = O.RefSpectrum(), O.RefSpectrum()
+        r_main.feed(e_main[0][2])
+        for _, _, x in e_sub:
+            r_sub.feed(x)
+        for sp, r in ((sp_main, r_main), (sp_sub, r_sub)):
+            smooth, pwr, stats = sp.read()
+            rs, rp, _, rstats = r.get()
+            assert np.abs(pwr[s] - rp).max() <= TOL_DB and np.abs(smooth[s] - rs).max() <= TOL_DB
+            assert np.abs(stats[s] - rstats).max() <= TOL_DB
+            r.close()
+    sp_main.close(); sp_sub.close(); bank.close()
+
+
+@pytest.mark.gpu
 def test_spectrum_argument_errors():
     import ctypes as C
     h = C.c_void_p()
