@@ -71,6 +71,24 @@ def base_streams(plan, n_base, n_samples):
     return [synth.make_iq(plan.fs, n_samples, car, stream=s) for s in range(n_base)]
 
 
+def bind_to_gpu_cpus(index):
+    """Pin this process to the CPU cores NVML reports as local to GPU `index`, so that the pinned staging
+    buffers of the end-to-end leg live on that GPU's NUMA node (matters from 2 ranks up). Best effort."""
+    try:
+        import pynvml
+        pynvml.nvmlInit()
+        h = pynvml.nvmlDeviceGetHandleByIndex(index)
+        words = pynvml.nvmlDeviceGetCpuAffinity(h, (os.cpu_count() + 63) // 64)
+        cpus = {64 * w + b for w, m in enumerate(words) for b in range(64) if (m >> b) & 1}
+        cpus &= os.sched_getaffinity(0)
+        if cpus:
+            os.sched_setaffinity(0, cpus)
+            return len(cpus)
+    except Exception:
+        pass
+    return None
+
+
 class ClockSampler(threading.Thread):
     """Samples SM clock and throttle reasons of one GPU through NVML while the timed regions run."""
 
@@ -188,6 +206,7 @@ def b200_arm(args):
     torch.cuda.set_device(local_rank)
     dev = torch.device("cuda", local_rank)
 
+    numa = bind_to_gpu_cpus(local_rank)          # before the pinned buffers are allocated (first touch)
     plan_path = os.path.join(ROOT, "plans", args.plan + ".ini")
     plan = B.Plan(plan_path)
     S, NB, Bk = args.streams, args.blocks, plan.block
@@ -318,7 +337,8 @@ def b200_arm(args):
                                "input %.0f MB per GPU per step, larger than L2" % (
                                    args.plan, S, S * world, NB, NB / plan.bufsplit, S * row / 1e6),
                    "plan": args.plan, "streams_per_gpu": S, "blocks_per_step": NB, "sample_rate": fs,
-                   "l2_policy": "input larger than L2 (no flush)", "parallelism": "streams sharded, no collective"},
+                   "l2_policy": "input larger than L2 (no flush)", "parallelism": "streams sharded, no collective",
+                   "cpus_bound_per_rank": numa},
         "realtime_x": value * 1e6 / fs,
         "clocks": clocks,
         "e2e": {"value": e2e_value, "unit": "MS/s", "h2d_bytes_per_step": S * row,

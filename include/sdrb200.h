@@ -290,6 +290,47 @@ int sdrb_publisher_send(sdrb_publisher *p, const char *topic, uint32_t rate, con
 int sdrb_publisher_send_block(sdrb_publisher *p, const sdrb_plan *plan, const int16_t *h_pcm_record);
 void sdrb_publisher_close(sdrb_publisher *p);
 
+/* ---- ingest front ends, host side (the library opens no socket and no dongle) ---- */
+/* rtl_tcp client protocol as spoken by sdrj (sdrj.cpp:31-74, 125-188). Feed whatever the socket
+ * delivers: the 12-byte dongle header "RTL0" + tuner type + gain count (big endian, sdrj.cpp:134-149)
+ * is recognised at the start of the stream, everything after it is uint8 IQ, cut into callback
+ * blocks of block_bytes (0 = the reference's (sample_rate/4)*2, sdrj.cpp:46). A stream that does
+ * not start with "RTL0" (a recording) is all samples. */
+typedef struct sdrb_rtltcp sdrb_rtltcp;
+int sdrb_rtltcp_create(int sample_rate, size_t block_bytes, sdrb_rtltcp **out);
+void sdrb_rtltcp_destroy(sdrb_rtltcp *f);
+size_t sdrb_rtltcp_block_bytes(const sdrb_rtltcp *f);
+int sdrb_rtltcp_feed(sdrb_rtltcp *f, const uint8_t *bytes, size_t n);    /* >= 0: complete blocks waiting */
+int sdrb_rtltcp_header(const sdrb_rtltcp *f, uint32_t *tuner_type, uint32_t *gain_count);   /* 1 once seen */
+int sdrb_rtltcp_pop(sdrb_rtltcp *f, uint8_t *dst_block);                 /* 1 = one block copied, 0 = none */
+/* Commands (sdrj.h:10-16; sdrj::sendCommand, sdrj.cpp:168-188): 1 command byte + value, MSB first. */
+#define SDRB_RTLTCP_SET_FREQ 0x01
+#define SDRB_RTLTCP_SET_SAMPLE_RATE 0x02
+#define SDRB_RTLTCP_SET_TUNER_GAIN_MODE 0x03
+#define SDRB_RTLTCP_SET_GAIN 0x04
+#define SDRB_RTLTCP_SET_FREQ_COR 0x05
+#define SDRB_RTLTCP_SET_AGC_MODE 0x08
+#define SDRB_RTLTCP_SET_TUNER_GAIN_INDEX 0x0d
+void sdrb_rtltcp_command(uint8_t cmd, uint32_t value, uint8_t out[5]);
+/* What sdrj::start_tcp_rtl sends after connecting (sdrj.cpp:56-66): AGC off, manual gain, gain
+ * index, sample rate, centre frequency -- 25 bytes. */
+int sdrb_rtltcp_start_sequence(int sample_rate, int frequency, int gain_index, uint8_t out[25]);
+
+/* The hand-over ring between the librtlsdr callback thread and the demodulator thread
+ * (jonti/sdr.cpp:100-184; N_BUFFERS = 20, jonti/sdr.h:83). push = sdr::rtlsdr_callback: returns 1,
+ * or 0 when all buffers are in use and the new one is DROPPED, like the reference. pop =
+ * sdr::demod_dispatcher: waits (timeout_ms < 0: for ever) and lends the oldest buffer until
+ * sdrb_ring_release. Buffers hold raw bytes and are pinned when `pinned` != 0, so that
+ * sdrb_bank_process_host can DMA straight out of them. One producer, one consumer. */
+typedef struct sdrb_ring sdrb_ring;
+int sdrb_ring_create(size_t block_bytes, int n_buffers /* 0 = 20 */, int pinned, sdrb_ring **out);
+void sdrb_ring_destroy(sdrb_ring *r);
+int sdrb_ring_push(sdrb_ring *r, const uint8_t *bytes, uint32_t len);
+int sdrb_ring_pop(sdrb_ring *r, const uint8_t **bytes, uint32_t *len, int timeout_ms);
+int sdrb_ring_release(sdrb_ring *r);
+void sdrb_ring_cancel(sdrb_ring *r);
+int sdrb_ring_stats(sdrb_ring *r, uint64_t *pushed, uint64_t *dropped, int *used);
+
 const char *sdrb_last_error(void);
 const char *sdrb_version(void);
 

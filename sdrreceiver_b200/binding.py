@@ -118,6 +118,21 @@ def lib():
         "sdrb_bank_read_input": (i, [vp, i, i, vp]),
         "sdrb_bank_copy_sub": (i, [vp, i, i, vp, vp]),
         "sdrb_bank_read_sub": (i, [vp, i, i, vp]),
+        "sdrb_rtltcp_create": (i, [i, sz, P(vp)]),
+        "sdrb_rtltcp_destroy": (None, [vp]),
+        "sdrb_rtltcp_block_bytes": (sz, [vp]),
+        "sdrb_rtltcp_feed": (i, [vp, vp, sz]),
+        "sdrb_rtltcp_header": (i, [vp, P(C.c_uint32), P(C.c_uint32)]),
+        "sdrb_rtltcp_pop": (i, [vp, vp]),
+        "sdrb_rtltcp_command": (None, [C.c_uint8, C.c_uint32, vp]),
+        "sdrb_rtltcp_start_sequence": (i, [i, i, i, vp]),
+        "sdrb_ring_create": (i, [sz, i, i, P(vp)]),
+        "sdrb_ring_destroy": (None, [vp]),
+        "sdrb_ring_push": (i, [vp, vp, C.c_uint32]),
+        "sdrb_ring_pop": (i, [vp, P(vp), P(C.c_uint32), i]),
+        "sdrb_ring_release": (i, [vp]),
+        "sdrb_ring_cancel": (None, [vp]),
+        "sdrb_ring_stats": (i, [vp, P(C.c_uint64), P(C.c_uint64), P(i)]),
         "sdrb_publisher_open": (i, [C.c_char_p, i, P(vp)]),
         "sdrb_publisher_send": (i, [vp, C.c_char_p, C.c_uint32, vp, C.c_uint32]),
         "sdrb_publisher_send_block": (i, [vp, vp, vp]),

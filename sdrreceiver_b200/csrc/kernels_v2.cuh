@@ -54,8 +54,9 @@ template <> struct StLay<4> { static constexpr int STR = 6, PADT = 3; };
 template <> struct StLay<2> { static constexpr int STR = 2, PADT = 6; };
 template <int N> constexpr int st_elems() { return (V2_THREADS + StLay<N>::PADT) * StLay<N>::STR; }
 
-constexpr int V2_SA = 0;
-constexpr int V2_SB = V2_SA + st_elems<16>();
+constexpr int V2_SA = 0;                                        // two copies, alternating from VFO to VFO
+constexpr int V2_SA_LEN = st_elems<16>();
+constexpr int V2_SB = V2_SA + 2 * V2_SA_LEN;
 constexpr int V2_SC = V2_SB + st_elems<8>();
 constexpr int V2_SD = V2_SC + st_elems<4>();
 constexpr int V2_SEND = V2_SD + st_elems<2>();                  // then 16 bytes of misc
@@ -168,7 +169,8 @@ template <int MAXS, class P>
 __device__ __forceinline__ void cascade_loop(const float2 (&x)[44], const P &p, int count,
                                              float2 *__restrict__ sm, int t, int v0, long long n_abs, int k0, int L,
                                              bool store, size_t out_off /* stream*out_stride */, int b) {
-    float2 *sA = sm + V2_SA, *sB = sm + V2_SB, *sC = sm + V2_SC, *sD = sm + V2_SD;
+    float2 *sB = sm + V2_SB, *sC = sm + V2_SC, *sD = sm + V2_SD;
+    int prevS = 1, flip = 0;
     const bool head = (v0 == 0);
     const bool fast = (k0 >= LUT_STEADY + 10) && (k0 + V2_CHUNK <= L) && !head;
     float2 xc[44];                                        // addressable copy for the exact path only
@@ -197,7 +199,14 @@ __device__ __forceinline__ void cascade_loop(const float2 (&x)[44], const P &p, 
             }
             continue;
         }
-        __syncthreads();                                  // readers of the previous VFO are done with the scratch
+        // The stage-1 array alternates between two copies, so a VFO that follows one with >= 2 stages
+        // needs no barrier here: whoever still reads the other copy's stage-1 data has not yet passed
+        // the previous VFO's first barrier, and everything behind it (sB, sC, sD) is only rewritten
+        // after this VFO's own barriers. After a 1-stage VFO (no barrier of its own) one is needed.
+        float2 *sA = sm + V2_SA + flip * V2_SA_LEN;
+        flip ^= 1;
+        if (prevS < 2) __syncthreads();
+        prevS = V.S;
         // stage 1 straight into the scratch (two outputs per 16-byte store): nothing but the input stays in registers
         float4 *pa = reinterpret_cast<float4 *>(sA + (t + StLay<16>::PADT) * StLay<16>::STR);
         if (fast) {
