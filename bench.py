@@ -323,12 +323,37 @@ def b200_arm(args):
     sm_mhz = clocks["sm_mhz"] or 1965.0
     fp32_peak = 148 * 128 * 2 * sm_mhz * 1e6 / 1e12
     step_ms = max_dev_ms / args.steps
+    # DRAM traffic of that kernel class from the committed ncu --set full capture (same plan and bank
+    # size), per "launch" = the class's launches of one callback, like `achieved`
+    traffic, traffic_src = None, None
+    try:
+        with open(os.path.join(ROOT, "profiles", "r01_traffic.json")) as f:
+            tj = json.load(f)
+        if tj["config"]["plan"] == args.plan and tj["config"]["streams_per_gpu"] == S:
+            traffic, traffic_src = tj["per_class_per_callback"].get(dom), "profiles/r01_traffic.json (ncu --set full)"
+    except Exception:
+        pass
+    samples_per_callback = S * Bk
     roofline = {
         "bound": "hbm", "kernel": dom, "achieved": achieved, "peak": peak, "unit": "GB/s",
-        "frac": achieved / peak, "traffic": None, "peak_source": peak_src,
+        "frac": achieved / peak, "traffic": traffic, "traffic_source": traffic_src, "peak_source": peak_src,
+        "launch": "the %s kernels of one callback (%d streams x %d samples)" % (dom, S, Bk),
+        "alg_bytes_per_launch": alg_bytes[dom] * samples_per_callback, "launch_ms": dom_ms / NB,
         "kernel_ms_per_step": dom_ms, "share_of_step": dom_ms / step_ms if step_ms > 0 else None,
         "alg_bytes_per_sample": alg_bytes[dom],
     }
+    # the same kernel against the FP32 roofline (it is FP32-issue bound): algorithmic
+    # flops by SURVEY.md 8(d)'s counting rule
+    hb = lambda decim: sum(20.0 / 2 ** a for a in range(1, decim + 1))
+    alg_flops = {
+        "ingest_main": 10.0 + sum(6.0 + hb(m["decim"]) for m in plan.mains),
+        "sub_cascade": sum((s["Fs"] / fs) * (6.0 + hb(s["decim"])) for s in plan.subs),
+        "usb_audio": sum((s["out_rate"] / fs) * (2.0 * 62 + 1 + 2.0 * s["n_lpf_taps"] + 2.0) for s in plan.subs),
+    }
+    if dom in alg_flops and dom_ms > 0:
+        tf = alg_flops[dom] * samples_per_step / (dom_ms * 1e-3) / 1e12
+        roofline["fp32"] = {"achieved_tflops": tf, "peak_tflops": fp32_peak, "frac": tf / fp32_peak,
+                            "alg_flops_per_sample": alg_flops[dom]}
     line = {
         "metric": METRIC, "value": value, "unit": "MS/s", "n_gpus": world, "steps": args.steps, "warmup": args.warmup,
         "ms_per_step": step_ms, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
