@@ -38,8 +38,8 @@ HBM_FALLBACK_GBS = 6650.0
 def parse_args():
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
-    ap.add_argument("--steps", type=int, default=20)
-    ap.add_argument("--warmup", type=int, default=3)
+    ap.add_argument("--steps", type=int, default=50)
+    ap.add_argument("--warmup", type=int, default=5)
     ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
     ap.add_argument("--plan", default="25E")
     ap.add_argument("--streams", type=int, default=128, help="streams per GPU")
@@ -126,7 +126,7 @@ class ClockSampler(threading.Thread):
                         self.reasons.add(k)
             except Exception:
                 pass
-            time.sleep(0.02)
+            time.sleep(0.05)      # NVML queries take driver locks: keep them rare next to ~130 launches per step
 
     def summary(self):
         if not self.samples:

@@ -224,6 +224,12 @@ int sdrb_nco_mix(const float *d_table_cf32, int table_len, int64_t n0, const flo
  * and is updated with the reference's off-by-one carry (jonti/dsp.cpp:163-173). */
 int sdrb_halfband11(const float *d_in_cf32, float *d_out_cf32, float *d_hist_cf32, int n_ch, int n,
                     void *cuda_stream);
+/* The same class with its other filter lengths (halfbanddecimator.h:28-63, .cpp:10-34): taps = 11,
+ * 23 or 51 use the reference's tables; any other odd length behaves like the reference, whose
+ * switch has no case for it (15 and 21 have tables that are never loaded): all outputs are 0.
+ * d_hist = `taps` complex samples per channel, zero for a fresh object. Any even n >= 2. */
+int sdrb_halfband(int taps, const float *d_in_cf32, float *d_out_cf32, float *d_hist_cf32, int n_ch, int n,
+                  void *cuda_stream);
 /* FIR::FIRUpdateAndProcess over a block (jonti/dsp.cpp:59-71): newest sample excluded;
  * d_hist = last ntaps inputs per channel (updated); decim >= 1 keeps every decim-th output
  * starting with the first (vfo::usb_decimdemod, vfo.cpp:334-387). Any block length n >= 1. */

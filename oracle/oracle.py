@@ -51,6 +51,7 @@ def lib():
         L.orc_oscillator.restype = None; L.orc_oscillator.argtypes = [d, d, vp, l]
         L.orc_oscillator_table.restype = i; L.orc_oscillator_table.argtypes = [d, d, vp, l]
         L.orc_halfband.restype = None; L.orc_halfband.argtypes = [vp, i, i, vp]
+        L.orc_halfband_n.restype = None; L.orc_halfband_n.argtypes = [i, vp, i, i, vp]
         L.orc_fir.restype = None; L.orc_fir.argtypes = [i, vp, vp, l, i, vp]
         L.orc_hilbert_points.restype = None; L.orc_hilbert_points.argtypes = [i, i, vp]
         L.orc_usb.restype = None; L.orc_usb.argtypes = [i, i, vp, l, vp]

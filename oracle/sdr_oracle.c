@@ -541,6 +541,55 @@ void orc_halfband(const float *in_iq, int block, int nblocks, float *out_iq) {
     free(h.i.queue); free(h.q.queue);
 }
 
+/* HalfBandDecimator with any filter length (halfbanddecimator.cpp:4-41; dsp.cpp:96-173): tables for 11,
+ * 23 and 51 taps are loaded and summed by the switch in FIRUpdateAndProcessHalfBandQueue; every other
+ * length has all-zero points and no case, so the output is 0. Same queue handling as the 11-tap arm. */
+static const float hb23_tab[23] = {
+    -0.00014987651418332164, 0.0f, 0.0014748633283609852f, 0.0f, -0.0074416944990005314f, 0.0f, 0.026163522731980929f, 0.0f,
+    -0.077593699116544707f, 0.0f, 0.30754683719791986f, 0.5f, 0.30754683719791986f, 0.0f, -0.077593699116544707f, 0.0f,
+    0.026163522731980929f, 0.0f, -0.0074416944990005314f, 0.0f, 0.0014748633283609852f, 0.0f, -0.00014987651418332164f};
+static const float hb51_tab[51] = {
+    0.0010175926971811044, 0.0, -0.0013058886799502411, 0.0, 0.0020730260200910026, 0.0, -0.0034255790572079265, 0.0,
+    0.005490505092950141, 0.0, -0.008434405740804745, 0.0, 0.012502602797600649, 0.0, -0.01810260996706492, 0.0,
+    0.026000146160530365, 0.0, -0.037851497102093665, 0.0, 0.05801218485928863, 0.0, -0.1025751653146947, 0.0,
+    0.31684426465520726, 0.499509647157934, 0.3168442646552072, 0.0, -0.10257516531469468, 0.0, 0.05801218485928862, 0.0,
+    -0.03785149710209366, 0.0, 0.02600014616053035, 0.0, -0.018102609967064916, 0.0, 0.012502602797600643, 0.0,
+    -0.008434405740804745, 0.0, 0.005490505092950138, 0.0, -0.0034255790572079218, 0.0, 0.0020730260200910026, 0.0,
+    -0.0013058886799502405, 0.0, 0.0010175926971811044};
+
+static void hbn_arm(const float *points, int N, const float *in, int stride, int block, int nblocks, float *out) {
+    float *queue = (float *)calloc((size_t)block + N, sizeof(float));
+    int qptr = N, b, i, k, step;
+    for (b = 0; b < nblocks; b++) {
+        step = 0;
+        for (i = 0; i < block; i++) {
+            queue[qptr++] = in[(size_t)stride * ((long)b * block + i)];
+            if (i % 2 == 0) {                                       /* halfbanddecimator.cpp:49-60 */
+                const float *q = queue + (qptr - N);
+                float outsum = 0;
+                if (N == 11 || N == 23 || N == 51) {
+                    float acc = points[0] * (q[0] + q[N - 1]);
+                    for (k = 2; k < (N - 1) / 2; k += 2) acc = acc + points[k] * (q[k] + q[N - 1 - k]);
+                    acc = acc + points[(N - 1) / 2] * q[(N - 1) / 2];
+                    outsum += acc;
+                }
+                out[(size_t)stride * ((long)b * (block / 2) + step)] = outsum;
+                step++;
+            }
+        }
+        if (qptr >= N) memmove(queue, queue + ((qptr - 1) - N), sizeof(float) * N);   /* dsp.cpp:163-173 */
+        qptr = N;
+    }
+    free(queue);
+}
+
+void orc_halfband_n(int taps, const float *in_iq, int block, int nblocks, float *out_iq) {
+    static float zeros[256];
+    const float *pts = taps == 11 ? hb11 : taps == 23 ? hb23_tab : taps == 51 ? hb51_tab : zeros;
+    hbn_arm(pts, taps, in_iq, 2, block, nblocks, out_iq);
+    hbn_arm(pts, taps, in_iq + 1, 2, block, nblocks, out_iq + 1);
+}
+
 void orc_fir(int ntaps, const float *taps, const float *in, long n, int every, float *out) {
     fir_t f;
     long i, m = 0;

@@ -101,6 +101,7 @@ def lib():
         "sdrb_nco_table": (l, [d, d, vp, l]),
         "sdrb_nco_mix": (i, [vp, i, C.c_int64, vp, vp, i, i, vp]),
         "sdrb_halfband11": (i, [vp, vp, vp, i, i, vp]),
+        "sdrb_halfband": (i, [i, vp, vp, vp, i, i, vp]),
         "sdrb_fir": (i, [vp, i, vp, vp, vp, i, i, i, vp]),
         "sdrb_fir_ex": (i, [vp, i, vp, vp, vp, i, i, i, i, vp]),
         "sdrb_usb_demod": (i, [vp, vp, vp, vp, i, i, vp]),

@@ -11,6 +11,7 @@
 #include <map>
 #include <new>
 #include <string>
+#include <utility>
 #include <vector>
 
 #include "plan.hpp"
@@ -208,6 +209,7 @@ struct sdrb_bank {
     DevBuf d_iq, d_pcm, d_tap, d_cf, d_fwd;
     cudaStream_t s_copy_in = nullptr, s_compute = nullptr, s_copy_out = nullptr;
     std::vector<cudaEvent_t> ev_in, ev_done;
+    std::vector<std::pair<int, int>> host_groups;      // (first stream, count) of each pipeline group of process_host
     // DC recursion runs on side streams, one callback ahead of the ingest kernel
     static constexpr int kSide = 8;
     cudaStream_t s_dc[kSide] = {nullptr};
@@ -938,7 +940,35 @@ extern "C" int sdrb_bank_process_host(sdrb_bank *b, const uint8_t *h_iq, size_t 
     // chunks overlap on three streams (+ one DC side stream per group); a chunk's kernels start when
     // its copy has landed. Callback-major order gives every group's sequential DC walk the time of
     // the other groups' copies before its next callback arrives.
-    const int n_groups = std::min(b->n_streams, sdrb_bank::kSide);
+    // Stream groups: four equal shares by default; SDRB_HOST_GROUPS="w0,w1,.." (at most 8 weights) sets relative sizes,
+    // e.g. a small last group shortens the un-overlapped tail (DC walk + filters + copy-out of the final chunk).
+    if (b->host_groups.empty()) {
+        std::vector<double> w;
+        if (const char *e = getenv("SDRB_HOST_GROUPS")) {
+            for (const char *p = e; *p && (int)w.size() < sdrb_bank::kSide;) {
+                char *end = nullptr;
+                const double v = strtod(p, &end);
+                if (end == p) break;
+                if (v > 0) w.push_back(v);
+                p = *end ? end + 1 : end;
+            }
+        }
+        // four equal groups measured best on B200/PCIe Gen5 (tools/host_groups_sweep.py: 8.38 ms per step vs 8.56
+        // with eight and 9.07 with two, 128 receivers x 4 callbacks): fewer, larger copies, still a short tail
+        if (w.empty()) w.assign((size_t)std::min(b->n_streams, 4), 1.0);
+        double tot = 0, acc = 0;
+        for (double v : w) tot += v;
+        int s0 = 0;
+        for (size_t g = 0; g < w.size() && s0 < b->n_streams; g++) {
+            acc += w[g];
+            int s1 = g + 1 == w.size() ? b->n_streams : (int)llround(acc / tot * b->n_streams);
+            s1 = std::min(std::max(s1, s0 + 1), b->n_streams);
+            b->host_groups.push_back({s0, s1 - s0});
+            s0 = s1;
+        }
+        if (s0 < b->n_streams) b->host_groups.back().second += b->n_streams - s0;
+    }
+    const int n_groups = (int)b->host_groups.size();
     const size_t need_ev = (size_t)n_groups * (size_t)b->max_blocks;
     while (b->ev_in.size() < need_ev) {
         cudaEvent_t e1, e2;
@@ -947,7 +977,6 @@ extern "C" int sdrb_bank_process_host(sdrb_bank *b, const uint8_t *h_iq, size_t 
         b->ev_in.push_back(e1); b->ev_done.push_back(e2);
     }
     b->last_launches = 0;
-    const int per = (b->n_streams + n_groups - 1) / n_groups;
     const size_t cb_in = (size_t)h.block * 2, cb_out = (size_t)h.pcm_per_block;
     const bool dc = h.correct_dc != 0;
     CallCtx c;
@@ -960,7 +989,7 @@ extern "C" int sdrb_bank_process_host(sdrb_bank *b, const uint8_t *h_iq, size_t 
     b->ev_end_valid[0] = b->ev_end_valid[1] = false;
     for (int cb = 0; cb < n_blocks; cb++)
         for (int g = 0; g < n_groups; g++) {
-            const int s0 = g * per, ns = std::min(per, b->n_streams - s0);
+            const int s0 = b->host_groups[(size_t)g].first, ns = b->host_groups[(size_t)g].second;
             if (ns <= 0) break;
             CU_TRY(cudaMemcpy2DAsync((uint8_t *)b->d_iq.p + (size_t)s0 * in_max + (size_t)cb * cb_in, in_max,
                                      h_iq + (size_t)s0 * iq_stride + (size_t)cb * cb_in, iq_stride, cb_in, (size_t)ns,
@@ -969,7 +998,7 @@ extern "C" int sdrb_bank_process_host(sdrb_bank *b, const uint8_t *h_iq, size_t 
         }
     for (int cb = 0; cb < n_blocks; cb++)
         for (int g = 0; g < n_groups; g++) {
-            const int s0 = g * per, ns = std::min(per, b->n_streams - s0);
+            const int s0 = b->host_groups[(size_t)g].first, ns = b->host_groups[(size_t)g].second;
             if (ns <= 0) break;
             cudaEvent_t ein = b->ev_in[(size_t)g * b->max_blocks + cb], eout = b->ev_done[(size_t)g * b->max_blocks + cb];
             if (dc && (rc = enqueue_dc_cb(b, c, s0, ns, b->s_dc[g], cb, ein, b->ev_dc[g][(size_t)cb], &b->last_launches)) != SDRB_OK)
@@ -1101,6 +1130,32 @@ extern "C" int sdrb_halfband11(const float *d_in, float *d_out, float *d_hist, i
         (const float2 *)d_in, (float2 *)d_out, (const float2 *)d_hist, n);
     prim_halfband11_carry<<<(unsigned)n_ch, 32, 0, st>>>((const float2 *)d_in, (float2 *)d_hist, n);
     CU_TRY(cudaGetLastError());
+    return SDRB_OK;
+}
+
+extern "C" int sdrb_halfband(int taps, const float *d_in, float *d_out, float *d_hist, int n_ch, int n, void *cuda_stream) {
+    if (taps == 11 && n >= 12) return sdrb_halfband11(d_in, d_out, d_hist, n_ch, n, cuda_stream);
+    if (!d_in || !d_out || !d_hist || n_ch <= 0 || n < 2 || (n & 1) || taps < 3 || taps > 255 || !(taps & 1)) {
+        set_error("sdrb_halfband: needs an odd filter length 3..255 and an even block"); return SDRB_E_INVALID;
+    }
+    cudaStream_t st = (cudaStream_t)cuda_stream;
+    const float *coef = nullptr;
+    int nz = 0;                                               // lengths without a `case` in dsp.cpp:106-136 output zeros
+    static const float hb11_host[4] = {HB_P0, HB_P2, HB_P4, HB_P5};
+    float *d_c11 = nullptr;
+    if (taps == 23) { CU_TRY(cudaGetSymbolAddress((void **)&coef, c_hb23)); nz = 7; }
+    else if (taps == 51) { CU_TRY(cudaGetSymbolAddress((void **)&coef, c_hb51)); nz = 14; }
+    else if (taps == 11) {                                    // blocks shorter than 12 samples (per-sample facade use)
+        CU_TRY(cudaMalloc(&d_c11, sizeof(hb11_host)));
+        CU_TRY(cudaMemcpyAsync(d_c11, hb11_host, sizeof(hb11_host), cudaMemcpyHostToDevice, st));
+        coef = d_c11; nz = 4;
+    }
+    prim_halfband_n<<<dim3((unsigned)((n / 2 + 255) / 256), (unsigned)n_ch), 256, 0, st>>>(
+        (const float2 *)d_in, (float2 *)d_out, (const float2 *)d_hist, n, taps, coef, nz);
+    prim_halfband_n_carry<<<(unsigned)n_ch, 64, sizeof(float2) * (size_t)taps, st>>>((const float2 *)d_in, (float2 *)d_hist, n, taps);
+    cudaError_t e = cudaGetLastError();
+    if (d_c11) { cudaStreamSynchronize(st); cudaFree(d_c11); }
+    if (e != cudaSuccess) { set_error(std::string("sdrb_halfband: ") + cudaGetErrorString(e)); return SDRB_E_CUDA; }
     return SDRB_OK;
 }
 

@@ -40,6 +40,54 @@ __global__ void prim_halfband11_carry(const float2 *__restrict__ in, float2 *__r
     if (threadIdx.x < 11) hist[(size_t)blockIdx.x * 11 + threadIdx.x] = in[(size_t)blockIdx.x * n + (n - 12 + threadIdx.x)];
 }
 
+// HalfBandDecimator with the 23- and 51-tap tables (halfbanddecimator.h:28-63; dsp.cpp:106-136). vfo.cpp
+// only ever builds the 11-tap one (vfo.cpp:130), these back the class facade. Same queue rule as the
+// 11-tap stage for any length N: window slot t = 2m+1 in [hist(N) | block], history carried with the
+// off-by-one of FIRQueueBackToFront. Other lengths (15, 21 have tables but no `case`): the reference's
+// switch falls through and every output is 0 -- reproduced by NZ = 0.
+__constant__ float c_hb23[7] = {-0.00014987651418332164f, 0.0014748633283609852f, -0.0074416944990005314f, 0.026163522731980929f,
+                                -0.077593699116544707f, 0.30754683719791986f, 0.5f};
+__constant__ float c_hb51[14] = {0.0010175926971811044f, -0.0013058886799502411f, 0.0020730260200910026f, -0.0034255790572079265f,
+                                 0.005490505092950141f,  -0.008434405740804745f,  0.012502602797600649f,  -0.01810260996706492f,
+                                 0.026000146160530365f,  -0.037851497102093665f,  0.05801218485928863f,   -0.1025751653146947f,
+                                 0.31684426465520726f,   0.499509647157934f};
+
+// coef: the even-indexed points 0, 2, .., N-3 followed by the centre point; NZ = (N+1)/4 + 1 of them, or 0
+__global__ void __launch_bounds__(256) prim_halfband_n(const float2 *__restrict__ in, float2 *__restrict__ out,
+                                                        const float2 *__restrict__ hist, int n, int N, const float *coef, int NZ) {
+    const int m = blockIdx.x * 256 + threadIdx.x;
+    if (m >= n / 2) return;
+    const float2 *x = in + (size_t)blockIdx.y * n;
+    const float2 *h = hist + (size_t)blockIdx.y * N;
+    auto q = [&](int j) -> float2 { return j < N ? h[j] : x[j - N]; };
+    const int t = 2 * m + 1;
+    float2 y = make_float2(0.f, 0.f);
+    for (int k = 0; k + 1 < NZ; ++k) {                       // points[2k]*(q[t+2k] + q[t+N-1-2k]), summed in the reference's order
+        const float2 a = q(t + 2 * k), b = q(t + N - 1 - 2 * k);
+        y.x = __fadd_rn(y.x, __fmul_rn(coef[k], __fadd_rn(a.x, b.x)));
+        y.y = __fadd_rn(y.y, __fmul_rn(coef[k], __fadd_rn(a.y, b.y)));
+    }
+    if (NZ > 0) {
+        const float2 c = q(t + (N - 1) / 2);
+        y.x = __fadd_rn(y.x, __fmul_rn(coef[NZ - 1], c.x));
+        y.y = __fadd_rn(y.y, __fmul_rn(coef[NZ - 1], c.y));
+    }
+    out[(size_t)blockIdx.y * (n / 2) + m] = y;
+}
+
+// FIRQueueBackToFront for any N and any even block length: new head = q[B-1 .. B+N-2] of q = [hist | block]
+__global__ void prim_halfband_n_carry(const float2 *__restrict__ in, float2 *__restrict__ hist, int n, int N) {
+    extern __shared__ float2 hstage[];
+    const float2 *x = in + (size_t)blockIdx.x * n;
+    float2 *h = hist + (size_t)blockIdx.x * N;
+    for (int j = threadIdx.x; j < N; j += blockDim.x) {
+        const int c = n - 1 + j;
+        hstage[j] = c < N ? h[c] : x[c - N];
+    }
+    __syncthreads();
+    for (int j = threadIdx.x; j < N; j += blockDim.x) h[j] = hstage[j];
+}
+
 // FIR::FIRUpdateAndProcess (dsp.cpp:59-71): y[m] = sum_i taps[i] * x[decim*m - N + i]  (newest excluded),
 // or with inc = 1 the FIRHilbert form (dsp.cpp:218-231): y[m] = sum_i taps[i] * x[decim*m - N + 1 + i].
 __global__ void __launch_bounds__(256) prim_fir(const float *__restrict__ taps, int N, const float *__restrict__ in,

@@ -59,11 +59,11 @@ const float *Oscillator::deviceTable() {
 }
 
 // ------------------------------------------------------------------ HalfBandDecimator
-HalfBandDecimator::HalfBandDecimator(int taps, int inlen) : d_in(nullptr), d_out(nullptr), d_hist(nullptr), cap(0) {
-    if (taps != 11) throw Error("HalfBandDecimator: only the 11-tap filter (the one vfo.cpp uses) runs on the GPU");
+HalfBandDecimator::HalfBandDecimator(int taps, int inlen) : d_in(nullptr), d_out(nullptr), d_hist(nullptr), cap(0), ntaps(taps) {
+    if (taps < 3 || taps > 255 || !(taps & 1)) throw Error("HalfBandDecimator: odd filter length 3..255");
     (void)inlen;                                            // the reference only sizes its queue with it
-    d_hist = (float *)dev_alloc(sizeof(float) * 22);
-    dev_zero(d_hist, sizeof(float) * 22);
+    d_hist = (float *)dev_alloc(sizeof(float) * 2 * (size_t)taps);
+    dev_zero(d_hist, sizeof(float) * 2 * (size_t)taps);
 }
 HalfBandDecimator::~HalfBandDecimator() { dev_free(d_in); dev_free(d_out); dev_free(d_hist); }
 void HalfBandDecimator::decimate(const std::vector<cpx_typef> &in, std::vector<cpx_typef> &out) {
@@ -76,7 +76,7 @@ void HalfBandDecimator::decimate(const std::vector<cpx_typef> &in, std::vector<c
     }
     if ((int)out.size() < n / 2) throw Error("HalfBandDecimator::decimate: out must hold in.size()/2 samples");
     to_dev(d_in, in.data(), sizeof(cpx_typef) * (size_t)n);
-    check(sdrb_halfband11(d_in, d_out, d_hist, 1, n, nullptr), "sdrb_halfband11");
+    check(sdrb_halfband(ntaps, d_in, d_out, d_hist, 1, n, nullptr), "sdrb_halfband");
     to_host(out.data(), d_out, sizeof(cpx_typef) * (size_t)(n / 2));
 }
 

@@ -174,9 +174,17 @@ static int run_prims(int argc, char **argv) {
             hb.decimate(in, o);
             append(out + "/hb.cf32", o.data(), o.size());
         }
+        for (int taps : {23, 51, 15}) {                  // the other tables; 15 has no case in the reference: zeros
+            HalfBandDecimator h2(taps, 48000);
+            for (int b = 0; b < 3; b++) {
+                for (int i = 0; i < 64; i++) in[(size_t)i] = cpx_typef(x[2 * (64 * b + i)], x[2 * (64 * b + i) + 1]);
+                h2.decimate(in, o);
+                append(out + "/hb" + std::to_string(taps) + ".cf32", o.data(), o.size());
+            }
+        }
         bool threw = false;
-        try { HalfBandDecimator bad(23, 100); } catch (const sdrb_host::Error &) { threw = true; }
-        printf("hb23_throws %d\n", threw ? 1 : 0);
+        try { HalfBandDecimator bad(24, 100); } catch (const sdrb_host::Error &) { threw = true; }
+        printf("hb_even_throws %d\n", threw ? 1 : 0);
     }
     {   // FIR per-sample API in the usb_decimdemod pattern (process every 5th, update the others)
         firfilter filt;

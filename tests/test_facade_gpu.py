@@ -137,7 +137,7 @@ def test_spectrum_signals_like_the_reference(tmp_path):
 
 def test_class_facades(tmp_path):
     out = run("prims", tmp_path)
-    assert out == {"hb23_throws": "1", "lowpass_throws": "1"}
+    assert out == {"hb_even_throws": "1", "lowpass_throws": "1"}
     L = O.lib()
     x = np.fromfile(tmp_path / "input.f32", dtype=np.float32)
     # Oscillator: bit-identical, including the start-up entry and the wrap
@@ -150,6 +150,12 @@ def test_class_facades(tmp_path):
     want = np.zeros(2 * 96, np.float32)
     L.orc_halfband(_p(x), 64, 3, _p(want))
     assert np.abs(got - want).max() <= 1e-5
+    # ... and the 23/51-tap tables; a length without a case in the reference (15) filters to zeros
+    for taps in (23, 51, 15):
+        got = np.fromfile(tmp_path / ("hb%d.cf32" % taps), dtype=np.float32)
+        want = np.zeros(2 * 96, np.float32)
+        L.orc_halfband_n(taps, _p(x), 64, 3, _p(want))
+        assert np.abs(got - want).max() <= 1e-5 and (taps != 15 or not got.any())
     # FIR per-sample API in the /5 pattern, taps from firfilter::low_pass
     taps = np.fromfile(tmp_path / "taps49.f32", dtype=np.float32)
     ref_taps = np.zeros(64, np.float32)

@@ -52,6 +52,20 @@ def test_halfband_block_edge(block, nblocks):
         assert np.allclose(got[m + 5:2 * m], stream[m + 5:2 * m], atol=1e-5)
 
 
+@pytest.mark.parametrize("taps", [11, 23, 51, 15, 21])
+@pytest.mark.parametrize("block,nblocks", [(64, 4), (8, 6), (3000, 2)])
+def test_halfband_other_lengths(taps, block, nblocks):
+    """HalfBandDecimator(taps, ...) for every table in halfbanddecimator.h: 11/23/51 filter, 15/21 are never
+    loaded (no switch case, halfbanddecimator.cpp:10-34) and produce zeros. Bit-identical to the class."""
+    rng = np.random.default_rng(taps)
+    x = rng.standard_normal(2 * block * nblocks).astype(np.float32)
+    a = np.zeros(block * nblocks, np.float32); b = np.ones_like(a)
+    O.ref_prims().ref_halfband(taps, block, _p(x), block, nblocks, _p(a))
+    O.lib().orc_halfband_n(taps, _p(x), block, nblocks, _p(b))
+    assert np.array_equal(a, b)
+    assert a.any() == (taps in (11, 23, 51))
+
+
 @pytest.mark.parametrize("ntaps,every", [(47, 1), (49, 5), (73, 6), (155, 1)])
 def test_fir_excludes_newest(ntaps, every):
     rng = np.random.default_rng(2)

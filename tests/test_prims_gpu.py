@@ -65,6 +65,32 @@ def test_halfband11_blocks_and_carry(block):
     assert L.sdrb_halfband11(d_in.data_ptr(), d_out.data_ptr(), hist.data_ptr(), n_ch, 7, None) == -1
 
 
+@pytest.mark.parametrize("taps", [11, 23, 51, 15])
+@pytest.mark.parametrize("block", [8, 64, 3000])
+def test_halfband_other_lengths_blocks_and_carry(taps, block):
+    import torch
+    L = B.lib()
+    nblocks, n_ch = 4, 2
+    rng = np.random.default_rng(taps + block)
+    x = rng.standard_normal((n_ch, nblocks, block, 2)).astype(np.float32)
+    want = np.zeros((n_ch, nblocks * block // 2, 2), np.float32)
+    for c in range(n_ch):
+        O.lib().orc_halfband_n(taps, _p(np.ascontiguousarray(x[c])), block, nblocks, _p(want[c]))
+    hist = torch.zeros((n_ch, taps, 2), dtype=torch.float32, device="cuda")
+    got = []
+    for b in range(nblocks):
+        d_in = dev(x[:, b])
+        d_out = torch.full((n_ch, block // 2, 2), 7.0, dtype=torch.float32, device="cuda")
+        assert L.sdrb_halfband(taps, d_in.data_ptr(), d_out.data_ptr(), hist.data_ptr(), n_ch, block, None) == 0
+        got.append(d_out.cpu().numpy())
+    got = np.concatenate(got, axis=1)
+    if taps == 11 and block >= 12:
+        assert np.abs(got - want).max() <= 1e-6 * max(1.0, np.abs(want).max())   # the fused-multiply production kernel
+    else:
+        assert np.array_equal(got, want)                                         # same float operations, same order
+    assert L.sdrb_halfband(24, d_in.data_ptr(), d_out.data_ptr(), hist.data_ptr(), n_ch, block, None) == -1
+
+
 @pytest.mark.parametrize("ntaps,decim", [(47, 1), (49, 5), (73, 6)])
 def test_fir_blocks_and_carry(ntaps, decim):
     import torch
