@@ -392,23 +392,35 @@ __global__ void __launch_bounds__(V2_THREADS, V2_MINB) k1_v2(const __grid_consta
     const int t = threadIdx.x;
     const int B = p.block, L = p.lut_len;
     const int v0 = tile * K1V2_ADV - K1V2_HT * V2_CHUNK + t * V2_CHUNK;
-    const long long blk = p.blocks_done[stream] + b;
-    if (t == 0) sBase[0] = (int)((blk * (long long)B) % L);
     const bool in_block = v0 < B;
-    const bool first_ever = (blk == 0);
 
-    // raw bytes of samples v0-16 .. v0+31: six 16-byte pieces of 8 samples
+    // raw bytes of samples v0-16 .. v0+31: six 16-byte pieces of 8 samples. The loads depend on nothing but
+    // the thread's coordinates, so they are in flight together with the stream's callback counter; what
+    // lies before stream sample 0 is blanked afterwards.
     uint4 raw[6];
 #pragma unroll
     for (int q = 0; q < 6; ++q) {
         const int c = v0 - 16 + 8 * q;
         raw[q] = make_uint4(0x7f7f7f7fu, 0x7f7f7f7fu, 0x7f7f7f7fu, 0x7f7f7f7fu);   // 127 -> 0.0
-        if (in_block && !(first_ever && c < 0)) {
+        if (in_block) {
             const uint8_t *src = (b == 0 && c < 0) ? p.tail + (size_t)stream * (2 * RAW_TAIL) + 2 * (RAW_TAIL + c)
                                                    : p.iq + (size_t)stream * p.iq_stride + ((size_t)b * B + c) * 2;
             raw[q] = __ldg(reinterpret_cast<const uint4 *>(src));
         }
     }
+    uint2 teI = make_uint2(0u, 2u), teQ = make_uint2(0u, 2u);     // DC block-start states (mode 2 = plain float bits: 0.0f)
+    if (DC && in_block) {
+        const int dblk = (b * B + v0 + RAW_TAIL) / DC_BLK;       // table index incl. the carried entries
+        const uint2 *te = p.dc_table + ((size_t)stream * p.dc_stride + dblk) * 2;
+        teI = __ldg(te);
+        teQ = __ldg(te + 1);
+    }
+    const long long blk = p.blocks_done[stream] + b;
+    if (t == 0) sBase[0] = (int)((blk * (long long)B) % L);
+    const bool first_ever = (blk == 0);
+#pragma unroll
+    for (int q = 0; q < 6; ++q)
+        if (first_ever && v0 - 16 + 8 * q < 0) raw[q] = make_uint4(0x7f7f7f7fu, 0x7f7f7f7fu, 0x7f7f7f7fu, 0x7f7f7f7fu);
     float2 x[44];                   // x[i] = sample v0 - 12 + i
     {
         float2 y[8];
@@ -442,13 +454,11 @@ __global__ void __launch_bounds__(V2_THREADS, V2_MINB) k1_v2(const __grid_consta
         const int excl = inc - tot;
         const int pcount = 32 * g;
         const float PI_ = (float)((excl & 0xffff) - 127 * pcount), PQ_ = (float)((int)((unsigned)excl >> 16) - 127 * pcount);
-        const int dblk = (b * B + v0 + RAW_TAIL) / DC_BLK;           // table index incl. the carried entries
-        const uint2 *te = p.dc_table + ((size_t)stream * p.dc_stride + dblk) * 2;
         const DcAnchor AI = p.dc_anchor[2 * stream], AQ = p.dc_anchor[2 * stream + 1];
         float bI = 0.f, bQ = 0.f;
         if (in_block && !(first_ever && v0 < 0)) {
-            bI = dc_decode(__ldg(te), AI);
-            bQ = dc_decode(__ldg(te + 1), AQ);
+            bI = dc_decode(teI, AI);
+            bQ = dc_decode(teQ, AQ);
         }
         const float decay = 1.0f - DC_C * (float)pcount;
         // negated state after sample v0-1
