@@ -189,6 +189,15 @@ int sdrb_bank_copy_dc_trace(sdrb_bank *bank, int n_blocks, float *d_out, uint8_t
  */
 int sdrb_bank_process_host(sdrb_bank *bank, const uint8_t *h_iq, size_t iq_stride, int n_blocks,
                            int16_t *h_pcm, float *h_tap);
+/* The same call without the final wait: returns once everything is enqueued. Several calls may be
+ * in flight; the library orders them chunk by chunk, so the copy-in of the next call overlaps the
+ * filters and the copy-out of the current one and the PCIe link never idles between calls. Each
+ * call in flight needs its own h_iq / h_pcm / h_tap (pinned) until sdrb_bank_host_wait has
+ * returned. Every other entry point waits for outstanding asynchronous calls first. */
+int sdrb_bank_process_host_async(sdrb_bank *bank, const uint8_t *h_iq, size_t iq_stride, int n_blocks,
+                                 int16_t *h_pcm, float *h_tap);
+int sdrb_bank_host_wait(sdrb_bank *bank);                               /* all of them */
+int sdrb_bank_host_wait_until(sdrb_bank *bank, int max_in_flight);      /* oldest first, until <= max_in_flight remain */
 /* vfo::process entry (vfo.cpp:235-296): the caller supplies complex float samples (what
  * sdrj::demodData hands to the main VFOs, i.e. already converted and DC-corrected by the
  * caller); everything from the main-VFO mix on runs on the GPU. h_in: cf32, stream s at

@@ -92,6 +92,9 @@ def lib():
         "sdrb_compress_iq": (i, [vp, vp, i, i, i, i, vp]),
         "sdrb_bank_process_host": (i, [vp, vp, sz, i, vp, vp]),
         "sdrb_bank_process_cf32_host": (i, [vp, vp, sz, i, vp, vp]),
+        "sdrb_bank_process_host_async": (i, [vp, vp, sz, i, vp, vp]),
+        "sdrb_bank_host_wait": (i, [vp]),
+        "sdrb_bank_host_wait_until": (i, [vp, i]),
         "sdrb_bank_read_main": (i, [vp, i, i, vp]),
         "sdrb_bank_last_launches": (i, [vp]),
         "sdrb_bank_set_timing": (i, [vp, i]),
@@ -290,6 +293,13 @@ class Bank:
     def process_host(self, h_iq_ptr, iq_stride, n_blocks, h_pcm_ptr, h_tap_ptr=None):
         _check(lib().sdrb_bank_process_host(self.h, h_iq_ptr, iq_stride, n_blocks, h_pcm_ptr, h_tap_ptr),
                "sdrb_bank_process_host")
+
+    def process_host_async(self, h_iq_ptr, iq_stride, n_blocks, h_pcm_ptr, h_tap_ptr=None):
+        _check(lib().sdrb_bank_process_host_async(self.h, h_iq_ptr, iq_stride, n_blocks, h_pcm_ptr, h_tap_ptr),
+               "sdrb_bank_process_host_async")
+
+    def host_wait(self, max_in_flight=0):
+        _check(lib().sdrb_bank_host_wait_until(self.h, max_in_flight), "sdrb_bank_host_wait_until")
 
     def process_numpy(self, iq, n_blocks, want_tap=False):
         """iq: uint8 [n_streams, n_blocks*block*2] -> (pcm int16 [n_streams, n_blocks, pcm_per_block], tap)."""

@@ -7,6 +7,7 @@
 #include <cmath>
 #include <cstdio>
 #include <cstring>
+#include <deque>
 #include <functional>
 #include <map>
 #include <new>
@@ -208,7 +209,10 @@ struct sdrb_bank {
     // host staging for process_host
     DevBuf d_iq, d_pcm, d_tap, d_cf, d_fwd;
     cudaStream_t s_copy_in = nullptr, s_compute = nullptr, s_copy_out = nullptr;
-    std::vector<cudaEvent_t> ev_in, ev_done;
+    std::vector<cudaEvent_t> ev_in, ev_done, ev_free, ev_out;   // per (group, callback) chunk of process_host
+    bool host_inflight = false, host_inflight_tap = false;       // sdrb_bank_process_host_async calls not yet waited for
+    int host_inflight_blocks = 0;
+    std::deque<cudaEvent_t> host_calls;                          // one completion event per call in flight, oldest first
     std::vector<std::pair<int, int>> host_groups;      // (first stream, count) of each pipeline group of process_host
     // DC recursion runs on side streams, one callback ahead of the ingest kernel
     static constexpr int kSide = 8;
@@ -227,11 +231,14 @@ struct sdrb_bank {
 extern "C" void sdrb_bank_destroy(sdrb_bank *b) {
     if (!b) return;
     cudaSetDevice(b->device);
+    cudaDeviceSynchronize();                                 // asynchronous host calls may still be in flight
     DevBuf *all[] = {&b->luts, &b->taps, &b->blocks_done, &b->dc_state, &b->raw_tail, &b->cf_tail, &b->dc_anchor, &b->dc_stats, &b->dc_table,
                      &b->main_out, &b->zbuf, &b->dbuf, &b->cascdev, &b->rfdev, &b->latedev, &b->usbdev, &b->carry,
                      &b->d_iq, &b->d_pcm, &b->d_tap, &b->d_cf, &b->d_fwd};
     for (DevBuf *d : all) d->release();
     for (cudaEvent_t e : b->ev_in) cudaEventDestroy(e);
+    for (cudaEvent_t e : b->ev_free) cudaEventDestroy(e);
+    for (cudaEvent_t e : b->ev_out) cudaEventDestroy(e);
     for (cudaEvent_t e : b->ev_done) cudaEventDestroy(e);
     for (cudaEvent_t e : b->tev) cudaEventDestroy(e);
     for (int k = 0; k < sdrb_bank::kSide; k++) {
@@ -545,6 +552,8 @@ extern "C" int sdrb_bank_blocks_done(sdrb_bank *b, int stream, int64_t *blocks) 
     return SDRB_OK;
 }
 
+static int host_drain(sdrb_bank *b);   // waits for asynchronous host calls still in flight (defined with process_host)
+
 // Per-kernel timing (bench.py roofline): when enabled, a cudaEvent pair brackets every launch
 // on its own stream; sdrb_bank_kernel_times() folds them into per-class totals after a
 // synchronize. Classes: 0 DC recursion, 1 ingest+main VFOs, 2 sub-VFO cascades, 3 /late FIR,
@@ -759,6 +768,7 @@ extern "C" int sdrb_bank_process_device_ex(sdrb_bank *b, const uint8_t *d_iq, si
     int rc = check_process_args(b, d_iq, iq_stride, n_blocks, d_pcm);
     if (rc != SDRB_OK) return rc;
     CU_TRY(cudaSetDevice(b->device));
+    { const int drc = host_drain(b); if (drc != SDRB_OK) return drc; }
     b->last_launches = 0;
     CallCtx c;
     c.d_iq = d_iq; c.iq_stride = iq_stride; c.n_blocks = n_blocks; c.d_pcm = d_pcm; c.d_tap = d_tap;
@@ -775,6 +785,7 @@ extern "C" int sdrb_bank_copy_main(sdrb_bank *b, int main_idx, int n_blocks, flo
         set_error("sdrb_bank_copy_main: bad argument"); return SDRB_E_INVALID;
     }
     CU_TRY(cudaSetDevice(b->device));
+    { const int drc = host_drain(b); if (drc != SDRB_OK) return drc; }
     const MainVfo &m = b->plan->h.mains[(size_t)main_idx];
     // The carry kernel has already moved the tail to the front, but the body is intact.
     const size_t row = (size_t)n_blocks * m.block_out * sizeof(float2);
@@ -801,6 +812,7 @@ extern "C" int sdrb_bank_copy_forward(sdrb_bank *b, int main_idx, int n_blocks, 
         set_error("sdrb_bank_copy_forward: bad argument"); return SDRB_E_INVALID;
     }
     CU_TRY(cudaSetDevice(b->device));
+    { const int drc = host_drain(b); if (drc != SDRB_OK) return drc; }
     return forward_launch(b, main_idx, n_blocks, d_out, (cudaStream_t)cuda_stream);
 }
 
@@ -809,6 +821,7 @@ extern "C" int sdrb_bank_read_forward(sdrb_bank *b, int main_idx, int n_blocks, 
         set_error("sdrb_bank_read_forward: bad argument"); return SDRB_E_INVALID;
     }
     CU_TRY(cudaSetDevice(b->device));
+    { const int drc = host_drain(b); if (drc != SDRB_OK) return drc; }
     const MainVfo &m = b->plan->h.mains[(size_t)main_idx];
     const size_t bytes = (size_t)b->n_streams * (size_t)n_blocks * (size_t)m.fwd_bytes;
     if (b->d_fwd.bytes < bytes) {
@@ -861,6 +874,7 @@ extern "C" int sdrb_bank_copy_input(sdrb_bank *b, int cb, int n, float *d_out, v
     int rc = check_input_args(b, cb, n, d_out, "sdrb_bank_copy_input");
     if (rc != SDRB_OK) return rc;
     CU_TRY(cudaSetDevice(b->device));
+    { const int drc = host_drain(b); if (drc != SDRB_OK) return drc; }
     return input_launch(b, cb, n, (float2 *)d_out, (cudaStream_t)cuda_stream);
 }
 
@@ -869,6 +883,7 @@ extern "C" int sdrb_bank_copy_sub(sdrb_bank *b, int sub_idx, int n_blocks, float
         set_error("sdrb_bank_copy_sub: bad argument"); return SDRB_E_INVALID;
     }
     CU_TRY(cudaSetDevice(b->device));
+    { const int drc = host_drain(b); if (drc != SDRB_OK) return drc; }
     const SubVfo &s = b->plan->h.subs[(size_t)sub_idx];
     const size_t row = (size_t)n_blocks * s.block_z * sizeof(float2);
     CU_TRY(cudaMemcpy2DAsync(d_out, row, (float2 *)b->zbuf.p + b->sub_z_off[(size_t)sub_idx] + b->sub_z_hist[(size_t)sub_idx],
@@ -894,6 +909,7 @@ extern "C" int sdrb_bank_read_input(sdrb_bank *b, int cb, int n, float *h_out) {
     int rc = check_input_args(b, cb, n, h_out, "sdrb_bank_read_input");
     if (rc != SDRB_OK) return rc;
     CU_TRY(cudaSetDevice(b->device));
+    { const int drc = host_drain(b); if (drc != SDRB_OK) return drc; }
     return read_back(b, (size_t)b->n_streams * (size_t)n * sizeof(float2), h_out,
                      [&](void *d, cudaStream_t st) { return input_launch(b, cb, n, (float2 *)d, st); });
 }
@@ -903,6 +919,7 @@ extern "C" int sdrb_bank_read_sub(sdrb_bank *b, int sub_idx, int n_blocks, float
         set_error("sdrb_bank_read_sub: bad argument"); return SDRB_E_INVALID;
     }
     CU_TRY(cudaSetDevice(b->device));
+    { const int drc = host_drain(b); if (drc != SDRB_OK) return drc; }
     const size_t bytes = (size_t)b->n_streams * (size_t)n_blocks * (size_t)b->plan->h.subs[(size_t)sub_idx].block_z * sizeof(float2);
     return read_back(b, bytes, h_out, [&](void *d, cudaStream_t st) { return sdrb_bank_copy_sub(b, sub_idx, n_blocks, (float *)d, st); });
 }
@@ -912,6 +929,7 @@ extern "C" int sdrb_bank_copy_dc_trace(sdrb_bank *b, int n_blocks, float *d_out,
         set_error("sdrb_bank_copy_dc_trace: bad argument or plan without correct_dc_bias"); return SDRB_E_INVALID;
     }
     CU_TRY(cudaSetDevice(b->device));
+    { const int drc = host_drain(b); if (drc != SDRB_OK) return drc; }
     const int n = n_blocks * (b->plan->h.block / DC_BLK);
     dc_trace_gather<<<dim3((unsigned)((n + 255) / 256), (unsigned)b->n_streams), 256, 0, (cudaStream_t)cuda_stream>>>(
         b->table_buf(b->dc_par ^ 1), b->anchor_buf(b->dc_par ^ 1), b->dc_stride + DC_HALO_BLKS, n, (float2 *)d_out,
@@ -920,11 +938,48 @@ extern "C" int sdrb_bank_copy_dc_trace(sdrb_bank *b, int n_blocks, float *d_out,
     return SDRB_OK;
 }
 
-extern "C" int sdrb_bank_process_host(sdrb_bank *b, const uint8_t *h_iq, size_t iq_stride, int n_blocks,
-                                      int16_t *h_pcm, float *h_tap) {
+// Waits for every sdrb_bank_process_host_async call still in flight.
+static int host_drain(sdrb_bank *b) {
+    if (!b->host_inflight) return SDRB_OK;
+    CU_TRY(cudaStreamSynchronize(b->s_copy_out));
+    CU_TRY(cudaStreamSynchronize(b->s_compute));
+    for (cudaEvent_t e : b->host_calls) cudaEventDestroy(e);
+    b->host_calls.clear();
+    b->host_inflight = false;
+    return SDRB_OK;
+}
+
+extern "C" int sdrb_bank_host_wait(sdrb_bank *b) {
+    if (!b) { set_error("sdrb_bank_host_wait: NULL bank"); return SDRB_E_INVALID; }
+    CU_TRY(cudaSetDevice(b->device));
+    return host_drain(b);
+}
+
+// Waits until at most max_in_flight asynchronous host calls are unfinished (oldest first): their
+// h_pcm / h_tap are complete and their host buffers may be reused.
+extern "C" int sdrb_bank_host_wait_until(sdrb_bank *b, int max_in_flight) {
+    if (!b || max_in_flight < 0) { set_error("sdrb_bank_host_wait_until: bad argument"); return SDRB_E_INVALID; }
+    CU_TRY(cudaSetDevice(b->device));
+    if (max_in_flight == 0) return host_drain(b);
+    while ((int)b->host_calls.size() > max_in_flight) {
+        CU_TRY(cudaEventSynchronize(b->host_calls.front()));
+        cudaEventDestroy(b->host_calls.front());
+        b->host_calls.pop_front();
+    }
+    return SDRB_OK;
+}
+
+// Enqueues one host call. Consecutive calls may be in flight together (the staging buffers are shared,
+// so per chunk: the copy-in of call n+1 waits until call n no longer reads that region, the filters of
+// call n+1 wait until call n's copy-out of that region is done).
+static int host_enqueue(sdrb_bank *b, const uint8_t *h_iq, size_t iq_stride, int n_blocks, int16_t *h_pcm, float *h_tap) {
     int rc = check_process_args(b, h_iq, iq_stride, n_blocks, h_pcm);
     if (rc != SDRB_OK) return rc;
     CU_TRY(cudaSetDevice(b->device));
+    if (b->host_inflight && (n_blocks != b->host_inflight_blocks || (h_tap != nullptr) != b->host_inflight_tap)) {
+        rc = host_drain(b);                                  // a different chunk layout: do not overlap with it
+        if (rc != SDRB_OK) return rc;
+    }
     const HostPlan &h = b->plan->h;
     const size_t in_row = (size_t)n_blocks * h.block * 2;
     const size_t rec = (size_t)n_blocks * h.pcm_per_block;
@@ -971,11 +1026,14 @@ extern "C" int sdrb_bank_process_host(sdrb_bank *b, const uint8_t *h_iq, size_t 
     const int n_groups = (int)b->host_groups.size();
     const size_t need_ev = (size_t)n_groups * (size_t)b->max_blocks;
     while (b->ev_in.size() < need_ev) {
-        cudaEvent_t e1, e2;
+        cudaEvent_t e1, e2, e3, e4;
         CU_TRY(cudaEventCreateWithFlags(&e1, cudaEventDisableTiming));
         CU_TRY(cudaEventCreateWithFlags(&e2, cudaEventDisableTiming));
-        b->ev_in.push_back(e1); b->ev_done.push_back(e2);
+        CU_TRY(cudaEventCreateWithFlags(&e3, cudaEventDisableTiming));
+        CU_TRY(cudaEventCreateWithFlags(&e4, cudaEventDisableTiming));
+        b->ev_in.push_back(e1); b->ev_done.push_back(e2); b->ev_free.push_back(e3); b->ev_out.push_back(e4);
     }
+    const bool chained = b->host_inflight;                  // an earlier call may still be running: honour its events
     b->last_launches = 0;
     const size_t cb_in = (size_t)h.block * 2, cb_out = (size_t)h.pcm_per_block;
     const bool dc = h.correct_dc != 0;
@@ -985,12 +1043,14 @@ extern "C" int sdrb_bank_process_host(sdrb_bank *b, const uint8_t *h_iq, size_t 
     c.par = b->dc_par;
     b->last_iq = c.d_iq; b->last_iq_stride = c.iq_stride; b->last_cf = nullptr; b->last_cf_stride = 0;
     b->last_blocks = n_blocks; b->last_par = c.par;
-    b->dc_par ^= 1;                                       // the call is synchronous: no event bookkeeping needed
+    b->dc_par ^= 1;                                       // host calls order themselves with per-chunk events
     b->ev_end_valid[0] = b->ev_end_valid[1] = false;
     for (int cb = 0; cb < n_blocks; cb++)
         for (int g = 0; g < n_groups; g++) {
             const int s0 = b->host_groups[(size_t)g].first, ns = b->host_groups[(size_t)g].second;
             if (ns <= 0) break;
+            // the previous call reads this input region until the filters of the NEXT callback (halo) resp. the carry are done
+            if (chained) CU_TRY(cudaStreamWaitEvent(b->s_copy_in, b->ev_free[(size_t)g * b->max_blocks + cb], 0));
             CU_TRY(cudaMemcpy2DAsync((uint8_t *)b->d_iq.p + (size_t)s0 * in_max + (size_t)cb * cb_in, in_max,
                                      h_iq + (size_t)s0 * iq_stride + (size_t)cb * cb_in, iq_stride, cb_in, (size_t)ns,
                                      cudaMemcpyHostToDevice, b->s_copy_in));
@@ -1001,12 +1061,18 @@ extern "C" int sdrb_bank_process_host(sdrb_bank *b, const uint8_t *h_iq, size_t 
             const int s0 = b->host_groups[(size_t)g].first, ns = b->host_groups[(size_t)g].second;
             if (ns <= 0) break;
             cudaEvent_t ein = b->ev_in[(size_t)g * b->max_blocks + cb], eout = b->ev_done[(size_t)g * b->max_blocks + cb];
+            // the previous call's copy-out of this output region must be over before it is rewritten
+            if (chained) CU_TRY(cudaStreamWaitEvent(b->s_compute, b->ev_out[(size_t)g * b->max_blocks + cb], 0));
             if (dc && (rc = enqueue_dc_cb(b, c, s0, ns, b->s_dc[g], cb, ein, b->ev_dc[g][(size_t)cb], &b->last_launches)) != SDRB_OK)
                 return rc;
             if ((rc = enqueue_main_cb(b, c, s0, ns, b->s_compute, cb, dc ? b->ev_dc[g][(size_t)cb] : ein, eout,
                                       &b->last_launches)) != SDRB_OK)
                 return rc;
             if (cb == n_blocks - 1 && (rc = enqueue_carry(b, c, s0, ns, b->s_compute, &b->last_launches)) != SDRB_OK) return rc;
+            // input region (cb-1, g) is free once this chunk's filters have run (they read its last samples as halo);
+            // region (last, g) once the carry has saved the tail
+            if (cb > 0) CU_TRY(cudaEventRecord(b->ev_free[(size_t)g * b->max_blocks + cb - 1], b->s_compute));
+            if (cb == n_blocks - 1) CU_TRY(cudaEventRecord(b->ev_free[(size_t)g * b->max_blocks + cb], b->s_compute));
             CU_TRY(cudaStreamWaitEvent(b->s_copy_out, eout, 0));
             const size_t off = (size_t)s0 * rec + (size_t)cb * cb_out;
             CU_TRY(cudaMemcpy2DAsync(h_pcm + off, rec * sizeof(int16_t), (int16_t *)b->d_pcm.p + off, rec * sizeof(int16_t),
@@ -1014,10 +1080,30 @@ extern "C" int sdrb_bank_process_host(sdrb_bank *b, const uint8_t *h_iq, size_t 
             if (h_tap)
                 CU_TRY(cudaMemcpy2DAsync(h_tap + off, rec * sizeof(float), (float *)b->d_tap.p + off, rec * sizeof(float),
                                          cb_out * sizeof(float), (size_t)ns, cudaMemcpyDeviceToHost, b->s_copy_out));
+            CU_TRY(cudaEventRecord(b->ev_out[(size_t)g * b->max_blocks + cb], b->s_copy_out));
         }
-    CU_TRY(cudaStreamSynchronize(b->s_copy_out));
-    CU_TRY(cudaStreamSynchronize(b->s_compute));
+    {
+        cudaEvent_t done;                                    // the copy-out stream is FIFO: this marks the call's last result
+        CU_TRY(cudaEventCreateWithFlags(&done, cudaEventDisableTiming));
+        CU_TRY(cudaEventRecord(done, b->s_copy_out));
+        b->host_calls.push_back(done);
+    }
+    b->host_inflight = true;
+    b->host_inflight_blocks = n_blocks;
+    b->host_inflight_tap = h_tap != nullptr;
     return SDRB_OK;
+}
+
+extern "C" int sdrb_bank_process_host_async(sdrb_bank *b, const uint8_t *h_iq, size_t iq_stride, int n_blocks,
+                                            int16_t *h_pcm, float *h_tap) {
+    return host_enqueue(b, h_iq, iq_stride, n_blocks, h_pcm, h_tap);
+}
+
+extern "C" int sdrb_bank_process_host(sdrb_bank *b, const uint8_t *h_iq, size_t iq_stride, int n_blocks,
+                                      int16_t *h_pcm, float *h_tap) {
+    int rc = host_enqueue(b, h_iq, iq_stride, n_blocks, h_pcm, h_tap);
+    if (rc != SDRB_OK) return rc;
+    return host_drain(b);
 }
 
 extern "C" int sdrb_bank_process_cf32_host(sdrb_bank *b, const float *h_in, size_t stride_samples, int n_blocks,
@@ -1027,6 +1113,7 @@ extern "C" int sdrb_bank_process_cf32_host(sdrb_bank *b, const float *h_in, size
         set_error("sdrb_bank_process_cf32_host: bad argument"); return SDRB_E_INVALID;
     }
     CU_TRY(cudaSetDevice(b->device));
+    { const int drc = host_drain(b); if (drc != SDRB_OK) return drc; }
     const HostPlan &h = b->plan->h;
     const size_t row = (size_t)n_blocks * h.block, rec = (size_t)n_blocks * h.pcm_per_block;
     const size_t cap = (size_t)b->max_blocks * h.block;
@@ -1058,6 +1145,7 @@ extern "C" int sdrb_bank_read_main(sdrb_bank *b, int main_idx, int n_blocks, flo
         set_error("sdrb_bank_read_main: bad argument"); return SDRB_E_INVALID;
     }
     CU_TRY(cudaSetDevice(b->device));
+    { const int drc = host_drain(b); if (drc != SDRB_OK) return drc; }
     const MainVfo &m = b->plan->h.mains[(size_t)main_idx];
     const size_t row = (size_t)n_blocks * m.block_out * sizeof(float2);
     CU_TRY(cudaMemcpy2D(h_out, row, (float2 *)b->main_out.p + b->main_off[(size_t)main_idx] + MAIN_HIST,
@@ -1278,6 +1366,7 @@ extern "C" int sdrb_bank_spectrum_feed(sdrb_bank *b, sdrb_spectrum *sp, int sour
         return SDRB_E_INVALID;
     }
     CU_TRY(cudaSetDevice(b->device));
+    { const int drc = host_drain(b); if (drc != SDRB_OK) return drc; }
     cudaStream_t st = (cudaStream_t)cuda_stream;
     if (source < 0) {
         const int n = std::min(b->plan->h.block, FFT_N) / DC_BLK * DC_BLK;

@@ -173,6 +173,45 @@ def test_overlapped_device_calls_with_input_ready_event():
     assert np.array_equal(pcm_a, pcm_h)
 
 
+def test_async_host_calls_pipeline_bit_identical():
+    """sdrb_bank_process_host_async: eight calls, up to three in flight (shared staging buffers ordered chunk by
+    chunk), rotating host buffers -- bit-identical to the synchronous calls, tap included."""
+    op = OP.build_plan(plan_path("25E")); plan = B.Plan(plan_path("25E"))
+    n_streams, calls, nb = 5, 8, 2
+    iq = np.stack([make_input(op, calls * nb, stream=s) for s in range(n_streams)])
+    row = plan.block * 2 * nb
+    pcm_s, tap_s, _ = run_gpu(plan, iq, [nb] * calls)
+    bank = B.Bank(plan, n_streams, nb)
+    depth = 3
+    ins = [B.PinnedBuffer(n_streams * row) for _ in range(depth)]
+    outs = [B.PinnedBuffer(n_streams * nb * plan.pcm_per_block * 2) for _ in range(depth)]
+    taps = [B.PinnedBuffer(n_streams * nb * plan.pcm_per_block * 4) for _ in range(depth)]
+    got_p, got_t = [], []
+
+    def collect(k):
+        got_p.append(outs[k % depth].view(np.int16).reshape(n_streams, nb, -1).copy())
+        got_t.append(taps[k % depth].view(np.float32).reshape(n_streams, nb, -1).copy())
+
+    for k in range(calls):
+        if k >= depth:
+            bank.host_wait(depth - 1)                        # call k-depth is complete: its buffers may be reused
+            collect(k - depth)
+        ins[k % depth].array.reshape(n_streams, row)[:] = iq[:, k * row:(k + 1) * row]
+        bank.process_host_async(ins[k % depth].ptr, row, nb, outs[k % depth].ptr, taps[k % depth].ptr)
+    bank.host_wait()
+    for k in range(max(calls - depth, 0), calls):
+        collect(k)
+    assert np.array_equal(np.concatenate(got_p, axis=1), pcm_s)
+    assert np.array_equal(np.concatenate(got_t, axis=1), tap_s)
+    # a synchronous call right after asynchronous ones drains them first
+    bank.process_host_async(ins[0].ptr, row, nb, outs[0].ptr, None)
+    pcm2, _ = bank.process_numpy(iq[:, :row], nb)
+    assert bank.blocks_done(0) == (calls + 2) * nb
+    bank.close()
+    for b in ins + outs + taps:
+        b.close()
+
+
 def test_argument_errors():
     plan = B.Plan(plan_path("54W_288K"))
     bank = B.Bank(plan, 1, 2)
