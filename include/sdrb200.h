@@ -115,6 +115,13 @@ void sdrb_plan_destroy(sdrb_plan *plan);
 int sdrb_plan_get_info(const sdrb_plan *plan, sdrb_plan_info *info);
 int sdrb_plan_get_main(const sdrb_plan *plan, int idx, sdrb_main_info *info);
 int sdrb_plan_get_sub(const sdrb_plan *plan, int idx, sdrb_sub_info *info);
+/* Any key of the ini file the plan was compiled from, named as QSettings names it ("tuner_gain",
+ * "remote_rtl", "auto_start", "disable_fft", "main_vfos/2/zmq_topic", "vfos/3/gain", ...): the
+ * operational keys MainWindow reads for the device and the GUI (mainwindow.cpp:51-96) are not used by
+ * the hot path but stay available to the application through the same parser. Returns the value's
+ * length (copied, truncated to out_len-1, NUL-terminated) or -1 if the key is absent / the plan was
+ * built from a description. */
+int sdrb_plan_get_setting(const sdrb_plan *plan, const char *key, char *out, size_t out_len);
 /* Host copies of the tables vfo::init builds (vfo.cpp:60-137), for inspection/tests:
  * kind 0 = main NCO table (cf32, (int)Fs entries), 1 = sub NCO table, 2 = sub /late FIR
  * taps, 3 = sub low-pass taps, 4 = Hilbert points (125). Returns the element count

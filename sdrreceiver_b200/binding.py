@@ -79,6 +79,7 @@ def lib():
         "sdrb_plan_get_main": (i, [vp, i, P(MainInfo)]),
         "sdrb_plan_get_sub": (i, [vp, i, P(SubInfo)]),
         "sdrb_plan_copy_table": (l, [vp, i, i, vp, l]),
+        "sdrb_plan_get_setting": (i, [vp, C.c_char_p, C.c_char_p, sz]),
         "sdrb_bank_create": (i, [vp, i, i, i, P(vp)]),
         "sdrb_bank_destroy": (None, [vp]),
         "sdrb_bank_reset": (i, [vp, i]),
@@ -208,6 +209,12 @@ class Plan:
             d.subs[k].decim, d.subs[k].late = s["decim"], s.get("late", 0)
             d.subs[k].filter_bw, d.subs[k].gain = s.get("filterbw", 0), s.get("gain", 0.01)
         return cls(desc=d)
+
+    def setting(self, key, default=None):
+        """Value of an ini key as QSettings names it, or `default`."""
+        buf = C.create_string_buffer(512)
+        n = lib().sdrb_plan_get_setting(self.h, key.encode(), buf, 512)
+        return default if n < 0 else buf.value.decode()
 
     def table(self, kind, idx):
         L = lib()

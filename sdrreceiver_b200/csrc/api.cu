@@ -109,6 +109,18 @@ extern "C" int sdrb_plan_get_sub(const sdrb_plan *plan, int idx, sdrb_sub_info *
     return SDRB_OK;
 }
 
+extern "C" int sdrb_plan_get_setting(const sdrb_plan *plan, const char *key, char *out, size_t out_len) {
+    if (!plan || !key) { set_error("sdrb_plan_get_setting: NULL argument"); return SDRB_E_INVALID; }
+    auto it = plan->h.settings.find(key);
+    if (it == plan->h.settings.end()) return -1;
+    if (out && out_len) {
+        const size_t n = std::min(out_len - 1, it->second.size());
+        memcpy(out, it->second.data(), n);
+        out[n] = 0;
+    }
+    return (int)it->second.size();
+}
+
 extern "C" long sdrb_plan_copy_table(const sdrb_plan *plan, int kind, int idx, float *dst, long max_elems) {
     if (!plan) { set_error("sdrb_plan_copy_table: NULL plan"); return SDRB_E_INVALID; }
     const HostPlan &h = plan->h;

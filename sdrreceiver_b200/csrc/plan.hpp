@@ -3,6 +3,7 @@
 // api.cu (device upload, launches).
 #pragma once
 #include <cstdint>
+#include <map>
 #include <string>
 #include <vector>
 #include "../../include/sdrb200.h"
@@ -51,6 +52,10 @@ struct HostPlan {
     std::vector<SubVfo> subs;
     int pcm_per_block = 0;
     double alg_bytes = 0, alg_flops = 0;
+    // every key of the ini file as QSettings would name it ("group/key", arrays "vfos/3/gain"): the keys the
+    // hot path does not use (tuner_gain, remote_rtl, auto_start*, disable_fft, ... mainwindow.cpp:51-96) stay
+    // readable through sdrb_plan_get_setting for the application that owns the device and the GUI
+    std::map<std::string, std::string> settings;
 };
 
 void set_error(const std::string &msg);

@@ -239,6 +239,7 @@ int plan_from_ini(const char *path, HostPlan &p) {
         return SDRB_E_IO;
     }
     p = HostPlan();
+    p.settings = ini.kv;
     p.fs = ini.num("sample_rate");
     if (p.fs != 288000 && p.fs != 1536000 && p.fs != 1920000) {       // mainwindow.cpp:31-47
         set_error("sample_rate setting not supported, only 288000, 1536000, 1920000 are");

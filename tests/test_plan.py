@@ -117,3 +117,17 @@ def test_plan_from_desc_equals_ini():
     b = B.Plan.from_desc(a.fs, a.block, a.bufsplit, a.correct_dc, a.mains, a.subs)
     assert [s["samples_out"] for s in a.subs] == [s["samples_out"] for s in b.subs]
     assert np.array_equal(a.table(1, 3), b.table(1, 3)) and np.array_equal(a.table(3, 5), b.table(3, 5))
+
+
+def test_operational_ini_keys_stay_readable(tmp_path):
+    """Keys MainWindow reads for the device/GUI (mainwindow.cpp:51-96) are not hot-path inputs but the same
+    parser hands them to the application."""
+    src = open(plan_path("54W_288K")).read().replace("sample_rate=288000", "sample_rate=288000\ntuner_gain=496\nauto_start=1\n"
+                                                     "remote_rtl=192.168.1.5:1234\nremote_rtl_gain_idx=14\ndisable_fft=1")
+    p = tmp_path / "ops.ini"
+    p.write_text(src)
+    plan = B.Plan(str(p))
+    assert plan.setting("tuner_gain") == "496" and plan.setting("auto_start") == "1" and plan.setting("disable_fft") == "1"
+    assert plan.setting("remote_rtl") == "192.168.1.5:1234" and plan.setting("remote_rtl_gain_idx") == "14"
+    assert plan.setting("vfos/1/topic") == plan.subs[0]["topic"] and plan.setting("main_vfos/size") == "1"
+    assert plan.setting("no_such_key") is None and plan.setting("no_such_key", "x") == "x"
