@@ -10,7 +10,7 @@ import os
 import numpy as np
 
 _HERE = os.path.dirname(os.path.abspath(__file__))
-LIB_PATH = os.path.join(_HERE, "libsdrb200.so")
+LIB_PATH = os.environ.get("SDRB_LIB") or os.path.join(_HERE, "libsdrb200.so")   # SDRB_LIB: kernel-variant experiments
 
 SDRB_MAX_MAIN, SDRB_MAX_SUB = 8, 256
 

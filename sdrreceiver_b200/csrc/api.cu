@@ -157,10 +157,37 @@ struct DevBuf {
     void release() { if (p) cudaFree(p); p = nullptr; }
 };
 
+// CTA size of a k1_v2 / k2a_v2 launch with `halo` halo threads per tile. Occupancy is 12 warps per SM
+// at any size (168 registers); measured on B200, a 64-thread CTA runs ~10 % and a 96-thread CTA ~3 %
+// faster per thread than a 128-thread one (shorter barrier domains), and (NT - halo)/NT of the
+// threads do useful work. `env` (64, 96 or 128) overrides the choice for tuning runs.
+static int v2_pick_threads(int halo, const char *env) {
+    if (const char *e = getenv(env)) {
+        const int v = atoi(e);
+        if ((v == 64 || v == 96 || v == 128) && v > 2 * halo) return v;
+    }
+    static const int nt[3] = {64, 96, 128};
+    static const double speed[3] = {1.10, 1.03, 1.00};
+    int best = 128; double best_score = 0.0;
+    for (int i = 0; i < 3; i++) {
+        const double score = speed[i] * (double)(nt[i] - halo) / (double)nt[i];
+        if (score > best_score) { best_score = score; best = nt[i]; }
+    }
+    return best;
+}
+
+template <int NT>
+static void launch_k1_v2(const K1V2Params &q, bool dc, int ns, int block, cudaStream_t st) {
+    const dim3 grid((unsigned)ns, (unsigned)((block + k1v2_adv<NT>() - 1) / k1v2_adv<NT>()), 1u);
+    if (dc) k1_v2<true, NT><<<grid, NT, V2L<NT>::SMEM, st>>>(q);
+    else k1_v2<false, NT><<<grid, NT, V2L<NT>::SMEM, st>>>(q);
+}
+
 struct SubGroup {           // sub VFOs of one main VFO (at most V2_MAX_VFO) -> one k2a_v2 launch
     int main_idx;
     int tiles;              // tiles per callback
     int halo;               // halo threads in front of every tile
+    int threads;            // CTA size of this group's launch (64, 96 or 128)
     int first, count;       // range in the device CascVfo / Rf arrays (sorted by group)
     int lut_len, block_in;  // Oscillator table length and callback size of the group's sub VFOs
 };
@@ -202,6 +229,7 @@ struct sdrb_bank {
     // descriptors
     K1Params k1{};          // cf32-input variant (vfo::process entry)
     K1V2Params k1v2{};
+    int k1_threads = 64;
     std::vector<K2V2Params> k2v2;                 // one prebuilt parameter block per sub-VFO group
     DevBuf cascdev, rfdev, latedev, usbdev, carry;
     std::vector<SubGroup> groups;
@@ -398,7 +426,8 @@ extern "C" int sdrb_bank_create(const sdrb_plan *plan, int device, int n_streams
         if (g.count) b->groups.push_back(g);
     }
     for (SubGroup &g : b->groups) {
-        const int adv = (V2_THREADS - g.halo) * V2_CHUNK;
+        g.threads = v2_pick_threads(g.halo, "SDRB_K2A_THREADS");
+        const int adv = (g.threads - g.halo) * V2_CHUNK;
         const SubVfo &s0v = h.subs[(size_t)order[(size_t)g.first]];
         g.lut_len = (int)s0v.lut.size(); g.block_in = s0v.block_in;
         g.tiles = (g.block_in + adv - 1) / adv;
@@ -506,9 +535,16 @@ extern "C" int sdrb_bank_create(const sdrb_plan *plan, int device, int n_streams
     b->uv_smem = sizeof(float) * (2 * (size_t)(64 + b->uv_np_max) + (size_t)UV_WARPS * b->uv_warp_floats);
     BANK_CU(cudaFuncSetAttribute(k2b_v2, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)b->uv_smem));
     BANK_CU(cudaFuncSetAttribute(k0_dc_walk, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)DCW_SMEM));
-    BANK_CU(cudaFuncSetAttribute(k2a_v2, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)V2_SMEM));
-    BANK_CU(cudaFuncSetAttribute(k1_v2<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)V2_SMEM));
-    BANK_CU(cudaFuncSetAttribute(k1_v2<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)V2_SMEM));
+    BANK_CU(cudaFuncSetAttribute(k2a_v2<64>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)V2L<64>::SMEM));
+    BANK_CU(cudaFuncSetAttribute(k2a_v2<96>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)V2L<96>::SMEM));
+    BANK_CU(cudaFuncSetAttribute(k2a_v2<128>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)V2L<128>::SMEM));
+    BANK_CU(cudaFuncSetAttribute(k1_v2<true, 64>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)V2L<64>::SMEM));
+    BANK_CU(cudaFuncSetAttribute(k1_v2<false, 64>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)V2L<64>::SMEM));
+    BANK_CU(cudaFuncSetAttribute(k1_v2<true, 96>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)V2L<96>::SMEM));
+    BANK_CU(cudaFuncSetAttribute(k1_v2<false, 96>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)V2L<96>::SMEM));
+    BANK_CU(cudaFuncSetAttribute(k1_v2<true, 128>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)V2L<128>::SMEM));
+    BANK_CU(cudaFuncSetAttribute(k1_v2<false, 128>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)V2L<128>::SMEM));
+    b->k1_threads = v2_pick_threads(K1V2_HT, "SDRB_K1_THREADS");
     BANK_CU(cudaStreamCreateWithFlags(&b->s_copy_in, cudaStreamNonBlocking));
     BANK_CU(cudaStreamCreateWithFlags(&b->s_compute, cudaStreamNonBlocking));
     BANK_CU(cudaStreamCreateWithFlags(&b->s_copy_out, cudaStreamNonBlocking));
@@ -634,17 +670,20 @@ static int enqueue_main_cb(sdrb_bank *b, const CallCtx &c, int s0, int ns, cudaS
         K1V2Params q = b->k1v2;
         q.iq = c.d_iq; q.iq_stride = c.iq_stride; q.stream0 = s0; q.b0 = cb;
         q.dc_table = b->table_buf(c.par); q.dc_anchor = b->anchor_buf(c.par);
-        const dim3 grid((unsigned)ns, (unsigned)((h.block + K1V2_ADV - 1) / K1V2_ADV), 1u);
         TimedScope t(b, st, 1);
-        if (h.correct_dc) k1_v2<true><<<grid, V2_THREADS, V2_SMEM, st>>>(q);
-        else k1_v2<false><<<grid, V2_THREADS, V2_SMEM, st>>>(q);
+        if (b->k1_threads == 64) launch_k1_v2<64>(q, h.correct_dc, ns, h.block, st);
+        else if (b->k1_threads == 96) launch_k1_v2<96>(q, h.correct_dc, ns, h.block, st);
+        else launch_k1_v2<128>(q, h.correct_dc, ns, h.block, st);
     }
     (*nl)++;
     for (const SubGroup &g : b->groups) {
         K2V2Params &kp = b->k2v2[(size_t)(&g - b->groups.data())];
         kp.stream0 = s0; kp.b0 = cb;
         TimedScope t(b, st, 2);
-        k2a_v2<<<dim3((unsigned)ns, (unsigned)g.tiles, 1u), V2_THREADS, V2_SMEM, st>>>(kp);
+        const dim3 grid((unsigned)ns, (unsigned)g.tiles, 1u);
+        if (g.threads == 64) k2a_v2<64><<<grid, 64, V2L<64>::SMEM, st>>>(kp);
+        else if (g.threads == 96) k2a_v2<96><<<grid, 96, V2L<96>::SMEM, st>>>(kp);
+        else k2a_v2<128><<<grid, 128, V2L<128>::SMEM, st>>>(kp);
         (*nl)++;
     }
     if (b->n_late) {

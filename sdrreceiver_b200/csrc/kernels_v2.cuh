@@ -24,14 +24,19 @@
 
 namespace sdrb {
 
-constexpr int V2_THREADS = 128;
 constexpr int V2_CHUNK = 32;
-constexpr int V2_MINB = 3;
 constexpr int RF_LEN = 48;             // per VFO: Rf[j], j = -10..31 at index j + 10; padded to 48
 constexpr int V2_MAX_VFO = 16;         // VFOs per launch (descriptors + Rf tables in the kernel parameters)
 constexpr int LUT_STEADY = 512;        // table entries needed by the start-up transient (94 measured)
 constexpr int K1V2_HT = 4;             // halo threads of k1_v2: one DC block, covers 3 half-band stages
-constexpr int K1V2_ADV = (V2_THREADS - K1V2_HT) * V2_CHUNK;
+// CTA size: 168 registers per thread allow 12 warps per SM whatever the CTA size, so a smaller CTA
+// costs nothing in occupancy; it shortens every barrier domain (the stage transitions are where the
+// warps stall) and costs halo threads: HT of NT threads recompute the previous tile's tail. Measured
+// on B200 (25E): ingest 0.87 -> 0.79 ms per step at 64 threads (4 halo threads); the sub-VFO cascade
+// gains the same ~9 % per useful thread, which the 11 halo threads of a 5-stage group give back. The
+// host picks 64, 96 or 128 threads per launch (api.cu: v2_pick_threads).
+template <int NT> constexpr int v2_minb() { return 384 / NT; }    // 12 warps per SM
+template <int NT> constexpr int k1v2_adv() { return (NT - K1V2_HT) * V2_CHUNK; }    // host side
 
 struct CascVfo {
     const float2 *lut;          // Oscillator table of this VFO
@@ -52,15 +57,17 @@ template <> struct StLay<16> { static constexpr int STR = 18, PADT = 1; };
 template <> struct StLay<8> { static constexpr int STR = 10, PADT = 2; };
 template <> struct StLay<4> { static constexpr int STR = 6, PADT = 3; };
 template <> struct StLay<2> { static constexpr int STR = 2, PADT = 6; };
-template <int N> constexpr int st_elems() { return (V2_THREADS + StLay<N>::PADT) * StLay<N>::STR; }
+template <int N, int NT> constexpr int st_elems() { return (NT + StLay<N>::PADT) * StLay<N>::STR; }
 
-constexpr int V2_SA = 0;                                        // two copies, alternating from VFO to VFO
-constexpr int V2_SA_LEN = st_elems<16>();
-constexpr int V2_SB = V2_SA + 2 * V2_SA_LEN;
-constexpr int V2_SC = V2_SB + st_elems<8>();
-constexpr int V2_SD = V2_SC + st_elems<4>();
-constexpr int V2_SEND = V2_SD + st_elems<2>();                  // then 16 bytes of misc
-constexpr size_t V2_SMEM = (size_t)V2_SEND * sizeof(float2) + 16;
+template <int NT> struct V2L {                                  // scratch offsets (float2) of a CTA of NT threads
+    static constexpr int SA = 0;                                // two copies, alternating from VFO to VFO
+    static constexpr int SA_LEN = st_elems<16, NT>();
+    static constexpr int SB = SA + 2 * SA_LEN;
+    static constexpr int SC = SB + st_elems<8, NT>();
+    static constexpr int SD = SC + st_elems<4, NT>();
+    static constexpr int SEND = SD + st_elems<2, NT>();         // then 16 bytes of misc
+    static constexpr size_t SMEM = (size_t)SEND * sizeof(float2) + 16;
+};
 
 template <int N>
 __device__ __forceinline__ int st_pos(int c_rel) {              // CTA-relative sample, may be negative
@@ -165,11 +172,11 @@ __device__ __noinline__ void stage1_exact(const float2 *xc, const float2 *__rest
 //   n_abs     absolute stream index of sample v0 (negative: before the stream began)
 //   k0        n_abs mod L
 //   P         the kernel's parameter struct (__grid_constant__): P::vfos[], P::rf[]
-template <int MAXS, class P>
+template <int MAXS, int NT, class P>
 __device__ __forceinline__ void cascade_loop(const float2 (&x)[44], const P &p, int count,
                                              float2 *__restrict__ sm, int t, int v0, long long n_abs, int k0, int L,
                                              bool store, size_t out_off /* stream*out_stride */, int b) {
-    float2 *sB = sm + V2_SB, *sC = sm + V2_SC, *sD = sm + V2_SD;
+    float2 *sB = sm + V2L<NT>::SB, *sC = sm + V2L<NT>::SC, *sD = sm + V2L<NT>::SD;
     int prevS = 1, flip = 0;
     const bool head = (v0 == 0);
     const bool fast = (k0 >= LUT_STEADY + 10) && (k0 + V2_CHUNK <= L) && !head;
@@ -203,7 +210,7 @@ __device__ __forceinline__ void cascade_loop(const float2 (&x)[44], const P &p, 
         // needs no barrier here: whoever still reads the other copy's stage-1 data has not yet passed
         // the previous VFO's first barrier, and everything behind it (sB, sC, sD) is only rewritten
         // after this VFO's own barriers. After a 1-stage VFO (no barrier of its own) one is needed.
-        float2 *sA = sm + V2_SA + flip * V2_SA_LEN;
+        float2 *sA = sm + V2L<NT>::SA + flip * V2L<NT>::SA_LEN;
         flip ^= 1;
         if (prevS < 2) __syncthreads();
         prevS = V.S;
@@ -281,16 +288,17 @@ struct K2V2Params {
     int count, lut_len, block_in, HT, stream0, b0;
 };
 
-__global__ void __launch_bounds__(V2_THREADS, V2_MINB) k2a_v2(const __grid_constant__ K2V2Params p) {
+template <int NT>
+__global__ void __launch_bounds__(NT, v2_minb<NT>()) k2a_v2(const __grid_constant__ K2V2Params p) {
     extern __shared__ __align__(16) unsigned char smem_raw[];
     float2 *sm = reinterpret_cast<float2 *>(smem_raw);
-    int *sBase = reinterpret_cast<int *>(sm + V2_SEND);
+    int *sBase = reinterpret_cast<int *>(sm + V2L<NT>::SEND);
 
     const int stream = p.stream0 + blockIdx.x;
     const int tile = blockIdx.y, b = p.b0 + blockIdx.z;
     const int t = threadIdx.x;
     const int B = p.block_in, L = p.lut_len;
-    const int v0 = tile * ((V2_THREADS - p.HT) * V2_CHUNK) - p.HT * V2_CHUNK + t * V2_CHUNK;
+    const int v0 = tile * ((NT - p.HT) * V2_CHUNK) - p.HT * V2_CHUNK + t * V2_CHUNK;
     const long long blk = p.blocks_done[stream] + b;
     if (t == 0) sBase[0] = (int)((blk * (long long)B) % L);
     const bool in_block = v0 < B;
@@ -312,7 +320,7 @@ __global__ void __launch_bounds__(V2_THREADS, V2_MINB) k2a_v2(const __grid_const
     int k0 = sBase[0] + v0;
     if (k0 < 0) k0 += L;
     if (k0 >= L) k0 -= L;
-    cascade_loop<5>(x, p, p.count, sm, t, v0, blk * (long long)B + v0, k0, L, in_block && t >= p.HT,
+    cascade_loop<5, NT>(x, p, p.count, sm, t, v0, blk * (long long)B + v0, k0, L, in_block && t >= p.HT,
                     (size_t)stream * p.out_stride, b);
 }
 
@@ -381,17 +389,18 @@ __global__ void __launch_bounds__(64) k_input_samples(const uint8_t *__restrict_
     }
 }
 
-template <bool DC>
-__global__ void __launch_bounds__(V2_THREADS, V2_MINB) k1_v2(const __grid_constant__ K1V2Params p) {
+template <bool DC, int NT>
+__global__ void __launch_bounds__(NT, v2_minb<NT>()) k1_v2(const __grid_constant__ K1V2Params p) {
     extern __shared__ __align__(16) unsigned char smem_raw[];
     float2 *sm = reinterpret_cast<float2 *>(smem_raw);
-    int *sBase = reinterpret_cast<int *>(sm + V2_SEND);
+    int *sBase = reinterpret_cast<int *>(sm + V2L<NT>::SEND);
 
     const int stream = p.stream0 + blockIdx.x;
     const int tile = blockIdx.y, b = p.b0 + blockIdx.z;
     const int t = threadIdx.x;
     const int B = p.block, L = p.lut_len;
-    const int v0 = tile * K1V2_ADV - K1V2_HT * V2_CHUNK + t * V2_CHUNK;
+    constexpr int ADV = (NT - K1V2_HT) * V2_CHUNK;
+    const int v0 = tile * ADV - K1V2_HT * V2_CHUNK + t * V2_CHUNK;
     const bool in_block = v0 < B;
 
     // raw bytes of samples v0-16 .. v0+31: six 16-byte pieces of 8 samples. The loads depend on nothing but
@@ -487,7 +496,7 @@ __global__ void __launch_bounds__(V2_THREADS, V2_MINB) k1_v2(const __grid_consta
     int k0 = sBase[0] + v0;
     if (k0 < 0) k0 += L;
     if (k0 >= L) k0 -= L;
-    cascade_loop<3>(x, p, p.n_main, sm, t, v0, blk * (long long)B + v0, k0, L, in_block && t >= K1V2_HT,
+    cascade_loop<3, NT>(x, p, p.n_main, sm, t, v0, blk * (long long)B + v0, k0, L, in_block && t >= K1V2_HT,
                     (size_t)stream * (size_t)p.out_stride, b);
 }
 
