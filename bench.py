@@ -335,7 +335,13 @@ def b200_arm(args):
     achieved = alg_bytes[dom] * samples_per_step / (dom_ms * 1e-3) / 1e9 if dom_ms > 0 else 0.0
     clocks = sampler.summary()
     sm_mhz = clocks["sm_mhz"] or 1965.0
-    fp32_peak = 148 * 128 * 2 * sm_mhz * 1e6 / 1e12
+    fp32_nominal = 148 * 128 * 2 * sm_mhz * 1e6 / 1e12
+    # FP32 denominator: an FMA loop measured on this device after the timed region (scalar FFMA and packed
+    # FFMA2 chains, the better of the two); the nominal figure is kept beside it
+    fp32_probe = {"ffma": B.probe_fp32_tflops(False), "ffma2": B.probe_fp32_tflops(True)}
+    fp32_peak = max(fp32_probe.values())
+    fp32_src = ("measured FMA loop (sdrb_probe_fp32_tflops): FFMA %.1f, FFMA2 %.1f TFLOP/s; nominal 148 SM x 128 lanes x 2 x "
+                "%.0f MHz = %.1f" % (fp32_probe["ffma"], fp32_probe["ffma2"], sm_mhz, fp32_nominal))
     step_ms = max_dev_ms / args.steps
     # DRAM traffic of that kernel class from the committed ncu --set full capture (same plan and bank
     # size), per "launch" = the class's launches of one callback, like `achieved`
@@ -367,7 +373,7 @@ def b200_arm(args):
     if dom in alg_flops and dom_ms > 0:
         tf = alg_flops[dom] * samples_per_step / (dom_ms * 1e-3) / 1e12
         roofline["fp32"] = {"achieved_tflops": tf, "peak_tflops": fp32_peak, "frac": tf / fp32_peak,
-                            "alg_flops_per_sample": alg_flops[dom]}
+                            "alg_flops_per_sample": alg_flops[dom], "peak_source": fp32_src}
     line = {
         "metric": METRIC, "value": value, "unit": "MS/s", "n_gpus": world, "steps": args.steps, "warmup": args.warmup,
         "ms_per_step": step_ms, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
@@ -395,7 +401,7 @@ def b200_arm(args):
                                        "peak_tflops": fp32_peak,
                                        "frac": plan.alg_flops * samples_per_step / (step_ms * 1e-3) / 1e12 / fp32_peak,
                                        "alg_flops_per_sample": plan.alg_flops,
-                                       "peak_source": "148 SM x 128 lanes x 2 x median SM clock under load"}},
+                                       "peak_source": fp32_src}},
         "kernels_ms_per_step": per_step_ms,
         "kernel_launches_per_step": launches_per_step,
         "digests": digests,

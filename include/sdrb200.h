@@ -225,6 +225,12 @@ int sdrb_bank_last_launches(const sdrb_bank *bank);
 int sdrb_bank_set_timing(sdrb_bank *bank, int on);
 int sdrb_bank_kernel_times(sdrb_bank *bank, double *ms, long *calls);
 
+/* FP32 peak of the current device, measured: a register-only loop of independent FMA chains on every
+ * SM, timed with CUDA events (best of `reps`). packed = 0: scalar FFMA; 1: FFMA2 (fma.rn.f32x2, the
+ * form the half-band and USB kernels use). Result in TFLOP/s (2 flop per FMA lane). This is the FP32
+ * denominator of bench.py's roofline ("measure an FMA-loop peak on the box"). */
+int sdrb_probe_fp32_tflops(int packed, int reps, double *tflops);
+
 void *sdrb_host_alloc(size_t bytes);   /* cudaHostAlloc'd (pinned) */
 void sdrb_host_free(void *p);
 

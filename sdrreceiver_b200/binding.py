@@ -100,6 +100,7 @@ def lib():
         "sdrb_bank_last_launches": (i, [vp]),
         "sdrb_bank_set_timing": (i, [vp, i]),
         "sdrb_bank_kernel_times": (i, [vp, vp, vp]),
+        "sdrb_probe_fp32_tflops": (i, [i, i, P(d)]),
         "sdrb_host_alloc": (vp, [sz]),
         "sdrb_host_free": (None, [vp]),
         "sdrb_nco_table": (l, [d, d, vp, l]),
@@ -407,6 +408,13 @@ class PinnedBuffer:
             self.array = None
             lib().sdrb_host_free(self.ptr)
             self.ptr = None
+
+
+def probe_fp32_tflops(packed=False, reps=5):
+    """Measured FP32 FMA peak of the current device in TFLOP/s (sdrb_probe_fp32_tflops)."""
+    v = C.c_double(0.0)
+    _check(lib().sdrb_probe_fp32_tflops(1 if packed else 0, reps, C.byref(v)), "sdrb_probe_fp32_tflops")
+    return v.value
 
 
 def split_pcm(plan, pcm):

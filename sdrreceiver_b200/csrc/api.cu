@@ -1206,6 +1206,76 @@ extern "C" int sdrb_bank_read_main(sdrb_bank *b, int main_idx, int n_blocks, flo
 
 extern "C" int sdrb_bank_last_launches(const sdrb_bank *b) { return b ? b->last_launches : 0; }
 
+// ---- FP32 peak probe ----
+namespace sdrb {
+template <bool PACKED>
+__global__ void __launch_bounds__(256) k_probe_fma(float *sink, int iters, float a, float b) {
+    // 8 independent chains per thread; operands from registers only
+    if constexpr (PACKED) {
+        float2 c[8];
+#pragma unroll
+        for (int k = 0; k < 8; ++k) c[k] = make_float2((float)(threadIdx.x + k), (float)k);
+        const float2 a2 = make_float2(a, a), b2 = make_float2(b, b);
+        for (int i = 0; i < iters; ++i) {
+#pragma unroll
+            for (int u = 0; u < 8; ++u) {
+#pragma unroll
+                for (int k = 0; k < 8; ++k) c[k] = fma2(c[k], a2, b2);
+            }
+        }
+        float acc = 0.f;
+#pragma unroll
+        for (int k = 0; k < 8; ++k) acc += c[k].x + c[k].y;
+        if (acc == 123.456f) sink[0] = acc;
+    } else {
+        float c[16];
+#pragma unroll
+        for (int k = 0; k < 16; ++k) c[k] = (float)(threadIdx.x + k);
+        for (int i = 0; i < iters; ++i) {
+#pragma unroll
+            for (int u = 0; u < 8; ++u) {
+#pragma unroll
+                for (int k = 0; k < 16; ++k) c[k] = fmaf(c[k], a, b);
+            }
+        }
+        float acc = 0.f;
+#pragma unroll
+        for (int k = 0; k < 16; ++k) acc += c[k];
+        if (acc == 123.456f) sink[0] = acc;
+    }
+}
+}  // namespace sdrb
+
+extern "C" int sdrb_probe_fp32_tflops(int packed, int reps, double *tflops) {
+    if (!tflops || reps < 1) { set_error("sdrb_probe_fp32_tflops: bad arguments"); return SDRB_E_INVALID; }
+    int dev = 0, sms = 0;
+    if (cudaGetDevice(&dev) != cudaSuccess || cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev) != cudaSuccess) {
+        set_error("sdrb_probe_fp32_tflops: no CUDA device"); return SDRB_E_CUDA;
+    }
+    float *sink = nullptr;
+    cudaEvent_t e0, e1;
+    if (cudaMalloc(&sink, 4) != cudaSuccess) { set_error("sdrb_probe_fp32_tflops: cudaMalloc failed"); return SDRB_E_CUDA; }
+    cudaEventCreate(&e0); cudaEventCreate(&e1);
+    const int iters = 4096, ctas = sms * 8, threads = 256;
+    const double flop = (double)ctas * threads * (double)iters * 8.0 * 16.0 * 2.0;      // 16 FMA lanes per inner step, either form
+    double best = 0.0;
+    for (int r = 0; r < reps + 1; ++r) {                     // first pass warms up
+        cudaEventRecord(e0);
+        if (packed) sdrb::k_probe_fma<true><<<ctas, threads>>>(sink, iters, 0.999f, 0.001f);
+        else sdrb::k_probe_fma<false><<<ctas, threads>>>(sink, iters, 0.999f, 0.001f);
+        cudaEventRecord(e1);
+        if (cudaEventSynchronize(e1) != cudaSuccess) break;
+        float ms = 0.f;
+        cudaEventElapsedTime(&ms, e0, e1);
+        if (r > 0 && ms > 0.f) best = std::max(best, flop / (ms * 1e-3) / 1e12);
+    }
+    cudaEventDestroy(e0); cudaEventDestroy(e1); cudaFree(sink);
+    const cudaError_t e = cudaGetLastError();
+    if (e != cudaSuccess || best <= 0.0) { set_error(std::string("sdrb_probe_fp32_tflops: ") + cudaGetErrorString(e)); return SDRB_E_CUDA; }
+    *tflops = best;
+    return SDRB_OK;
+}
+
 extern "C" void *sdrb_host_alloc(size_t bytes) {
     void *p = nullptr;
     if (cudaHostAlloc(&p, bytes, cudaHostAllocDefault) != cudaSuccess) {

@@ -315,3 +315,19 @@ def test_dc_state_is_bit_identical(dc, sigma, n_blocks, splits):
         want = O.dc_trace(iq[s], 128).view(np.float32).reshape(-1, 2)
         assert np.array_equal(got[s].view(np.uint32), want.view(np.uint32)), (s, np.abs(got[s] - want).max())
     bank.close()
+
+
+@pytest.mark.gpu
+@pytest.mark.parametrize("k1_threads,k2a_threads", [(128, 64), (96, 96), (64, 128)])
+def test_every_cta_size_of_the_cascade_kernels(k1_threads, k2a_threads):
+    """k1_v2 / k2a_v2 exist for 64-, 96- and 128-thread CTAs and the host picks one per launch
+    (api.cu: v2_pick_threads). SDRB_K1_THREADS / SDRB_K2A_THREADS force a size: every instantiation
+    must pass the same oracle comparison as the default (smoke(): 54W_288K and 25E, 1e-4 rel-L2, +-1 LSB)."""
+    import subprocess
+    import sys
+    root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    env = dict(os.environ, SDRB_K1_THREADS=str(k1_threads), SDRB_K2A_THREADS=str(k2a_threads))
+    r = subprocess.run([sys.executable, "-c", "import __graft_entry__ as g; g.smoke()"], cwd=root, env=env,
+                       capture_output=True, text=True, timeout=600)
+    assert r.returncode == 0, r.stdout[-2000:] + r.stderr[-2000:]
+    assert "smoke 25E: 27 sub VFOs" in r.stdout

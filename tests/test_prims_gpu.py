@@ -162,3 +162,13 @@ def test_spectrum_fft_against_kiss_fft():
     got = d_y.cpu().numpy()
     assert np.linalg.norm(got - want) / np.linalg.norm(want) <= 1e-4
     assert L.sdrb_spectrum_fft(d_x.data_ptr(), d_y.data_ptr(), 3, 4096, 0, None) == -1
+
+
+@pytest.mark.gpu
+def test_fp32_peak_probe_is_plausible():
+    """sdrb_probe_fp32_tflops: the FMA-loop peak bench.py divides by. A B200 has 148 SMs x 128 FP32 lanes;
+    at 1.0-2.1 GHz that is 38-80 TFLOP/s, and a register-only FMA loop reaches most of it."""
+    from sdrreceiver_b200 import binding as B
+    for packed in (False, True):
+        v = B.probe_fp32_tflops(packed, reps=3)
+        assert 25.0 < v < 90.0, (packed, v)
