@@ -588,6 +588,24 @@ __global__ void __launch_bounds__(UV_WARPS * 32, 4) k2b_v2(const K2bV2Params p) 
     const int n_lo = p.cb0 * D.samples_out, n_total = (p.cb0 + p.ncb) * D.samples_out;
     const int n0 = n_lo + blockIdx.z * tile_out;
     if (n0 >= n_total) return;
+    const int stream = p.stream0 + blockIdx.x * UV_WARPS + warp;
+    const bool live = stream < p.stream_end;
+    // ---- the tile's input, z-local q = 0..1152 (re rows: q - 66, im rows: q - 1): lane l owns q = 32 it + l.
+    // All 37 loads of the lane are issued before the coefficient staging and the barrier, so the tile costs
+    // one HBM/L2 latency, overlapped with the descriptor-dependent coefficient loads.
+    constexpr int NIT = (UV_USB + 128 + 1 + 31) / 32;
+    float2 v[NIT];
+    {
+        const long long zlo = (long long)n0 - NP - 128;
+        const long long room = (long long)n_total - zlo;                              // samples that exist from zlo on (> 0)
+        const int lim = (int)(room < (long long)(UV_USB + 128 + 1) ? room : (long long)(UV_USB + 128 + 1)) - lane;
+        const float2 *zq = D.src + (size_t)(live ? stream : p.stream0) * D.src_stride + D.src_hist + zlo + lane;
+#pragma unroll
+        for (int it = 0; it < NIT; ++it) {
+            v[it] = make_float2(0.f, 0.f);
+            if (live && 32 * it < lim) v[it] = __ldg(zq + 32 * it);
+        }
+    }
     // coefficient pairs (h, h), shared by the CTA's warps
     float2 *sHil2 = reinterpret_cast<float2 *>(uv_smem);
     float2 *sLpf2 = sHil2 + 64;
@@ -595,30 +613,26 @@ __global__ void __launch_bounds__(UV_WARPS * 32, 4) k2b_v2(const K2bV2Params p) 
     for (int e = threadIdx.x; e < 64; e += UV_WARPS * 32) { const float h = D.hil[e]; sHil2[e] = make_float2(h, h); }
     for (int e = threadIdx.x; e < NP; e += UV_WARPS * 32) { const float c = D.lpf[e]; sLpf2[e] = make_float2(c, c); }
     __syncthreads();                                        // the only CTA-wide barrier
-    const int stream = p.stream0 + blockIdx.x * UV_WARPS + warp;
-    if (stream >= p.stream_end) return;
+    if (!live) return;
 
     // ---- input rows: re (z-local 66..1089) and im (z-local 1..1152) ----
     float *sRe = wbase, *sIm = wbase + UV_RE_ROWS * UV_ROW;
-    const long long zlo = (long long)n0 - NP - 128;
-    const float2 *zp = D.src + (size_t)stream * D.src_stride + D.src_hist;
     {
-        // all 37 loads of the lane in flight before the first store: one HBM/L2 latency per tile, not nine
-        constexpr int NIT = (UV_USB + 128 + 1 + 31) / 32;
-        float2 v[NIT];
+        // u = q - 66 = 32 (it - 3) + (lane + 30), k = q - 1 = 32 (it - 1) + (lane + 31): row = it + const(lane),
+        // so every store is the lane's base pointer plus a compile-time offset; only the first and last rows
+        // depend on the lane
+        const int cr = lane + 30, ci = lane + 31;
+        const int hr = cr >> 5, hi = ci >> 5;
+        float *pr = sRe + (hr - 3) * UV_ROW + (cr & 31);
+        float *pi = sIm + (hi - 1) * UV_ROW + (ci & 31);
 #pragma unroll
         for (int it = 0; it < NIT; ++it) {
-            const int q = it * 32 + lane;
-            const long long zi = zlo + q;
-            v[it] = make_float2(0.f, 0.f);
-            if (q <= UV_USB + 128 && zi < n_total) v[it] = __ldg(zp + zi);
-        }
-#pragma unroll
-        for (int it = 0; it < NIT; ++it) {
-            const int q = it * 32 + lane;
-            const int u = q - 66, k = q - 1;
-            if (u >= 0 && u < UV_USB) sRe[(u >> 5) * UV_ROW + (u & 31)] = v[it].x;
-            if (k >= 0 && k < UV_USB + 128) sIm[(k >> 5) * UV_ROW + (k & 31)] = v[it].y;
+            if (it >= 3 && it <= UV_RE_ROWS + 1) pr[it * UV_ROW] = v[it].x;
+            else if (it == 2) { if (hr == 1) pr[it * UV_ROW] = v[it].x; }
+            else if (it == UV_RE_ROWS + 2) { if (hr == 0) pr[it * UV_ROW] = v[it].x; }
+            if (it >= 1 && it <= UV_IM_ROWS - 1) pi[it * UV_ROW] = v[it].y;
+            else if (it == 0) { if (hi == 1) pi[it * UV_ROW] = v[it].y; }
+            else if (it == UV_IM_ROWS) { if (hi == 0) pi[it * UV_ROW] = v[it].y; }
         }
     }
     __syncwarp();
