@@ -236,6 +236,7 @@ struct sdrb_bank {
     int n_late = 0, n_usb = 0, n_carry = 0;
     int max_usb_samples = 0, max_late_samples = 0;
     int uv_np_max = 0, uv_eo_rows = 0, uv_warp_floats = 0, uv_tiles = 0;   // k2b_v2 launch geometry
+    std::vector<unsigned short> uv_vfo_tiles;                              // tiles per callback of each USB VFO
     size_t uv_smem = 0;
     std::vector<size_t> main_off;           // per main: offset (float2 units) inside main_out per stream
     size_t main_stride = 0;                 // float2 per stream
@@ -478,6 +479,7 @@ extern "C" int sdrb_bank_create(const sdrb_plan *plan, int device, int n_streams
         b->max_usb_samples = std::max(b->max_usb_samples, s.samples_out);
         b->uv_np_max = std::max(b->uv_np_max, U.np);
         b->uv_tiles = std::max(b->uv_tiles, (s.samples_out + (UV_USB - U.np) - 1) / (UV_USB - U.np));
+        b->uv_vfo_tiles.push_back((unsigned short)((s.samples_out + (UV_USB - U.np) - 1) / (UV_USB - U.np)));
         CarryItem c; c.base = (float2 *)b->zbuf.p + z_off[i]; c.stride = (long long)(z_stride * sizeof(float2));
         c.hist_bytes = z_hist[i] * (int)sizeof(float2); c.block_bytes = s.block_z * (int)sizeof(float2);
         carry.push_back(c);
@@ -699,6 +701,7 @@ static int enqueue_main_cb(sdrb_bank *b, const CallCtx &c, int s0, int ns, cudaS
         up.n_blocks = c.n_blocks; up.cb0 = cb; up.ncb = 1; up.stream0 = s0; up.stream_end = s0 + ns;
         up.pcm_per_block = h.pcm_per_block; up.warp_floats = b->uv_warp_floats; up.eo_rows = b->uv_eo_rows;
         up.np_max = b->uv_np_max;
+        for (size_t k = 0; k < b->uv_vfo_tiles.size() && k < (size_t)SDRB_MAX_SUB; k++) up.tiles[k] = b->uv_vfo_tiles[k];
         TimedScope t(b, st, 4);
         k2b_v2<<<dim3((unsigned)((ns + UV_WARPS - 1) / UV_WARPS), (unsigned)b->n_usb, (unsigned)b->uv_tiles), UV_WARPS * 32,
                  b->uv_smem, st>>>(up);

@@ -534,6 +534,7 @@ struct K2bV2Params {
     int warp_floats;                        // shared floats per warp: max(input rows, 2 * E/O rows)
     int eo_rows;                            // rows of each of E and O
     int np_max;                             // longest (padded) low-pass of the plan
+    unsigned short tiles[SDRB_MAX_SUB];     // tiles per callback of each USB VFO: CTAs beyond it leave without touching memory
 };
 
 __device__ __forceinline__ constexpr int uv_off(int x) { return (x >> 4) * UV_ROW + (x & 15) * 2; }   // pair index -> float offset
@@ -579,8 +580,9 @@ __device__ __noinline__ void uv_store_ragged(const float *v, int k0, int tile_ou
     }
 }
 
-__global__ void __launch_bounds__(UV_WARPS * 32, 4) k2b_v2(const K2bV2Params p) {
+__global__ void __launch_bounds__(UV_WARPS * 32, 4) k2b_v2(const __grid_constant__ K2bV2Params p) {
     extern __shared__ __align__(16) float uv_smem[];
+    if (blockIdx.z >= p.tiles[blockIdx.y]) return;          // grid.z is the longest VFO's tile count
     const UsbDev &D = p.devs[blockIdx.y];
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
     const int NP = D.np;                                    // multiple of 16 (leading zeros)
