@@ -178,9 +178,10 @@ static int v2_pick_threads(int halo, const char *env) {
 
 template <int NT>
 static void launch_k1_v2(const K1V2Params &q, bool dc, int ns, int block, cudaStream_t st) {
-    const dim3 grid((unsigned)ns, (unsigned)((block + k1v2_adv<NT>() - 1) / k1v2_adv<NT>()), 1u);
-    if (dc) k1_v2<true, NT><<<grid, NT, V2L<NT>::SMEM, st>>>(q);
-    else k1_v2<false, NT><<<grid, NT, V2L<NT>::SMEM, st>>>(q);
+    const int tiles = (block + k1v2_adv<NT>() - 1) / k1v2_adv<NT>();
+    const dim3 grid((unsigned)ns, (unsigned)((tiles + K1_TPC - 1) / K1_TPC), 1u);
+    if (dc) k1_v2<true, NT><<<grid, NT, k1v2_smem<NT>(), st>>>(q);
+    else k1_v2<false, NT><<<grid, NT, k1v2_smem<NT>(), st>>>(q);
 }
 
 struct SubGroup {           // sub VFOs of one main VFO (at most V2_MAX_VFO) -> one k2a_v2 launch
@@ -540,12 +541,12 @@ extern "C" int sdrb_bank_create(const sdrb_plan *plan, int device, int n_streams
     BANK_CU(cudaFuncSetAttribute(k2a_v2<64>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)V2L<64>::SMEM));
     BANK_CU(cudaFuncSetAttribute(k2a_v2<96>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)V2L<96>::SMEM));
     BANK_CU(cudaFuncSetAttribute(k2a_v2<128>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)V2L<128>::SMEM));
-    BANK_CU(cudaFuncSetAttribute(k1_v2<true, 64>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)V2L<64>::SMEM));
-    BANK_CU(cudaFuncSetAttribute(k1_v2<false, 64>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)V2L<64>::SMEM));
-    BANK_CU(cudaFuncSetAttribute(k1_v2<true, 96>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)V2L<96>::SMEM));
-    BANK_CU(cudaFuncSetAttribute(k1_v2<false, 96>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)V2L<96>::SMEM));
-    BANK_CU(cudaFuncSetAttribute(k1_v2<true, 128>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)V2L<128>::SMEM));
-    BANK_CU(cudaFuncSetAttribute(k1_v2<false, 128>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)V2L<128>::SMEM));
+    BANK_CU((cudaFuncSetAttribute(k1_v2<true, 64>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)k1v2_smem<64>())));
+    BANK_CU((cudaFuncSetAttribute(k1_v2<false, 64>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)k1v2_smem<64>())));
+    BANK_CU((cudaFuncSetAttribute(k1_v2<true, 96>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)k1v2_smem<96>())));
+    BANK_CU((cudaFuncSetAttribute(k1_v2<false, 96>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)k1v2_smem<96>())));
+    BANK_CU((cudaFuncSetAttribute(k1_v2<true, 128>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)k1v2_smem<128>())));
+    BANK_CU((cudaFuncSetAttribute(k1_v2<false, 128>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)k1v2_smem<128>())));
     b->k1_threads = v2_pick_threads(K1V2_HT, "SDRB_K1_THREADS");
     BANK_CU(cudaStreamCreateWithFlags(&b->s_copy_in, cudaStreamNonBlocking));
     BANK_CU(cudaStreamCreateWithFlags(&b->s_compute, cudaStreamNonBlocking));

@@ -389,6 +389,15 @@ __global__ void __launch_bounds__(64) k_input_samples(const uint8_t *__restrict_
     }
 }
 
+// Tiles per CTA: a CTA walks K1_TPC consecutive tiles of its (stream, callback). While it filters tile i,
+// the raw bytes and DC block states of tile i+1 travel global -> shared with cp.async (every thread
+// fetches exactly the 96 + 16 bytes it will read back itself, so no barrier is involved); the global
+// load latency that used to open every CTA (15 % of the warps' time, profiles/r01_k2a_regions.md) is
+// paid once per CTA, and the per-stream constants (callback counter, DC anchors) are read once.
+constexpr int K1_TPC = 4;
+constexpr int K1_PF_BYTES = 112;                          // per thread: 6 x 16 raw bytes + 2 x 8 table bytes
+template <int NT> constexpr size_t k1v2_smem() { return V2L<NT>::SMEM + (size_t)NT * K1_PF_BYTES; }
+
 template <bool DC, int NT>
 __global__ void __launch_bounds__(NT, v2_minb<NT>()) k1_v2(const __grid_constant__ K1V2Params p) {
     extern __shared__ __align__(16) unsigned char smem_raw[];
@@ -396,108 +405,132 @@ __global__ void __launch_bounds__(NT, v2_minb<NT>()) k1_v2(const __grid_constant
     int *sBase = reinterpret_cast<int *>(sm + V2L<NT>::SEND);
 
     const int stream = p.stream0 + blockIdx.x;
-    const int tile = blockIdx.y, b = p.b0 + blockIdx.z;
+    const int b = p.b0 + blockIdx.z;
     const int t = threadIdx.x;
     const int B = p.block, L = p.lut_len;
     constexpr int ADV = (NT - K1V2_HT) * V2_CHUNK;
-    const int v0 = tile * ADV - K1V2_HT * V2_CHUNK + t * V2_CHUNK;
-    const bool in_block = v0 < B;
+    const int n_tiles = (B + ADV - 1) / ADV;
+    const int tile0 = blockIdx.y * K1_TPC;
+    unsigned char *pf = smem_raw + V2L<NT>::SMEM + (size_t)t * K1_PF_BYTES;     // this thread's prefetch record
 
-    // raw bytes of samples v0-16 .. v0+31: six 16-byte pieces of 8 samples. The loads depend on nothing but
-    // the thread's coordinates, so they are in flight together with the stream's callback counter; what
-    // lies before stream sample 0 is blanked afterwards.
-    uint4 raw[6];
+    // fetch of one tile: raw bytes of samples v0-16 .. v0+31 (six 16-byte pieces of 8 samples) and the DC
+    // block-start states; pieces that do not exist (past the callback) are simply not fetched
+    auto prefetch = [&](int tile) {
+        const int v0 = tile * ADV - K1V2_HT * V2_CHUNK + t * V2_CHUNK;
+        if (v0 < B) {
 #pragma unroll
-    for (int q = 0; q < 6; ++q) {
-        const int c = v0 - 16 + 8 * q;
-        raw[q] = make_uint4(0x7f7f7f7fu, 0x7f7f7f7fu, 0x7f7f7f7fu, 0x7f7f7f7fu);   // 127 -> 0.0
-        if (in_block) {
-            const uint8_t *src = (b == 0 && c < 0) ? p.tail + (size_t)stream * (2 * RAW_TAIL) + 2 * (RAW_TAIL + c)
-                                                   : p.iq + (size_t)stream * p.iq_stride + ((size_t)b * B + c) * 2;
-            raw[q] = __ldg(reinterpret_cast<const uint4 *>(src));
+            for (int q = 0; q < 6; ++q) {
+                const int c = v0 - 16 + 8 * q;
+                const uint8_t *src = (b == 0 && c < 0) ? p.tail + (size_t)stream * (2 * RAW_TAIL) + 2 * (RAW_TAIL + c)
+                                                       : p.iq + (size_t)stream * p.iq_stride + ((size_t)b * B + c) * 2;
+                cp_async16(pf + 16 * q, src);
+            }
+            if (DC) {
+                const int dblk = (b * B + v0 + RAW_TAIL) / DC_BLK;   // table index incl. the carried entries
+                cp_async16(pf + 96, p.dc_table + ((size_t)stream * p.dc_stride + dblk) * 2);
+            }
         }
-    }
-    uint2 teI = make_uint2(0u, 2u), teQ = make_uint2(0u, 2u);     // DC block-start states (mode 2 = plain float bits: 0.0f)
-    if (DC && in_block) {
-        const int dblk = (b * B + v0 + RAW_TAIL) / DC_BLK;       // table index incl. the carried entries
-        const uint2 *te = p.dc_table + ((size_t)stream * p.dc_stride + dblk) * 2;
-        teI = __ldg(te);
-        teQ = __ldg(te + 1);
-    }
+        cp_async_commit();
+    };
+    if (tile0 < n_tiles) prefetch(tile0);
     const long long blk = p.blocks_done[stream] + b;
     if (t == 0) sBase[0] = (int)((blk * (long long)B) % L);
     const bool first_ever = (blk == 0);
-#pragma unroll
-    for (int q = 0; q < 6; ++q)
-        if (first_ever && v0 - 16 + 8 * q < 0) raw[q] = make_uint4(0x7f7f7f7fu, 0x7f7f7f7fu, 0x7f7f7f7fu, 0x7f7f7f7fu);
-    float2 x[44];                   // x[i] = sample v0 - 12 + i
-    {
-        float2 y[8];
-        unpack8p(raw[0], y);
-#pragma unroll
-        for (int k = 4; k < 8; ++k) x[k - 4] = y[k];
-#pragma unroll
-        for (int q = 1; q < 6; ++q) {
-            unpack8p(raw[q], y);
-#pragma unroll
-            for (int k = 0; k < 8; ++k) x[8 * q - 4 + k] = y[k];
-        }
-    }
-    if (DC) {
-        // integer sums of the chunk's 32 samples per arm (bytes; I in even, Q in odd positions)
-        unsigned sI = 0u, sQ = 0u;
-#pragma unroll
-        for (int q = 2; q < 6; ++q) {
-            sI = __dp4a(raw[q].x, 0x00010001u, sI); sQ = __dp4a(raw[q].x, 0x01000100u, sQ);
-            sI = __dp4a(raw[q].y, 0x00010001u, sI); sQ = __dp4a(raw[q].y, 0x01000100u, sQ);
-            sI = __dp4a(raw[q].z, 0x00010001u, sI); sQ = __dp4a(raw[q].z, 0x01000100u, sQ);
-            sI = __dp4a(raw[q].w, 0x00010001u, sI); sQ = __dp4a(raw[q].w, 0x01000100u, sQ);
-        }
-        const int tot = (int)(sI | (sQ << 16));                 // 32*255 < 65536; prefix of 3 chunks < 65536 too
-        const int g = t & 3;                             // position of the chunk inside its DC block
-        int inc = tot;
-        int up = __shfl_up_sync(0xffffffffu, inc, 1, 4);
-        if (g >= 1) inc += up;
-        up = __shfl_up_sync(0xffffffffu, inc, 2, 4);
-        if (g >= 2) inc += up;
-        const int excl = inc - tot;
-        const int pcount = 32 * g;
-        const float PI_ = (float)((excl & 0xffff) - 127 * pcount), PQ_ = (float)((int)((unsigned)excl >> 16) - 127 * pcount);
-        const DcAnchor AI = p.dc_anchor[2 * stream], AQ = p.dc_anchor[2 * stream + 1];
-        float bI = 0.f, bQ = 0.f;
-        if (in_block && !(first_ever && v0 < 0)) {
-            bI = dc_decode(teI, AI);
-            bQ = dc_decode(teQ, AQ);
-        }
-        const float decay = 1.0f - DC_C * (float)pcount;
-        // negated state after sample v0-1
-        const float2 ns0 = make_float2(-(bI * decay + DC_C * PI_), -(bQ * decay + DC_C * PQ_));
-        float2 ns = ns0;
-#pragma unroll
-        for (int i = 12; i < 44; ++i) {                  // forwards: d = x - s, s += c*d, out = x - s
-            const float2 d = add2(x[i], ns);
-            ns = fma2(splat2(-DC_C), d, ns);
-            x[i] = add2(x[i], ns);
-        }
-        ns = ns0;
-#pragma unroll
-        for (int i = 11; i >= 1; --i) {                  // backwards: out = x - s_j, s_{j-1} = s_j - c*out
-            x[i] = add2(x[i], ns);
-            ns = fma2(splat2(DC_C), x[i], ns);
-        }
-    }
-    if (first_ever && v0 <= 0) {                         // nothing exists before stream sample 0
-        const int lim = v0 < 0 ? 44 : 12;
-#pragma unroll
-        for (int i = 0; i < 44; ++i)
-            if (i < lim) x[i] = make_float2(0.f, 0.f);
-    }
+    DcAnchor AI, AQ;
+    if (DC) { AI = p.dc_anchor[2 * stream]; AQ = p.dc_anchor[2 * stream + 1]; }
     __syncthreads();
-    int k0 = sBase[0] + v0;
-    if (k0 < 0) k0 += L;
-    if (k0 >= L) k0 -= L;
-    cascade_loop<3, NT>(x, p, p.n_main, sm, t, v0, blk * (long long)B + v0, k0, L, in_block && t >= K1V2_HT,
-                    (size_t)stream * (size_t)p.out_stride, b);
+    const int kbase = sBase[0];
+
+    for (int ti = 0; ti < K1_TPC; ++ti) {
+        const int tile = tile0 + ti;
+        if (tile >= n_tiles) break;
+        const int v0 = tile * ADV - K1V2_HT * V2_CHUNK + t * V2_CHUNK;
+        const bool in_block = v0 < B;
+        cp_async_wait<0>();
+        uint4 raw[6];
+        uint2 teI = make_uint2(0u, 2u), teQ = make_uint2(0u, 2u);     // DC block-start states (mode 2 = plain float bits: 0.0f)
+#pragma unroll
+        for (int q = 0; q < 6; ++q) {
+            raw[q] = make_uint4(0x7f7f7f7fu, 0x7f7f7f7fu, 0x7f7f7f7fu, 0x7f7f7f7fu);   // 127 -> 0.0
+            if (in_block && !(first_ever && v0 - 16 + 8 * q < 0)) raw[q] = *reinterpret_cast<const uint4 *>(pf + 16 * q);
+        }
+        if (DC && in_block) {
+            const uint4 te = *reinterpret_cast<const uint4 *>(pf + 96);
+            teI = make_uint2(te.x, te.y);
+            teQ = make_uint2(te.z, te.w);
+        }
+        float2 x[44];                   // x[i] = sample v0 - 12 + i
+        {
+            float2 y[8];
+            unpack8p(raw[0], y);
+#pragma unroll
+            for (int k = 4; k < 8; ++k) x[k - 4] = y[k];
+#pragma unroll
+            for (int q = 1; q < 6; ++q) {
+                unpack8p(raw[q], y);
+#pragma unroll
+                for (int k = 0; k < 8; ++k) x[8 * q - 4 + k] = y[k];
+            }
+        }
+        unsigned sI = 0u, sQ = 0u;
+        if (DC) {
+            // integer sums of the chunk's 32 samples per arm (bytes; I in even, Q in odd positions)
+#pragma unroll
+            for (int q = 2; q < 6; ++q) {
+                sI = __dp4a(raw[q].x, 0x00010001u, sI); sQ = __dp4a(raw[q].x, 0x01000100u, sQ);
+                sI = __dp4a(raw[q].y, 0x00010001u, sI); sQ = __dp4a(raw[q].y, 0x01000100u, sQ);
+                sI = __dp4a(raw[q].z, 0x00010001u, sI); sQ = __dp4a(raw[q].z, 0x01000100u, sQ);
+                sI = __dp4a(raw[q].w, 0x00010001u, sI); sQ = __dp4a(raw[q].w, 0x01000100u, sQ);
+            }
+        }
+        // the record has been consumed (its bytes are in registers): the next tile may overwrite it
+        if (ti + 1 < K1_TPC && tile + 1 < n_tiles) prefetch(tile + 1);
+        if (DC) {
+            const int tot = (int)(sI | (sQ << 16));                 // 32*255 < 65536; prefix of 3 chunks < 65536 too
+            const int g = t & 3;                             // position of the chunk inside its DC block
+            int inc = tot;
+            int up = __shfl_up_sync(0xffffffffu, inc, 1, 4);
+            if (g >= 1) inc += up;
+            up = __shfl_up_sync(0xffffffffu, inc, 2, 4);
+            if (g >= 2) inc += up;
+            const int excl = inc - tot;
+            const int pcount = 32 * g;
+            const float PI_ = (float)((excl & 0xffff) - 127 * pcount), PQ_ = (float)((int)((unsigned)excl >> 16) - 127 * pcount);
+            float bI = 0.f, bQ = 0.f;
+            if (in_block && !(first_ever && v0 < 0)) {
+                bI = dc_decode(teI, AI);
+                bQ = dc_decode(teQ, AQ);
+            }
+            const float decay = 1.0f - DC_C * (float)pcount;
+            // negated state after sample v0-1
+            const float2 ns0 = make_float2(-(bI * decay + DC_C * PI_), -(bQ * decay + DC_C * PQ_));
+            float2 ns = ns0;
+#pragma unroll
+            for (int i = 12; i < 44; ++i) {                  // forwards: d = x - s, s += c*d, out = x - s
+                const float2 d = add2(x[i], ns);
+                ns = fma2(splat2(-DC_C), d, ns);
+                x[i] = add2(x[i], ns);
+            }
+            ns = ns0;
+#pragma unroll
+            for (int i = 11; i >= 1; --i) {                  // backwards: out = x - s_j, s_{j-1} = s_j - c*out
+                x[i] = add2(x[i], ns);
+                ns = fma2(splat2(DC_C), x[i], ns);
+            }
+        }
+        if (first_ever && v0 <= 0) {                         // nothing exists before stream sample 0
+            const int lim = v0 < 0 ? 44 : 12;
+#pragma unroll
+            for (int i = 0; i < 44; ++i)
+                if (i < lim) x[i] = make_float2(0.f, 0.f);
+        }
+        int k0 = kbase + v0;
+        if (k0 < 0) k0 += L;
+        if (k0 >= L) k0 -= L;
+        cascade_loop<3, NT>(x, p, p.n_main, sm, t, v0, blk * (long long)B + v0, k0, L, in_block && t >= K1V2_HT,
+                            (size_t)stream * (size_t)p.out_stride, b);
+        __syncthreads();                                     // the scratch arrays are reused by the next tile
+    }
 }
 
 }  // namespace sdrb
