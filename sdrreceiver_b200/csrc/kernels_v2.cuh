@@ -326,7 +326,7 @@ __global__ void __launch_bounds__(NT, v2_minb<NT>()) k2a_v2(const __grid_constan
 
 // ------------------------------------------------------------------------------------
 // k1_v2: uint8 IQ -> float (sdr.cpp:43-49) -> DC removal (sdrj.cpp:277-283) -> every main VFO.
-// Tile = 252 chunks of 32 samples = 63 DC blocks; 4 halo threads (one DC block) in front.
+// Tile = NT - 4 chunks of 32 samples (a whole number of 128-sample DC blocks); 4 halo threads (one DC block) in front.
 //
 // DC: the block-start states come bit-exact from the walk kernel (k0_dc_walk). Inside a 128-sample
 // block the recursion is continued in real arithmetic: state before the thread's chunk =
