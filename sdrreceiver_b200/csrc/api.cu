@@ -236,6 +236,7 @@ struct sdrb_bank {
     std::vector<SubGroup> groups;
     int n_late = 0, n_usb = 0, n_carry = 0;
     int max_usb_samples = 0, max_late_samples = 0;
+    int late_factor = 0;            // the plan's /late factor if all late VFOs share it and their taps fit k2_late_v2, else -1
     int uv_np_max = 0, uv_eo_rows = 0, uv_warp_floats = 0, uv_tiles = 0;   // k2b_v2 launch geometry
     std::vector<unsigned short> uv_vfo_tiles;                              // tiles per callback of each USB VFO
     size_t uv_smem = 0;
@@ -465,6 +466,10 @@ extern "C" int sdrb_bank_create(const sdrb_plan *plan, int device, int n_streams
             L.late = s.late; L.ntaps = (int)s.dec_taps.size();
             latedev.push_back(L);
             b->max_late_samples = std::max(b->max_late_samples, s.samples_out);
+            {
+                const int lf = (L.ntaps <= L.late * LV_AMAX) ? L.late : -1;
+                b->late_factor = (b->late_factor == 0 || b->late_factor == lf) ? lf : -1;
+            }
             U.src = L.d; U.src_stride = L.d_stride; U.src_hist = L.d_hist;
             CarryItem c; c.base = L.d; c.stride = (long long)(d_stride * sizeof(float2));
             c.hist_bytes = L.d_hist * (int)sizeof(float2); c.block_bytes = s.samples_out * (int)sizeof(float2);
@@ -538,6 +543,8 @@ extern "C" int sdrb_bank_create(const sdrb_plan *plan, int device, int n_streams
     b->uv_smem = sizeof(float) * (2 * (size_t)(64 + b->uv_np_max) + (size_t)UV_WARPS * b->uv_warp_floats);
     BANK_CU(cudaFuncSetAttribute(k2b_v2, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)b->uv_smem));
     BANK_CU(cudaFuncSetAttribute(k0_dc_walk, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)DCW_SMEM));
+    BANK_CU(cudaFuncSetAttribute(k2_late_v2<5>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)lv_smem<5>()));
+    BANK_CU(cudaFuncSetAttribute(k2_late_v2<6>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)lv_smem<6>()));
     BANK_CU(cudaFuncSetAttribute(k2a_v2<64>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)V2L<64>::SMEM));
     BANK_CU(cudaFuncSetAttribute(k2a_v2<96>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)V2L<96>::SMEM));
     BANK_CU(cudaFuncSetAttribute(k2a_v2<128>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)V2L<128>::SMEM));
@@ -690,10 +697,16 @@ static int enqueue_main_cb(sdrb_bank *b, const CallCtx &c, int s0, int ns, cudaS
         (*nl)++;
     }
     if (b->n_late) {
-        const int tiles = (b->max_late_samples + LATE_TILE - 1) / LATE_TILE;
         TimedScope t(b, st, 3);
-        k2_late_fir<<<dim3((unsigned)ns, (unsigned)b->n_late, (unsigned)tiles), LATE_TILE, 0, st>>>(
-            (const LateDev *)b->latedev.p, cb, 1, s0);
+        if (b->late_factor == 5 || b->late_factor == 6) {           // every late VFO of the plan divides by the same 5 or 6
+            const dim3 grid((unsigned)ns, (unsigned)b->n_late, (unsigned)((b->max_late_samples + LV_TILE - 1) / LV_TILE));
+            if (b->late_factor == 5) k2_late_v2<5><<<grid, LV_THREADS, lv_smem<5>(), st>>>((const LateDev *)b->latedev.p, cb, 1, s0);
+            else k2_late_v2<6><<<grid, LV_THREADS, lv_smem<6>(), st>>>((const LateDev *)b->latedev.p, cb, 1, s0);
+        } else {
+            const int tiles = (b->max_late_samples + LATE_TILE - 1) / LATE_TILE;
+            k2_late_fir<<<dim3((unsigned)ns, (unsigned)b->n_late, (unsigned)tiles), LATE_TILE, 0, st>>>(
+                (const LateDev *)b->latedev.p, cb, 1, s0);
+        }
         (*nl)++;
     }
     if (b->n_usb) {

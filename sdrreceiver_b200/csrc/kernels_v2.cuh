@@ -193,7 +193,17 @@ __device__ __forceinline__ void cascade_loop(const float2 (&x)[44], const P &p, 
         if (fast && v + 1 < count) Fnext = __ldg(p.vfos[v + 1].lut + k0);   // one VFO ahead: never waited for
         float2 *outp = V.out + out_off + V.hist + (size_t)b * V.block_out;
         if (V.S == 0) {                                   // mixer only (vfo.cpp:237-245 with decimateCount 0)
-            if (store) {
+            if (store && fast) {
+                // rotating frame like the first half-band stage: lut[k0 + j] = F * Rf[j], no table reads per sample
+                // (the per-sample reads are 8-byte loads 256 bytes apart across a warp: 32 sectors per instruction)
+#pragma unroll
+                for (int q = 0; q < V2_CHUNK / 2; ++q) {
+                    const float4 r = p.rf[v].q[q + 5];    // Rf[2q], Rf[2q+1]
+                    const float2 a = cmul(F, cmul(make_float2(r.x, r.y), x[12 + 2 * q]));
+                    const float2 c = cmul(F, cmul(make_float2(r.z, r.w), x[13 + 2 * q]));
+                    *reinterpret_cast<float4 *>(outp + v0 + 2 * q) = make_float4(a.x, a.y, c.x, c.y);
+                }
+            } else if (store) {
 #pragma unroll
                 for (int j = 0; j < V2_CHUNK; j += 2) {
                     int i0 = k0 + j, i1 = k0 + j + 1;
@@ -751,6 +761,88 @@ __global__ void __launch_bounds__(UV_WARPS * 32, 4) k2b_v2(const __grid_constant
             v[2 * r + 1] = (acc[r].y * g) * 32768.0f;
         }
         uv_store_ragged(v, k0, tile_out, n0, n_total, D.samples_out, stream, p.n_blocks, p.pcm_per_block, D.pcm_offset, p.pcm, p.tap);
+    }
+}
+
+}  // namespace sdrb
+
+namespace sdrb {
+
+// ------------------------------------------------------------------------------------
+// k2_late_v2: the /5 and /6 decimating FIR of the "late" plans (vfo.cpp:346-384; fir_decI/Q of 49 / 73
+// taps on both arms), polyphase:  d[m] = sum_i c[i] z[L m - N + i],  i = L a + r  ->
+//   d[m] = sum_r sum_a c[L a + r] * zr[m + a],   zr[j] = z[L j - N + r].
+// A thread owns R = 8 consecutive outputs. Per phase r it loads the R + A - 1 samples zr[m0 .. m0+R+A-2]
+// once (LDS.64, stride L samples) and runs A x R packed FMAs on them (both arms at once, the tap as
+// (c, c)): 1.3 instructions per output and tap instead of the 4 of one-output-per-thread code.
+// Shared layout: one pad slot per thread segment of L*R samples, so the segment stride is odd in
+// 8-byte units and the strided loads of a warp are conflict free.
+// ------------------------------------------------------------------------------------
+constexpr int LV_THREADS = 128, LV_R = 8, LV_TILE = LV_THREADS * LV_R;
+constexpr int LV_AMAX = 16;                               // taps per phase the coefficient table is padded to
+template <int L> constexpr int lv_span() { return L * LV_TILE + L * LV_AMAX; }
+template <int L> constexpr size_t lv_smem() {
+    return (size_t)(lv_span<L>() + lv_span<L>() / (L * LV_R) + 2) * sizeof(float2) + (size_t)L * LV_AMAX * sizeof(float2);
+}
+
+template <int L>
+__global__ void __launch_bounds__(LV_THREADS, 4) k2_late_v2(const LateDev *__restrict__ devs, int cb0, int ncb, int stream0) {
+    extern __shared__ __align__(16) unsigned char lv_raw[];
+    constexpr int SEG = L * LV_R;                           // samples per thread segment
+    float2 *sz = reinterpret_cast<float2 *>(lv_raw);
+    constexpr int SPAN_MAX = L * LV_TILE + L * LV_AMAX;     // = lv_span<L>()
+    float2 *sc = sz + SPAN_MAX + SPAN_MAX / SEG + 2;        // (c, c) pairs, index L*a + r, zero padded
+    const LateDev &D = devs[blockIdx.y];
+    const int n_total = (cb0 + ncb) * D.samples_out;               // outputs exist up to here
+    const int m0 = cb0 * D.samples_out + blockIdx.z * LV_TILE;
+    if (m0 >= n_total) return;
+    const int stream = stream0 + blockIdx.x;
+    const int t = threadIdx.x;
+    const int N = D.ntaps;
+    const int A = (N + L - 1) / L;                          // taps per phase (10 for 49/5, 13 for 73/6)
+    const int span = L * LV_TILE + L * A;
+    const long long zlo = (long long)L * m0 - N;            // may be negative: history
+    const long long zmax = (long long)(cb0 + ncb) * D.block_z;
+    const float2 *zp = D.z + (size_t)stream * D.z_stride + D.z_hist;
+#pragma unroll 8
+    for (int e = t; e < span; e += LV_THREADS) {             // 8 independent loads in flight per thread
+        const long long zi = zlo + e;
+        sz[e + e / SEG] = (zi < zmax) ? __ldg(zp + zi) : make_float2(0.f, 0.f);
+    }
+    for (int e = t; e < L * LV_AMAX; e += LV_THREADS) {
+        const float c = e < N ? D.taps[e] : 0.f;
+        sc[e] = make_float2(c, c);
+    }
+    __syncthreads();
+    const int m = m0 + t * LV_R;
+    if (m >= n_total) return;
+    float2 acc[LV_R];
+#pragma unroll
+    for (int k = 0; k < LV_R; ++k) acc[k] = make_float2(0.f, 0.f);
+    const float2 *base = sz + t * (SEG + 1);                // logical sample L*(t*R) of the tile
+#pragma unroll 1
+    for (int r = 0; r < L; ++r) {
+        float2 w[LV_R + LV_AMAX - 1];
+#pragma unroll
+        for (int j = 0; j < LV_R + LV_AMAX - 1; ++j)
+            if (j < LV_R + A - 1) w[j] = base[L * j + r + j / LV_R];          // + one pad per segment crossed
+#pragma unroll
+        for (int a = 0; a < LV_AMAX; ++a) {
+            if (a < A) {
+                const float2 c2 = sc[L * a + r];
+#pragma unroll
+                for (int k = 0; k < LV_R; ++k) acc[k] = fma2(c2, w[k + a], acc[k]);
+            }
+        }
+    }
+    float2 *dst = D.d + (size_t)stream * D.d_stride + D.d_hist + m;
+    if (m + LV_R <= n_total && ((reinterpret_cast<uintptr_t>(dst) & 15) == 0)) {
+#pragma unroll
+        for (int k = 0; k < LV_R; k += 2)
+            *reinterpret_cast<float4 *>(dst + k) = make_float4(acc[k].x, acc[k].y, acc[k + 1].x, acc[k + 1].y);
+    } else {
+        for (int k = 0; k < LV_R; ++k)
+            if (m + k < n_total) dst[k] = acc[k];
     }
 }
 
