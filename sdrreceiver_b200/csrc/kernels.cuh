@@ -37,11 +37,8 @@ constexpr int RAW_TAIL = 256;          // raw samples carried between calls (K1 
 constexpr int K1_WARPS = 8;            // active warps per K1 CTA (+1 halo warp)
 constexpr int K1_THREADS = (K1_WARPS + 1) * 32;
 constexpr int K1_TILE = K1_WARPS * 256;
-constexpr int K2A_THREADS = 256;
-constexpr int K2A_CHUNK = 32;          // main-output samples owned by one K2A thread
 constexpr int HB_PAD = 8;              // leading pad chunks of every smem stage array
 constexpr int MAIN_HIST = 512;         // main-output samples kept in front of each call
-constexpr int USB_TILE = 1024;         // audio samples per K2B CTA
 constexpr int LATE_TILE = 256;
 constexpr int MAX_FIR_TAPS = 512;
 
@@ -85,20 +82,6 @@ struct K1Params {
     const long long *blocks_done;   // [n_streams]
     int dc_stride, block, n_blocks, correct_dc, n_main, stream0, b0;
     MainDev mains[SDRB_MAX_MAIN];
-};
-
-struct SubDev {
-    const float2 *lut;
-    const float2 *in;               // parent main output (with MAIN_HIST history)
-    float2 *z;                      // [n_streams][z_stride]: z_hist history + n_blocks*block_z
-    long long in_stride, z_stride;
-    int lut_len, block_in, block_z, z_hist;
-};
-
-struct K2aParams {
-    const SubDev *subs;             // device array, this launch's group
-    const long long *blocks_done;
-    int n_blocks, tiles, stream0, b0;     // this launch covers callbacks b0 .. b0 + gridDim.z/tiles - 1
 };
 
 struct LateDev {
@@ -767,180 +750,6 @@ __global__ void __launch_bounds__(K1_THREADS, 2) k1_ingest_main(const K1Params p
 }
 
 // ------------------------------------------------------------------------------------
-// K2A: per sub VFO NCO mix + S half-band stages.
-// Phase 1 (coalesced): every thread loads pairs of parent samples and table entries, mixes,
-// and stores into a padded smem array. Phase 2: every thread owns 32 consecutive mixed
-// samples in registers and runs the whole cascade (16, 8, 4, 2, 1 outputs per stage);
-// only the <= 12 trailing outputs per stage go through smem for the neighbours.
-// The first HT threads of a CTA recompute the filter halo in front of the tile.
-// ------------------------------------------------------------------------------------
-template <int S> struct K2aHalo { static constexpr int v = S <= 2 ? 1 : S == 3 ? 3 : S == 4 ? 5 : 11; };
-constexpr int K2A_A0_STR = 34;
-constexpr size_t K2A_SMEM_X = (size_t)(K2A_THREADS + HB_PAD) * K2A_A0_STR * sizeof(float2);
-constexpr size_t K2A_SMEM_Y = (size_t)(K2A_THREADS + HB_PAD) * 13 * sizeof(float2);
-constexpr size_t K2A_SMEM = K2A_SMEM_X + K2A_SMEM_Y + 16;
-
-template <int S>
-__global__ void __launch_bounds__(K2A_THREADS, 2) k2a_sub_cascade(const K2aParams p) {
-    extern __shared__ __align__(16) unsigned char smem_raw[];
-    float2 *sX = reinterpret_cast<float2 *>(smem_raw);
-    float2 *sY = reinterpret_cast<float2 *>(smem_raw + K2A_SMEM_X);
-    int *sBase = reinterpret_cast<int *>(smem_raw + K2A_SMEM_X + K2A_SMEM_Y);
-
-    constexpr int HT = K2aHalo<S>::v;
-    constexpr int ADV = (K2A_THREADS - HT) * K2A_CHUNK;
-    const SubDev &D = p.subs[blockIdx.y];
-    const int stream = p.stream0 + blockIdx.x;
-    const int tile = blockIdx.z % p.tiles, b = p.b0 + blockIdx.z / p.tiles;
-    const int t = threadIdx.x;
-    const int B = D.block_in;
-    const int r0 = tile * ADV - HT * K2A_CHUNK;           // callback coordinate of thread 0's chunk
-    const long long blk = p.blocks_done[stream] + b;
-    if (t == 0) sBase[0] = (int)((blk * (long long)B) % D.lut_len);
-    __syncthreads();
-    const int lut_base = sBase[0];
-    const bool first_ever = (blk == 0);
-    const float2 *inp = D.in + (size_t)stream * D.in_stride + MAIN_HIST + (size_t)b * B;
-
-    // ---- phase 1: coalesced load + mix ----
-    // Interior tiles (everything in range, table not wrapping inside the tile, not the very
-    // first callback) take a check-free path: fixed strides from one base pointer per operand.
-    const int lut_lo = lut_base + r0;
-    const bool interior = !first_ever && (r0 + K2A_THREADS * K2A_CHUNK <= B) &&
-                          ((lut_lo >= 0 && lut_lo + K2A_THREADS * K2A_CHUNK <= D.lut_len) ||
-                           (lut_lo < 0 && lut_lo + K2A_THREADS * K2A_CHUNK <= 0));
-    float4 *sdst = reinterpret_cast<float4 *>(sX + ((2 * t >> 5) + HB_PAD) * K2A_A0_STR + ((2 * t) & 31));
-    if (interior) {
-        const float4 *xp = reinterpret_cast<const float4 *>(inp + r0 + 2 * t);
-        const float4 *lp = reinterpret_cast<const float4 *>(D.lut + (lut_lo < 0 ? lut_lo + D.lut_len : lut_lo) + 2 * t);
-#pragma unroll 8
-        for (int j = 0; j < K2A_CHUNK / 2; ++j) {
-            const float4 xv = __ldg(xp + j * K2A_THREADS);
-            const float4 lv = __ldg(lp + j * K2A_THREADS);
-            const float2 m0 = cmul(make_float2(lv.x, lv.y), make_float2(xv.x, xv.y));
-            const float2 m1 = cmul(make_float2(lv.z, lv.w), make_float2(xv.z, xv.w));
-            // 512 samples = 16 chunks further on: 16 * K2A_A0_STR float2 = 8 * K2A_A0_STR float4
-            sdst[j * (8 * K2A_A0_STR)] = make_float4(m0.x, m0.y, m1.x, m1.y);
-        }
-    } else {
-#pragma unroll 2
-        for (int j = 0; j < K2A_CHUNK / 2; ++j) {
-            const int g = j * (2 * K2A_THREADS) + 2 * t;  // CTA-relative sample (even)
-            const int i = r0 + g;
-            float4 m = make_float4(0.f, 0.f, 0.f, 0.f);
-            if (i < B && !(first_ever && i < 0)) {
-                const float4 xv = __ldg(reinterpret_cast<const float4 *>(inp + i));
-                int idx = lut_base + i;
-                if (idx < 0) idx += D.lut_len;
-                if (idx >= D.lut_len) idx -= D.lut_len;
-                float4 lv = __ldg(reinterpret_cast<const float4 *>(D.lut + idx));
-                if (first_ever && i == 0) {
-                    const float2 last = __ldg(D.lut + (D.lut_len - 1));
-                    lv.x = last.x; lv.y = last.y;
-                }
-                const float2 m0 = cmul(make_float2(lv.x, lv.y), make_float2(xv.x, xv.y));
-                const float2 m1 = cmul(make_float2(lv.z, lv.w), make_float2(xv.z, xv.w));
-                m = make_float4(m0.x, m0.y, m1.x, m1.y);
-            }
-            sdst[j * (8 * K2A_A0_STR)] = m;
-        }
-    }
-    __syncthreads();
-
-    // ---- phase 2: register-resident cascade ----
-    const int v0 = r0 + t * K2A_CHUNK;
-    const bool store = (t >= HT) && (v0 < B);
-    float2 a0[32];
-    {
-        const float4 *s4 = reinterpret_cast<const float4 *>(sX + (t + HB_PAD) * K2A_A0_STR);
-#pragma unroll
-        for (int k = 0; k < 16; ++k) {
-            const float4 v = s4[k];
-            a0[2 * k] = make_float2(v.x, v.y);
-            a0[2 * k + 1] = make_float2(v.z, v.w);
-        }
-    }
-    float2 *zp = D.z + (size_t)stream * D.z_stride + D.z_hist + (size_t)b * D.block_z;
-    float2 a1[16];
-    hb_run<16, 32, K2A_A0_STR>(a0, a1, sX, t, v0);
-    if constexpr (S == 1) {
-        if (store) {
-            float4 *o4 = reinterpret_cast<float4 *>(zp + (v0 >> 1));
-#pragma unroll
-            for (int k = 0; k < 8; ++k) o4[k] = make_float4(a1[2 * k].x, a1[2 * k].y, a1[2 * k + 1].x, a1[2 * k + 1].y);
-        }
-        return;
-    }
-    hb_publish<16, 12, 13>(a1, sY, t);
-    __syncthreads();                                       // sX free from here on
-    float2 a2[8];
-    hb_run<8, 12, 13>(a1, a2, sY, t, v0 >> 1);
-    if constexpr (S == 2) {
-        if (store) {
-            float4 *o4 = reinterpret_cast<float4 *>(zp + (v0 >> 2));
-#pragma unroll
-            for (int k = 0; k < 4; ++k) o4[k] = make_float4(a2[2 * k].x, a2[2 * k].y, a2[2 * k + 1].x, a2[2 * k + 1].y);
-        }
-        return;
-    }
-    hb_publish<8, 8, 9>(a2, sX, t);
-    __syncthreads();                                       // sY free
-    float2 a3[4];
-    hb_run<4, 8, 9>(a2, a3, sX, t, v0 >> 2);
-    if constexpr (S == 3) {
-        if (store) {
-            float4 *o4 = reinterpret_cast<float4 *>(zp + (v0 >> 3));
-            o4[0] = make_float4(a3[0].x, a3[0].y, a3[1].x, a3[1].y);
-            o4[1] = make_float4(a3[2].x, a3[2].y, a3[3].x, a3[3].y);
-        }
-        return;
-    }
-    hb_publish<4, 4, 5>(a3, sY, t);
-    __syncthreads();                                       // sX free
-    float2 a4[2];
-    hb_run<2, 4, 5>(a3, a4, sY, t, v0 >> 3);
-    if constexpr (S == 4) {
-        if (store) *reinterpret_cast<float4 *>(zp + (v0 >> 4)) = make_float4(a4[0].x, a4[0].y, a4[1].x, a4[1].y);
-        return;
-    }
-    hb_publish<2, 2, 3>(a4, sX, t);
-    __syncthreads();
-    float2 a5[1];
-    hb_run<1, 2, 3>(a4, a5, sX, t, v0 >> 4);
-    if (store) zp[v0 >> 5] = a5[0];
-}
-
-// S = 0 (e.g. the 288 kS/s plan): the sub VFO only mixes.
-__global__ void __launch_bounds__(256) k2a_mix_only(const K2aParams p) {
-    const SubDev &D = p.subs[blockIdx.y];
-    const int stream = p.stream0 + blockIdx.x;
-    const int tile = blockIdx.z % p.tiles, b = p.b0 + blockIdx.z / p.tiles;
-    const int B = D.block_in;
-    const long long blk = p.blocks_done[stream] + b;
-    const int lut_base = (int)((blk * (long long)B) % D.lut_len);
-    const float2 *inp = D.in + (size_t)stream * D.in_stride + MAIN_HIST + (size_t)b * B;
-    float2 *zp = D.z + (size_t)stream * D.z_stride + D.z_hist + (size_t)b * D.block_z;
-    const int i = tile * 2048 + 2 * threadIdx.x;
-#pragma unroll
-    for (int j = 0; j < 4; ++j) {
-        const int ii = i + j * 512;
-        if (ii < B) {
-            const float4 xv = __ldg(reinterpret_cast<const float4 *>(inp + ii));
-            int idx = lut_base + ii;
-            if (idx >= D.lut_len) idx -= D.lut_len;
-            float4 lv = __ldg(reinterpret_cast<const float4 *>(D.lut + idx));
-            if (blk == 0 && ii == 0) {
-                const float2 last = __ldg(D.lut + (D.lut_len - 1));
-                lv.x = last.x; lv.y = last.y;
-            }
-            const float2 m0 = cmul(make_float2(lv.x, lv.y), make_float2(xv.x, xv.y));
-            const float2 m1 = cmul(make_float2(lv.z, lv.w), make_float2(xv.z, xv.w));
-            *reinterpret_cast<float4 *>(zp + ii) = make_float4(m0.x, m0.y, m1.x, m1.y);
-        }
-    }
-}
-
-// ------------------------------------------------------------------------------------
 // K2 late: d[m] = sum_i taps[i] * z[late*m - ntaps + i]  on both arms
 // (fir_decI/Q FIRUpdateAndProcess on the first sample of each group of `late`, FIRUpdate
 // on the others: vfo.cpp:346-384; newest sample excluded: dsp.cpp:59-71).
@@ -975,102 +784,6 @@ __global__ void __launch_bounds__(LATE_TILE) k2_late_fir(const LateDev *__restri
         ay = fmaf(c, v.y, ay);
     }
     D.d[(size_t)stream * D.d_stride + D.d_hist + m] = make_float2(ax, ay);
-}
-
-// ------------------------------------------------------------------------------------
-// K2B: USB demodulation + optional low-pass + gain + int16.
-//   usb[n] = re[n-62] - sum_{i=0..124} points[i]*im[n-124+i]      (vfo.cpp:316-324)
-// only odd i are non-zero, so every output touches 62 samples of one parity: the imaginary
-// arm is split into two parity planes and each thread produces 4 consecutive plane outputs
-// from a sliding register window (float4 smem loads, 16 FMA per load pair).
-//   out[n] = sum_{i<N} lpf[i]*usb[n-N+i]                           (dsp.cpp:59-71)
-//   pcm = (short)(out*gain*32768.0)                                (vfo.cpp:328)
-// ------------------------------------------------------------------------------------
-__device__ __forceinline__ void fir4(const float *__restrict__ x, const float *__restrict__ taps, int ntaps, float (&acc)[4]) {
-    float4 cur = *reinterpret_cast<const float4 *>(x);
-    acc[0] = acc[1] = acc[2] = acc[3] = 0.f;
-    for (int j = 0; j < ntaps; j += 4) {
-        const float4 nxt = *reinterpret_cast<const float4 *>(x + j + 4);
-        const float4 c = *reinterpret_cast<const float4 *>(taps + j);
-        acc[0] = fmaf(c.x, cur.x, acc[0]); acc[0] = fmaf(c.y, cur.y, acc[0]); acc[0] = fmaf(c.z, cur.z, acc[0]); acc[0] = fmaf(c.w, cur.w, acc[0]);
-        acc[1] = fmaf(c.x, cur.y, acc[1]); acc[1] = fmaf(c.y, cur.z, acc[1]); acc[1] = fmaf(c.z, cur.w, acc[1]); acc[1] = fmaf(c.w, nxt.x, acc[1]);
-        acc[2] = fmaf(c.x, cur.z, acc[2]); acc[2] = fmaf(c.y, cur.w, acc[2]); acc[2] = fmaf(c.z, nxt.x, acc[2]); acc[2] = fmaf(c.w, nxt.y, acc[2]);
-        acc[3] = fmaf(c.x, cur.w, acc[3]); acc[3] = fmaf(c.y, nxt.x, acc[3]); acc[3] = fmaf(c.z, nxt.y, acc[3]); acc[3] = fmaf(c.w, nxt.z, acc[3]);
-        cur = nxt;
-    }
-}
-
-constexpr int USB_SPAN = USB_TILE + MAX_FIR_TAPS + 128;     // z samples a CTA may need
-
-__global__ void __launch_bounds__(256) k2b_usb_audio(const UsbDev *__restrict__ devs, int n_blocks, int cb0, int ncb,
-                                                      int stream0, int pcm_per_block,
-                                                      int16_t *__restrict__ pcm, float *__restrict__ tap) {
-    __shared__ __align__(16) float sPlaneA[USB_SPAN / 2 + 8];    // im[zlo + 2j + 1]
-    __shared__ __align__(16) float sPlaneB[USB_SPAN / 2 + 8];    // im[zlo + 2j + 2]
-    __shared__ __align__(16) float sRe[USB_SPAN + 8];
-    __shared__ __align__(16) float sUsb[USB_TILE + MAX_FIR_TAPS + 8];
-    __shared__ __align__(16) float sHil[64];
-    __shared__ __align__(16) float sLpf[MAX_FIR_TAPS];
-
-    const UsbDev &D = devs[blockIdx.y];
-    const int stream = stream0 + blockIdx.x;
-    const int n_total = (cb0 + ncb) * D.samples_out;               // samples that exist so far in this call
-    const int n0 = cb0 * D.samples_out + blockIdx.z * USB_TILE;
-    if (n0 >= n_total) return;
-    const int t = threadIdx.x;
-    const int NP = D.np;
-    const int span = USB_TILE + NP + 128;                   // z-local q in [0, span)
-    const long long zlo = (long long)n0 - NP - 128;
-    const float2 *zp = D.src + (size_t)stream * D.src_stride + D.src_hist;
-    for (int e = t; e < span; e += 256) {
-        const long long zi = zlo + e;
-        const float2 v = (zi < n_total) ? zp[zi] : make_float2(0.f, 0.f);
-        sRe[e] = v.x;
-        if (e & 1) sPlaneA[e >> 1] = v.y;
-        else if (e >= 2) sPlaneB[(e >> 1) - 1] = v.y;
-    }
-    if (t < 64) sHil[t] = D.hil[t];
-    for (int e = t; e < NP; e += 256) sLpf[e] = D.lpf[e];
-    __syncthreads();
-
-    // Hilbert: usb index i = q - 128, q = 2w + par, i in [0, USB_TILE + NP)
-    const int n_usb = USB_TILE + NP;
-    const int per_par = (n_usb / 2 + 3) / 4;               // threads needed per parity
-    for (int it = t; it < 2 * per_par; it += 256) {
-        const int par = it >= per_par;
-        const int w0 = 64 + 4 * (par ? it - per_par : it); // first plane output of this thread
-        const float *plane = par ? sPlaneB : sPlaneA;
-        float acc[4];
-        fir4(plane + (w0 - 64), sHil, 64, acc);
-#pragma unroll
-        for (int r = 0; r < 4; ++r) {
-            const int q = 2 * (w0 + r) + par;
-            const int i = q - 128;
-            if (i < n_usb) sUsb[i] = sRe[q - 62] - acc[r];
-        }
-    }
-    __syncthreads();
-
-    // low-pass (or identity), gain, quantise, store 4 consecutive samples per thread
-    const int i4 = 4 * t;
-    float o[4];
-    if (NP > 0) {
-        fir4(sUsb + i4, sLpf, NP, o);
-    } else {
-        const float4 v = *reinterpret_cast<const float4 *>(sUsb + i4);
-        o[0] = v.x; o[1] = v.y; o[2] = v.z; o[3] = v.w;
-    }
-#pragma unroll
-    for (int r = 0; r < 4; ++r) {
-        const int n = n0 + i4 + r;
-        if (n < n_total) {
-            const int blk = n / D.samples_out, i = n - blk * D.samples_out;
-            const size_t at = ((size_t)stream * n_blocks + blk) * pcm_per_block + D.pcm_offset + i;
-            const float v = (o[r] * D.gain) * 32768.0f;     // exact power-of-two scaling
-            pcm[at] = (int16_t)__float2int_rz(v);
-            if (tap) tap[at] = v;
-        }
-    }
 }
 
 // ------------------------------------------------------------------------------------
