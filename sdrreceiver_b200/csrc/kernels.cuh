@@ -1,14 +1,16 @@
 // Hand-written sm_100a kernels of the SDRReceiver channelizer hot path.
 //
-// Pipeline per process call (all streams of a bank, n_blocks callbacks each):
-//   k0_dc_partial  -> k0_dc_scan           DC-removal IIR (sdrj.cpp:277-283) as a 2-level scan
-//   k1_ingest_main                          u8 -> f32 (sdr.cpp:43-49), DC, per main VFO NCO mix
-//                                           (vfo.cpp:237-245) + 11-tap half-band cascade
-//                                           (halfbanddecimator.cpp:43-72) -> cf32 main output
-//   k2a_sub_cascade<S>                      per sub VFO: NCO mix + S half-band stages -> cf32 z
-//   k2_late_fir                             /5 or /6 decimating FIR (vfo.cpp:334-387)
-//   k2b_usb_audio                           delay62 - Hilbert125 (vfo.cpp:316-324), optional
-//                                           low-pass, gain, int16 (vfo.cpp:328)
+// Pipeline per process call (all streams of a bank, n_blocks callbacks each); kernels marked (v2) live in
+// kernels_v2.cuh:
+//   k0_dc_anchor / k0_dc_blocks / k0_dc_walk  DC-removal IIR (sdrj.cpp:277-283) reproduced bit for bit, one callback
+//                                           ahead on a side stream
+//   k1_v2 (v2)                              u8 -> f32 (sdr.cpp:43-49), DC, per main VFO NCO mix (vfo.cpp:237-245) +
+//                                           11-tap half-band cascade (halfbanddecimator.cpp:43-72) -> cf32 main output
+//   k1_ingest_main<false>                   the same for cf32 input (vfo::process on a main VFO: no u8, no DC)
+//   k2a_v2 (v2)                             all sub VFOs of a main VFO: NCO mix + S half-band stages -> cf32 z
+//   k2_late_v2 (v2) / k2_late_fir           /5 or /6 decimating FIR (vfo.cpp:334-387); the second is the fallback
+//   k2b_v2 (v2)                             delay62 - Hilbert125 (vfo.cpp:316-324), optional low-pass, gain, int16
+//                                           (vfo.cpp:328)
 //   k3_carry                                filter tails / raw tail / counters for the next call
 //
 // Reference quirks reproduced on purpose:
