@@ -404,7 +404,10 @@ __global__ void __launch_bounds__(64) k_input_samples(const uint8_t *__restrict_
 // fetches exactly the 96 + 16 bytes it will read back itself, so no barrier is involved); the global
 // load latency that used to open every CTA (15 % of the warps' time, profiles/r01_k2a_regions.md) is
 // paid once per CTA, and the per-stream constants (callback counter, DC anchors) are read once.
-constexpr int K1_TPC = 4;
+#ifndef SDRB_K1_TPC
+#define SDRB_K1_TPC 4
+#endif
+constexpr int K1_TPC = SDRB_K1_TPC;
 constexpr int K1_PF_BYTES = 112;                          // per thread: 6 x 16 raw bytes + 2 x 8 table bytes
 template <int NT> constexpr size_t k1v2_smem() { return V2L<NT>::SMEM + (size_t)NT * K1_PF_BYTES; }
 
