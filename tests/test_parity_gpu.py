@@ -331,3 +331,29 @@ def test_every_cta_size_of_the_cascade_kernels(k1_threads, k2a_threads):
                        capture_output=True, text=True, timeout=600)
     assert r.returncode == 0, r.stdout[-2000:] + r.stderr[-2000:]
     assert "smoke 25E: 27 sub VFOs" in r.stdout
+
+
+@pytest.mark.gpu
+def test_bench_line_on_the_gpu():
+    """bench.py's B200 arm on a small bank: one JSON line with the keys the driver reads (value, e2e with the
+    bytes it moved, gpu_launches > 0, clocks, roofline with achieved/peak/frac/traffic) and a digest."""
+    import subprocess
+    import sys
+    root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    r = subprocess.run([sys.executable, "bench.py", "--steps", "3", "--warmup", "3", "--streams", "8", "--blocks", "2",
+                        "--no-cpu-baseline"], cwd=root, capture_output=True, text=True, timeout=900)
+    assert r.returncode == 0, r.stdout[-2000:] + r.stderr[-2000:]
+    lines = [x for x in r.stdout.splitlines() if x.startswith("{")]
+    assert len(lines) == 1, r.stdout[-2000:]
+    d = json.loads(lines[0])
+    assert d["unit"] == "MS/s" and d["n_gpus"] == 1 and d["steps"] == 3 and d["warmup"] == 3 and d["dtype"] == "f32"
+    assert d["value"] > 0 and d["ms_per_step"] > 0 and d["scaling"] == "weak" and d["vs_baseline"] is None
+    assert d["gpu_launches"] > 0
+    assert d["e2e"]["value"] > 0 and d["e2e"]["h2d_bytes_per_step"] == 8 * 2 * 384000 * 2 and d["e2e"]["d2h_bytes_per_step"] > 0
+    assert d["e2e"]["value"] < d["value"]                       # the host copies are inside the end-to-end region
+    rf = d["roofline"]
+    assert rf["bound"] == "hbm" and rf["unit"] == "GB/s" and rf["peak"] > 1000
+    assert abs(rf["frac"] - rf["achieved"] / rf["peak"]) < 1e-9
+    assert 25.0 < rf["fp32"]["peak_tflops"] < 90.0
+    assert set(d["clocks"]) >= {"sm_mhz", "sm_max_mhz", "reasons"}
+    assert d["digests"] and len(d["digests"][0]) == 3
