@@ -18,7 +18,12 @@
 //     conflict-free shared memory (one 16-byte load per pair); the thread's own samples never
 //     leave registers;
 //   * the FIRQueueBackToFront off-by-one (dsp.cpp:163-173) is one rule: a window slot at a
-//     negative callback coordinate c holds sample c-1.
+//     negative callback coordinate c holds sample c-1;
+//   * 168 registers per thread give 12 warps per SM whatever the CTA size, so the CTA size (64, 96
+//     or 128 threads, a template parameter) only trades barrier-domain size against halo threads;
+//     k1_v2 additionally walks K1_TPC consecutive tiles per CTA with the next tile's bytes
+//     prefetched by cp.async.
+// Also here: k2b_v2 (USB demodulation, one warp per tile) and k2_late_v2 (polyphase /5 and /6 FIR).
 #pragma once
 #include "kernels.cuh"
 
