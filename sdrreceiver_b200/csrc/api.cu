@@ -18,6 +18,7 @@
 #include "plan.hpp"
 #include "kernels.cuh"
 #include "kernels_v2.cuh"
+#include "kernels_v3.cuh"
 #include "prims.cuh"
 
 namespace sdrb {
@@ -191,6 +192,10 @@ struct SubGroup {           // sub VFOs of one main VFO (at most V2_MAX_VFO) -> 
     int threads;            // CTA size of this group's launch (64, 96 or 128)
     int first, count;       // range in the device CascVfo / Rf arrays (sorted by group)
     int lut_len, block_in;  // Oscillator table length and callback size of the group's sub VFOs
+    // k2a_v3 (kernels_v3.cuh): used when every sub VFO of the group has 1..5 half-band stages and the callback is a
+    // whole number of 128-sample tiles; otherwise the group stays on k2a_v2
+    bool v3 = false;
+    int v3_maxs = 5, v3_nsw = 1;
 };
 
 // Rf[j] = (rot/|rot|)^j, j = -10..31 (index j + 10), rot = the float rotation the Oscillator table is
@@ -232,6 +237,9 @@ struct sdrb_bank {
     K1V2Params k1v2{};
     int k1_threads = 64;
     std::vector<K2V2Params> k2v2;                 // one prebuilt parameter block per sub-VFO group
+    std::vector<K3Params> k3;                     // ... and for the groups that run k2a_v3
+    DevBuf k3_rrel;
+    bool per_cb = false;                          // SDRB_PER_CB=1: device-resident calls launch every kernel class per callback
     DevBuf cascdev, rfdev, latedev, usbdev, carry;
     std::vector<SubGroup> groups;
     int n_late = 0, n_usb = 0, n_carry = 0;
@@ -239,6 +247,7 @@ struct sdrb_bank {
     int late_factor = 0;            // the plan's /late factor if all late VFOs share it and their taps fit k2_late_v2, else -1
     int uv_np_max = 0, uv_eo_rows = 0, uv_warp_floats = 0, uv_tiles = 0;   // k2b_v2 launch geometry
     std::vector<unsigned short> uv_vfo_tiles;                              // tiles per callback of each USB VFO
+    std::vector<int> uv_vfo_out, uv_vfo_np;                                // samples per callback and padded low-pass length of each USB VFO
     size_t uv_smem = 0;
     std::vector<size_t> main_off;           // per main: offset (float2 units) inside main_out per stream
     size_t main_stride = 0;                 // float2 per stream
@@ -277,7 +286,7 @@ extern "C" void sdrb_bank_destroy(sdrb_bank *b) {
     cudaDeviceSynchronize();                                 // asynchronous host calls may still be in flight
     DevBuf *all[] = {&b->luts, &b->taps, &b->blocks_done, &b->dc_state, &b->raw_tail, &b->cf_tail, &b->dc_anchor, &b->dc_stats, &b->dc_table,
                      &b->main_out, &b->zbuf, &b->dbuf, &b->cascdev, &b->rfdev, &b->latedev, &b->usbdev, &b->carry,
-                     &b->d_iq, &b->d_pcm, &b->d_tap, &b->d_cf, &b->d_fwd};
+                     &b->d_iq, &b->d_pcm, &b->d_tap, &b->d_cf, &b->d_fwd, &b->k3_rrel};
     for (DevBuf *d : all) d->release();
     for (cudaEvent_t e : b->ev_in) cudaEventDestroy(e);
     for (cudaEvent_t e : b->ev_free) cudaEventDestroy(e);
@@ -486,6 +495,7 @@ extern "C" int sdrb_bank_create(const sdrb_plan *plan, int device, int n_streams
         b->uv_np_max = std::max(b->uv_np_max, U.np);
         b->uv_tiles = std::max(b->uv_tiles, (s.samples_out + (UV_USB - U.np) - 1) / (UV_USB - U.np));
         b->uv_vfo_tiles.push_back((unsigned short)((s.samples_out + (UV_USB - U.np) - 1) / (UV_USB - U.np)));
+        b->uv_vfo_out.push_back(s.samples_out); b->uv_vfo_np.push_back(U.np);
         CarryItem c; c.base = (float2 *)b->zbuf.p + z_off[i]; c.stride = (long long)(z_stride * sizeof(float2));
         c.hist_bytes = z_hist[i] * (int)sizeof(float2); c.block_bytes = s.block_z * (int)sizeof(float2);
         carry.push_back(c);
@@ -533,6 +543,46 @@ extern "C" int sdrb_bank_create(const sdrb_plan *plan, int device, int n_streams
         kp.blocks_done = (const long long *)b->blocks_done.p;
         kp.in_stride = (long long)b->main_stride; kp.out_stride = (long long)b->z_stride;
         kp.count = g.count; kp.lut_len = g.lut_len; kp.block_in = g.block_in; kp.HT = g.halo;
+    }
+    // k2a_v3 parameter blocks: folded taps and rotation tables per sub VFO (kernels_v3.cuh)
+    {
+        const char *ev3 = getenv("SDRB_K2A_V3");
+        const bool want_v3 = !(ev3 && atoi(ev3) == 0);
+        b->per_cb = getenv("SDRB_PER_CB") && atoi(getenv("SDRB_PER_CB")) != 0;
+        b->k3.assign(b->groups.size(), K3Params{});
+        std::vector<float2> rrel(std::max<size_t>(cascdev.size(), 1) * K3_OUT1);
+        BANK_TRY(b->k3_rrel.alloc(sizeof(float2) * rrel.size()));
+        for (size_t gi = 0; gi < b->groups.size(); gi++) {
+            SubGroup &g = b->groups[gi];
+            K3Params &kp = b->k3[gi];
+            bool ok = want_v3 && g.count <= K3_MAX_VFO && g.block_in % K3_TILE == 0 && g.block_in / K3_TILE >= 8 &&
+                      g.lut_len >= 4 * K3_LUT_STEADY && MAIN_HIST >= (K3_WARM + 1) * K3_TILE;
+            int maxs = 0;
+            for (int v = 0; v < g.count; v++) {
+                const SubVfo &sv = h.subs[(size_t)order[(size_t)(g.first + v)]];
+                if (sv.decim < 1 || sv.decim > 5) ok = false;
+                maxs = std::max(maxs, sv.decim);
+                K3Vfo &V = kp.v[v];
+                k3_fill_vfo((double)sv.fs, sv.mixer, std::max(sv.decim, 1), V, &rrel[(size_t)(g.first + v) * K3_OUT1]);
+                V.lut = cascdev[(size_t)(g.first + v)].lut; V.out = cascdev[(size_t)(g.first + v)].out;
+                V.block_out = cascdev[(size_t)(g.first + v)].block_out; V.hist = cascdev[(size_t)(g.first + v)].hist; V.pad = 0;
+            }
+            kp.rrel = (const float2 *)b->k3_rrel.p + (size_t)g.first * K3_OUT1;
+            kp.in = (const float2 *)b->main_out.p + b->main_off[(size_t)g.main_idx];
+            kp.blocks_done = (const long long *)b->blocks_done.p;
+            kp.in_stride = (long long)b->main_stride; kp.out_stride = (long long)b->z_stride;
+            kp.hist_in = MAIN_HIST; kp.count = g.count; kp.lut_len = g.lut_len; kp.block_in = g.block_in;
+            kp.n_tiles = g.block_in / K3_TILE;
+            g.v3 = ok;
+            g.v3_maxs = maxs <= 2 ? 2 : (maxs == 3 ? 3 : 5);
+            g.v3_nsw = std::max(1, std::min(8, (32 / std::max(g.count, 1)) & ~1));
+            if (32 / std::max(g.count, 1) < 2) g.v3_nsw = 1;
+            kp.nsw = g.v3_nsw;
+        }
+        BANK_CU(cudaMemcpy(b->k3_rrel.p, rrel.data(), sizeof(float2) * rrel.size(), cudaMemcpyHostToDevice));
+        BANK_CU(cudaFuncSetAttribute(k2a_v3<2>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)k3_cta_smem_bytes(K3_MAX_VFO, K3_WARPS)));
+        BANK_CU(cudaFuncSetAttribute(k2a_v3<3>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)k3_cta_smem_bytes(K3_MAX_VFO, K3_WARPS)));
+        BANK_CU(cudaFuncSetAttribute(k2a_v3<5>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)k3_cta_smem_bytes(K3_MAX_VFO, K3_WARPS)));
     }
     if (!latedev.empty()) BANK_CU(cudaMemcpy(b->latedev.p, latedev.data(), sizeof(LateDev) * latedev.size(), cudaMemcpyHostToDevice));
     if (!usbdev.empty()) BANK_CU(cudaMemcpy(b->usbdev.p, usbdev.data(), sizeof(UsbDev) * usbdev.size(), cudaMemcpyHostToDevice));
@@ -662,10 +712,8 @@ static int enqueue_dc_cb(sdrb_bank *b, const CallCtx &c, int s0, int ns, cudaStr
     return SDRB_OK;
 }
 
-// Everything after the DC stage for callback cb: ingest + main VFOs, sub-VFO cascades, /late FIR,
-// USB audio. `wait` (optional) gates the first kernel; `out_done` (optional) is recorded at the end.
-static int enqueue_main_cb(sdrb_bank *b, const CallCtx &c, int s0, int ns, cudaStream_t st, int cb, cudaEvent_t wait,
-                           cudaEvent_t out_done, int *nl) {
+// Ingest + main VFOs of callback cb. `wait` (optional) gates the kernel.
+static int enqueue_ingest_cb(sdrb_bank *b, const CallCtx &c, int s0, int ns, cudaStream_t st, int cb, cudaEvent_t wait, int *nl) {
     const HostPlan &h = b->plan->h;
     if (wait) CU_TRY(cudaStreamWaitEvent(st, wait, 0));
     K1Params k1 = b->k1;
@@ -686,43 +734,99 @@ static int enqueue_main_cb(sdrb_bank *b, const CallCtx &c, int s0, int ns, cudaS
         else launch_k1_v2<128>(q, h.correct_dc, ns, h.block, st);
     }
     (*nl)++;
+    return SDRB_OK;
+}
+
+// k2a_v3 launch geometry: one warp per (stream group, span, callback); spans are chosen so that the grid holds about
+// two warps per resident slot (148 SMs x 10 warps), never shorter than 16 tiles (3 warm-up tiles are recomputed per span)
+static void k3_geometry(const SubGroup &g, K3Params &kp, int ns, int ncb, dim3 *grid) {
+    const int sgroups = (ns + g.v3_nsw - 1) / g.v3_nsw;
+    int target = 148 * 10 * 2;
+    if (const char *e = getenv("SDRB_K3_WARPS")) { const int v = atoi(e); if (v > 0) target = v; }
+    int spans = std::max(1, target / std::max(1, sgroups * ncb));
+    int tps = std::max(16, (kp.n_tiles + spans - 1) / spans);
+    tps = std::min(tps, kp.n_tiles);
+    spans = (kp.n_tiles + tps - 1) / tps;
+    kp.tiles_per_span = tps;
+    *grid = dim3((unsigned)((sgroups + K3_WARPS - 1) / K3_WARPS), (unsigned)spans, (unsigned)ncb);
+}
+
+// Sub-VFO cascades of callbacks cb0 .. cb0+ncb-1.
+static int enqueue_subs(sdrb_bank *b, const CallCtx &c, int s0, int ns, cudaStream_t st, int cb0, int ncb, int *nl) {
     for (const SubGroup &g : b->groups) {
-        K2V2Params &kp = b->k2v2[(size_t)(&g - b->groups.data())];
-        kp.stream0 = s0; kp.b0 = cb;
+        const size_t gi = (size_t)(&g - b->groups.data());
+        if (g.v3) {
+            K3Params &kp = b->k3[gi];
+            kp.stream0 = s0; kp.stream_end = s0 + ns; kp.b0 = cb0;
+            dim3 grid;
+            k3_geometry(g, kp, ns, ncb, &grid);
+            const size_t smem = k3_cta_smem_bytes(g.count, K3_WARPS);
+            TimedScope t(b, st, 2);
+            if (g.v3_maxs == 2) k2a_v3<2><<<grid, K3_WARPS * 32, smem, st>>>(kp);
+            else if (g.v3_maxs == 3) k2a_v3<3><<<grid, K3_WARPS * 32, smem, st>>>(kp);
+            else k2a_v3<5><<<grid, K3_WARPS * 32, smem, st>>>(kp);
+            (*nl)++;
+            continue;
+        }
+        K2V2Params &kp = b->k2v2[gi];
+        kp.stream0 = s0; kp.b0 = cb0;
         TimedScope t(b, st, 2);
-        const dim3 grid((unsigned)ns, (unsigned)g.tiles, 1u);
+        const dim3 grid((unsigned)ns, (unsigned)g.tiles, (unsigned)ncb);
         if (g.threads == 64) k2a_v2<64><<<grid, 64, V2L<64>::SMEM, st>>>(kp);
         else if (g.threads == 96) k2a_v2<96><<<grid, 96, V2L<96>::SMEM, st>>>(kp);
         else k2a_v2<128><<<grid, 128, V2L<128>::SMEM, st>>>(kp);
         (*nl)++;
     }
+    return SDRB_OK;
+}
+
+// /late FIR and USB audio of callbacks cb0 .. cb0+ncb-1. `out_done` (optional) is recorded at the end.
+static int enqueue_audio(sdrb_bank *b, const CallCtx &c, int s0, int ns, cudaStream_t st, int cb0, int ncb, cudaEvent_t out_done,
+                         int *nl) {
+    const HostPlan &h = b->plan->h;
     if (b->n_late) {
         TimedScope t(b, st, 3);
         if (b->late_factor == 5 || b->late_factor == 6) {           // every late VFO of the plan divides by the same 5 or 6
-            const dim3 grid((unsigned)ns, (unsigned)b->n_late, (unsigned)((b->max_late_samples + LV_TILE - 1) / LV_TILE));
-            if (b->late_factor == 5) k2_late_v2<5><<<grid, LV_THREADS, lv_smem<5>(), st>>>((const LateDev *)b->latedev.p, cb, 1, s0);
-            else k2_late_v2<6><<<grid, LV_THREADS, lv_smem<6>(), st>>>((const LateDev *)b->latedev.p, cb, 1, s0);
+            const dim3 grid((unsigned)ns, (unsigned)b->n_late, (unsigned)((ncb * b->max_late_samples + LV_TILE - 1) / LV_TILE));
+            if (b->late_factor == 5) k2_late_v2<5><<<grid, LV_THREADS, lv_smem<5>(), st>>>((const LateDev *)b->latedev.p, cb0, ncb, s0);
+            else k2_late_v2<6><<<grid, LV_THREADS, lv_smem<6>(), st>>>((const LateDev *)b->latedev.p, cb0, ncb, s0);
         } else {
-            const int tiles = (b->max_late_samples + LATE_TILE - 1) / LATE_TILE;
+            const int tiles = (ncb * b->max_late_samples + LATE_TILE - 1) / LATE_TILE;
             k2_late_fir<<<dim3((unsigned)ns, (unsigned)b->n_late, (unsigned)tiles), LATE_TILE, 0, st>>>(
-                (const LateDev *)b->latedev.p, cb, 1, s0);
+                (const LateDev *)b->latedev.p, cb0, ncb, s0);
         }
         (*nl)++;
     }
     if (b->n_usb) {
         K2bV2Params up;
         up.devs = (const UsbDev *)b->usbdev.p; up.pcm = c.d_pcm; up.tap = c.d_tap;
-        up.n_blocks = c.n_blocks; up.cb0 = cb; up.ncb = 1; up.stream0 = s0; up.stream_end = s0 + ns;
+        up.n_blocks = c.n_blocks; up.cb0 = cb0; up.ncb = ncb; up.stream0 = s0; up.stream_end = s0 + ns;
         up.pcm_per_block = h.pcm_per_block; up.warp_floats = b->uv_warp_floats; up.eo_rows = b->uv_eo_rows;
         up.np_max = b->uv_np_max;
-        for (size_t k = 0; k < b->uv_vfo_tiles.size() && k < (size_t)SDRB_MAX_SUB; k++) up.tiles[k] = b->uv_vfo_tiles[k];
+        int max_tiles = 0;
+        for (size_t k = 0; k < b->uv_vfo_out.size() && k < (size_t)SDRB_MAX_SUB; k++) {
+            const int tile_out = UV_USB - b->uv_vfo_np[k];
+            const int tiles = (ncb * b->uv_vfo_out[k] + tile_out - 1) / tile_out;
+            up.tiles[k] = (unsigned short)tiles;
+            max_tiles = std::max(max_tiles, tiles);
+        }
         TimedScope t(b, st, 4);
-        k2b_v2<<<dim3((unsigned)((ns + UV_WARPS - 1) / UV_WARPS), (unsigned)b->n_usb, (unsigned)b->uv_tiles), UV_WARPS * 32,
+        k2b_v2<<<dim3((unsigned)((ns + UV_WARPS - 1) / UV_WARPS), (unsigned)b->n_usb, (unsigned)max_tiles), UV_WARPS * 32,
                  b->uv_smem, st>>>(up);
         (*nl)++;
     }
     if (out_done) CU_TRY(cudaEventRecord(out_done, st));
     return SDRB_OK;
+}
+
+// Everything after the DC stage for callback cb: ingest + main VFOs, sub-VFO cascades, /late FIR,
+// USB audio. `wait` (optional) gates the first kernel; `out_done` (optional) is recorded at the end.
+static int enqueue_main_cb(sdrb_bank *b, const CallCtx &c, int s0, int ns, cudaStream_t st, int cb, cudaEvent_t wait,
+                           cudaEvent_t out_done, int *nl) {
+    int rc;
+    if ((rc = enqueue_ingest_cb(b, c, s0, ns, st, cb, wait, nl)) != SDRB_OK) return rc;
+    if ((rc = enqueue_subs(b, c, s0, ns, st, cb, 1, nl)) != SDRB_OK) return rc;
+    return enqueue_audio(b, c, s0, ns, st, cb, 1, out_done, nl);
 }
 
 // End of a call: filter tails, raw tail and callback counters for the next call.
@@ -764,9 +868,18 @@ static int enqueue_all(sdrb_bank *b, CallCtx &c, cudaStream_t st, int *launches,
         for (int cb = 0; cb < c.n_blocks; cb++)
             if ((rc = enqueue_dc_cb(b, c, 0, ns, sd, cb, nullptr, b->ev_dc[0][(size_t)cb], launches)) != SDRB_OK) return rc;
     }
-    for (int cb = 0; cb < c.n_blocks; cb++)
-        if ((rc = enqueue_main_cb(b, c, 0, ns, st, cb, dc ? b->ev_dc[0][(size_t)cb] : nullptr, nullptr, launches)) != SDRB_OK)
-            return rc;
+    if (b->per_cb) {
+        for (int cb = 0; cb < c.n_blocks; cb++)
+            if ((rc = enqueue_main_cb(b, c, 0, ns, st, cb, dc ? b->ev_dc[0][(size_t)cb] : nullptr, nullptr, launches)) != SDRB_OK)
+                return rc;
+    } else {
+        // kernel class by kernel class over all callbacks of the call: the sub-VFO warps of k2a_v3 walk long spans
+        // (their warm-up tiles amortise), and the DC walk of the next call has the whole cascade/audio phase to hide in
+        for (int cb = 0; cb < c.n_blocks; cb++)
+            if ((rc = enqueue_ingest_cb(b, c, 0, ns, st, cb, dc ? b->ev_dc[0][(size_t)cb] : nullptr, launches)) != SDRB_OK) return rc;
+        if ((rc = enqueue_subs(b, c, 0, ns, st, 0, c.n_blocks, launches)) != SDRB_OK) return rc;
+        if ((rc = enqueue_audio(b, c, 0, ns, st, 0, c.n_blocks, nullptr, launches)) != SDRB_OK) return rc;
+    }
     if ((rc = enqueue_carry(b, c, 0, ns, st, launches)) != SDRB_OK) return rc;
     if (dc) {
         CU_TRY(cudaEventRecord(b->ev_end[c.par], st));
