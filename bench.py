@@ -46,6 +46,8 @@ def parse_args():
     ap.add_argument("--blocks", type=int, default=4, help="callbacks per stream per step")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-e2e", action="store_true")
+    ap.add_argument("--no-zmq", action="store_true", help="skip the publish-inclusive end-to-end leg")
+    ap.add_argument("--no-plans", action="store_true", help="skip the short runs of the other BASELINE configurations")
     return ap.parse_args()
 
 
@@ -165,13 +167,21 @@ def run_reference_cpu(plan, plan_path, cores, blocks_timed, skip):
     return total, worst
 
 
+class RefPlan:
+    """What run_reference_cpu needs of a plan, from oracle/plan.py (reference arm) -- same attribute names as binding.Plan."""
+
+    def __init__(self, op):
+        self.fs, self.block, self.center, self.subs = op["Fs"], op["block"], op["center"], op["subs"]
+
+
 def reference_arm(args):
     rank, _, world = dist_env()
     if rank != 0:
         return
     plan_path = os.path.join(ROOT, "plans", args.plan + ".ini")
-    from sdrreceiver_b200 import binding as B
-    plan = B.Plan(plan_path)                 # plan arithmetic only; no GPU is touched on this arm
+    # plan arithmetic from the oracle's own ini reader: this arm never loads libsdrb200.so
+    from oracle import plan as OP
+    plan = RefPlan(OP.build_plan(plan_path))
     op = {"Fs": plan.fs, "block": plan.block}
     cores = os.cpu_count() or 1
     # each step = every core pushes `--blocks` callbacks of its own stream through the reference
@@ -195,6 +205,122 @@ def reference_arm(args):
 # --------------------------------------------------------------------------------------
 # B200 arm
 # --------------------------------------------------------------------------------------
+CLASSES = ["dc_scan", "ingest_main", "sub_cascade", "late_fir", "usb_audio", "carry"]
+
+
+def alg_tables(plan):
+    """Algorithmic bytes and flops per input complex sample of every kernel class (DESIGN.md section 4,
+    SURVEY.md 8(d)'s counting rule)."""
+    fs = plan.fs
+    main_out_b = 8.0 * sum(m["out_rate"] for m in plan.mains) / fs
+    z_b = 8.0 * sum(s["out_rate"] * (s["late"] or 1) for s in plan.subs) / fs
+    d_b = 8.0 * sum(s["out_rate"] for s in plan.subs if s["late"]) / fs
+    usb_in_b = 8.0 * sum(s["out_rate"] for s in plan.subs) / fs
+    pcm_b = 2.0 * sum(s["out_rate"] for s in plan.subs) / fs
+    alg_bytes = {"dc_scan": 2.0, "ingest_main": 2.0 + main_out_b, "sub_cascade": main_out_b + z_b,
+                 "late_fir": (z_b + d_b) if d_b else 0.0, "usb_audio": usb_in_b + pcm_b, "carry": 0.0}
+    hb = lambda decim: sum(20.0 / 2 ** a for a in range(1, decim + 1))
+    alg_flops = {
+        "dc_scan": 8.0 if plan.correct_dc else 0.0,
+        "ingest_main": 2.0 + sum(6.0 + hb(m["decim"]) for m in plan.mains),
+        "sub_cascade": sum((s["Fs"] / fs) * (6.0 + hb(s["decim"])) for s in plan.subs),
+        "late_fir": sum((s["out_rate"] / fs) * 4.0 * s["n_dec_taps"] for s in plan.subs if s["late"]),
+        "usb_audio": sum((s["out_rate"] / fs) * (2.0 * 62 + 1 + 2.0 * s["n_lpf_taps"] + 2.0) for s in plan.subs),
+        "carry": 0.0,
+    }
+    return alg_bytes, alg_flops
+
+
+class Resident:
+    """One bank with its input resident in HBM: the kernel-only leg, for the headline plan and the other BASELINE configs."""
+
+    def __init__(self, B, torch, shard, plan, S, NB, dev, local_rank, rank, world, canary):
+        self.B, self.torch, self.plan, self.S, self.NB, self.dev = B, torch, plan, S, NB, dev
+        Bk = plan.block
+        self.row = NB * Bk * 2
+        self.samples_per_step = S * NB * Bk
+        base = base_streams(plan, 2, NB * Bk)
+        self.pin_in = B.PinnedBuffer(S * self.row)
+        h_iq = self.pin_in.array.reshape(S, self.row)
+        for s, g in enumerate(shard.stream_ids(rank, world, S)):
+            # local slot 0 of every rank is the canary: identical bytes everywhere, its digest must agree across ranks
+            h_iq[s] = base[0] if (canary and s == 0) else np.roll(base[g % 2], 2 * 977 * g)
+        self.d_iq = torch.from_numpy(h_iq).to(dev)
+        self.d_pcm = torch.empty((S, NB, plan.pcm_per_block), dtype=torch.int16, device=dev)
+        self.bank = B.Bank(plan, S, NB, device=local_rank)
+        self.stream = torch.cuda.Stream(device=dev)
+        torch.cuda.synchronize()
+        self.in_ready = torch.cuda.Event()
+        self.in_ready.record(self.stream)
+        self.in_ready.synchronize()
+        self.after_step = None
+
+    def step(self):
+        self.bank.process_device(self.d_iq.data_ptr(), self.row, self.NB, self.d_pcm.data_ptr(), None, self.stream.cuda_stream,
+                                 self.in_ready.cuda_event)
+        if self.after_step:
+            self.after_step()
+
+    def timed(self, steps, warmup, barrier):
+        torch = self.torch
+        for _ in range(warmup):
+            self.step()
+        barrier()
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        e0.record(self.stream)
+        for _ in range(steps):
+            self.step()
+        e1.record(self.stream)
+        barrier()
+        launches = self.bank.last_launches * steps
+        dev_ms = e0.elapsed_time(e1)
+        # second pass over the same steps with a CUDA-event pair around every launch (on the stream it is launched
+        # on): per-class durations for the roofline, kept out of the number above
+        self.bank.set_timing(True)
+        for _ in range(steps):
+            self.step()
+        torch.cuda.synchronize()
+        kt = self.bank.kernel_times()
+        self.bank.set_timing(False)
+        return dev_ms, launches, {k: v[0] / steps for k, v in kt.items()}, {k: v[1] / steps for k, v in kt.items()}
+
+
+def class_rooflines(plan, per_step_ms, samples_per_step, hbm_peak_gbs, fp32_peak):
+    """Both roofline axes of every kernel class from its CUDA-event time: algorithmic bytes resp. flops / time / peak."""
+    alg_bytes, alg_flops = alg_tables(plan)
+    out = {}
+    for k, ms in per_step_ms.items():
+        if ms <= 0:
+            continue
+        gbs = alg_bytes[k] * samples_per_step / (ms * 1e-3) / 1e9
+        tf = alg_flops[k] * samples_per_step / (ms * 1e-3) / 1e12
+        out[k] = {"ms_per_step": ms, "hbm_gbs": gbs, "hbm_frac": gbs / hbm_peak_gbs, "fp32_tflops": tf,
+                  "fp32_frac": tf / fp32_peak, "alg_bytes_per_sample": alg_bytes[k], "alg_flops_per_sample": alg_flops[k]}
+    return out
+
+
+def canary_check(B, plan, local_rank):
+    """Parity verdict of this rank: a fresh one-receiver bank runs the canary's first callback and is compared with
+    tests/golden/canary_25E_1block.npz (int16 of the unmodified reference, tools/make_golden.py): +-1 LSB."""
+    import hashlib
+    from sdrreceiver_b200 import synth
+    gold = os.path.join(ROOT, "tests", "golden", "canary_%s_1block.npz" % os.path.basename(plan.path).replace(".ini", ""))
+    if not os.path.exists(gold):
+        return None, "no golden file for this plan"
+    g = np.load(gold)
+    iq = synth.make_iq(plan.fs, plan.block, synth.carriers_for_plan(plan.center, plan.subs), stream=0)
+    if not np.array_equal(np.frombuffer(hashlib.sha256(iq.tobytes()).digest(), np.uint8), g["input_sha256"]):
+        return None, "synthetic input differs from the golden file's"
+    bank = B.Bank(plan, 1, 1, device=local_rank)
+    pcm, _ = bank.process_numpy(iq[None, :], 1)
+    bank.close()
+    got = B.split_pcm(plan, pcm[0])
+    worst = 0
+    for s in plan.subs:
+        worst = max(worst, int(np.abs(got[s["topic"]].astype(np.int32) - g["pcm_" + s["topic"]].astype(np.int32)).max()))
+    return worst, "max |int16 difference| over %d sub VFOs x %d samples vs the unmodified reference" % (len(plan.subs), plan.pcm_per_block)
+
+
 def b200_arm(args):
     import torch
     import torch.distributed as dist
@@ -209,37 +335,23 @@ def b200_arm(args):
     numa = bind_to_gpu_cpus(local_rank)          # before the pinned buffers are allocated (first touch)
     plan_path = os.path.join(ROOT, "plans", args.plan + ".ini")
     plan = B.Plan(plan_path)
+    plan.path = plan_path
     S, NB, Bk = args.streams, args.blocks, plan.block
-    row = NB * Bk * 2
-    samples_per_step = S * NB * Bk
+
+    def barrier():
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize()
 
     # ---- input: stream s of rank r is global stream r + world*s (independent units, no exchange)
-    n_base = 2
-    base = base_streams(plan, n_base, NB * Bk)
-    pin_in = B.PinnedBuffer(S * row)
-    h_iq = pin_in.array.reshape(S, row)
-    for s, g in enumerate(shard.stream_ids(rank, world, S)):
-        h_iq[s] = np.roll(base[g % n_base], 2 * 977 * g)
-    d_iq = torch.from_numpy(h_iq).to(dev)                      # resident copy for the kernel metric
-    d_pcm = torch.empty((S, NB, plan.pcm_per_block), dtype=torch.int16, device=dev)
+    R = Resident(B, torch, shard, plan, S, NB, dev, local_rank, rank, world, canary=True)
+    row, samples_per_step, bank = R.row, R.samples_per_step, R.bank
+    pin_in = R.pin_in
     pin_out = B.PinnedBuffer(S * NB * plan.pcm_per_block * 2)
     # the end-to-end leg keeps two calls in flight: a second pair of pinned host buffers
     pin_in2 = B.PinnedBuffer(S * row)
     pin_in2.array[:] = pin_in.array
     pin_out2 = B.PinnedBuffer(S * NB * plan.pcm_per_block * 2)
-
-    bank = B.Bank(plan, S, NB, device=local_rank)
-    stream = torch.cuda.Stream(device=dev)
-
-    # the input is resident before the timed region: tell the library so with an event (a streaming
-    # caller would record it after the copy that fills its next input buffer)
-    torch.cuda.synchronize()
-    in_ready = torch.cuda.Event()
-    in_ready.record(stream)
-    in_ready.synchronize()
-
-    def step_device():
-        bank.process_device(d_iq.data_ptr(), row, NB, d_pcm.data_ptr(), None, stream.cuda_stream, in_ready.cuda_event)
 
     host_bufs = [(pin_in.ptr, pin_out.ptr), (pin_in2.ptr, pin_out2.ptr)]
     host_step = [0]
@@ -252,34 +364,11 @@ def b200_arm(args):
         bank.process_host_async(i, row, NB, o, None)
         bank.host_wait(1)
 
-    def barrier():
-        if world > 1:
-            dist.barrier()
-        torch.cuda.synchronize()
-
     sampler = ClockSampler(local_rank)
     sampler.start()
 
     # ---- kernel metric: inputs resident in HBM (393 MB per step > 126 MB L2) ----
-    for _ in range(args.warmup):
-        step_device()
-    barrier()
-    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-    e0.record(stream)
-    for _ in range(args.steps):
-        step_device()
-    e1.record(stream)
-    barrier()
-    launches = bank.last_launches * args.steps
-    dev_ms = e0.elapsed_time(e1)
-    # second pass over the same steps with a CUDA-event pair around every launch (on the stream it
-    # is launched on): per-kernel durations for the roofline, kept out of the number above
-    bank.set_timing(True)
-    for _ in range(args.steps):
-        step_device()
-    torch.cuda.synchronize()
-    ktimes = bank.kernel_times()
-    bank.set_timing(False)
+    dev_ms, launches, per_step_ms, launches_per_step = R.timed(args.steps, args.warmup, barrier)
 
     # ---- end to end through the host-facing call ----
     e2e_ms = None
@@ -298,41 +387,36 @@ def b200_arm(args):
     sampler.stop_flag = True
     sampler.join(timeout=2)
 
-    # timings + output digest of every rank, gathered over NCCL (the only collective in the job)
-    digest = shard.pcm_digest(d_pcm.cpu().numpy())
+    # ---- end to end including the ZMQ publish leg (vfo::transmitData, zmqpublisher.cpp:82-96) ----
+    zmq_leg = None
+    if not args.no_e2e and not args.no_zmq:
+        try:
+            zmq_leg = publish_leg(B, plan, bank, host_bufs, row, S, NB, rank, args)
+        except Exception as ex:           # reported, never required for the GPU number
+            zmq_leg = {"value": None, "error": str(ex)[:200]}
+
+    # ---- parity verdict: this rank's canary against the reference's golden output, and -- gathered over NCCL with the
+    # timings -- the canary digest of every rank, which must agree (identical bytes, identical history on every rank)
+    lsb, lsb_what = canary_check(B, plan, local_rank)
+    pcm_host = R.d_pcm.cpu().numpy()
+    digest = shard.pcm_digest(pcm_host) + shard.pcm_digest(pcm_host[0]) + [-1 if lsb is None else int(lsb)]
     stats_all, digests = shard.gather([dev_ms, e2e_ms if e2e_ms is not None else 0.0, float(samples_per_step)],
                                       digest, device=dev)
     if rank != 0:
         if world > 1:
             dist.destroy_process_group()
         return
+    verdict = shard.parity_verdict(digests)
 
     agg = shard.aggregate(stats_all, args.steps)
-    max_dev_ms, max_e2e_ms, total_samples = agg["dev_ms"], agg["e2e_ms"], agg["total_samples"]
+    max_dev_ms, max_e2e_ms = agg["dev_ms"], agg["e2e_ms"]
     value = agg["value_msps"]
     e2e_value = agg["e2e_msps"] if e2e_ms is not None else None
 
-    # ---- roofline of the dominant kernel class (rank 0's events) ----
+    # ---- rooflines (rank 0's events): every class on both axes; the headline object is the class with the largest share
+    # of the step ON THE LAUNCHING STREAM; the DC recursion runs beside it on a side stream and is reported with it
     fs = plan.fs
-    main_out_b = 8.0 * sum(m["out_rate"] for m in plan.mains) / fs
-    z_b = 8.0 * sum(s["out_rate"] * (s["late"] or 1) for s in plan.subs) / fs
-    d_b = 8.0 * sum(s["out_rate"] for s in plan.subs if s["late"]) / fs
-    usb_in_b = 8.0 * sum(s["out_rate"] for s in plan.subs) / fs
-    pcm_b = 2.0 * sum(s["out_rate"] for s in plan.subs) / fs
-    alg_bytes = {                                   # algorithmic bytes per input complex sample
-        "dc_scan": 2.0,
-        "ingest_main": 2.0 + main_out_b,
-        "sub_cascade": main_out_b + z_b,
-        "late_fir": z_b if d_b else 0.0,
-        "usb_audio": usb_in_b + pcm_b,
-        "carry": 0.0,
-    }
     peak, peak_src = hbm_peak()
-    per_step_ms = {k: v[0] / args.steps for k, v in ktimes.items()}      # sum of that class's launches in one step
-    launches_per_step = {k: v[1] / args.steps for k, v in ktimes.items()}
-    dom = max((k for k in per_step_ms if k != "dc_scan"), key=lambda k: per_step_ms[k])   # dc_scan runs on the side stream
-    dom_ms = per_step_ms[dom]
-    achieved = alg_bytes[dom] * samples_per_step / (dom_ms * 1e-3) / 1e9 if dom_ms > 0 else 0.0
     clocks = sampler.summary()
     sm_mhz = clocks["sm_mhz"] or 1965.0
     fp32_nominal = 148 * 128 * 2 * sm_mhz * 1e6 / 1e12
@@ -343,37 +427,39 @@ def b200_arm(args):
     fp32_src = ("measured FMA loop (sdrb_probe_fp32_tflops): FFMA %.1f, FFMA2 %.1f TFLOP/s; nominal 148 SM x 128 lanes x 2 x "
                 "%.0f MHz = %.1f" % (fp32_probe["ffma"], fp32_probe["ffma2"], sm_mhz, fp32_nominal))
     step_ms = max_dev_ms / args.steps
-    # DRAM traffic of that kernel class from the committed ncu --set full capture (same plan and bank
-    # size), per "launch" = the class's launches of one callback, like `achieved`
+    per_class = class_rooflines(plan, per_step_ms, samples_per_step, peak, fp32_peak)
+    longest = max(per_class, key=lambda k: per_class[k]["ms_per_step"])
+    dom = max((k for k in per_class if k != "dc_scan"), key=lambda k: per_class[k]["ms_per_step"])
+    dc_cls = per_class[dom]
     traffic, traffic_src = None, None
-    try:
-        with open(os.path.join(ROOT, "profiles", "r01_traffic.json")) as f:
-            tj = json.load(f)
-        if tj["config"]["plan"] == args.plan and tj["config"]["streams_per_gpu"] == S:
-            traffic, traffic_src = tj["per_class_per_callback"].get(dom), "profiles/r01_traffic.json (ncu --set full)"
-    except Exception:
-        pass
+    for fn in ("r02_traffic.json", "r01_traffic.json"):
+        try:
+            with open(os.path.join(ROOT, "profiles", fn)) as f:
+                tj = json.load(f)
+            if tj["config"]["plan"] == args.plan and tj["config"]["streams_per_gpu"] == S and dom in tj["per_class_per_callback"]:
+                traffic, traffic_src = tj["per_class_per_callback"][dom], "profiles/%s (ncu --set full)" % fn
+                break
+        except Exception:
+            pass
     samples_per_callback = S * Bk
+    fp32_bound = dc_cls["fp32_frac"] >= dc_cls["hbm_frac"]
     roofline = {
-        "bound": "hbm", "kernel": dom, "achieved": achieved, "peak": peak, "unit": "GB/s",
-        "frac": achieved / peak, "traffic": traffic, "traffic_source": traffic_src, "peak_source": peak_src,
+        "bound": "fp32" if fp32_bound else "hbm", "kernel": dom,
+        "achieved": dc_cls["fp32_tflops"] if fp32_bound else dc_cls["hbm_gbs"],
+        "peak": fp32_peak if fp32_bound else peak, "unit": "TFLOP/s" if fp32_bound else "GB/s",
+        "frac": dc_cls["fp32_frac"] if fp32_bound else dc_cls["hbm_frac"],
+        "traffic": traffic, "traffic_source": traffic_src,
+        "peak_source": fp32_src if fp32_bound else peak_src,
         "launch": "the %s kernels of one callback (%d streams x %d samples)" % (dom, S, Bk),
-        "alg_bytes_per_launch": alg_bytes[dom] * samples_per_callback, "launch_ms": dom_ms / NB,
-        "kernel_ms_per_step": dom_ms, "share_of_step": dom_ms / step_ms if step_ms > 0 else None,
-        "alg_bytes_per_sample": alg_bytes[dom],
+        "alg_flops_per_launch": dc_cls["alg_flops_per_sample"] * samples_per_callback,
+        "alg_bytes_per_launch": dc_cls["alg_bytes_per_sample"] * samples_per_callback, "launch_ms": dc_cls["ms_per_step"] / NB,
+        "kernel_ms_per_step": dc_cls["ms_per_step"], "share_of_step": dc_cls["ms_per_step"] / step_ms if step_ms > 0 else None,
+        "hbm": {"achieved": dc_cls["hbm_gbs"], "peak": peak, "unit": "GB/s", "frac": dc_cls["hbm_frac"], "peak_source": peak_src},
+        "fp32": {"achieved_tflops": dc_cls["fp32_tflops"], "peak_tflops": fp32_peak, "frac": dc_cls["fp32_frac"],
+                 "alg_flops_per_sample": dc_cls["alg_flops_per_sample"], "peak_source": fp32_src},
+        "longest_class_any_stream": longest,
+        "per_class": per_class,
     }
-    # the same kernel against the FP32 roofline (it is FP32-issue bound): algorithmic
-    # flops by SURVEY.md 8(d)'s counting rule
-    hb = lambda decim: sum(20.0 / 2 ** a for a in range(1, decim + 1))
-    alg_flops = {
-        "ingest_main": 10.0 + sum(6.0 + hb(m["decim"]) for m in plan.mains),
-        "sub_cascade": sum((s["Fs"] / fs) * (6.0 + hb(s["decim"])) for s in plan.subs),
-        "usb_audio": sum((s["out_rate"] / fs) * (2.0 * 62 + 1 + 2.0 * s["n_lpf_taps"] + 2.0) for s in plan.subs),
-    }
-    if dom in alg_flops and dom_ms > 0:
-        tf = alg_flops[dom] * samples_per_step / (dom_ms * 1e-3) / 1e12
-        roofline["fp32"] = {"achieved_tflops": tf, "peak_tflops": fp32_peak, "frac": tf / fp32_peak,
-                            "alg_flops_per_sample": alg_flops[dom], "peak_source": fp32_src}
     line = {
         "metric": METRIC, "value": value, "unit": "MS/s", "n_gpus": world, "steps": args.steps, "warmup": args.warmup,
         "ms_per_step": step_ms, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
@@ -391,21 +477,35 @@ def b200_arm(args):
                 "timing": "host wall clock around K sdrb_bank_process_host_async calls, two in flight, last result waited for "
                           "(pinned host buffers in and out every step)",
                 "realtime_x": (e2e_value * 1e6 / fs) if e2e_value else None} if e2e_ms is not None else None,
+        "e2e_zmq": zmq_leg,
         "gpu_launches": launches,
+        "parity_ok": verdict["ok"], "parity": dict(verdict, what=lsb_what),
         "roofline": roofline,
-        "roofline_pipeline": {"bound": "hbm", "achieved": plan.alg_bytes * samples_per_step / (step_ms * 1e-3) / 1e9,
-                              "peak": peak, "unit": "GB/s",
-                              "frac": plan.alg_bytes * samples_per_step / (step_ms * 1e-3) / 1e9 / peak,
-                              "alg_bytes_per_sample": plan.alg_bytes,
-                              "fp32": {"achieved_tflops": plan.alg_flops * samples_per_step / (step_ms * 1e-3) / 1e12,
-                                       "peak_tflops": fp32_peak,
-                                       "frac": plan.alg_flops * samples_per_step / (step_ms * 1e-3) / 1e12 / fp32_peak,
-                                       "alg_flops_per_sample": plan.alg_flops,
-                                       "peak_source": fp32_src}},
+        "roofline_pipeline": {"bound": "fp32", "achieved": plan.alg_flops * samples_per_step / (step_ms * 1e-3) / 1e12,
+                              "peak": fp32_peak, "unit": "TFLOP/s",
+                              "frac": plan.alg_flops * samples_per_step / (step_ms * 1e-3) / 1e12 / fp32_peak,
+                              "alg_flops_per_sample": plan.alg_flops, "peak_source": fp32_src,
+                              "hbm": {"achieved": plan.alg_bytes * samples_per_step / (step_ms * 1e-3) / 1e9, "peak": peak,
+                                      "unit": "GB/s", "frac": plan.alg_bytes * samples_per_step / (step_ms * 1e-3) / 1e9 / peak,
+                                      "alg_bytes_per_sample": plan.alg_bytes}},
         "kernels_ms_per_step": per_step_ms,
         "kernel_launches_per_step": launches_per_step,
         "digests": digests,
     }
+    # ---- the other BASELINE.json configurations, short runs (5 steps): value and per-class times ----
+    if world == 1 and not args.no_plans:
+        R.bank.close()
+        del R
+        torch.cuda.empty_cache()
+        extra = {}
+        for name in EXTRA_PLANS:
+            if name == args.plan:
+                continue
+            try:
+                extra[name] = extra_plan(B, torch, shard, name, S, NB, dev, local_rank, peak, fp32_peak, barrier)
+            except Exception as ex:
+                extra[name] = {"error": str(ex)[:200]}
+        line["plans"] = extra
     if world == 1 and not args.no_cpu_baseline:
         try:
             cores = os.cpu_count() or 1
@@ -418,6 +518,122 @@ def b200_arm(args):
     print(json.dumps(line))
     if world > 1:
         dist.destroy_process_group()
+
+
+EXTRA_PLANS = ["54W_288K", "54W_all", "CBAND_143E"]
+
+
+def extra_plan(B, torch, shard, name, S, NB, dev, local_rank, peak, fp32_peak, barrier):
+    """Kernel-only leg of another BASELINE.json configuration: same bank size, 3 warm-up + 5 timed steps. CBAND_143E runs with
+    the spectrum path fed as the reference's GUI would (fftHandlerSlot): "Main" on every 4th callback and one selected
+    sub VFO on every callback, for every receiver of the bank."""
+    plan = B.Plan(os.path.join(ROOT, "plans", name + ".ini"))
+    R = Resident(B, torch, shard, plan, S, NB, dev, local_rank, 0, 1, canary=False)
+    out = {}
+    spec_ms = None
+    if name.startswith("CBAND"):
+        spec_main, spec_sub = B.Spectrum(S, device=local_rank), B.Spectrum(S, device=local_rank)
+        ev = [torch.cuda.Event(enable_timing=True) for _ in range(2)]
+        acc = {"ms": 0.0, "n": 0, "count": [0]}
+
+        def feed():
+            st = R.stream.cuda_stream
+            ev[0].record(R.stream)
+            for cb in range(NB):
+                acc["count"][0] += 1
+                if acc["count"][0] % 4 == 1:                       # sdrj.cpp:296-303: first emit, then every 4th callback
+                    R.bank.spectrum_feed(spec_main, -1, cb, None, st)
+                R.bank.spectrum_feed(spec_sub, 0, cb, None, st)    # vfo.cpp:290-293: the selected VFO, every callback
+            ev[1].record(R.stream)
+        R.after_step = feed
+    dev_ms, launches, per_step_ms, _ = R.timed(5, 3, barrier)
+    if name.startswith("CBAND"):
+        # the feeds of one step, timed on their own after the run
+        torch.cuda.synchronize()
+        R.after_step()
+        torch.cuda.synchronize()
+        spec_ms = ev[0].elapsed_time(ev[1])
+        spec_main.close(); spec_sub.close()
+    step_ms = dev_ms / 5
+    out = {"value": R.samples_per_step / (step_ms * 1e-3) / 1e6, "unit": "MS/s", "ms_per_step": step_ms, "steps": 5, "warmup": 3,
+           "realtime_x": R.samples_per_step / (step_ms * 1e-3) / plan.fs, "kernels_ms_per_step": per_step_ms,
+           "per_class": class_rooflines(plan, per_step_ms, R.samples_per_step, peak, fp32_peak), "gpu_launches": launches}
+    if spec_ms is not None:
+        out["spectrum_feed_ms_per_step"] = spec_ms
+        out["spectrum_feeds_per_step"] = "%d displays x (%d sub-VFO feeds + 1 Main feed)" % (S, NB)
+    R.bank.close()
+    return out
+
+
+def publish_leg(B, plan, bank, host_bufs, row, S, NB, rank, args):
+    """The path's last hop: every callback record of every receiver is sent as the reference does (3 frames per sub VFO:
+    topic, rate, int16 payload) into a SUB socket of this process over ipc. Timed with the host call that produces the
+    records: K steps of process_host_async (two in flight) + sdrb_publisher_send_block for the step that just completed."""
+    import ctypes as C
+    import threading
+    import zmq
+    lib = B.lib()
+    ep = "ipc:///tmp/sdrb_bench_%d_%d" % (os.getpid(), rank)
+    ctx = zmq.Context.instance()
+    sub = ctx.socket(zmq.SUB)
+    sub.setsockopt(zmq.RCVHWM, 0)
+    sub.setsockopt(zmq.SUBSCRIBE, b"")
+    n_rx = [0, 0]
+    stop = [False]
+
+    def drain():
+        while not stop[0]:
+            try:
+                parts = sub.recv_multipart(flags=zmq.NOBLOCK, copy=False)
+                n_rx[0] += 1
+                n_rx[1] += len(parts[2].buffer) if len(parts) == 3 else 0
+            except zmq.Again:
+                time.sleep(0.0002)
+
+    pub = C.c_void_p()
+    B._check(lib.sdrb_publisher_open(ep.encode(), 1, C.byref(pub)), "sdrb_publisher_open")
+    sub.connect(ep)
+    th = threading.Thread(target=drain, daemon=True)
+    th.start()
+    time.sleep(0.3)
+    steps = max(2, min(args.steps, 10))
+    sent = 0
+    step_no = [0]
+
+    def one():
+        i, o = host_bufs[step_no[0] & 1]
+        step_no[0] += 1
+        bank.process_host_async(i, row, NB, o, None)
+        bank.host_wait(1)
+
+    def publish(o):
+        n = 0
+        for s in range(S):
+            for cb in range(NB):
+                rec = o + 2 * (s * NB + cb) * plan.pcm_per_block
+                r = lib.sdrb_publisher_send_block(pub, plan.h, C.c_void_p(rec))
+                if r < 0:
+                    raise RuntimeError("sdrb_publisher_send_block failed")
+                n += r
+        return n
+
+    one()
+    bank.host_wait(0)
+    t0 = time.perf_counter()
+    for k in range(steps):
+        one()                                   # step k+1 is in flight while step k's records are published
+        sent += publish(host_bufs[(step_no[0] - 2) & 1][1])
+    bank.host_wait(0)
+    secs = time.perf_counter() - t0
+    time.sleep(0.5)
+    stop[0] = True
+    th.join(timeout=2)
+    lib.sdrb_publisher_close(pub)
+    sub.close(0)
+    samples = S * NB * plan.block * steps
+    return {"value": samples / secs / 1e6, "unit": "MS/s", "realtime_x": samples / secs / plan.fs, "steps": steps,
+            "messages_sent": sent, "messages_per_s": sent / secs, "messages_received": n_rx[0], "payload_bytes_received": n_rx[1],
+            "transport": "ipc PUB -> SUB in this process, one publisher thread", "ms_per_step": 1e3 * secs / steps}
 
 
 def main():

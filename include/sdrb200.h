@@ -316,6 +316,9 @@ int sdrb_publisher_open(const char *address, int bind, sdrb_publisher **out);
 int sdrb_publisher_send(sdrb_publisher *p, const char *topic, uint32_t rate, const void *payload, uint32_t len);
 /* One multipart message per sub VFO per callback per stream from a process_host result. */
 int sdrb_publisher_send_block(sdrb_publisher *p, const sdrb_plan *plan, const int16_t *h_pcm_record);
+/* Closes socket and context. The reference never closes its sockets (they end with the process, queued frames are
+ * dropped): close() does the same with ZMQ_LINGER 0. Set SDRB_ZMQ_LINGER_MS (milliseconds, -1 = wait for ever, libzmq's
+ * default) before sdrb_publisher_open to let queued frames drain first. */
 void sdrb_publisher_close(sdrb_publisher *p);
 
 /* ---- ingest front ends, host side (the library opens no socket and no dongle) ---- */

@@ -137,7 +137,7 @@ extern "C" long sdrb_plan_copy_table(const sdrb_plan *plan, int kind, int idx, f
         else if (kind == 4) { src = s.hilbert.data(); n = (long)s.hilbert.size(); }
         else { set_error("sdrb_plan_copy_table: unknown kind"); return SDRB_E_INVALID; }
     } else { set_error("sdrb_plan_copy_table: index out of range"); return SDRB_E_INVALID; }
-    if (dst && n > 0) memcpy(dst, src, sizeof(float) * (size_t)(std::min(n, max_elems) * width));
+    if (dst && n > 0 && max_elems > 0) memcpy(dst, src, sizeof(float) * (size_t)(std::min(n, max_elems) * width));
     return n;
 }
 
@@ -265,6 +265,10 @@ struct sdrb_bank {
     bool host_inflight = false, host_inflight_tap = false;       // sdrb_bank_process_host_async calls not yet waited for
     int host_inflight_blocks = 0;
     std::deque<cudaEvent_t> host_calls;                          // one completion event per call in flight, oldest first
+    // end of the last device-resident call (recorded on the caller's stream): a host call that follows waits for it,
+    // its internal streams never see the caller's stream otherwise
+    cudaEvent_t ev_device_tail = nullptr;
+    bool device_tail_pending = false;
     std::vector<std::pair<int, int>> host_groups;      // (first stream, count) of each pipeline group of process_host
     // DC recursion runs on side streams, one callback ahead of the ingest kernel
     static constexpr int kSide = 8;
@@ -293,6 +297,8 @@ extern "C" void sdrb_bank_destroy(sdrb_bank *b) {
     for (cudaEvent_t e : b->ev_out) cudaEventDestroy(e);
     for (cudaEvent_t e : b->ev_done) cudaEventDestroy(e);
     for (cudaEvent_t e : b->tev) cudaEventDestroy(e);
+    for (cudaEvent_t e : b->host_calls) cudaEventDestroy(e);
+    if (b->ev_device_tail) cudaEventDestroy(b->ev_device_tail);
     for (int k = 0; k < sdrb_bank::kSide; k++) {
         if (b->s_dc[k]) cudaStreamDestroy(b->s_dc[k]);
         if (b->ev_entry[k]) cudaEventDestroy(b->ev_entry[k]);
@@ -886,6 +892,9 @@ static int enqueue_all(sdrb_bank *b, CallCtx &c, cudaStream_t st, int *launches,
         b->ev_end_valid[c.par] = true;
     }
     b->dc_par ^= 1;
+    if (!b->ev_device_tail) CU_TRY(cudaEventCreateWithFlags(&b->ev_device_tail, cudaEventDisableTiming));
+    CU_TRY(cudaEventRecord(b->ev_device_tail, st));
+    b->device_tail_pending = true;
     return SDRB_OK;
 }
 
@@ -1215,6 +1224,15 @@ static int host_enqueue(sdrb_bank *b, const uint8_t *h_iq, size_t iq_stride, int
         b->ev_in.push_back(e1); b->ev_done.push_back(e2); b->ev_free.push_back(e3); b->ev_out.push_back(e4);
     }
     const bool chained = b->host_inflight;                  // an earlier call may still be running: honour its events
+    if (b->device_tail_pending) {
+        // a device-resident call on a caller's stream came before this one: its state updates (carry, counters, DC state)
+        // must be complete before any of our internal streams touches the bank
+        CU_TRY(cudaStreamWaitEvent(b->s_copy_in, b->ev_device_tail, 0));
+        CU_TRY(cudaStreamWaitEvent(b->s_compute, b->ev_device_tail, 0));
+        for (int k = 0; k < sdrb_bank::kSide; k++)
+            if (b->s_dc[k]) CU_TRY(cudaStreamWaitEvent(b->s_dc[k], b->ev_device_tail, 0));
+        b->device_tail_pending = false;
+    }
     b->last_launches = 0;
     const size_t cb_in = (size_t)h.block * 2, cb_out = (size_t)h.pcm_per_block;
     const bool dc = h.correct_dc != 0;
@@ -1426,7 +1444,7 @@ extern "C" const char *sdrb_version(void) { return "sdrb200 0.1 (sm_100a)"; }
 extern "C" long sdrb_nco_table(double sample_rate, double frequency, float *dst, long max_entries) {
     if (sample_rate < 1.0) { set_error("sdrb_nco_table: sample_rate < 1"); return SDRB_E_INVALID; }
     const std::vector<cf32> q = nco_table(sample_rate, frequency);
-    if (dst) memcpy(dst, q.data(), sizeof(cf32) * (size_t)std::min<long>((long)q.size(), max_entries));
+    if (dst && max_entries > 0) memcpy(dst, q.data(), sizeof(cf32) * (size_t)std::min<long>((long)q.size(), max_entries));
     return (long)q.size();
 }
 
@@ -1434,7 +1452,7 @@ extern "C" int sdrb_low_pass(double gain, double fs, double cutoff, double tw, f
     std::vector<float> t;
     const int n = low_pass_hamming(gain, fs, cutoff, tw, t);
     if (n < 0) return n;
-    if (taps) memcpy(taps, t.data(), sizeof(float) * (size_t)std::min(n, max_taps));
+    if (taps && max_taps > 0) memcpy(taps, t.data(), sizeof(float) * (size_t)std::min(n, max_taps));
     return n;
 }
 

@@ -807,7 +807,18 @@ __global__ void __launch_bounds__(128) k3_carry(const CarryItem *__restrict__ it
         unsigned char *base = reinterpret_cast<unsigned char *>(it.base) + (size_t)stream * it.stride;
         const uint4 *src = reinterpret_cast<const uint4 *>(base + (size_t)n_blocks * it.block_bytes);
         uint4 *dst = reinterpret_cast<uint4 *>(base);
-        for (int e = threadIdx.x; e < it.hist_bytes / 16; e += 128) dst[e] = src[e];
+        // The tail moves towards the front of the same buffer; with a call shorter than the history the two ranges
+        // overlap. Chunk by chunk in rising order, every chunk read completely before it is written: a later chunk's
+        // source lies above everything written so far, so nothing is clobbered before it has been read.
+        const int n16 = it.hist_bytes / 16;
+        for (int e0 = 0; e0 < n16; e0 += 128) {
+            const int e = e0 + threadIdx.x;
+            uint4 v = make_uint4(0u, 0u, 0u, 0u);
+            if (e < n16) v = src[e];
+            __syncthreads();
+            if (e < n16) dst[e] = v;
+            __syncthreads();
+        }
     } else {
         if (iq) {
             const uint4 *src = reinterpret_cast<const uint4 *>(iq + (size_t)stream * iq_stride + ((size_t)n_blocks * block - RAW_TAIL) * 2);

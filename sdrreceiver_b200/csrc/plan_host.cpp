@@ -179,6 +179,13 @@ static int finish_plan(HostPlan &p) {
         m.n_subs++;
         s.fs = m.out_rate;
         s.block_in = m.out_rate / p.bufsplit;                           // mainwindow.cpp:223
+        // the parent writes block >> decim samples per callback and the sub VFO reads out_rate / bufsplit: the two agree
+        // only if block * bufsplit == sample_rate (true for every ini plan by construction, mainwindow.cpp:67-80)
+        if (s.block_in != m.block_out) {
+            set_error("plan: block * bufsplit must equal sample_rate (sub VFO '" + s.topic + "' would read " +
+                      std::to_string(s.block_in) + " samples per callback, its main VFO writes " + std::to_string(m.block_out) + ")");
+            return SDRB_E_INVALID;
+        }
         if (s.decim < 0 || s.decim > 5 || (s.late != 0 && s.late != 5 && s.late != 6)) {
             set_error("plan: sub VFO '" + s.topic + "' needs 0..5 half-band stages and late in {0,5,6}");
             return SDRB_E_INVALID;

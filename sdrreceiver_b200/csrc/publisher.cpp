@@ -7,6 +7,7 @@
 #include <glob.h>
 
 #include <cstring>
+#include <cstdlib>
 #include <string>
 
 #include "plan.hpp"
@@ -75,8 +76,13 @@ extern "C" int sdrb_publisher_open(const char *address, int bind, sdrb_publisher
     p->ctx = g_zmq.ctx_new();
     p->sock = p->ctx ? g_zmq.socket(p->ctx, kPUB) : nullptr;
     if (!p->sock) { sdrb::set_error("zmq_socket failed"); delete p; return SDRB_E_ZMQ; }
-    // same options, same values as ZmqPublisher::connect (zmqpublisher.cpp:24-37)
-    const int keepalive = 1, cnt = 10, idle = 1, intvl = 1, reconnect = 1000, reconnect_max = 0, linger = 0;
+    // same options, same values as ZmqPublisher::connect (zmqpublisher.cpp:24-37). One addition, documented in
+    // include/sdrb200.h: ZMQ_LINGER. The reference never closes its sockets -- they die with the process and whatever is
+    // still queued is dropped; sdrb_publisher_close() reproduces that with linger 0 unless SDRB_ZMQ_LINGER_MS asks it to
+    // wait (-1 = libzmq's default, wait for ever).
+    const int keepalive = 1, cnt = 10, idle = 1, intvl = 1, reconnect = 1000, reconnect_max = 0;
+    int linger = 0;
+    if (const char *e = getenv("SDRB_ZMQ_LINGER_MS")) linger = atoi(e);
     g_zmq.setsockopt(p->sock, kKEEPALIVE, &keepalive, sizeof(int));
     g_zmq.setsockopt(p->sock, kKEEPALIVE_CNT, &cnt, sizeof(int));
     g_zmq.setsockopt(p->sock, kKEEPALIVE_IDLE, &idle, sizeof(int));

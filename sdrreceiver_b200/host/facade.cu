@@ -257,6 +257,11 @@ void vfo::fftVFOSlot(std::string topic) { emitFFT = (topic == zmqTopic); }
 
 void vfo::init(int spb, bool bind, int late) {
     // vfo.cpp:60-176: sizes and publisher wiring; the DSP objects themselves live in the GPU plan
+    // The BFO mix of vfo.cpp:103,307-313,346-352 (osc_bfo, active when offsetbw > 1) is not built: nothing in the
+    // reference ever calls setOffsetBandwidth, so the branch is dead there. Refuse loudly instead of producing audio
+    // without the mix.
+    if (offsetbw > 1)
+        throw Error("vfo::init: setOffsetBandwidth(>1) selects the BFO mix (vfo.cpp:307-313), which this library does not implement");
     samplesPerBuffer = spb;
     lateDecimate = late;
     int targetRate = (int)(Fs / (pow(2, decimateCount)));
@@ -294,7 +299,18 @@ static void fill_main_desc(sdrb_main_desc &d, double mixer, int decim, const std
     d.compress_style = cstyle == 1 ? 1 : 2;                  // vfo.cpp:393: 1 = 4-bit arms, anything else int8 pairs
 }
 
+// A sub VFO must have been init()ed with exactly what its parent delivers per callback (mainwindow.cpp:134,223 keeps the
+// two equal: buflen/2 >> decimateCount == main_out/bufsplit); the reference would index out of bounds otherwise (vfo.cpp:244).
+static void check_tree_sizes(int Fs, int samplesPerBuffer, int decimateCount, const std::vector<vfo *> *subs, const char *who) {
+    if (samplesPerBuffer <= 0 || Fs % samplesPerBuffer != 0)
+        throw Error(std::string(who) + ": Fs must be a whole multiple of samplesPerBuffer (callbacks per second)");
+    for (size_t i = 0; subs && i < subs->size(); i++)
+        if ((*subs)[i]->getSamplesPerBuffer() != (samplesPerBuffer >> decimateCount))
+            throw Error(std::string(who) + ": a sub VFO was init()ed with a samplesPerBuffer that is not its parent's samplesPerBuffer >> decimateCount");
+}
+
 void vfo::compile_tree() {
+    check_tree_sizes(Fs, samplesPerBuffer, decimateCount, mpVFOs, "vfo");
     sdrb_plan_desc *d = new sdrb_plan_desc();
     memset(d, 0, sizeof(*d));
     d->sample_rate = Fs; d->block = samplesPerBuffer; d->bufsplit = Fs / samplesPerBuffer; d->correct_dc = 0;
@@ -377,6 +393,10 @@ void sdrj::compile_tree(int block) {
     sdrb_plan_desc *d = new sdrb_plan_desc();
     memset(d, 0, sizeof(*d));
     const vfo *m0 = (*mpVFOs)[0];
+    for (const vfo *mv : *mpVFOs) {
+        if (mv->Fs != m0->Fs || mv->samplesPerBuffer != block) { delete d; throw Error("sdrj: every main VFO must be init()ed with the callback size and Fs of the input"); }
+        try { check_tree_sizes(mv->Fs, block, mv->decimateCount, mv->mpVFOs, "sdrj"); } catch (...) { delete d; throw; }
+    }
     d->sample_rate = m0->Fs; d->block = block; d->bufsplit = m0->Fs / block; d->correct_dc = correctDC ? 1 : 0;
     d->n_main = (int)mpVFOs->size();
     if (d->n_main > SDRB_MAX_MAIN) { delete d; throw Error("sdrj: too many main VFOs"); }

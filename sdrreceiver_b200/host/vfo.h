@@ -56,6 +56,7 @@ public:
     // ... and for a childless root: the vfo::compress payload (transmit_iq, vfo.h:69)
     const std::vector<signed char> &lastForward() const { return transmit_iq; }
     uint32_t getOutputRate() const { return outputRate; }
+    int getSamplesPerBuffer() const { return samplesPerBuffer; }
     const std::string &getZmqTopic() const { return zmqTopic; }
 
 private:

@@ -46,6 +46,21 @@ def gather(stats, digest, device=None):
     return torch.stack(ss).cpu().numpy(), [[int(v) for v in t.tolist()] for t in dd]
 
 
+def parity_verdict(digests):
+    """Parity verdict of a run from the gathered per-rank rows:
+        [rank digest (3 ints), canary digest (3 ints), canary max |LSB difference| vs the reference's golden output or -1]
+    The canary is local stream 0 of every rank: identical bytes and history everywhere, so its digest must agree
+    across ranks; every rank's own comparison with the golden file must be within +-1 LSB."""
+    rows = [list(r) for r in digests]
+    canary = [tuple(r[3:6]) for r in rows]
+    lsb = [int(r[6]) for r in rows]
+    equal = all(c == canary[0] for c in canary)
+    checked = all(v >= 0 for v in lsb)
+    within = checked and all(v <= 1 for v in lsb)
+    return {"ok": bool(equal and within), "canary_digests_equal": bool(equal), "ranks": len(rows),
+            "canary_max_lsb_vs_reference": (max(lsb) if checked else None), "checked_against_golden": bool(checked)}
+
+
 def aggregate(stats_all, steps):
     """Whole-job numbers from the gathered rows [device_ms, e2e_ms, samples_per_step]:
     time = max over ranks, samples = sum over ranks."""

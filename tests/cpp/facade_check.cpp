@@ -150,6 +150,30 @@ static int run_vfo(int argc, char **argv) {
     bool threw = false;
     try { VFOsub[0][0]->process(samples); } catch (const sdrb_host::Error &) { threw = true; }
     printf("leaf_process_throws %d\n", threw ? 1 : 0);
+    {
+        // never accept-and-ignore: the BFO mix (vfo.cpp:307-313) is not implemented, init() must say so
+        vfo v;
+        v.setFs(48000); v.setDecimationCount(0); v.setOffsetBandwidth(1500);
+        bool t2 = false;
+        try { v.init(12000, true, 0); } catch (const sdrb_host::Error &) { t2 = true; }
+        printf("bfo_init_throws %d\n", t2 ? 1 : 0);
+    }
+    {
+        // a sub VFO init()ed with a callback size its parent does not deliver (out-of-bounds reads before the check)
+        vfo *main = new vfo, *leaf = new vfo;
+        std::vector<vfo *> subs{leaf};
+        main->setFs(1536000); main->setDecimationCount(2); main->setDemodUSB(false); main->setCompressonStyle(1);
+        main->setZmqAddress(""); main->init(384000, false);
+        leaf->setFs(384000); leaf->setDecimationCount(3); leaf->setZmqTopic("BAD01"); leaf->init(128000, true);
+        main->setVFOs(&subs);
+        std::vector<cpx_typef> x(384000);
+        bool t3 = false;
+        try { main->process(x); } catch (const sdrb_host::Error &) { t3 = true; }
+        printf("mismatched_sub_size_throws %d\n", t3 ? 1 : 0);
+        subs.clear();
+        main->setVFOs(nullptr);
+        delete main; delete leaf;
+    }
     return 0;
 }
 

@@ -22,8 +22,10 @@ def _line(out):
 
 @pytest.mark.skipif(not O.have_ref(), reason="oracle/_ref not built (needs /root/reference once)")
 def test_reference_arm_json_line():
+    # SDRB_LIB points nowhere: the arm must not load the product library at all (it would fail loudly if it tried)
+    env = dict(os.environ, SDRB_LIB="/nonexistent/libsdrb200.so")
     r = subprocess.run([sys.executable, "bench.py", "--impl", "reference", "--steps", "1", "--warmup", "1", "--blocks", "1"],
-                       cwd=ROOT, capture_output=True, text=True, timeout=600)
+                       cwd=ROOT, env=env, capture_output=True, text=True, timeout=600)
     assert r.returncode == 0, r.stderr[-2000:]
     d = _line(r.stdout)
     assert d["impl"] == "reference" and d["unit"] == "MS/s" and d["higher_is_better"] is True

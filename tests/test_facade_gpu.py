@@ -50,6 +50,7 @@ def test_vfo_process_on_a_main_vfo(tmp_path):
     iq.tofile(tmp_path / "iq.u8")
     out = run("vfo", plan_path("25E"), tmp_path / "iq.u8", tmp_path, n_blocks)
     assert out["leaf_process_throws"] == "1"
+    assert out["bfo_init_throws"] == "1" and out["mismatched_sub_size_throws"] == "1"
     sub = dict(op, dc=False, mains=[op["mains"][0]], subs=[dict(s) for s in op["subs"] if s["main"] == 0])
     orc = O.Oracle(sub, main_tap=True)
     orc.process(iq)

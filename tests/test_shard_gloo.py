@@ -54,6 +54,16 @@ def test_world2_sharding_and_gather():
     assert digests == [want0, want1]
 
 
+def test_parity_verdict():
+    ok = [[1, 2, 3, 7, 8, 9, 1], [4, 5, 6, 7, 8, 9, 0]]
+    v = shard.parity_verdict(ok)
+    assert v["ok"] and v["canary_digests_equal"] and v["canary_max_lsb_vs_reference"] == 1 and v["ranks"] == 2
+    assert not shard.parity_verdict([[1, 2, 3, 7, 8, 9, 0], [4, 5, 6, 7, 8, 0, 0]])["ok"]          # one rank's canary differs
+    assert not shard.parity_verdict([[1, 2, 3, 7, 8, 9, 2]])["ok"]                                # off by 2 LSB
+    v = shard.parity_verdict([[1, 2, 3, 7, 8, 9, -1]])                                           # no golden file: not a pass
+    assert not v["ok"] and not v["checked_against_golden"]
+
+
 def test_partition_is_exact():
     for world in (1, 2, 4, 8):
         seen = sorted(g for r in range(world) for g in shard.stream_ids(r, world, 1024 // world))

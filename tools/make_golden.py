@@ -85,6 +85,11 @@ def main():
             "tap_l2": {k: float(np.linalg.norm(v.astype(np.float64))) for k, v in taps.items()},
             "pcm_head": {k: v[:8].tolist() for k, v in outs.items()},
         }
+    # ---- the bench's canary: first callback of stream 0 of the 25E plan from a reset receiver, full int16 ----
+    op, iq = plan_input("25E", 1)
+    outs, _, _ = O.run_ref(os.path.join(ROOT, "plans", "25E.ini"), iq)
+    np.savez_compressed(os.path.join(GOLD, "canary_25E_1block.npz"), input_sha256=np.frombuffer(hashlib.sha256(iq.tobytes()).digest(), np.uint8),
+                        **{"pcm_" + k: v for k, v in outs.items()})
     with open(os.path.join(GOLD, "plan_digests.json"), "w") as f:
         json.dump(dig, f, indent=1, sort_keys=True)
     print("golden written to", GOLD)
