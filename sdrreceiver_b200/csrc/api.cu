@@ -240,6 +240,7 @@ struct sdrb_bank {
     std::vector<K3Params> k3;                     // ... and for the groups that run k2a_v3
     DevBuf k3_rrel;
     bool per_cb = false;                          // SDRB_PER_CB=1: device-resident calls launch every kernel class per callback
+    int dbg_only = 0;                             // SDRB_DEBUG_ONLY=dc|filters: profiling aid, device-resident calls skip the other half (results are then meaningless)
     DevBuf cascdev, rfdev, latedev, usbdev, carry;
     std::vector<SubGroup> groups;
     int n_late = 0, n_usb = 0, n_carry = 0;
@@ -555,6 +556,7 @@ extern "C" int sdrb_bank_create(const sdrb_plan *plan, int device, int n_streams
         const char *ev3 = getenv("SDRB_K2A_V3");
         const bool want_v3 = !(ev3 && atoi(ev3) == 0);
         b->per_cb = getenv("SDRB_PER_CB") && atoi(getenv("SDRB_PER_CB")) != 0;
+        if (const char *e = getenv("SDRB_DEBUG_ONLY")) b->dbg_only = !strcmp(e, "dc") ? 1 : (!strcmp(e, "filters") ? 2 : 0);
         b->k3.assign(b->groups.size(), K3Params{});
         std::vector<float2> rrel(std::max<size_t>(cascdev.size(), 1) * K3_OUT1);
         BANK_TRY(b->k3_rrel.alloc(sizeof(float2) * rrel.size()));
@@ -586,9 +588,9 @@ extern "C" int sdrb_bank_create(const sdrb_plan *plan, int device, int n_streams
             kp.nsw = g.v3_nsw;
         }
         BANK_CU(cudaMemcpy(b->k3_rrel.p, rrel.data(), sizeof(float2) * rrel.size(), cudaMemcpyHostToDevice));
-        BANK_CU(cudaFuncSetAttribute(k2a_v3<2>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)k3_cta_smem_bytes(K3_MAX_VFO, K3_WARPS)));
-        BANK_CU(cudaFuncSetAttribute(k2a_v3<3>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)k3_cta_smem_bytes(K3_MAX_VFO, K3_WARPS)));
-        BANK_CU(cudaFuncSetAttribute(k2a_v3<5>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)k3_cta_smem_bytes(K3_MAX_VFO, K3_WARPS)));
+        BANK_CU(cudaFuncSetAttribute(k2a_v3<2>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)k3_cta_smem_bytes(K3_MAX_VFO, K3_WARPS, 32)));
+        BANK_CU(cudaFuncSetAttribute(k2a_v3<3>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)k3_cta_smem_bytes(K3_MAX_VFO, K3_WARPS, 32)));
+        BANK_CU(cudaFuncSetAttribute(k2a_v3<5>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)k3_cta_smem_bytes(K3_MAX_VFO, K3_WARPS, 32)));
     }
     if (!latedev.empty()) BANK_CU(cudaMemcpy(b->latedev.p, latedev.data(), sizeof(LateDev) * latedev.size(), cudaMemcpyHostToDevice));
     if (!usbdev.empty()) BANK_CU(cudaMemcpy(b->usbdev.p, usbdev.data(), sizeof(UsbDev) * usbdev.size(), cudaMemcpyHostToDevice));
@@ -766,7 +768,7 @@ static int enqueue_subs(sdrb_bank *b, const CallCtx &c, int s0, int ns, cudaStre
             kp.stream0 = s0; kp.stream_end = s0 + ns; kp.b0 = cb0;
             dim3 grid;
             k3_geometry(g, kp, ns, ncb, &grid);
-            const size_t smem = k3_cta_smem_bytes(g.count, K3_WARPS);
+            const size_t smem = k3_cta_smem_bytes(g.count, K3_WARPS, g.v3_nsw * g.count);
             TimedScope t(b, st, 2);
             if (g.v3_maxs == 2) k2a_v3<2><<<grid, K3_WARPS * 32, smem, st>>>(kp);
             else if (g.v3_maxs == 3) k2a_v3<3><<<grid, K3_WARPS * 32, smem, st>>>(kp);
@@ -871,10 +873,17 @@ static int enqueue_all(sdrb_bank *b, CallCtx &c, cudaStream_t st, int *launches,
             CU_TRY(cudaEventRecord(b->ev_entry[0], st));         // everything queued before this call
             CU_TRY(cudaStreamWaitEvent(sd, b->ev_entry[0], 0));
         }
-        for (int cb = 0; cb < c.n_blocks; cb++)
+        for (int cb = 0; cb < c.n_blocks; cb++) {
+            if (b->dbg_only == 2 && b->ev_end_valid[0] && b->ev_end_valid[1]) {      // filters only: reuse the tables of the first two calls
+                CU_TRY(cudaEventRecord(b->ev_dc[0][(size_t)cb], sd));
+                continue;
+            }
             if ((rc = enqueue_dc_cb(b, c, 0, ns, sd, cb, nullptr, b->ev_dc[0][(size_t)cb], launches)) != SDRB_OK) return rc;
+        }
     }
-    if (b->per_cb) {
+    if (b->dbg_only == 1) {
+        for (int cb = 0; cb < c.n_blocks; cb++) CU_TRY(cudaStreamWaitEvent(st, b->ev_dc[0][(size_t)cb], 0));
+    } else if (b->per_cb) {
         for (int cb = 0; cb < c.n_blocks; cb++)
             if ((rc = enqueue_main_cb(b, c, 0, ns, st, cb, dc ? b->ev_dc[0][(size_t)cb] : nullptr, nullptr, launches)) != SDRB_OK)
                 return rc;

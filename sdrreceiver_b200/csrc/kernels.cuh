@@ -454,18 +454,22 @@ __global__ void __launch_bounds__(64) k0_dc_walk(const uint8_t *__restrict__ iq,
         uint2 *to = tab + (size_t)batch * DCW_BATCH * 2;
         bool raw_ready = false;
         int j0 = 0;
+        // exclusive prefix of the block totals, once per batch: a run that restarts at block j0 only rebases it
+        unsigned excl;
+        {
+            unsigned inc = (unsigned)S.D;
+#pragma unroll
+            for (int o = 1; o < 32; o <<= 1) {
+                const unsigned v = __shfl_up_sync(0xffffffffu, inc, o);
+                if (lane >= o) inc += v;
+            }
+            excl = inc - (unsigned)S.D;
+        }
         while (j0 < nb) {
             int n = j0;                                             // block to be handled on its own
             if (V < win) {
                 // ---- speculative run of translations from block j0 ----
-                const unsigned d = lane >= j0 ? (unsigned)S.D : 0u;
-                unsigned inc = d;
-#pragma unroll
-                for (int o = 1; o < 32; o <<= 1) {
-                    const unsigned v = __shfl_up_sync(0xffffffffu, inc, o);
-                    if (lane >= o) inc += v;
-                }
-                const unsigned V0 = V + (inc - d);
+                const unsigned V0 = V + (excl - __shfl_sync(0xffffffffu, excl, j0));
                 const unsigned V1 = V0 - (unsigned)DC_BLK * (unsigned)(lane - j0);
                 const bool ok0 = lane < j0 || V0 < S.ta;
                 const bool ok1 = lane < j0 || (V1 >= S.tb && V1 < S.tb_hi);

@@ -160,10 +160,20 @@ struct K3Hist {
     float2 h2[11], h3[11], h4[11], h5[11];
 };
 
-// Shared memory of a CTA: [rrel: count*64 float2][slot table: K3_MAX_SLOTS ushort][per warp: ring 32 rows + 32 dst pointers]
-K3_HD size_t k3_warp_smem_bytes() { return (size_t)32 * K3_ROW * sizeof(float2) + 32 * sizeof(float2 *); }
-K3_HD size_t k3_cta_smem_bytes(int count, int warps) {
-    return (size_t)count * K3_OUT1 * sizeof(float2) + K3_MAX_SLOTS * sizeof(unsigned short) + (size_t)warps * k3_warp_smem_bytes();
+// Shared memory of a CTA: [rrel: count*64 float2][slot table: K3_MAX_SLOTS ushort][per warp: ring of `rows` rows,
+// 32 dst pointers, 32 table anchors (float2), 32 per-stream table bases (int2)]
+K3_HD size_t k3_warp_smem_bytes(int rows) {
+    return (size_t)rows * K3_ROW * sizeof(float2) + 32 * sizeof(float2 *) + 32 * sizeof(float2) + 32 * sizeof(int2);
+}
+K3_HD size_t k3_cta_smem_bytes(int count, int warps, int rows) {
+    return (size_t)count * K3_OUT1 * sizeof(float2) + K3_MAX_SLOTS * sizeof(unsigned short) + (size_t)warps * k3_warp_smem_bytes(rows);
+}
+K3_HD void k3_prefetch_l1(const void *p) {
+#ifdef __CUDA_ARCH__
+    asm volatile("prefetch.global.L1 [%0];" ::"l"(p));
+#else
+    (void)p;
+#endif
 }
 
 // One warp's work: streams sbase .. sbase+nsw-1, tiles of span `span` of callback b.
@@ -171,8 +181,8 @@ K3_HD size_t k3_cta_smem_bytes(int count, int warps) {
 //   sdst    32 pointers, private to the warp
 //   srrel   the CTA's copy of p.rrel;  stab: slot table (v << 8 | 16-byte chunk), n_slots entries per stream
 template <int MAXS, class Env>
-K3_HD void k3_unit(Env &env, const K3Params &p, int sg, int span, int b, float2 *ring, float2 **sdst, const float2 *srrel,
-                   const unsigned short *stab, int n_slots) {
+K3_HD void k3_unit(Env &env, const K3Params &p, int sg, int span, int b, float2 *ring, float2 **sdst, float2 *sF, int2 *sK,
+                   const float2 *srrel, const unsigned short *stab, int n_slots) {
     const int lane = env.lane;
     const int nv = p.count, nsw = p.nsw, B = p.block_in, L = p.lut_len;
     const int sbase = p.stream0 + sg * nsw;
@@ -192,19 +202,36 @@ K3_HD void k3_unit(Env &env, const K3Params &p, int sg, int span, int b, float2 
         H.h2[i] = make_float2(0.f, 0.f); H.h3[i] = make_float2(0.f, 0.f);
         H.h4[i] = make_float2(0.f, 0.f); H.h5[i] = make_float2(0.f, 0.f);
     }
-    const float2 *myrow = ring + lane * K3_ROW;
+    const float2 *myrow = ring + (rowB ? lane : 0) * K3_ROW;      // lanes without a row read row 0 and store nothing
+    const int SBw = rowB ? SB : 0;
+    // per stream of the warp: table index of callback coordinate 0 and "this callback starts the stream" (oscillator.cpp:26-30)
+    if (lane < nsw) {
+        int kb = 0, zero = 0;
+        if (sbase + lane < p.stream_end) {
+            const long long blk = k3_ldg(p.blocks_done + sbase + lane) + b;
+            kb = (int)((blk * (long long)B) % L);
+            zero = blk == 0;
+        }
+        sK[lane] = make_int2(kb, zero);
+    }
+    env.sync();
+    const float2 *lutB = p.v[rowB ? vB : 0].lut;
+    const int kbB = sK[rowB ? sB : 0].x;
+    auto wrapL = [L](int k) { if (k < 0) k += L; if (k >= L) k -= L; return k; };
+    // the table entry of this row's (stream, VFO) at the first sample of the coming tile, fetched one tile ahead
+    float2 Fpre = k3_ldg(lutB + wrapL(kbB + (t_begin - K3_WARM) * K3_TILE));
 
     for (int t = t_begin - K3_WARM; t < t_end; ++t) {
         const int c0 = t * K3_TILE;                          // callback coordinate of the tile's first sample (may be negative)
+        sF[lane] = Fpre;
+        env.sync();
+        Fpre = k3_ldg(lutB + wrapL(kbB + c0 + K3_TILE));
         // =============================== role A ===============================
         for (int s0 = 0; s0 < nsw; s0 += 2) {
             const int strA = sbase + s0, strB = sbase + s0 + 1;
             const bool hasA = strA < p.stream_end, hasB = (s0 + 1 < nsw) && strB < p.stream_end;
-            const long long nA = hasA ? (k3_ldg(p.blocks_done + strA) + b) * (long long)B + c0 : 0;   // absolute index of sample c0
-            const long long nB = hasB ? (k3_ldg(p.blocks_done + strB) + b) * (long long)B + c0 : nA;
-            int kaA = (int)(nA % L), kaB = (int)(nB % L);
-            if (kaA < 0) kaA += L;
-            if (kaB < 0) kaB += L;
+            const int2 baseA = sK[s0], baseB = sK[hasB ? s0 + 1 : s0];
+            const int kaA = wrapL(baseA.x + c0), kaB = wrapL(baseB.x + c0);      // table index of sample c0
             const bool fastA = c0 != 0 && kaA >= K3_LUT_STEADY + 16 && kaA + K3_TILE + 8 <= L;
             const bool fastB = c0 != 0 && kaB >= K3_LUT_STEADY + 16 && kaB + K3_TILE + 8 <= L;
             const float2 *inA = p.in + (size_t)(hasA ? strA : sbase) * (size_t)p.in_stride + p.hist_in + (long long)b * B + c0 + 4 * lane;
@@ -238,14 +265,9 @@ K3_HD void k3_unit(Env &env, const K3Params &p, int sg, int span, int b, float2 
                     }
                 }
                 const bool sameK = kaA == kaB;
-                float2 FnA = k3_ldg(p.v[0].lut + kaA), FnB = k3_ldg(p.v[0].lut + kaB);
 #pragma unroll 2
                 for (int v = 0; v < nv; ++v) {
-                    const float2 FA = FnA, FB = FnB;
-                    if (v + 1 < nv) {                                    // one VFO ahead
-                        FnA = k3_ldg(p.v[v + 1].lut + kaA);
-                        FnB = k3_ldg(p.v[v + 1].lut + kaB);
-                    }
+                    const float2 FA = sF[s0 * nv + v], FB = sF[(hasB ? s0 + 1 : s0) * nv + v];
                     const float4 rr = *reinterpret_cast<const float4 *>(srrel + v * K3_OUT1 + 2 * lane);
                     const float2 a1 = p.v[v].A[0], a3 = p.v[v].A[1], a5 = p.v[v].A[2];
                     const float2 b1 = p.v[v].Bc[0], b3 = p.v[v].Bc[1], b5 = p.v[v].Bc[2];
@@ -274,7 +296,8 @@ K3_HD void k3_unit(Env &env, const K3Params &p, int sg, int span, int b, float2 
 #pragma unroll 1
                 for (int q = 0; q < 2; ++q) {
                     if (!(q ? hasB : hasA)) continue;
-                    const long long n0 = (q ? nB : nA) + 4 * lane;           // absolute index of sample c0 + 4l
+                    const int k0 = (q ? kaB : kaA) + 4 * lane;               // table index of sample c0 + 4l
+                    const bool zero = (q ? baseB.y : baseA.y) != 0;          // this callback starts the stream
                     const float4 *xp = reinterpret_cast<const float4 *>((q ? inB : inA) - 12);
                     float2 xe[16];                                           // xe[i] = sample c0 + 4l - 12 + i
 #pragma unroll
@@ -292,10 +315,8 @@ K3_HD void k3_unit(Env &env, const K3Params &p, int sg, int span, int b, float2 
                         for (int i = 0; i < 13; ++i) {
                             const int c = c0 + 4 * lane - 10 + i;             // window slot coordinate
                             const int sh = (head && c < 0) ? 1 : 0;           // a slot at a negative coordinate holds sample c - 1
-                            const long long n = n0 - 10 + i - sh;
-                            int k = (int)(n % L);
-                            if (k < 0) k += L;
-                            if (n == 0) k = L - 1;                            // oscillator.cpp:26-30
+                            int k = wrapL(k0 - 10 + i - sh);
+                            if (zero && c - sh == 0) k = L - 1;               // stream sample 0 uses the last entry (oscillator.cpp:26-30)
                             u[i] = k3_cmul(k3_ldg(lut + k), sh ? xe[1 + i] : xe[2 + i]);
                         }
                         const float sc = 1.0f / (float)(1 << p.v[v].S);
@@ -307,6 +328,12 @@ K3_HD void k3_unit(Env &env, const K3Params &p, int sg, int span, int b, float2 
                     }
                 }
             }
+        }
+        // the coming tile's input lines into L1 while role B runs (10 lines of 128 bytes cover 128 + 14 samples)
+        if (t + 1 < t_end) {
+            for (int s = 0; s < nsw && sbase + s < p.stream_end; ++s)
+                if (lane < 10)
+                    k3_prefetch_l1(p.in + (size_t)(sbase + s) * (size_t)p.in_stride + p.hist_in + (long long)b * B + c0 + K3_TILE - 16 + 16 * lane);
         }
         env.sync();
         // =============================== role B ===============================
@@ -326,11 +353,11 @@ K3_HD void k3_unit(Env &env, const K3Params &p, int sg, int span, int b, float2 
                 in[2 * i] = make_float2(v.x, v.y);
                 in[2 * i + 1] = make_float2(v.z, v.w);
             }
-            float2 *wr = ring + lane * K3_ROW;               // outputs go to the front of the row (always behind the read position)
+            float2 *wr = ring + (rowB ? lane : 0) * K3_ROW;  // outputs go to the front of the row (always behind the read position)
             if (MAXS >= 2) {
                 float2 o2[8];
                 k3_stage<16>(H.h2, in, o2);
-                if (SB == 2) {
+                if (SBw == 2) {
 #pragma unroll
                     for (int r = 0; r < 4; ++r)
                         *reinterpret_cast<float4 *>(wr + 8 * sub + 2 * r) = make_float4(o2[2 * r].x, o2[2 * r].y, o2[2 * r + 1].x, o2[2 * r + 1].y);
@@ -338,7 +365,7 @@ K3_HD void k3_unit(Env &env, const K3Params &p, int sg, int span, int b, float2 
                 if (MAXS >= 3) {
                     float2 o3[4];
                     k3_stage<8>(H.h3, o2, o3);
-                    if (SB == 3) {
+                    if (SBw == 3) {
 #pragma unroll
                         for (int r = 0; r < 2; ++r)
                             *reinterpret_cast<float4 *>(wr + 4 * sub + 2 * r) = make_float4(o3[2 * r].x, o3[2 * r].y, o3[2 * r + 1].x, o3[2 * r + 1].y);
@@ -346,11 +373,11 @@ K3_HD void k3_unit(Env &env, const K3Params &p, int sg, int span, int b, float2 
                     if (MAXS >= 4) {
                         float2 o4[2];
                         k3_stage<4>(H.h4, o3, o4);
-                        if (SB == 4) *reinterpret_cast<float4 *>(wr + 2 * sub) = make_float4(o4[0].x, o4[0].y, o4[1].x, o4[1].y);
+                        if (SBw == 4) *reinterpret_cast<float4 *>(wr + 2 * sub) = make_float4(o4[0].x, o4[0].y, o4[1].x, o4[1].y);
                         if (MAXS >= 5) {
                             float2 o5[1];
                             k3_stage<2>(H.h5, o4, o5);
-                            if (SB == 5) wr[sub] = o5[0];
+                            if (SBw == 5) wr[sub] = o5[0];
                         }
                     }
                 }
@@ -401,12 +428,15 @@ __global__ void __launch_bounds__(K3_WARPS * 32, 5) k2a_v3(const __grid_constant
         n_slots += n;
     }
     __syncthreads();
-    float2 *ring = reinterpret_cast<float2 *>(wbase + (size_t)warp * k3_warp_smem_bytes());
-    float2 **sdst = reinterpret_cast<float2 **>(ring + 32 * K3_ROW);
+    const int rows = p.nsw * p.count;
+    float2 *ring = reinterpret_cast<float2 *>(wbase + (size_t)warp * k3_warp_smem_bytes(rows));
+    float2 **sdst = reinterpret_cast<float2 **>(ring + rows * K3_ROW);
+    float2 *sF = reinterpret_cast<float2 *>(sdst + 32);
+    int2 *sK = reinterpret_cast<int2 *>(sF + 32);
     const int sg = blockIdx.x * K3_WARPS + warp;
     if (p.stream0 + sg * p.nsw >= p.stream_end) return;
     K3DevEnv env{lane};
-    k3_unit<MAXS>(env, p, sg, (int)blockIdx.y, p.b0 + (int)blockIdx.z, ring, sdst, srrel, stab, n_slots);
+    k3_unit<MAXS>(env, p, sg, (int)blockIdx.y, p.b0 + (int)blockIdx.z, ring, sdst, sF, sK, srrel, stab, n_slots);
 }
 #endif
 

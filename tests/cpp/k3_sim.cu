@@ -81,14 +81,16 @@ static void run_units(const K3Params &p, int n_cb, int n_spans) {
     for (int cb = 0; cb < n_cb; ++cb)
         for (int span = 0; span < n_spans; ++span)
             for (int sg = 0; sg < n_groups; ++sg) {
-                std::vector<float2> ring((size_t)32 * K3_ROW, make_float2(NAN, NAN));
+                std::vector<float2> ring((size_t)p.nsw * p.count * K3_ROW, make_float2(NAN, NAN));
                 std::vector<float2 *> sdst(32, nullptr);
+                std::vector<float2> sF(32, make_float2(NAN, NAN));
+                std::vector<int2> sK(32, make_int2(0, 0));
                 std::barrier<> bar(32);
                 std::vector<std::thread> th;
                 for (int lane = 0; lane < 32; ++lane)
                     th.emplace_back([&, lane]() {
                         HostEnv env{lane, &bar};
-                        k3_unit<MAXS>(env, p, sg, span, p.b0 + cb, ring.data(), sdst.data(), p.rrel, stab.data(), n_slots);
+                        k3_unit<MAXS>(env, p, sg, span, p.b0 + cb, ring.data(), sdst.data(), sF.data(), sK.data(), p.rrel, stab.data(), n_slots);
                     });
                 for (auto &t : th) t.join();
             }

@@ -138,3 +138,35 @@ def test_whole_plan_bit_identical(name):
         s = by_topic[topic]
         assert rate == s["out_rate"] and nbytes == 2 * s["samples_out"]
     orc.close()
+
+
+@pytest.mark.parametrize("name,n_blocks", [("25E", 16), ("CBAND_143E", 13)])
+def test_whole_plan_bit_identical_over_seconds(name, n_blocks):
+    """The restatement against the unmodified reference over 4 s (25E) / 3.25 s (CBAND_143E) of signal: every
+    Oscillator table wraps three or four times (the tables are one second long), the DC recursion passes its approach
+    and sits in the lock-in regime for the last second or more (it starts from zero; lock-in after about 2.3 s at a
+    bias of 0.5 LSB), and every half-band stage sees 12-15 callback edges. int16, float tap and both main-VFO taps
+    must be bit-identical over the WHOLE run."""
+    ini = plan_path(name)
+    op = OP.build_plan(ini)
+    iq = synth.make_iq(op["Fs"], op["block"] * n_blocks, synth.carriers_for_plan(op["center"], op["subs"]),
+                       level=level_for(op))
+    orc = O.Oracle(op, main_tap=True)
+    orc.process(iq)
+    outs, frames, mains = O.run_ref(ini, iq, main_tap=True)
+    taps, _, _ = O.run_ref(ini, iq, float_tap=True)
+    assert len(frames) == n_blocks * len(op["subs"])
+    for k, s in enumerate(op["subs"]):
+        assert orc.pcm(k).size == n_blocks * s["samples_out"]
+        assert np.array_equal(orc.pcm(k), outs[s["topic"]]), s["topic"]
+        assert np.array_equal(orc.tap(k), taps[s["topic"]]), s["topic"]
+    for k in range(len(op["mains"])):
+        assert np.array_equal(orc.main_tap(k), mains[k])
+    # the DC trace itself: the restatement's per-sample state against what the reference subtracts (its fftData emission
+    # of the DC-corrected input at callback 8 -- well inside the lock-in regime -- pins 8192 consecutive samples)
+    if op["dc"]:
+        emits = O.run_ref(ini, iq, blocks=9, fft="Main")[3]
+        cb, who, buf = [e for e in emits if e[1] == "sdrj"][-1]
+        mine = O.input_samples(iq[: 2 * op["block"] * (cb + 1)], True)[cb * op["block"]: cb * op["block"] + buf.size]
+        assert cb >= 8 and np.array_equal(mine, buf)
+    orc.close()

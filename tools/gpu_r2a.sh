@@ -9,3 +9,6 @@ SDRB_K2A_V3=0 timeout 300 python bench.py --steps 20 --warmup 5 --no-cpu-baselin
 SDRB_K2A_V3=0 SDRB_PER_CB=1 timeout 300 python bench.py --steps 20 --warmup 5 --no-cpu-baseline --no-e2e --no-plans > gpurun_out/a_bench_v2_percb.log 2>&1
 for w in 1480 4440 8880; do SDRB_K3_WARPS=$w timeout 300 python bench.py --steps 20 --warmup 5 --no-cpu-baseline --no-e2e --no-plans > gpurun_out/a_bench_v3_w$w.log 2>&1; done
 tail -3 gpurun_out/a_tests.log
+# DC recursion alone / filters alone (profiling knobs; outputs meaningless)
+SDRB_DEBUG_ONLY=dc timeout 300 python bench.py --steps 20 --warmup 5 --no-cpu-baseline --no-e2e --no-plans > gpurun_out/a_bench_only_dc.log 2>&1
+SDRB_DEBUG_ONLY=filters timeout 300 python bench.py --steps 20 --warmup 5 --no-cpu-baseline --no-e2e --no-plans > gpurun_out/a_bench_only_filters.log 2>&1
