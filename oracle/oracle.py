@@ -194,12 +194,16 @@ def dc_trace(iq_u8, every=32):
     return out.view(np.complex64)
 
 
-def run_ref(ini_path, iq_u8, float_tap=False, main_tap=False, blocks=None, fft=None):
+def run_ref(ini_path, iq_u8, float_tap=False, main_tap=False, blocks=None, fft=None, via=None):
     """Run the unmodified reference on `iq_u8`. Returns (outputs, frames, mains):
     outputs[topic] = int16 (or float32) array, frames = list of (topic_bytes, rate,
     payload_bytes, parts), mains[k] = complex64 decimate[decimateCount] of main k.
     fft="Main" or a sub VFO topic: the combo-box selection; a 4th value is returned, the list of
-    (callback, "sdrj"|"vfo", complex64 buffer) the reference emitted through its fftData signals."""
+    (callback, "sdrj"|"vfo", complex64 buffer) the reference emitted through its fftData signals.
+    via="callback[:N]": the bytes enter through sdr::rtlsdr_callback, N callbacks queued per dispatcher run
+    (jonti/sdr.cpp:100-184); via="rtltcp:S1,S2,..": through sdrj::start_tcp_rtl / sdrj::readyRead with arrivals of
+    S1, S2, .. bytes (sdrj.cpp:31-74,125-166). With `via` a 4th value is returned: {"tcp_tx": bytes the client wrote,
+    "ingest": the harness's one-line report as a dict}."""
     exe = os.path.join(REF_DIR, "sdr_ref_f32" if float_tap else "sdr_ref_i16")
     with tempfile.TemporaryDirectory() as d:
         inp = os.path.join(d, "iq.u8")
@@ -211,6 +215,8 @@ def run_ref(ini_path, iq_u8, float_tap=False, main_tap=False, blocks=None, fft=N
             cmd += ["--blocks", str(blocks)]
         if fft is not None:
             cmd += ["--fft", fft]
+        if via is not None:
+            cmd += ["--via", via]
         subprocess.run(cmd, check=True)
         outs, frames, mains = {}, [], {}
         for fn in sorted(os.listdir(d)):
@@ -222,6 +228,15 @@ def run_ref(ini_path, iq_u8, float_tap=False, main_tap=False, blocks=None, fft=N
             for line in f:
                 t, rate, nb, parts = line.split()
                 frames.append((bytes.fromhex(t), int(rate), int(nb), int(parts)))
+        if via is not None:
+            info = {"tcp_tx": b"", "ingest": {}}
+            if os.path.exists(os.path.join(d, "tcp_tx.bin")):
+                with open(os.path.join(d, "tcp_tx.bin"), "rb") as f:
+                    info["tcp_tx"] = f.read()
+            with open(os.path.join(d, "ingest.txt")) as f:
+                w = f.read().split()
+                info["ingest"] = {w[i]: int(w[i + 1]) for i in range(0, len(w) - 1, 2)}
+            return outs, frames, mains, info
         if fft is not None:
             emits, data, at = [], np.fromfile(os.path.join(d, "fft.cf32"), dtype=np.complex64), 0
             with open(os.path.join(d, "fft.txt")) as f:

@@ -31,7 +31,19 @@
 #include <string>
 #include <vector>
 
+#include <complex>
+#include <cstring>
+#include <cmath>
+#include "qshim_core.h"
+// The two ingest entry points of the reference are private members (sdr::rtlsdr_callback / sdr::demod_dispatcher,
+// jonti/sdr.h:64-79; sdrj::readyRead / sdrj::sendCommand, a private slot and a private member of sdrj.h). The reference's
+// translation units are compiled untouched; only THIS file sees their headers with the access specifiers opened, so
+// that the harness can call what librtlsdr's thread, the dispatcher thread and Qt's event loop call in the application.
+#define private public
+#define protected public
 #include "sdrj.h"
+#undef private
+#undef protected
 
 // ---- moc stand-ins (signals are plain functions once Q_OBJECT is empty) ----
 // With --fft SEL the two fftData signals write what they carry (the spectrum display's input,
@@ -45,11 +57,14 @@ static void fft_emit(const char *who, const std::vector<cpx_typef> &v) {
 }
 void vfo::fftData(const std::vector<cpx_typef> &v) { fft_emit("vfo", v); }
 void sdrj::fftData(const std::vector<cpx_typef> &v) { fft_emit("sdrj", v); }
-void sdr::audio_signal_out(const float *, int) {}
+// MainWindow connects sdr::audio_signal_out to sdrj::demodData (mainwindow.cpp:260)
+static sdrj *g_audio_sink = 0;
+void sdr::audio_signal_out(const float *d, int n) { if (g_audio_sink) g_audio_sink->demodData(d, n); }
 
 // ---- librtlsdr: no device ----
 extern "C" {
-int rtlsdr_open(rtlsdr_dev_t **, uint32_t) { return -1; }
+static bool g_have_dongle = false;
+int rtlsdr_open(rtlsdr_dev_t **, uint32_t) { return g_have_dongle ? 0 : -1; }
 int rtlsdr_close(rtlsdr_dev_t *) { return 0; }
 int rtlsdr_reset_buffer(rtlsdr_dev_t *) { return 0; }
 int rtlsdr_set_sample_rate(rtlsdr_dev_t *, uint32_t) { return 0; }
@@ -126,6 +141,13 @@ int main(int argc, char **argv) {
     long max_blocks = -1, skip_blocks = 0;
     bool main_tap = false, timing = false;
     const char *fft_sel = 0;
+    // --via callback[:N]   bytes enter through sdr::rtlsdr_callback (librtlsdr's thread, jonti/sdr.cpp:100-145), N callbacks
+    //                      (default 1) are queued before the dispatcher (sdr::demod_dispatcher, :147-184) runs until it
+    //                      would sleep; more than 20 queued = the reference drops the rest ("Dropped RTL buffer!!")
+    // --via rtltcp:S1,S2.. bytes enter through the rtl_tcp client (sdrj::start_tcp_rtl / sdrj::readyRead, sdrj.cpp:31-74,
+    //                      125-166): the 12-byte dongle header arrives first, then the stream in pieces of S1, S2, .. bytes
+    //                      (cyclic), one readyRead per arrival; what the client wrote goes to DIR/tcp_tx.bin
+    std::string via;
     for (int i = 1; i < argc; i++) {
         std::string a = argv[i];
         if (a == "--ini" && i + 1 < argc) ini_path = argv[++i];
@@ -136,6 +158,7 @@ int main(int argc, char **argv) {
         else if (a == "--time") timing = true;
         else if (a == "--skip" && i + 1 < argc) skip_blocks = atol(argv[++i]);
         else if (a == "--fft" && i + 1 < argc) fft_sel = argv[++i];
+        else if (a == "--via" && i + 1 < argc) via = argv[++i];
         else { fprintf(stderr, "unknown argument %s\n", argv[i]); return 2; }
     }
     if (!ini_path || !in_path || (!out_dir && !timing)) {
@@ -269,15 +292,8 @@ int main(int argc, char **argv) {
 
     std::vector<float> fl(buflen);
     double seconds = 0;
-    for (long b = 0; b < nblocks; b++) {
-        const unsigned char *src = iq.data() + b * (long)buflen;
-        g_callback = b;
-        auto t0 = std::chrono::steady_clock::now();
-        for (int i = 0; i < buflen; i++) fl[i] = radio->floats.at(src[i]);   // sdr.cpp:122-129
-        radio->demodData(fl.data(), buflen);
-        auto t1 = std::chrono::steady_clock::now();
-        if (b >= skip_blocks) seconds += std::chrono::duration<double>(t1 - t0).count();
-        if (timing) continue;
+    // everything the callbacks published since the last call goes to the files
+    auto flush_outputs = [&]() {
         for (const ZmqMessage &m : g_messages) {
             std::string topic = m.parts.size() > 0 ? m.parts[0] : "";
             unsigned rate = 0;
@@ -291,6 +307,70 @@ int main(int argc, char **argv) {
             if (fp && plen) fwrite(m.parts[2].data(), 1, plen, fp);
         }
         g_messages.clear();
+    };
+    if (via.compare(0, 8, "callback") == 0 && !timing) {
+        // librtlsdr's thread and the dispatcher thread, played in turn by this one thread
+        const int burst = via.size() > 9 ? atoi(via.c_str() + 9) : 1;
+        g_have_dongle = true;
+        g_audio_sink = radio;
+        if (!radio->OpenRtl(0)) { fprintf(stderr, "OpenRtl failed\n"); return 1; }
+        radio->StartRtl(Fs, center_frequency, buflen);             // QtConcurrent::run is inert in the shim: no threads start
+        long b = 0, delivered = 0;
+        while (b < nblocks) {
+            for (int k = 0; k < burst && b < nblocks; k++, b++)
+                radio->rtlsdr_callback(iq.data() + b * (long)buflen, (uint32_t)buflen);
+            try { radio->demod_dispatcher(); } catch (const QShimWouldBlock &) {}
+            delivered += 0;
+            flush_outputs();
+        }
+        FILE *st = fopen((std::string(out_dir) + "/ingest.txt").c_str(), "w");
+        fprintf(st, "callbacks %ld burst %d\n", nblocks, burst);
+        fclose(st);
+    } else if (via.compare(0, 6, "rtltcp") == 0 && !timing) {
+        std::vector<long> sizes;
+        for (const char *q = via.c_str() + (via.size() > 7 ? 7 : via.size()); *q;) {
+            char *e = 0;
+            long v = strtol(q, &e, 10);
+            if (e == q) break;
+            if (v > 0) sizes.push_back(v);
+            q = *e ? e + 1 : e;
+        }
+        if (sizes.empty()) sizes.push_back(65536);
+        qshim_tcp_connect_ok = true;
+        int gain = 14;
+        if (!radio->start_tcp_rtl("127.0.0.1:1234", Fs, center_frequency, gain)) { fprintf(stderr, "start_tcp_rtl failed\n"); return 1; }
+        QTcpSocket *sock = qshim_last_socket;
+        FILE *tx = fopen((std::string(out_dir) + "/tcp_tx.bin").c_str(), "wb");
+        fwrite(sock->tx.data(), 1, sock->tx.size(), tx);
+        fclose(tx);
+        // rtl_tcp greets with "RTL0" + tuner type + gain count (12 bytes), delivered on its own
+        const unsigned char hello[12] = {'R', 'T', 'L', '0', 0, 0, 0, 5, 0, 0, 0, 29};
+        sock->rx.append((const char *)hello, 12);
+        radio->readyRead();
+        long at = 0, total = nblocks * (long)buflen, k = 0, calls = 0;
+        while (at < total) {
+            long n = sizes[(size_t)(k++ % (long)sizes.size())];
+            if (n > total - at) n = total - at;
+            sock->rx.append((const char *)iq.data() + at, (size_t)n);
+            at += n;
+            radio->readyRead();                                       // one signal per arrival
+            calls++;
+            flush_outputs();
+        }
+        FILE *st = fopen((std::string(out_dir) + "/ingest.txt").c_str(), "w");
+        fprintf(st, "arrivals %ld left_in_socket %zu block_bytes %d\n", calls, sock->rx.size(), (int)radio->tcpFloats.size());
+        fclose(st);
+    } else
+    for (long b = 0; b < nblocks; b++) {
+        const unsigned char *src = iq.data() + b * (long)buflen;
+        g_callback = b;
+        auto t0 = std::chrono::steady_clock::now();
+        for (int i = 0; i < buflen; i++) fl[i] = radio->floats.at(src[i]);   // sdr.cpp:122-129
+        radio->demodData(fl.data(), buflen);
+        auto t1 = std::chrono::steady_clock::now();
+        if (b >= skip_blocks) seconds += std::chrono::duration<double>(t1 - t0).count();
+        if (timing) continue;
+        flush_outputs();
         for (size_t k = 0; k < mtap.size(); k++) {
             vfo *mv = VFOmain.at((int)k);
             // getOutRate() == Fs / 2^decimateCount  (vfo.cpp:217-222)

@@ -186,22 +186,41 @@ public:
     void unlock() {}
 };
 
+// The oracle is single-threaded: where the reference's dispatcher thread would go to sleep (jonti/sdr.cpp:152-157:
+// buffers_used == 0), wait() throws instead, so a harness that plays both threads gets control back at exactly that point.
+struct QShimWouldBlock {};
 class QWaitCondition {
 public:
-    bool wait(QMutex *) { return true; }
+    bool wait(QMutex *) { throw QShimWouldBlock(); }
     void wakeAll() {}
 };
 
+// In-memory socket: the harness plays rtl_tcp. Bytes it appends to `rx` are what bytesAvailable()/read()/readAll() see,
+// what the reference write()s collects in `tx`. qshim_tcp_connect_ok decides what waitForConnected() answers and
+// qshim_last_socket points at the socket most recently constructed (sdrj::start_tcp_rtl creates its own, sdrj.cpp:35).
+class QTcpSocket;
+// one instance across translation units (function-local statics of inline functions are shared)
+inline QTcpSocket *&qshim_last_socket_ref() { static QTcpSocket *p = 0; return p; }
+inline bool &qshim_tcp_connect_ok_ref() { static bool v = false; return v; }
+#define qshim_last_socket (qshim_last_socket_ref())
+#define qshim_tcp_connect_ok (qshim_tcp_connect_ok_ref())
 class QTcpSocket : public QObject {
 public:
-    QTcpSocket(QObject * = 0) {}
-    void connectToHost(const QString &, int) {}
-    bool waitForConnected(int) { return false; }
+    std::string rx, tx, host;
+    int port;
+    QTcpSocket(QObject * = 0) : port(0) { qshim_last_socket = this; }
+    void connectToHost(const QString &h, int p) { host = h.toStdString(); port = p; }
+    bool waitForConnected(int) { return qshim_tcp_connect_ok; }
     QString errorString() const { return QString("no network in the oracle"); }
-    qint64 bytesAvailable() const { return 0; }
-    QByteArray readAll() { return QByteArray(); }
-    QByteArray read(qint64) { return QByteArray(); }
-    qint64 write(const QByteArray &) { return 0; }
+    qint64 bytesAvailable() const { return (qint64)rx.size(); }
+    QByteArray readAll() { QByteArray r(rx.data(), (int)rx.size()); rx.clear(); return r; }
+    QByteArray read(qint64 n) {
+        if (n > (qint64)rx.size()) n = (qint64)rx.size();
+        QByteArray r(rx.data(), (int)n);
+        rx.erase(0, (size_t)n);
+        return r;
+    }
+    qint64 write(const QByteArray &b) { tx.append(b.data(), (size_t)b.size()); return b.size(); }
     void disconnectFromHost() {}
 };
 
