@@ -240,6 +240,7 @@ struct sdrb_bank {
     std::vector<K3Params> k3;                     // ... and for the groups that run k2a_v3
     DevBuf k3_rrel;
     bool per_cb = false;                          // SDRB_PER_CB=1: device-resident calls launch every kernel class per callback
+    int dcw_ring = 2;                             // shared-memory ring depth of k0_dc_walk (SDRB_DCW_RING=4: the round-1 size)
     int dbg_only = 0;                             // SDRB_DEBUG_ONLY=dc|filters: profiling aid, device-resident calls skip the other half (results are then meaningless)
     DevBuf cascdev, rfdev, latedev, usbdev, carry;
     std::vector<SubGroup> groups;
@@ -600,7 +601,9 @@ extern "C" int sdrb_bank_create(const sdrb_plan *plan, int device, int n_streams
     b->uv_warp_floats = std::max(UV_IN_FLOATS, 2 * b->uv_eo_rows * UV_ROW);
     b->uv_smem = sizeof(float) * (2 * (size_t)(64 + b->uv_np_max) + (size_t)UV_WARPS * b->uv_warp_floats);
     BANK_CU(cudaFuncSetAttribute(k2b_v2, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)b->uv_smem));
-    BANK_CU(cudaFuncSetAttribute(k0_dc_walk, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)DCW_SMEM));
+    BANK_CU(cudaFuncSetAttribute(k0_dc_walk<2>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)dcw_smem<2>()));
+    BANK_CU(cudaFuncSetAttribute(k0_dc_walk<4>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)dcw_smem<4>()));
+    if (const char *e = getenv("SDRB_DCW_RING")) b->dcw_ring = atoi(e) == 4 ? 4 : 2;
     BANK_CU(cudaFuncSetAttribute(k2_late_v2<5>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)lv_smem<5>()));
     BANK_CU(cudaFuncSetAttribute(k2_late_v2<6>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)lv_smem<6>()));
     BANK_CU(cudaFuncSetAttribute(k2a_v2<64>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)V2L<64>::SMEM));
@@ -711,9 +714,14 @@ static int enqueue_dc_cb(sdrb_bank *b, const CallCtx &c, int s0, int ns, cudaStr
     }
     {
         TimedScope t(b, sd, 0);
-        k0_dc_walk<<<(unsigned)ns, 64, DCW_SMEM, sd>>>(c.d_iq, c.iq_stride, (const DcStats *)b->dc_stats.p, b->dc_stride,
-                                                b->anchor_buf(c.par), (float2 *)b->dc_state.p,
-                                                b->table_buf(c.par), b->dc_stride + DC_HALO_BLKS, cb * per_cb, per_cb, s0);
+        if (b->dcw_ring == 4)
+            k0_dc_walk<4><<<(unsigned)ns, 64, dcw_smem<4>(), sd>>>(c.d_iq, c.iq_stride, (const DcStats *)b->dc_stats.p, b->dc_stride,
+                                                                  b->anchor_buf(c.par), (float2 *)b->dc_state.p, b->table_buf(c.par),
+                                                                  b->dc_stride + DC_HALO_BLKS, cb * per_cb, per_cb, s0);
+        else
+            k0_dc_walk<2><<<(unsigned)ns, 64, dcw_smem<2>(), sd>>>(c.d_iq, c.iq_stride, (const DcStats *)b->dc_stats.p, b->dc_stride,
+                                                                  b->anchor_buf(c.par), (float2 *)b->dc_state.p, b->table_buf(c.par),
+                                                                  b->dc_stride + DC_HALO_BLKS, cb * per_cb, per_cb, s0);
     }
     (*nl) += 2;
     CU_TRY(cudaEventRecord(done, sd));

@@ -379,9 +379,11 @@ __global__ void __launch_bounds__(128) k0_dc_blocks(const uint8_t *__restrict__ 
 // that a straddling block never waits for HBM.
 // Table entry per block and arm: {V, 0|1} (translations / integer solve), {float bits, 2} (stepped).
 constexpr int DCW_BATCH = 32;
-constexpr int DCW_RING = 4;
 constexpr int DCW_SLOT16 = DCW_BATCH * (2 * DC_BLK / 16);                    // uint4 per ring slot
-constexpr size_t DCW_SMEM = (size_t)2 * DCW_RING * DCW_SLOT16 * 16 + 2 * DC_BLK * sizeof(float);
+// Ring depth: the raw bytes of RING batches per arm sit in shared memory (8 KB per batch and arm). Two CTAs of the walk per SM
+// next to the filter kernels is what matters: with four slots (66.5 KB) a walk CTA displaced two of the six k1_v2 CTAs of its SM
+// for as long as it ran; two slots (33.5 KB) cost the walk nothing -- a batch takes thousands of cycles, HBM latency is hundreds.
+template <int RING> constexpr size_t dcw_smem() { return (size_t)2 * RING * DCW_SLOT16 * 16 + 2 * DC_BLK * sizeof(float); }
 
 __device__ __forceinline__ void cp_async16(void *smem, const void *gmem) {
     const unsigned sa = (unsigned)__cvta_generic_to_shared(smem);
@@ -390,6 +392,7 @@ __device__ __forceinline__ void cp_async16(void *smem, const void *gmem) {
 __device__ __forceinline__ void cp_async_commit() { asm volatile("cp.async.commit_group;\n" ::); }
 template <int N> __device__ __forceinline__ void cp_async_wait() { asm volatile("cp.async.wait_group %0;\n" ::"n"(N)); }
 
+template <int DCW_RING>
 __global__ void __launch_bounds__(64) k0_dc_walk(const uint8_t *__restrict__ iq, size_t iq_stride,
                                                   const DcStats *__restrict__ stats, int stats_stride,
                                                   const DcAnchor *__restrict__ anchors, float2 *__restrict__ dc_state,
@@ -439,14 +442,13 @@ __global__ void __launch_bounds__(64) k0_dc_walk(const uint8_t *__restrict__ iq,
         s = arm ? st0.y : st0.x;
         if (A.ok && s * A.sgn > 0.f) V = __float_as_uint(fabsf(s)) - lo1;
     }
-    prefetch(0);
-    prefetch(1);
-    prefetch(2);
+#pragma unroll
+    for (int i = 0; i < DCW_RING - 1; ++i) prefetch(i);
     DcStats Snext = load_stats(0);
     for (int batch = 0; batch < n_batch; ++batch) {
-        cp_async_wait<3>();                                         // the slot about to be refilled has landed (and been consumed)
+        cp_async_wait<DCW_RING - 1>();                              // the slot about to be refilled has landed (and been consumed)
         __syncwarp();
-        prefetch(batch + 3);
+        prefetch(batch + DCW_RING - 1);
         const DcStats S = Snext;
         if (batch + 1 < n_batch) Snext = load_stats(batch + 1);
         const int nb = min(DCW_BATCH, n_blk - batch * DCW_BATCH);
@@ -499,7 +501,7 @@ __global__ void __launch_bounds__(64) k0_dc_walk(const uint8_t *__restrict__ iq,
                 continue;
             }
             if (!raw_ready) {
-                cp_async_wait<3>();                                 // this batch's bytes have landed
+                cp_async_wait<DCW_RING - 1>();                      // this batch's bytes have landed
                 __syncwarp();
                 raw_ready = true;
             }

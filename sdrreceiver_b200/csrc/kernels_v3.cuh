@@ -31,6 +31,7 @@
 #include <cuda_runtime.h>
 #include <stdint.h>
 #include <math.h>
+#include <string.h>
 
 namespace sdrb {
 
@@ -163,10 +164,24 @@ struct K3Hist {
 // Shared memory of a CTA: [rrel: count*64 float2][slot table: K3_MAX_SLOTS ushort][per warp: ring of `rows` rows,
 // 32 dst pointers, 32 table anchors (float2), 32 per-stream table bases (int2)]
 K3_HD size_t k3_warp_smem_bytes(int rows) {
-    return (size_t)rows * K3_ROW * sizeof(float2) + 32 * sizeof(float2 *) + 32 * sizeof(float2) + 32 * sizeof(int2);
+    return (size_t)rows * K3_ROW * sizeof(float2) + 32 * sizeof(float2 *) + 64 * sizeof(float2) + 32 * sizeof(int2);
 }
 K3_HD size_t k3_cta_smem_bytes(int count, int warps, int rows) {
     return (size_t)count * K3_OUT1 * sizeof(float2) + K3_MAX_SLOTS * sizeof(unsigned short) + (size_t)warps * k3_warp_smem_bytes(rows);
+}
+// 8 bytes global -> shared without passing through a register (LDGSTS); k3_async_wait() makes them visible to the issuing thread
+K3_HD void k3_async_copy8(void *smem, const void *gmem) {
+#ifdef __CUDA_ARCH__
+    const unsigned sa = (unsigned)__cvta_generic_to_shared(smem);
+    asm volatile("cp.async.ca.shared.global [%0], [%1], 8;\n" ::"r"(sa), "l"(gmem));
+#else
+    memcpy(smem, gmem, 8);
+#endif
+}
+K3_HD void k3_async_wait() {
+#ifdef __CUDA_ARCH__
+    asm volatile("cp.async.wait_all;\n" ::: "memory");
+#endif
 }
 K3_HD void k3_prefetch_l1(const void *p) {
 #ifdef __CUDA_ARCH__
@@ -218,14 +233,24 @@ K3_HD void k3_unit(Env &env, const K3Params &p, int sg, int span, int b, float2 
     const float2 *lutB = p.v[rowB ? vB : 0].lut;
     const int kbB = sK[rowB ? sB : 0].x;
     auto wrapL = [L](int k) { if (k < 0) k += L; if (k >= L) k -= L; return k; };
-    // the table entry of this row's (stream, VFO) at the first sample of the coming tile, fetched one tile ahead
-    float2 Fpre = k3_ldg(lutB + wrapL(kbB + (t_begin - K3_WARM) * K3_TILE));
+    // the table entry of this row's (stream, VFO) at the first sample of a tile travels global -> shared one tile ahead
+    // (sF is two buffers of 32 entries): no register holds it while the previous tile is being worked on
+    k3_async_copy8(sF + lane, lutB + wrapL(kbB + (t_begin - K3_WARM) * K3_TILE));
+    int fpar = 0;
 
     for (int t = t_begin - K3_WARM; t < t_end; ++t) {
         const int c0 = t * K3_TILE;                          // callback coordinate of the tile's first sample (may be negative)
-        sF[lane] = Fpre;
+        k3_async_wait();
         env.sync();
-        Fpre = k3_ldg(lutB + wrapL(kbB + c0 + K3_TILE));
+        const float2 *sFt = sF + 32 * fpar;                  // this tile's anchors
+        fpar ^= 1;
+        k3_async_copy8(sF + 32 * fpar + lane, lutB + wrapL(kbB + c0 + K3_TILE));
+        // the coming tile's input lines into L1 (10 lines of 128 bytes cover 128 + 14 samples): they have this whole tile to arrive
+        if (t + 1 < t_end) {
+            for (int s = 0; s < nsw && sbase + s < p.stream_end; ++s)
+                if (lane < 10)
+                    k3_prefetch_l1(p.in + (size_t)(sbase + s) * (size_t)p.in_stride + p.hist_in + (long long)b * B + c0 + K3_TILE - 16 + 16 * lane);
+        }
         // =============================== role A ===============================
         for (int s0 = 0; s0 < nsw; s0 += 2) {
             const int strA = sbase + s0, strB = sbase + s0 + 1;
@@ -236,7 +261,7 @@ K3_HD void k3_unit(Env &env, const K3Params &p, int sg, int span, int b, float2 
             const bool fastB = c0 != 0 && kaB >= K3_LUT_STEADY + 16 && kaB + K3_TILE + 8 <= L;
             const float2 *inA = p.in + (size_t)(hasA ? strA : sbase) * (size_t)p.in_stride + p.hist_in + (long long)b * B + c0 + 4 * lane;
             const float2 *inB = p.in + (size_t)(hasB ? strB : sbase) * (size_t)p.in_stride + p.hist_in + (long long)b * B + c0 + 4 * lane;
-            if (fastA && fastB) {
+            if (env.all(fastA && fastB)) {              // a vote: the compiler then knows the branch (and the VFO loop in it) is warp-uniform
                 // ---- sums and differences, once for all VFOs ----
                 // x[i] = sample c0 + 4l - 10 + i; outputs m' = 0, 1 have centres i = 5, 7
                 float2 cen[2][2], sm[2][2][3], df[2][2][3];          // [stream][output][d]
@@ -264,29 +289,55 @@ K3_HD void k3_unit(Env &env, const K3Params &p, int sg, int span, int b, float2 
                         }
                     }
                 }
-                const bool sameK = kaA == kaB;
+                const bool sameK = env.all(kaA == kaB);
+                // software pipeline: the rotation-table pair and the anchors of VFO v+1 are fetched while VFO v is computed
+                float4 rr_n = *reinterpret_cast<const float4 *>(srrel + 2 * lane);
+                float2 FA_n = sFt[s0 * nv], FB_n = sFt[(hasB ? s0 + 1 : s0) * nv];
 #pragma unroll 2
                 for (int v = 0; v < nv; ++v) {
-                    const float2 FA = sF[s0 * nv + v], FB = sF[(hasB ? s0 + 1 : s0) * nv + v];
-                    const float4 rr = *reinterpret_cast<const float4 *>(srrel + v * K3_OUT1 + 2 * lane);
+                    const float4 rr = rr_n;
+                    const float2 FA = FA_n, FB = FB_n;
+                    if (v + 1 < nv) {
+                        rr_n = *reinterpret_cast<const float4 *>(srrel + (v + 1) * K3_OUT1 + 2 * lane);
+                        FA_n = sFt[s0 * nv + v + 1];
+                        FB_n = sFt[(hasB ? s0 + 1 : s0) * nv + v + 1];
+                    }
                     const float2 a1 = p.v[v].A[0], a3 = p.v[v].A[1], a5 = p.v[v].A[2];
                     const float2 b1 = p.v[v].Bc[0], b3 = p.v[v].Bc[1], b5 = p.v[v].Bc[2];
-                    const float2 G0 = k3_cmul(FA, make_float2(rr.x, rr.y)), G1 = k3_cmul(FA, make_float2(rr.z, rr.w));
-                    float2 H0 = G0, H1 = G1;
-                    if (!sameK) { H0 = k3_cmul(FB, make_float2(rr.x, rr.y)); H1 = k3_cmul(FB, make_float2(rr.z, rr.w)); }
+                    float2 G[2][2];                                      // [stream][output]
+                    G[0][0] = k3_cmul(FA, make_float2(rr.x, rr.y));
+                    G[0][1] = k3_cmul(FA, make_float2(rr.z, rr.w));
+                    G[1][0] = G[0][0]; G[1][1] = G[0][1];
+                    if (!sameK) { G[1][0] = k3_cmul(FB, make_float2(rr.x, rr.y)); G[1][1] = k3_cmul(FB, make_float2(rr.z, rr.w)); }
+                    // the four outputs (2 streams x 2) advance together, tap by tap: four independent FFMA2 chains
+                    float2 acc[2][2];
+#pragma unroll
+                    for (int q = 0; q < 2; ++q)
+#pragma unroll
+                        for (int m = 0; m < 2; ++m) acc[q][m] = k3_fma(a1, sm[q][m][0], cen[q][m]);
+#pragma unroll
+                    for (int q = 0; q < 2; ++q)
+#pragma unroll
+                        for (int m = 0; m < 2; ++m) acc[q][m] = k3_fma(b1, df[q][m][0], acc[q][m]);
+#pragma unroll
+                    for (int q = 0; q < 2; ++q)
+#pragma unroll
+                        for (int m = 0; m < 2; ++m) acc[q][m] = k3_fma(a3, sm[q][m][1], acc[q][m]);
+#pragma unroll
+                    for (int q = 0; q < 2; ++q)
+#pragma unroll
+                        for (int m = 0; m < 2; ++m) acc[q][m] = k3_fma(b3, df[q][m][1], acc[q][m]);
+#pragma unroll
+                    for (int q = 0; q < 2; ++q)
+#pragma unroll
+                        for (int m = 0; m < 2; ++m) acc[q][m] = k3_fma(a5, sm[q][m][2], acc[q][m]);
+#pragma unroll
+                    for (int q = 0; q < 2; ++q)
+#pragma unroll
+                        for (int m = 0; m < 2; ++m) acc[q][m] = k3_fma(b5, df[q][m][2], acc[q][m]);
 #pragma unroll
                     for (int q = 0; q < 2; ++q) {
-                        float2 acc[2];
-#pragma unroll
-                        for (int m = 0; m < 2; ++m) {
-                            float2 a = k3_fma(a1, sm[q][m][0], cen[q][m]);
-                            a = k3_fma(b1, df[q][m][0], a);
-                            a = k3_fma(a3, sm[q][m][1], a);
-                            a = k3_fma(b3, df[q][m][1], a);
-                            a = k3_fma(a5, sm[q][m][2], a);
-                            acc[m] = k3_fma(b5, df[q][m][2], a);
-                        }
-                        const float2 o0 = k3_cmul(q ? H0 : G0, acc[0]), o1 = k3_cmul(q ? H1 : G1, acc[1]);
+                        const float2 o0 = k3_cmul(G[q][0], acc[q][0]), o1 = k3_cmul(G[q][1], acc[q][1]);
                         if (q ? hasB : hasA)
                             *reinterpret_cast<float4 *>(ring + ((s0 + q) * nv + v) * K3_ROW + 2 * lane) = make_float4(o0.x, o0.y, o1.x, o1.y);
                     }
@@ -328,12 +379,6 @@ K3_HD void k3_unit(Env &env, const K3Params &p, int sg, int span, int b, float2 
                     }
                 }
             }
-        }
-        // the coming tile's input lines into L1 while role B runs (10 lines of 128 bytes cover 128 + 14 samples)
-        if (t + 1 < t_end) {
-            for (int s = 0; s < nsw && sbase + s < p.stream_end; ++s)
-                if (lane < 10)
-                    k3_prefetch_l1(p.in + (size_t)(sbase + s) * (size_t)p.in_stride + p.hist_in + (long long)b * B + c0 + K3_TILE - 16 + 16 * lane);
         }
         env.sync();
         // =============================== role B ===============================
@@ -407,6 +452,7 @@ K3_HD void k3_unit(Env &env, const K3Params &p, int sg, int span, int b, float2 
 struct K3DevEnv {
     int lane;
     __device__ __forceinline__ void sync() { __syncwarp(); }
+    __device__ __forceinline__ bool all(bool v) { return __all_sync(0xffffffffu, v) != 0; }
 };
 
 constexpr int K3_WARPS = 2;                                 // independent warps per CTA (they only share the read-only tables)
@@ -432,7 +478,7 @@ __global__ void __launch_bounds__(K3_WARPS * 32, 5) k2a_v3(const __grid_constant
     float2 *ring = reinterpret_cast<float2 *>(wbase + (size_t)warp * k3_warp_smem_bytes(rows));
     float2 **sdst = reinterpret_cast<float2 **>(ring + rows * K3_ROW);
     float2 *sF = reinterpret_cast<float2 *>(sdst + 32);
-    int2 *sK = reinterpret_cast<int2 *>(sF + 32);
+    int2 *sK = reinterpret_cast<int2 *>(sF + 64);
     const int sg = blockIdx.x * K3_WARPS + warp;
     if (p.stream0 + sg * p.nsw >= p.stream_end) return;
     K3DevEnv env{lane};

@@ -20,6 +20,7 @@ struct HostEnv {
     int lane;
     std::barrier<> *bar;
     void sync() { bar->arrive_and_wait(); }
+    bool all(bool v) { return v; }                 // every lane evaluates the same warp-uniform condition
 };
 
 // ---- reference: one sub VFO front end over n_cb callbacks of B samples, state carried across ----
@@ -83,7 +84,7 @@ static void run_units(const K3Params &p, int n_cb, int n_spans) {
             for (int sg = 0; sg < n_groups; ++sg) {
                 std::vector<float2> ring((size_t)p.nsw * p.count * K3_ROW, make_float2(NAN, NAN));
                 std::vector<float2 *> sdst(32, nullptr);
-                std::vector<float2> sF(32, make_float2(NAN, NAN));
+                std::vector<float2> sF(64, make_float2(NAN, NAN));
                 std::vector<int2> sK(32, make_int2(0, 0));
                 std::barrier<> bar(32);
                 std::vector<std::thread> th;
