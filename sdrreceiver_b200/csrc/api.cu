@@ -589,9 +589,9 @@ extern "C" int sdrb_bank_create(const sdrb_plan *plan, int device, int n_streams
             kp.nsw = g.v3_nsw;
         }
         BANK_CU(cudaMemcpy(b->k3_rrel.p, rrel.data(), sizeof(float2) * rrel.size(), cudaMemcpyHostToDevice));
-        BANK_CU(cudaFuncSetAttribute(k2a_v3<2>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)k3_cta_smem_bytes(K3_MAX_VFO, K3_WARPS, 32)));
-        BANK_CU(cudaFuncSetAttribute(k2a_v3<3>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)k3_cta_smem_bytes(K3_MAX_VFO, K3_WARPS, 32)));
-        BANK_CU(cudaFuncSetAttribute(k2a_v3<5>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)k3_cta_smem_bytes(K3_MAX_VFO, K3_WARPS, 32)));
+        BANK_CU(cudaFuncSetAttribute(k2a_v3<2>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)k3_cta_smem_bytes(K3_MAX_VFO, K3_WARPS, 32, 8)));
+        BANK_CU(cudaFuncSetAttribute(k2a_v3<3>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)k3_cta_smem_bytes(K3_MAX_VFO, K3_WARPS, 32, 8)));
+        BANK_CU(cudaFuncSetAttribute(k2a_v3<5>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)k3_cta_smem_bytes(K3_MAX_VFO, K3_WARPS, 32, 8)));
     }
     if (!latedev.empty()) BANK_CU(cudaMemcpy(b->latedev.p, latedev.data(), sizeof(LateDev) * latedev.size(), cudaMemcpyHostToDevice));
     if (!usbdev.empty()) BANK_CU(cudaMemcpy(b->usbdev.p, usbdev.data(), sizeof(UsbDev) * usbdev.size(), cudaMemcpyHostToDevice));
@@ -776,7 +776,7 @@ static int enqueue_subs(sdrb_bank *b, const CallCtx &c, int s0, int ns, cudaStre
             kp.stream0 = s0; kp.stream_end = s0 + ns; kp.b0 = cb0;
             dim3 grid;
             k3_geometry(g, kp, ns, ncb, &grid);
-            const size_t smem = k3_cta_smem_bytes(g.count, K3_WARPS, g.v3_nsw * g.count);
+            const size_t smem = k3_cta_smem_bytes(g.count, K3_WARPS, g.v3_nsw * g.count, g.v3_nsw);
             TimedScope t(b, st, 2);
             if (g.v3_maxs == 2) k2a_v3<2><<<grid, K3_WARPS * 32, smem, st>>>(kp);
             else if (g.v3_maxs == 3) k2a_v3<3><<<grid, K3_WARPS * 32, smem, st>>>(kp);
