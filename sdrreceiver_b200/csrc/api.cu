@@ -240,6 +240,7 @@ struct sdrb_bank {
     std::vector<K3Params> k3;                     // ... and for the groups that run k2a_v3
     DevBuf k3_rrel;
     bool per_cb = false;                          // SDRB_PER_CB=1: device-resident calls launch every kernel class per callback
+    int k3_regs5 = 168;                           // register cap of the 5-stage k2a_v3 instantiation (SDRB_K3_REGS=168|200|232)
     int dcw_ring = 2;                             // shared-memory ring depth of k0_dc_walk (SDRB_DCW_RING=4: the round-1 size)
     int dbg_only = 0;                             // SDRB_DEBUG_ONLY=dc|filters: profiling aid, device-resident calls skip the other half (results are then meaningless)
     DevBuf cascdev, rfdev, latedev, usbdev, carry;
@@ -589,9 +590,10 @@ extern "C" int sdrb_bank_create(const sdrb_plan *plan, int device, int n_streams
             kp.nsw = g.v3_nsw;
         }
         BANK_CU(cudaMemcpy(b->k3_rrel.p, rrel.data(), sizeof(float2) * rrel.size(), cudaMemcpyHostToDevice));
-        BANK_CU(cudaFuncSetAttribute(k2a_v3<2>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)k3_cta_smem_bytes(K3_MAX_VFO, K3_WARPS, 32, 8)));
-        BANK_CU(cudaFuncSetAttribute(k2a_v3<3>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)k3_cta_smem_bytes(K3_MAX_VFO, K3_WARPS, 32, 8)));
-        BANK_CU(cudaFuncSetAttribute(k2a_v3<5>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)k3_cta_smem_bytes(K3_MAX_VFO, K3_WARPS, 32, 8)));
+#define K3_ATTR(S_, R_) BANK_CU((cudaFuncSetAttribute(k2a_v3<S_, R_>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)k3_cta_smem_bytes(K3_MAX_VFO, K3_WARPS, 32))))
+        K3_ATTR(2, 168); K3_ATTR(3, 168); K3_ATTR(5, 168); K3_ATTR(5, 200); K3_ATTR(5, 232);
+#undef K3_ATTR
+        if (const char *e = getenv("SDRB_K3_REGS")) { const int v = atoi(e); if (v == 168 || v == 200 || v == 232) b->k3_regs5 = v; }
     }
     if (!latedev.empty()) BANK_CU(cudaMemcpy(b->latedev.p, latedev.data(), sizeof(LateDev) * latedev.size(), cudaMemcpyHostToDevice));
     if (!usbdev.empty()) BANK_CU(cudaMemcpy(b->usbdev.p, usbdev.data(), sizeof(UsbDev) * usbdev.size(), cudaMemcpyHostToDevice));
@@ -776,11 +778,13 @@ static int enqueue_subs(sdrb_bank *b, const CallCtx &c, int s0, int ns, cudaStre
             kp.stream0 = s0; kp.stream_end = s0 + ns; kp.b0 = cb0;
             dim3 grid;
             k3_geometry(g, kp, ns, ncb, &grid);
-            const size_t smem = k3_cta_smem_bytes(g.count, K3_WARPS, g.v3_nsw * g.count, g.v3_nsw);
+            const size_t smem = k3_cta_smem_bytes(g.count, K3_WARPS, g.v3_nsw * g.count);
             TimedScope t(b, st, 2);
-            if (g.v3_maxs == 2) k2a_v3<2><<<grid, K3_WARPS * 32, smem, st>>>(kp);
-            else if (g.v3_maxs == 3) k2a_v3<3><<<grid, K3_WARPS * 32, smem, st>>>(kp);
-            else k2a_v3<5><<<grid, K3_WARPS * 32, smem, st>>>(kp);
+            if (g.v3_maxs == 2) k2a_v3<2, 168><<<grid, K3_WARPS * 32, smem, st>>>(kp);
+            else if (g.v3_maxs == 3) k2a_v3<3, 168><<<grid, K3_WARPS * 32, smem, st>>>(kp);
+            else if (b->k3_regs5 == 232) k2a_v3<5, 232><<<grid, K3_WARPS * 32, smem, st>>>(kp);
+            else if (b->k3_regs5 == 200) k2a_v3<5, 200><<<grid, K3_WARPS * 32, smem, st>>>(kp);
+            else k2a_v3<5, 168><<<grid, K3_WARPS * 32, smem, st>>>(kp);
             (*nl)++;
             continue;
         }

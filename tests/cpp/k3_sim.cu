@@ -86,13 +86,12 @@ static void run_units(const K3Params &p, int n_cb, int n_spans) {
                 std::vector<float2 *> sdst(32, nullptr);
                 std::vector<float2> sF(64, make_float2(NAN, NAN));
                 std::vector<int2> sK(32, make_int2(0, 0));
-                std::vector<float2> sX((size_t)p.nsw * K3_XS, make_float2(NAN, NAN));
                 std::barrier<> bar(32);
                 std::vector<std::thread> th;
                 for (int lane = 0; lane < 32; ++lane)
                     th.emplace_back([&, lane]() {
                         HostEnv env{lane, &bar};
-                        k3_unit<MAXS>(env, p, sg, span, p.b0 + cb, ring.data(), sdst.data(), sF.data(), sK.data(), sX.data(), p.rrel, stab.data(), n_slots);
+                        k3_unit<MAXS>(env, p, sg, span, p.b0 + cb, ring.data(), sdst.data(), sF.data(), sK.data(), p.rrel, stab.data(), n_slots);
                     });
                 for (auto &t : th) t.join();
             }
