@@ -223,13 +223,14 @@ struct sdrb_bank {
     // state
     DevBuf blocks_done, dc_state, raw_tail, cf_tail;
     // work
-    DevBuf dc_anchor, dc_stats, dc_table, main_out, zbuf, dbuf;
+    DevBuf dc_anchor, dc_stats, dc_table, dc_qtab, main_out, zbuf, dbuf;
     int dc_stride = 0;                      // DC blocks (of 32 samples) per stream in dc_stats; table has DC_HALO_BLKS more
     // dc_anchor and dc_table exist twice and alternate from call to call: the DC pre-pass of call
     // n+1 (side stream) may then run while the filters of call n still read call n's table.
     int dc_par = 0;                         // buffer the NEXT call writes
     cudaEvent_t ev_end[2] = {nullptr, nullptr};   // end of the last call that used buffer 0 / 1
     bool ev_end_valid[2] = {false, false};
+    int *qtab_buf(int par) const { return (int *)dc_qtab.p + (size_t)par * 512 * (size_t)n_streams; }
     DcAnchor *anchor_buf(int par) const { return (DcAnchor *)dc_anchor.p + (size_t)par * 2 * (size_t)n_streams; }
     uint2 *table_buf(int par) const { return (uint2 *)dc_table.p + (size_t)par * 2 * (size_t)n_streams * (size_t)(dc_stride + DC_HALO_BLKS); }
     // descriptors
@@ -240,7 +241,7 @@ struct sdrb_bank {
     std::vector<K3Params> k3;                     // ... and for the groups that run k2a_v3
     DevBuf k3_rrel;
     bool per_cb = false;                          // SDRB_PER_CB=1: device-resident calls launch every kernel class per callback
-    int k3_regs5 = 168;                           // register cap of the 5-stage k2a_v3 instantiation (SDRB_K3_REGS=168|200|232)
+    int k3_regs5 = 232;                           // register cap of the 5-stage k2a_v3 instantiation (SDRB_K3_REGS=168|200|232)
     int dcw_ring = 2;                             // shared-memory ring depth of k0_dc_walk (SDRB_DCW_RING=4: the round-1 size)
     int dbg_only = 0;                             // SDRB_DEBUG_ONLY=dc|filters: profiling aid, device-resident calls skip the other half (results are then meaningless)
     DevBuf cascdev, rfdev, latedev, usbdev, carry;
@@ -291,7 +292,7 @@ extern "C" void sdrb_bank_destroy(sdrb_bank *b) {
     if (!b) return;
     cudaSetDevice(b->device);
     cudaDeviceSynchronize();                                 // asynchronous host calls may still be in flight
-    DevBuf *all[] = {&b->luts, &b->taps, &b->blocks_done, &b->dc_state, &b->raw_tail, &b->cf_tail, &b->dc_anchor, &b->dc_stats, &b->dc_table,
+    DevBuf *all[] = {&b->luts, &b->taps, &b->blocks_done, &b->dc_state, &b->raw_tail, &b->cf_tail, &b->dc_anchor, &b->dc_stats, &b->dc_table, &b->dc_qtab,
                      &b->main_out, &b->zbuf, &b->dbuf, &b->cascdev, &b->rfdev, &b->latedev, &b->usbdev, &b->carry,
                      &b->d_iq, &b->d_pcm, &b->d_tap, &b->d_cf, &b->d_fwd, &b->k3_rrel};
     for (DevBuf *d : all) d->release();
@@ -387,6 +388,7 @@ extern "C" int sdrb_bank_create(const sdrb_plan *plan, int device, int n_streams
     // ---- work buffers ----
     b->dc_stride = max_blocks * (h.block / DC_BLK);
     BANK_TRY(b->dc_anchor.alloc(2 * sizeof(DcAnchor) * 2 * (size_t)n_streams));
+    BANK_TRY(b->dc_qtab.alloc(2 * sizeof(int) * 512 * (size_t)n_streams));
     BANK_TRY(b->dc_stats.alloc(h.correct_dc ? sizeof(DcStats) * 2 * (size_t)n_streams * (size_t)b->dc_stride + 1024 : 16));
     BANK_TRY(b->dc_table.alloc(h.correct_dc ? 2 * sizeof(uint2) * 2 * (size_t)n_streams * (size_t)(b->dc_stride + DC_HALO_BLKS) : 64));
     {
@@ -706,23 +708,24 @@ static int enqueue_dc_cb(sdrb_bank *b, const CallCtx &c, int s0, int ns, cudaStr
         TimedScope t(b, sd, 0);
         k0_dc_anchor<<<(unsigned)((2 * ns + 127) / 128), 128, 0, sd>>>((const float2 *)b->dc_state.p,
                                                                       b->anchor_buf(c.par), ns, s0);
-        (*nl)++;
+        k0_dc_qtab<<<(unsigned)(2 * ns), 256, 0, sd>>>(b->anchor_buf(c.par), b->qtab_buf(c.par), s0);
+        (*nl) += 2;
     }
     {
         TimedScope t(b, sd, 0);
         k0_dc_blocks<<<dim3((unsigned)((per_cb + 127) / 128), (unsigned)ns), 128, 0, sd>>>(
-            c.d_iq, c.iq_stride, b->anchor_buf(c.par), (DcStats *)b->dc_stats.p, b->dc_stride, cb * per_cb,
+            c.d_iq, c.iq_stride, b->anchor_buf(c.par), b->qtab_buf(c.par), (DcStats *)b->dc_stats.p, b->dc_stride, cb * per_cb,
             per_cb, s0);
     }
     {
         TimedScope t(b, sd, 0);
         if (b->dcw_ring == 4)
             k0_dc_walk<4><<<(unsigned)ns, 64, dcw_smem<4>(), sd>>>(c.d_iq, c.iq_stride, (const DcStats *)b->dc_stats.p, b->dc_stride,
-                                                                  b->anchor_buf(c.par), (float2 *)b->dc_state.p, b->table_buf(c.par),
+                                                                  b->anchor_buf(c.par), b->qtab_buf(c.par), (float2 *)b->dc_state.p, b->table_buf(c.par),
                                                                   b->dc_stride + DC_HALO_BLKS, cb * per_cb, per_cb, s0);
         else
             k0_dc_walk<2><<<(unsigned)ns, 64, dcw_smem<2>(), sd>>>(c.d_iq, c.iq_stride, (const DcStats *)b->dc_stats.p, b->dc_stride,
-                                                                  b->anchor_buf(c.par), (float2 *)b->dc_state.p, b->table_buf(c.par),
+                                                                  b->anchor_buf(c.par), b->qtab_buf(c.par), (float2 *)b->dc_state.p, b->table_buf(c.par),
                                                                   b->dc_stride + DC_HALO_BLKS, cb * per_cb, per_cb, s0);
     }
     (*nl) += 2;

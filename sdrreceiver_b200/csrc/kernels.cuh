@@ -314,10 +314,30 @@ __global__ void __launch_bounds__(128) k0_dc_anchor(const float2 *__restrict__ d
     anchors[2 * stream + arm] = A;
 }
 
+// The increment of a sample depends only on its byte (256 values) and on the call's anchor: d(byte) = Q - r0 with
+// Q = RN_even(fl(c*x)/ulp), or DC_QTIE where the rounding would be a half-way case (the block is then stepped in float).
+// One table of 256 ints per stream and arm, built once per call right after the anchor: the block statistics and the
+// walk's integer solves look increments up instead of redoing five float operations per sample.
+#define DC_QTIE ((int)0x80000000)
+__global__ void __launch_bounds__(256) k0_dc_qtab(const DcAnchor *__restrict__ anchors, int *__restrict__ qtab, int stream0) {
+    const int sa = 2 * stream0 + blockIdx.x;                       // (stream, arm)
+    const DcAnchor A = anchors[sa];
+    bool tie = false;
+    int d = 0;
+    if (A.ok) {
+        const float q = dc_incr(A, (float)((int)threadIdx.x - 127), tie);
+        d = (int)q - A.r0;
+    }
+    qtab[(size_t)sa * 256 + threadIdx.x] = tie ? DC_QTIE : d;
+}
+
 __global__ void __launch_bounds__(128) k0_dc_blocks(const uint8_t *__restrict__ iq, size_t iq_stride,
-                                                     const DcAnchor *__restrict__ anchors, DcStats *__restrict__ stats,
-                                                     int stats_stride, int blk0, int n_blk, int stream0) {
+                                                     const DcAnchor *__restrict__ anchors, const int *__restrict__ qtab,
+                                                     DcStats *__restrict__ stats, int stats_stride, int blk0, int n_blk, int stream0) {
+    __shared__ int sq[2][257];                                     // +1: the two arms start in different banks
     const int stream = stream0 + blockIdx.y;
+    for (int e = threadIdx.x; e < 512; e += 128) sq[e >> 8][e & 255] = qtab[(size_t)stream * 512 + e];
+    __syncthreads();
     const int blk = blk0 + blockIdx.x * 128 + threadIdx.x;
     if (blk >= blk0 + n_blk) return;
     const DcAnchor AI = anchors[2 * stream], AQ = anchors[2 * stream + 1];
@@ -325,33 +345,34 @@ __global__ void __launch_bounds__(128) k0_dc_blocks(const uint8_t *__restrict__ 
     DcStats bad; bad.D = 0; bad.ta = 0u; bad.tb = 0xFFFFFFFFu; bad.tb_hi = 0u;
     if (!AI.ok && !AQ.ok) { out[0] = bad; out[1] = bad; return; }
     const uint4 *src = reinterpret_cast<const uint4 *>(iq + (size_t)stream * iq_stride + (size_t)blk * (2 * DC_BLK));
-    float uI = 0.f, uQ = 0.f, amaxI = 0.f, amaxQ = 0.f, bminI = 0.f, bminQ = 0.f, bmaxI = 0.f, bmaxQ = 0.f;
-    bool badI = !AI.ok, badQ = !AQ.ok;
-    const float r0I = (float)AI.r0, r0Q = (float)AQ.r0;
-#pragma unroll 4
+    // integer ulps: u = prefix of the increments before sample k; amax = max u, bmin/bmax = min/max of u - k
+    int uI = 0, uQ = 0, amaxI = 0, amaxQ = 0, bminI = 0, bminQ = 0, bmaxI = 0, bmaxQ = 0;
+    int tieI = 0, tieQ = 0;
+#pragma unroll 2
     for (int v = 0; v < DC_BLK / 8; ++v) {
-        float2 x[8];
-        unpack8(__ldg(src + v), x);
+        const uint4 raw = __ldg(src + v);
+        const unsigned w[4] = {raw.x, raw.y, raw.z, raw.w};
 #pragma unroll
         for (int k = 0; k < 8; ++k) {
-            const float kk = (float)(8 * v + k);
-            amaxI = fmaxf(amaxI, uI); bminI = fminf(bminI, uI - kk); bmaxI = fmaxf(bmaxI, uI - kk);
-            amaxQ = fmaxf(amaxQ, uQ); bminQ = fminf(bminQ, uQ - kk); bmaxQ = fmaxf(bmaxQ, uQ - kk);
-            bool t1, t2;
-            uI += dc_incr(AI, x[k].x, t1) - r0I;
-            uQ += dc_incr(AQ, x[k].y, t2) - r0Q;
-            badI |= t1; badQ |= t2;
+            const unsigned pr = w[k >> 1] >> (16 * (k & 1));
+            const int kk = 8 * v + k;
+            amaxI = max(amaxI, uI); bminI = min(bminI, uI - kk); bmaxI = max(bmaxI, uI - kk);
+            amaxQ = max(amaxQ, uQ); bminQ = min(bminQ, uQ - kk); bmaxQ = max(bmaxQ, uQ - kk);
+            const int dI = sq[0][pr & 0xffu], dQ = sq[1][(pr >> 8) & 0xffu];
+            tieI |= (dI == DC_QTIE); tieQ |= (dQ == DC_QTIE);
+            uI += dI; uQ += dQ;
         }
     }
+    const bool badI = !AI.ok || tieI, badQ = !AQ.ok || tieQ;
     // amax >= 0 >= bmin by construction (the k = 0 term), so ta <= T - lo1 <= tb
     DcStats sI, sQ;
     long long t;
     const long long lo1I = (long long)AI.lo + 1, lo1Q = (long long)AQ.lo + 1;
-    sI.D = (int)uI;
+    sI.D = uI;
     t = (long long)AI.T - (long long)amaxI - lo1I; sI.ta = t > 0 ? (unsigned)t : 0u;
     t = (long long)AI.T - (long long)bminI - lo1I; sI.tb = t > 0 ? (unsigned)t : 0u;
     t = (long long)AI.hi - (long long)bmaxI - lo1I; sI.tb_hi = t > 0 ? (unsigned)t : 0u;
-    sQ.D = (int)uQ;
+    sQ.D = uQ;
     t = (long long)AQ.T - (long long)amaxQ - lo1Q; sQ.ta = t > 0 ? (unsigned)t : 0u;
     t = (long long)AQ.T - (long long)bminQ - lo1Q; sQ.tb = t > 0 ? (unsigned)t : 0u;
     t = (long long)AQ.hi - (long long)bmaxQ - lo1Q; sQ.tb_hi = t > 0 ? (unsigned)t : 0u;
@@ -395,7 +416,8 @@ template <int N> __device__ __forceinline__ void cp_async_wait() { asm volatile(
 template <int DCW_RING>
 __global__ void __launch_bounds__(64) k0_dc_walk(const uint8_t *__restrict__ iq, size_t iq_stride,
                                                   const DcStats *__restrict__ stats, int stats_stride,
-                                                  const DcAnchor *__restrict__ anchors, float2 *__restrict__ dc_state,
+                                                  const DcAnchor *__restrict__ anchors, const int *__restrict__ qtab,
+                                                  float2 *__restrict__ dc_state,
                                                   uint2 *__restrict__ table, int table_stride, int blk0, int n_blk,
                                                   int stream0) {
     extern __shared__ __align__(16) unsigned char dcw_smem[];
@@ -408,6 +430,10 @@ __global__ void __launch_bounds__(64) k0_dc_walk(const uint8_t *__restrict__ iq,
     uint2 *tab = table + ((size_t)stream * table_stride + DC_HALO_BLKS + blk0) * 2 + arm;
     const int n_batch = (n_blk + DCW_BATCH - 1) / DCW_BATCH;
     const unsigned lt_mask = (1u << lane) - 1u;
+    __shared__ int s_qtab[2][256];                                  // this stream's increment tables (k0_dc_qtab), one per arm
+    for (int e = lane; e < 256; e += 32) s_qtab[arm][e] = qtab[((size_t)stream * 2 + arm) * 256 + e];
+    __syncwarp();
+    const int *sqt = s_qtab[arm];
 
     auto prefetch = [&](int batch) {
         if (batch < n_batch) {
@@ -508,12 +534,10 @@ __global__ void __launch_bounds__(64) k0_dc_walk(const uint8_t *__restrict__ iq,
             // the lane's 4 samples of this arm
             const uint2 rw = *reinterpret_cast<const uint2 *>(reinterpret_cast<const unsigned char *>(slot + (size_t)n * (2 * DC_BLK / 16)) + lane * 8);
             const unsigned w0 = arm ? rw.x >> 8 : rw.x, w1 = arm ? rw.y >> 8 : rw.y;
-            const float x0 = u8_to_f<0>(w0), x1 = u8_to_f<2>(w0), x2 = u8_to_f<0>(w1), x3 = u8_to_f<2>(w1);
             bool solved = false;
             if (V < win) {
-                bool t0, t1, t2, t3;
-                const int d0 = (int)(dc_incr(A, x0, t0) - r0f), d1 = (int)(dc_incr(A, x1, t1) - r0f);
-                const int d2 = (int)(dc_incr(A, x2, t2) - r0f), d3 = (int)(dc_incr(A, x3, t3) - r0f);
+                const int d0 = sqt[w0 & 0xffu], d1 = sqt[(w0 >> 16) & 0xffu], d2 = sqt[w1 & 0xffu], d3 = sqt[(w1 >> 16) & 0xffu];
+                const bool tie = (d0 == DC_QTIE) | (d1 == DC_QTIE) | (d2 == DC_QTIE) | (d3 == DC_QTIE);
                 const int p1 = d0, p2 = p1 + d1, p3 = p2 + d2, tot = p3 + d3;
                 int inc = tot;
 #pragma unroll
@@ -542,7 +566,7 @@ __global__ void __launch_bounds__(64) k0_dc_walk(const uint8_t *__restrict__ iq,
                 // margin built into the anchor) and no increment may be a rounding tie
                 const int hiw = (int)win;
                 const bool inside = (base - c0 < hiw) && (base + p1 - c1 < hiw) && (base + p2 - c2 < hiw) && (base + p3 - c3 < hiw);
-                const bool fine = inside && !(t0 | t1 | t2 | t3);
+                const bool fine = inside && !tie;
                 const int total = __shfl_sync(0xffffffffu, inc, 31);
                 const int ctot = __popc(b0) + __popc(b1) + __popc(b2) + __popc(b3);
                 const int vend = (int)V + total - ctot;
@@ -554,6 +578,7 @@ __global__ void __launch_bounds__(64) k0_dc_walk(const uint8_t *__restrict__ iq,
             }
             if (!solved) {
                 // real float steps (sdrj.cpp:281) on lane 0; the other lanes only provide fl(c*x)
+                const float x0 = u8_to_f<0>(w0), x1 = u8_to_f<2>(w0), x2 = u8_to_f<0>(w1), x3 = u8_to_f<2>(w1);
                 if (V != 0xFFFFFFFFu) s = __uint_as_float((V + lo1) | sign_bit);
                 __syncwarp();
                 *reinterpret_cast<float4 *>(sq + 4 * lane) = make_float4(__fmul_rn(DC_C, x0), __fmul_rn(DC_C, x1), __fmul_rn(DC_C, x2), __fmul_rn(DC_C, x3));
