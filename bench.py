@@ -611,10 +611,9 @@ def publish_leg(B, plan, bank, host_bufs, row, S, NB, rank, args):
         for s in range(S):
             for cb in range(NB):
                 rec = o + 2 * (s * NB + cb) * plan.pcm_per_block
-                r = lib.sdrb_publisher_send_block(pub, plan.h, C.c_void_p(rec))
-                if r < 0:
+                if lib.sdrb_publisher_send_block(pub, plan.h, C.c_void_p(rec)) != 0:
                     raise RuntimeError("sdrb_publisher_send_block failed")
-                n += r
+                n += len(plan.subs)
         return n
 
     one()

@@ -239,6 +239,9 @@ struct sdrb_bank {
     int k1_threads = 64;
     std::vector<K2V2Params> k2v2;                 // one prebuilt parameter block per sub-VFO group
     std::vector<K3Params> k3;                     // ... and for the groups that run k2a_v3
+    std::vector<bool> sub_fused;                  // NCO mix fused into the /late FIR kernel: z exists only on demand
+    std::vector<CascVfo> sub_casc;
+    std::vector<RfTab> sub_rf;
     DevBuf k3_rrel;
     bool per_cb = false;                          // SDRB_PER_CB=1: device-resident calls launch every kernel class per callback
     int k3_regs5 = 232;                           // register cap of the 5-stage k2a_v3 instantiation (SDRB_K3_REGS=168|200|232)
@@ -437,11 +440,23 @@ extern "C" int sdrb_bank_create(const sdrb_plan *plan, int device, int n_streams
     // sub VFOs grouped by parent main VFO: one k2a_v2 launch per group, the parent's output is
     // read once per thread and kept in registers for all sub VFOs of the group
     static const int kHalo[6] = {0, 0, 1, 2, 5, 11};    // halo chunks a cascade of S stages needs (+1 sample/stage at callback heads)
+    // /late factor of the plan (k2_late_v2 handles one factor per launch) and the sub VFOs whose NCO mix is fused into that
+    // kernel: no half-band stages and a /5 or /6 FIR behind -- their full-rate z is then never written nor read back
+    for (const SubVfo &s : h.subs)
+        if (s.late > 0) {
+            const int lf = ((int)s.dec_taps.size() <= s.late * LV_AMAX) ? s.late : -1;
+            b->late_factor = (b->late_factor == 0 || b->late_factor == lf) ? lf : -1;
+        }
+    {
+        const char *ef = getenv("SDRB_FUSE_LATE");
+        const bool want = !(ef && atoi(ef) == 0) && (b->late_factor == 5 || b->late_factor == 6);
+        for (const SubVfo &s : h.subs) b->sub_fused.push_back(want && s.late > 0 && s.decim == 0);
+    }
     std::vector<int> order;
     for (size_t mi = 0; mi < h.mains.size(); mi++) {
         SubGroup g; g.main_idx = (int)mi; g.first = (int)order.size(); g.count = 0; g.tiles = 0; g.halo = 0;
         for (size_t i = 0; i < h.subs.size(); i++) {
-            if (h.subs[i].main_idx != (int)mi) continue;
+            if (h.subs[i].main_idx != (int)mi || b->sub_fused[i]) continue;
             if (g.count == V2_MAX_VFO) { b->groups.push_back(g); g.first = (int)order.size(); g.count = 0; g.halo = 0; }
             order.push_back((int)i); g.count++;
             g.halo = std::max(g.halo, kHalo[h.subs[i].decim]);
@@ -473,6 +488,18 @@ extern "C" int sdrb_bank_create(const sdrb_plan *plan, int device, int n_streams
     }
     b->z_stride = z_stride;
     b->sub_z_off = z_off; b->sub_z_hist = z_hist;
+    // every sub VFO's own descriptor and rotation table: the inspection entry points produce the z of a fused VFO on demand
+    b->sub_casc.resize(h.subs.size()); b->sub_rf.resize(h.subs.size());
+    for (size_t i = 0; i < h.subs.size(); i++) {
+        const SubVfo &s = h.subs[i];
+        CascVfo &D = b->sub_casc[i];
+        D.lut = (const float2 *)b->luts.p + sub_lut_off[i];
+        D.out = (float2 *)b->zbuf.p + z_off[i];
+        D.S = s.decim; D.block_out = s.block_z; D.hist = z_hist[i]; D.pad = 0;
+        float2 rf[RF_LEN];
+        rf_table((double)s.fs, s.mixer, rf);
+        memcpy(b->sub_rf[i].q, rf, sizeof(RfTab));
+    }
     for (size_t i = 0; i < h.subs.size(); i++) {
         const SubVfo &s = h.subs[i];
         UsbDev U;
@@ -484,12 +511,14 @@ extern "C" int sdrb_bank_create(const sdrb_plan *plan, int device, int n_streams
             L.z_stride = (long long)z_stride; L.d_stride = (long long)d_stride;
             L.z_hist = z_hist[i]; L.d_hist = d_hist[i]; L.block_z = s.block_z; L.samples_out = s.samples_out;
             L.late = s.late; L.ntaps = (int)s.dec_taps.size();
+            L.mix_lut = nullptr; L.blocks_done = (const long long *)b->blocks_done.p; L.lut_len = (int)s.lut.size(); L.pad = 0;
+            if (b->sub_fused[i]) {
+                L.z = (const float2 *)b->main_out.p + b->main_off[(size_t)s.main_idx];
+                L.z_stride = (long long)b->main_stride; L.z_hist = MAIN_HIST;
+                L.mix_lut = (const float2 *)b->luts.p + sub_lut_off[i];
+            }
             latedev.push_back(L);
             b->max_late_samples = std::max(b->max_late_samples, s.samples_out);
-            {
-                const int lf = (L.ntaps <= L.late * LV_AMAX) ? L.late : -1;
-                b->late_factor = (b->late_factor == 0 || b->late_factor == lf) ? lf : -1;
-            }
             U.src = L.d; U.src_stride = L.d_stride; U.src_hist = L.d_hist;
             CarryItem c; c.base = L.d; c.stride = (long long)(d_stride * sizeof(float2));
             c.hist_bytes = L.d_hist * (int)sizeof(float2); c.block_bytes = s.samples_out * (int)sizeof(float2);
@@ -1092,6 +1121,25 @@ extern "C" int sdrb_bank_copy_input(sdrb_bank *b, int cb, int n, float *d_out, v
     return input_launch(b, cb, n, (float2 *)d_out, (cudaStream_t)cuda_stream);
 }
 
+// z (decimate[decimateCount], vfo.cpp:290-293) of a sub VFO whose mix is fused into the /late kernel: produced here, on demand,
+// for the callbacks of the last call -- the parent's output of that call is still in place, the callback counters have moved on.
+static int ensure_sub_z(sdrb_bank *b, int sub_idx, cudaStream_t st) {
+    if (!b->sub_fused[(size_t)sub_idx] || b->last_blocks <= 0) return SDRB_OK;
+    const SubVfo &s = b->plan->h.subs[(size_t)sub_idx];
+    K2V2Params kp{};
+    kp.vfos[0] = b->sub_casc[(size_t)sub_idx];
+    kp.rf[0] = b->sub_rf[(size_t)sub_idx];
+    kp.in = (const float2 *)b->main_out.p + b->main_off[(size_t)s.main_idx];
+    kp.blocks_done = (const long long *)b->blocks_done.p;
+    kp.in_stride = (long long)b->main_stride; kp.out_stride = (long long)b->z_stride;
+    kp.count = 1; kp.lut_len = (int)s.lut.size(); kp.block_in = s.block_in; kp.HT = 0; kp.stream0 = 0; kp.b0 = 0;
+    kp.blk_off = -b->last_blocks;
+    const int tiles = (s.block_in + 128 * V2_CHUNK - 1) / (128 * V2_CHUNK);
+    k2a_v2<128><<<dim3((unsigned)b->n_streams, (unsigned)tiles, (unsigned)b->last_blocks), 128, V2L<128>::SMEM, st>>>(kp);
+    CU_TRY(cudaGetLastError());
+    return SDRB_OK;
+}
+
 extern "C" int sdrb_bank_copy_sub(sdrb_bank *b, int sub_idx, int n_blocks, float *d_out, void *cuda_stream) {
     if (!b || !d_out || sub_idx < 0 || sub_idx >= (int)b->plan->h.subs.size() || n_blocks <= 0 || n_blocks > b->max_blocks) {
         set_error("sdrb_bank_copy_sub: bad argument"); return SDRB_E_INVALID;
@@ -1100,6 +1148,7 @@ extern "C" int sdrb_bank_copy_sub(sdrb_bank *b, int sub_idx, int n_blocks, float
     { const int drc = host_drain(b); if (drc != SDRB_OK) return drc; }
     const SubVfo &s = b->plan->h.subs[(size_t)sub_idx];
     const size_t row = (size_t)n_blocks * s.block_z * sizeof(float2);
+    { const int zrc = ensure_sub_z(b, sub_idx, (cudaStream_t)cuda_stream); if (zrc != SDRB_OK) return zrc; }
     CU_TRY(cudaMemcpy2DAsync(d_out, row, (float2 *)b->zbuf.p + b->sub_z_off[(size_t)sub_idx] + b->sub_z_hist[(size_t)sub_idx],
                              b->z_stride * sizeof(float2), row, (size_t)b->n_streams, cudaMemcpyDeviceToDevice,
                              (cudaStream_t)cuda_stream));
@@ -1670,6 +1719,7 @@ extern "C" int sdrb_bank_spectrum_feed(sdrb_bank *b, sdrb_spectrum *sp, int sour
         return sdrb_spectrum_feed_device(sp, (const float *)sp->scratch.p, (size_t)n, n, d_fft_out, cuda_stream);
     }
     const SubVfo &s = b->plan->h.subs[(size_t)source];
+    { const int zrc = ensure_sub_z(b, source, st); if (zrc != SDRB_OK) return zrc; }
     const float2 *z = (const float2 *)b->zbuf.p + b->sub_z_off[(size_t)source] + b->sub_z_hist[(size_t)source] + (size_t)cb * s.block_z;
     return sdrb_spectrum_feed_device(sp, (const float *)z, b->z_stride, s.block_z, d_fft_out, cuda_stream);
 }

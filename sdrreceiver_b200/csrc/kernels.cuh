@@ -87,11 +87,16 @@ struct K1Params {
 };
 
 struct LateDev {
-    const float2 *z;                // pre-decimation samples (K2A output)
+    const float2 *z;                // pre-decimation samples (K2A output) -- or, for a fused mixer-only VFO, the parent's main output
     float2 *d;                      // [n_streams][d_stride]: d_hist + n_blocks*samples_out
     const float *taps;              // ntaps floats
     long long z_stride, d_stride;
     int z_hist, d_hist, block_z, samples_out, late, ntaps;
+    // Fused NCO mix (sub VFOs without half-band stages, vfo.cpp:237-245 with decimateCount 0): z is never written; the late
+    // kernel reads the parent's output and multiplies by the Oscillator table entry of each sample while it stages them.
+    const float2 *mix_lut;          // nullptr: z holds mixed samples already
+    const long long *blocks_done;   // [n_streams]: callbacks before this call (table index = (blocks_done*block_z + i) mod lut_len)
+    int lut_len, pad;
 };
 
 struct UsbDev {

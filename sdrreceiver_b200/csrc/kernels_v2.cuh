@@ -301,6 +301,7 @@ struct K2V2Params {
     const long long *blocks_done;
     long long in_stride, out_stride;
     int count, lut_len, block_in, HT, stream0, b0;
+    int blk_off, pad;               // added to the callback counter: -n for a replay of the last call's callbacks after the carry
 };
 
 template <int NT>
@@ -314,7 +315,7 @@ __global__ void __launch_bounds__(NT, v2_minb<NT>()) k2a_v2(const __grid_constan
     const int t = threadIdx.x;
     const int B = p.block_in, L = p.lut_len;
     const int v0 = tile * ((NT - p.HT) * V2_CHUNK) - p.HT * V2_CHUNK + t * V2_CHUNK;
-    const long long blk = p.blocks_done[stream] + b;
+    const long long blk = p.blocks_done[stream] + b + p.blk_off;
     if (t == 0) sBase[0] = (int)((blk * (long long)B) % L);
     const bool in_block = v0 < B;
     float2 x[44];
@@ -812,10 +813,32 @@ __global__ void __launch_bounds__(LV_THREADS, 4) k2_late_v2(const LateDev *__res
     const long long zlo = (long long)L * m0 - N;            // may be negative: history
     const long long zmax = (long long)(cb0 + ncb) * D.block_z;
     const float2 *zp = D.z + (size_t)stream * D.z_stride + D.z_hist;
+    if (D.mix_lut == nullptr) {
 #pragma unroll 8
-    for (int e = t; e < span; e += LV_THREADS) {             // 8 independent loads in flight per thread
-        const long long zi = zlo + e;
-        sz[e + e / SEG] = (zi < zmax) ? __ldg(zp + zi) : make_float2(0.f, 0.f);
+        for (int e = t; e < span; e += LV_THREADS) {         // 8 independent loads in flight per thread
+            const long long zi = zlo + e;
+            sz[e + e / SEG] = (zi < zmax) ? __ldg(zp + zi) : make_float2(0.f, 0.f);
+        }
+    } else {
+        // fused mixer: sample zi of this call is stream sample n0 + zi and uses table entry (n0 + zi) mod len -- entry len-1
+        // for stream sample 0 (oscillator.cpp:26-30,42-48). History in front of the call (zi < 0) is the parent's own history.
+        const int len = D.lut_len;
+        const long long n0 = D.blocks_done[stream] * (long long)D.block_z;
+        int k = (int)(((n0 + zlo + t) % len + len) % len);
+        const int kstep = LV_THREADS % len;
+#pragma unroll 4
+        for (int e = t; e < span; e += LV_THREADS) {
+            const long long zi = zlo + e;
+            float2 v = make_float2(0.f, 0.f);
+            if (zi < zmax) {
+                const float2 x = __ldg(zp + zi);
+                const float2 r = __ldg(D.mix_lut + ((n0 + zi == 0) ? len - 1 : k));
+                v = cmul(r, x);
+            }
+            sz[e + e / SEG] = v;
+            k += kstep;
+            if (k >= len) k -= len;
+        }
     }
     for (int e = t; e < L * LV_AMAX; e += LV_THREADS) {
         const float c = e < N ? D.taps[e] : 0.f;
