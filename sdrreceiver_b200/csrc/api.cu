@@ -178,9 +178,14 @@ static int v2_pick_threads(int halo, const char *env) {
 }
 
 template <int NT>
-static void launch_k1_v2(const K1V2Params &q, bool dc, int ns, int block, cudaStream_t st) {
+static void launch_k1_v2(const K1V2Params &q, bool dc, int ns, int block, cudaStream_t st, bool bulk = false) {
     const int tiles = (block + k1v2_adv<NT>() - 1) / k1v2_adv<NT>();
     const dim3 grid((unsigned)ns, (unsigned)((tiles + K1_TPC - 1) / K1_TPC), 1u);
+    if (NT == 64 && bulk) {          // the bulk-copy (TMA) prefetch variant exists for the default CTA size only: SDRB_K1_BULK=1
+        if (dc) k1_v2<true, 64, true><<<grid, 64, k1v2_smem_bulk<64>(), st>>>(q);
+        else k1_v2<false, 64, true><<<grid, 64, k1v2_smem_bulk<64>(), st>>>(q);
+        return;
+    }
     if (dc) k1_v2<true, NT><<<grid, NT, k1v2_smem<NT>(), st>>>(q);
     else k1_v2<false, NT><<<grid, NT, k1v2_smem<NT>(), st>>>(q);
 }
@@ -244,6 +249,8 @@ struct sdrb_bank {
     std::vector<RfTab> sub_rf;
     DevBuf k3_rrel;
     bool per_cb = false;                          // SDRB_PER_CB=1: device-resident calls launch every kernel class per callback
+    bool k1_bulk = false;                         // SDRB_K1_BULK=1: k1_v2 prefetches tiles with cp.async.bulk + mbarrier (measured, not the default)
+    int k3_cta_warps = K3_WARPS;                  // warps per k2a_v3 CTA (SDRB_K3_CTA_WARPS=1..4)
     int k3_regs5 = 232;                           // register cap of the 5-stage k2a_v3 instantiation (SDRB_K3_REGS=168|200|232)
     int dcw_ring = 2;                             // shared-memory ring depth of k0_dc_walk (SDRB_DCW_RING=4: the round-1 size)
     int dbg_only = 0;                             // SDRB_DEBUG_ONLY=dc|filters: profiling aid, device-resident calls skip the other half (results are then meaningless)
@@ -621,9 +628,10 @@ extern "C" int sdrb_bank_create(const sdrb_plan *plan, int device, int n_streams
             kp.nsw = g.v3_nsw;
         }
         BANK_CU(cudaMemcpy(b->k3_rrel.p, rrel.data(), sizeof(float2) * rrel.size(), cudaMemcpyHostToDevice));
-#define K3_ATTR(S_, R_) BANK_CU((cudaFuncSetAttribute(k2a_v3<S_, R_>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)k3_cta_smem_bytes(K3_MAX_VFO, K3_WARPS, 32))))
+#define K3_ATTR(S_, R_) BANK_CU((cudaFuncSetAttribute(k2a_v3<S_, R_>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)k3_cta_smem_bytes(K3_MAX_VFO, 4, 32))))
         K3_ATTR(2, 168); K3_ATTR(3, 168); K3_ATTR(5, 168); K3_ATTR(5, 200); K3_ATTR(5, 232);
 #undef K3_ATTR
+        if (const char *e = getenv("SDRB_K3_CTA_WARPS")) { const int v = atoi(e); if (v >= 1 && v <= 4) b->k3_cta_warps = v; }
         if (const char *e = getenv("SDRB_K3_REGS")) { const int v = atoi(e); if (v == 168 || v == 200 || v == 232) b->k3_regs5 = v; }
     }
     if (!latedev.empty()) BANK_CU(cudaMemcpy(b->latedev.p, latedev.data(), sizeof(LateDev) * latedev.size(), cudaMemcpyHostToDevice));
@@ -649,6 +657,9 @@ extern "C" int sdrb_bank_create(const sdrb_plan *plan, int device, int n_streams
     BANK_CU((cudaFuncSetAttribute(k1_v2<true, 128>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)k1v2_smem<128>())));
     BANK_CU((cudaFuncSetAttribute(k1_v2<false, 128>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)k1v2_smem<128>())));
     b->k1_threads = v2_pick_threads(K1V2_HT, "SDRB_K1_THREADS");
+    b->k1_bulk = getenv("SDRB_K1_BULK") && atoi(getenv("SDRB_K1_BULK")) != 0;
+    BANK_CU((cudaFuncSetAttribute(k1_v2<true, 64, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)k1v2_smem_bulk<64>())));
+    BANK_CU((cudaFuncSetAttribute(k1_v2<false, 64, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)k1v2_smem_bulk<64>())));
     BANK_CU(cudaStreamCreateWithFlags(&b->s_copy_in, cudaStreamNonBlocking));
     BANK_CU(cudaStreamCreateWithFlags(&b->s_compute, cudaStreamNonBlocking));
     BANK_CU(cudaStreamCreateWithFlags(&b->s_copy_out, cudaStreamNonBlocking));
@@ -779,7 +790,7 @@ static int enqueue_ingest_cb(sdrb_bank *b, const CallCtx &c, int s0, int ns, cud
         q.iq = c.d_iq; q.iq_stride = c.iq_stride; q.stream0 = s0; q.b0 = cb;
         q.dc_table = b->table_buf(c.par); q.dc_anchor = b->anchor_buf(c.par);
         TimedScope t(b, st, 1);
-        if (b->k1_threads == 64) launch_k1_v2<64>(q, h.correct_dc, ns, h.block, st);
+        if (b->k1_threads == 64) launch_k1_v2<64>(q, h.correct_dc, ns, h.block, st, b->k1_bulk);
         else if (b->k1_threads == 96) launch_k1_v2<96>(q, h.correct_dc, ns, h.block, st);
         else launch_k1_v2<128>(q, h.correct_dc, ns, h.block, st);
     }
@@ -789,7 +800,7 @@ static int enqueue_ingest_cb(sdrb_bank *b, const CallCtx &c, int s0, int ns, cud
 
 // k2a_v3 launch geometry: one warp per (stream group, span, callback); spans are chosen so that the grid holds about
 // two warps per resident slot (148 SMs x 10 warps), never shorter than 16 tiles (3 warm-up tiles are recomputed per span)
-static void k3_geometry(const SubGroup &g, K3Params &kp, int ns, int ncb, dim3 *grid) {
+static void k3_geometry(const SubGroup &g, K3Params &kp, int ns, int ncb, int cta_warps, dim3 *grid) {
     const int sgroups = (ns + g.v3_nsw - 1) / g.v3_nsw;
     int target = 148 * 10 * 2;
     if (const char *e = getenv("SDRB_K3_WARPS")) { const int v = atoi(e); if (v > 0) target = v; }
@@ -798,7 +809,7 @@ static void k3_geometry(const SubGroup &g, K3Params &kp, int ns, int ncb, dim3 *
     tps = std::min(tps, kp.n_tiles);
     spans = (kp.n_tiles + tps - 1) / tps;
     kp.tiles_per_span = tps;
-    *grid = dim3((unsigned)((sgroups + K3_WARPS - 1) / K3_WARPS), (unsigned)spans, (unsigned)ncb);
+    *grid = dim3((unsigned)((sgroups + cta_warps - 1) / cta_warps), (unsigned)spans, (unsigned)ncb);
 }
 
 // Sub-VFO cascades of callbacks cb0 .. cb0+ncb-1.
@@ -809,14 +820,15 @@ static int enqueue_subs(sdrb_bank *b, const CallCtx &c, int s0, int ns, cudaStre
             K3Params &kp = b->k3[gi];
             kp.stream0 = s0; kp.stream_end = s0 + ns; kp.b0 = cb0;
             dim3 grid;
-            k3_geometry(g, kp, ns, ncb, &grid);
-            const size_t smem = k3_cta_smem_bytes(g.count, K3_WARPS, g.v3_nsw * g.count);
+            const int cw = b->k3_cta_warps;
+            k3_geometry(g, kp, ns, ncb, cw, &grid);
+            const size_t smem = k3_cta_smem_bytes(g.count, cw, g.v3_nsw * g.count);
             TimedScope t(b, st, 2);
-            if (g.v3_maxs == 2) k2a_v3<2, 168><<<grid, K3_WARPS * 32, smem, st>>>(kp);
-            else if (g.v3_maxs == 3) k2a_v3<3, 168><<<grid, K3_WARPS * 32, smem, st>>>(kp);
-            else if (b->k3_regs5 == 232) k2a_v3<5, 232><<<grid, K3_WARPS * 32, smem, st>>>(kp);
-            else if (b->k3_regs5 == 200) k2a_v3<5, 200><<<grid, K3_WARPS * 32, smem, st>>>(kp);
-            else k2a_v3<5, 168><<<grid, K3_WARPS * 32, smem, st>>>(kp);
+            if (g.v3_maxs == 2) k2a_v3<2, 168><<<grid, cw * 32, smem, st>>>(kp);
+            else if (g.v3_maxs == 3) k2a_v3<3, 168><<<grid, cw * 32, smem, st>>>(kp);
+            else if (b->k3_regs5 == 232) k2a_v3<5, 232><<<grid, cw * 32, smem, st>>>(kp);
+            else if (b->k3_regs5 == 200) k2a_v3<5, 200><<<grid, cw * 32, smem, st>>>(kp);
+            else k2a_v3<5, 168><<<grid, cw * 32, smem, st>>>(kp);
             (*nl)++;
             continue;
         }

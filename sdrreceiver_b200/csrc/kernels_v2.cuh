@@ -414,10 +414,39 @@ __global__ void __launch_bounds__(64) k_input_samples(const uint8_t *__restrict_
 #define SDRB_K1_TPC 4
 #endif
 constexpr int K1_TPC = SDRB_K1_TPC;
+
+// ---- bulk-copy (TMA engine, cp.async.bulk + mbarrier) variant of the tile prefetch: one elected thread moves the whole
+// tile's raw bytes and DC block states with two or three bulk copies; everybody waits on the buffer's mbarrier ----
+__device__ __forceinline__ void mbar_init(unsigned long long *bar, unsigned count) {
+    asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;\n" ::"r"((unsigned)__cvta_generic_to_shared(bar)), "r"(count));
+}
+__device__ __forceinline__ void mbar_expect_tx(unsigned long long *bar, unsigned bytes) {
+    asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;\n" ::"r"((unsigned)__cvta_generic_to_shared(bar)), "r"(bytes) : "memory");
+}
+__device__ __forceinline__ void mbar_wait(unsigned long long *bar, unsigned parity) {
+    asm volatile(
+        "{\n"
+        ".reg .pred p;\n"
+        "WAIT_%=:\n"
+        "mbarrier.try_wait.parity.shared::cta.b64 p, [%0], %1;\n"
+        "@p bra DONE_%=;\n"
+        "bra WAIT_%=;\n"
+        "DONE_%=:\n"
+        "}\n" ::"r"((unsigned)__cvta_generic_to_shared(bar)), "r"(parity) : "memory");
+}
+__device__ __forceinline__ void bulk_g2s(void *smem, const void *gmem, unsigned bytes, unsigned long long *bar) {
+    asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];\n" ::"r"(
+                     (unsigned)__cvta_generic_to_shared(smem)),
+                 "l"(gmem), "r"(bytes), "r"((unsigned)__cvta_generic_to_shared(bar))
+                 : "memory");
+}
+template <int NT> constexpr int k1_bulk_raw_bytes() { return NT * 64 + 32; }                 // samples v0(0)-16 .. v0(NT-1)+31
+template <int NT> constexpr int k1_bulk_buf_bytes() { return k1_bulk_raw_bytes<NT>() + (NT / 4) * 16 + 16; }
+template <int NT> constexpr size_t k1v2_smem_bulk() { return V2L<NT>::SMEM + 2 * (size_t)k1_bulk_buf_bytes<NT>(); }
 constexpr int K1_PF_BYTES = 112;                          // per thread: 6 x 16 raw bytes + 2 x 8 table bytes
 template <int NT> constexpr size_t k1v2_smem() { return V2L<NT>::SMEM + (size_t)NT * K1_PF_BYTES; }
 
-template <bool DC, int NT>
+template <bool DC, int NT, bool BULK = false>
 __global__ void __launch_bounds__(NT, v2_minb<NT>()) k1_v2(const __grid_constant__ K1V2Params p) {
     extern __shared__ __align__(16) unsigned char smem_raw[];
     float2 *sm = reinterpret_cast<float2 *>(smem_raw);
@@ -431,6 +460,43 @@ __global__ void __launch_bounds__(NT, v2_minb<NT>()) k1_v2(const __grid_constant
     const int n_tiles = (B + ADV - 1) / ADV;
     const int tile0 = blockIdx.y * K1_TPC;
     unsigned char *pf = smem_raw + V2L<NT>::SMEM + (size_t)t * K1_PF_BYTES;     // this thread's prefetch record
+    constexpr int BULK_RAW = NT * 64 + 32, BULK_BUF = BULK_RAW + (NT / 4) * 16 + 16;   // = k1_bulk_raw_bytes / k1_bulk_buf_bytes
+    __shared__ __align__(8) unsigned long long pf_bar[2];
+    unsigned char *bulk0 = smem_raw + V2L<NT>::SMEM;                            // BULK: two buffers of k1_bulk_buf_bytes
+    if (BULK) {
+        if (t == 0) {
+            mbar_init(&pf_bar[0], 1);
+            mbar_init(&pf_bar[1], 1);
+            asm volatile("fence.mbarrier_init.release.cluster;\n" ::: "memory");
+        }
+        __syncthreads();
+    }
+    // BULK: thread 0 fetches tile `tile` into buffer `buf`: the raw bytes of samples first-16 .. (clipped to the callback; the
+    // part in front of callback 0 of a call comes from the carried tail) and the DC block states of the tile's NT/4 blocks
+    auto bulk_issue = [&](int tile, int buf) {
+        const int first = tile * ADV - K1V2_HT * V2_CHUNK - 16;                 // first sample of the window of thread 0
+        int n = NT * V2_CHUNK + 16;
+        if (first + n > B) n = B - first;
+        unsigned char *dst = bulk0 + (size_t)buf * BULK_BUF;
+        unsigned bytes = 2u * (unsigned)n;
+        int ntab = 0;
+        if (DC) {
+            const int dblk0 = (b * B + first + 16 + RAW_TAIL) / DC_BLK;
+            ntab = min(NT / 4, p.dc_stride - dblk0);
+            bytes += 16u * (unsigned)ntab;
+        }
+        mbar_expect_tx(&pf_bar[buf], bytes);
+        if (b == 0 && first < 0) {
+            bulk_g2s(dst, p.tail + (size_t)stream * (2 * RAW_TAIL) + 2 * (RAW_TAIL + first), 2u * (unsigned)(-first), &pf_bar[buf]);
+            bulk_g2s(dst + 2 * (-first), p.iq + (size_t)stream * p.iq_stride, 2u * (unsigned)(n + first), &pf_bar[buf]);
+        } else {
+            bulk_g2s(dst, p.iq + (size_t)stream * p.iq_stride + ((size_t)b * B + first) * 2, 2u * (unsigned)n, &pf_bar[buf]);
+        }
+        if (DC && ntab > 0) {
+            const int dblk0 = (b * B + first + 16 + RAW_TAIL) / DC_BLK;
+            bulk_g2s(dst + BULK_RAW, p.dc_table + ((size_t)stream * p.dc_stride + dblk0) * 2, 16u * (unsigned)ntab, &pf_bar[buf]);
+        }
+    };
 
     // fetch of one tile: raw bytes of samples v0-16 .. v0+31 (six 16-byte pieces of 8 samples) and the DC
     // block-start states; pieces that do not exist (past the callback) are simply not fetched
@@ -451,7 +517,8 @@ __global__ void __launch_bounds__(NT, v2_minb<NT>()) k1_v2(const __grid_constant
         }
         cp_async_commit();
     };
-    if (tile0 < n_tiles) prefetch(tile0);
+    if (BULK) { if (t == 0 && tile0 < n_tiles) bulk_issue(tile0, 0); }
+    else if (tile0 < n_tiles) prefetch(tile0);
     const long long blk = p.blocks_done[stream] + b;
     if (t == 0) sBase[0] = (int)((blk * (long long)B) % L);
     const bool first_ever = (blk == 0);
@@ -465,7 +532,12 @@ __global__ void __launch_bounds__(NT, v2_minb<NT>()) k1_v2(const __grid_constant
         if (tile >= n_tiles) break;
         const int v0 = tile * ADV - K1V2_HT * V2_CHUNK + t * V2_CHUNK;
         const bool in_block = v0 < B;
-        cp_async_wait<0>();
+        if (BULK) {
+            mbar_wait(&pf_bar[ti & 1], (unsigned)((ti >> 1) & 1));
+            pf = bulk0 + (size_t)(ti & 1) * BULK_BUF + 64 * t;    // this thread's 96 bytes of the shared window
+        } else {
+            cp_async_wait<0>();
+        }
         uint4 raw[6];
         uint2 teI = make_uint2(0u, 2u), teQ = make_uint2(0u, 2u);     // DC block-start states (mode 2 = plain float bits: 0.0f)
 #pragma unroll
@@ -474,7 +546,9 @@ __global__ void __launch_bounds__(NT, v2_minb<NT>()) k1_v2(const __grid_constant
             if (in_block && !(first_ever && v0 - 16 + 8 * q < 0)) raw[q] = *reinterpret_cast<const uint4 *>(pf + 16 * q);
         }
         if (DC && in_block) {
-            const uint4 te = *reinterpret_cast<const uint4 *>(pf + 96);
+            const uint4 te = BULK ? *reinterpret_cast<const uint4 *>(bulk0 + (size_t)(ti & 1) * BULK_BUF +
+                                                                      BULK_RAW + 16 * (t >> 2))
+                                  : *reinterpret_cast<const uint4 *>(pf + 96);
             teI = make_uint2(te.x, te.y);
             teQ = make_uint2(te.z, te.w);
         }
@@ -503,7 +577,10 @@ __global__ void __launch_bounds__(NT, v2_minb<NT>()) k1_v2(const __grid_constant
             }
         }
         // the record has been consumed (its bytes are in registers): the next tile may overwrite it
-        if (ti + 1 < K1_TPC && tile + 1 < n_tiles) prefetch(tile + 1);
+        if (ti + 1 < K1_TPC && tile + 1 < n_tiles) {
+            if (BULK) { if (t == 0) bulk_issue(tile + 1, (ti + 1) & 1); }     // that buffer was last read two tiles ago (barrier below)
+            else prefetch(tile + 1);
+        }
         if (DC) {
             const int tot = (int)(sI | (sQ << 16));                 // 32*255 < 65536; prefix of 3 chunks < 65536 too
             const int g = t & 3;                             // position of the chunk inside its DC block

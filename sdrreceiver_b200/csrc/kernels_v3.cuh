@@ -494,7 +494,8 @@ struct K3DevEnv {
     __device__ __forceinline__ bool all(bool v) { return __all_sync(0xffffffffu, v) != 0; }
 };
 
-constexpr int K3_WARPS = 2;                                 // independent warps per CTA (they only share the read-only tables)
+constexpr int K3_WARPS = 2;                                 // default warps per CTA; the kernel works with any CTA size (independent warps that
+                                                            // only share the read-only tables)
 
 // grid: x = ceil(stream groups / K3_WARPS), y = spans, z = callbacks
 // RC = register cap: 168 (12 warps per SM, the deep cascades then spill a history array), 200 (10 warps) or 232 (8 warps, no spills)
@@ -505,12 +506,12 @@ __global__ void __maxnreg__(RC) k2a_v3(const __grid_constant__ K3Params p) {
     unsigned short *stab = reinterpret_cast<unsigned short *>(srrel + p.count * K3_OUT1);
     unsigned char *wbase = reinterpret_cast<unsigned char *>(stab + K3_MAX_SLOTS);
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-    for (int e = threadIdx.x; e < p.count * K3_OUT1; e += K3_WARPS * 32) srrel[e] = p.rrel[e];
+    for (int e = threadIdx.x; e < p.count * K3_OUT1; e += blockDim.x) srrel[e] = p.rrel[e];
     // slot table: VFO v contributes 32 >> (S - 1) chunks of 16 bytes per tile
     int n_slots = 0;
     for (int v = 0; v < p.count; ++v) {
         const int n = 32 >> (p.v[v].S - 1);
-        for (int c = threadIdx.x; c < n; c += K3_WARPS * 32) stab[n_slots + c] = (unsigned short)((v << 8) | c);
+        for (int c = threadIdx.x; c < n; c += blockDim.x) stab[n_slots + c] = (unsigned short)((v << 8) | c);
         n_slots += n;
     }
     __syncthreads();
@@ -519,7 +520,7 @@ __global__ void __maxnreg__(RC) k2a_v3(const __grid_constant__ K3Params p) {
     float2 **sdst = reinterpret_cast<float2 **>(ring + rows * K3_ROW);
     float2 *sF = reinterpret_cast<float2 *>(sdst + 32);
     int2 *sK = reinterpret_cast<int2 *>(sF + 64);
-    const int sg = blockIdx.x * K3_WARPS + warp;
+    const int sg = blockIdx.x * (int)(blockDim.x >> 5) + warp;
     if (p.stream0 + sg * p.nsw >= p.stream_end) return;
     K3DevEnv env{lane};
     k3_unit<MAXS>(env, p, sg, (int)blockIdx.y, p.b0 + (int)blockIdx.z, ring, sdst, sF, sK, srrel, stab, n_slots);
