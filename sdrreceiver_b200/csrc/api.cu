@@ -181,7 +181,7 @@ template <int NT>
 static void launch_k1_v2(const K1V2Params &q, bool dc, int ns, int block, cudaStream_t st, bool bulk = false) {
     const int tiles = (block + k1v2_adv<NT>() - 1) / k1v2_adv<NT>();
     const dim3 grid((unsigned)ns, (unsigned)((tiles + K1_TPC - 1) / K1_TPC), 1u);
-    if (NT == 64 && bulk) {          // the bulk-copy (TMA) prefetch variant exists for the default CTA size only: SDRB_K1_BULK=1
+    if (NT == 64 && bulk) {          // the bulk-copy (TMA) prefetch exists for the default CTA size; SDRB_K1_BULK=0 turns it off
         if (dc) k1_v2<true, 64, true><<<grid, 64, k1v2_smem_bulk<64>(), st>>>(q);
         else k1_v2<false, 64, true><<<grid, 64, k1v2_smem_bulk<64>(), st>>>(q);
         return;
@@ -249,7 +249,7 @@ struct sdrb_bank {
     std::vector<RfTab> sub_rf;
     DevBuf k3_rrel;
     bool per_cb = false;                          // SDRB_PER_CB=1: device-resident calls launch every kernel class per callback
-    bool k1_bulk = false;                         // SDRB_K1_BULK=1: k1_v2 prefetches tiles with cp.async.bulk + mbarrier (measured, not the default)
+    bool k1_bulk = true;                          // k1_v2 (64-thread CTAs) prefetches tiles with cp.async.bulk + mbarrier; SDRB_K1_BULK=0: per-thread cp.async records
     int k3_cta_warps = K3_WARPS;                  // warps per k2a_v3 CTA (SDRB_K3_CTA_WARPS=1..4)
     int k3_regs5 = 232;                           // register cap of the 5-stage k2a_v3 instantiation (SDRB_K3_REGS=168|200|232)
     int dcw_ring = 2;                             // shared-memory ring depth of k0_dc_walk (SDRB_DCW_RING=4: the round-1 size)
@@ -657,7 +657,7 @@ extern "C" int sdrb_bank_create(const sdrb_plan *plan, int device, int n_streams
     BANK_CU((cudaFuncSetAttribute(k1_v2<true, 128>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)k1v2_smem<128>())));
     BANK_CU((cudaFuncSetAttribute(k1_v2<false, 128>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)k1v2_smem<128>())));
     b->k1_threads = v2_pick_threads(K1V2_HT, "SDRB_K1_THREADS");
-    b->k1_bulk = getenv("SDRB_K1_BULK") && atoi(getenv("SDRB_K1_BULK")) != 0;
+    b->k1_bulk = !(getenv("SDRB_K1_BULK") && atoi(getenv("SDRB_K1_BULK")) == 0);   // default on: 0.59 -> 0.535 ms per step (profiles/r02_experiments.md)
     BANK_CU((cudaFuncSetAttribute(k1_v2<true, 64, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)k1v2_smem_bulk<64>())));
     BANK_CU((cudaFuncSetAttribute(k1_v2<false, 64, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)k1v2_smem_bulk<64>())));
     BANK_CU(cudaStreamCreateWithFlags(&b->s_copy_in, cudaStreamNonBlocking));

@@ -51,40 +51,39 @@ private:
     int io_cap;
 };
 
+// DelayThing<T> (jonti/dsp.h:79-126): an integer delay line. Same public interface and behaviour -- a line of length + 1
+// slots, a sample comes back `length` calls after it went in, setLength() keeps what the line held (the reference
+// resize()s), findmaxpos() reports the first largest sample counted from the oldest -- written around one push() helper.
+// Pure data movement: it stays a host template (the kernels realise the 62-sample delay of vfo.cpp:136 as an index offset).
 template <class T>
-class DelayThing {                                        // dsp.h:79-126: pure data movement, stays on the host
+class DelayThing {
 public:
-    DelayThing() { setLength(12); }
+    DelayThing() : head(0) { setLength(12); }
     void setLength(int length) {
-        length++;
-        assert(length > 0);
-        buffer.assign((size_t)length, T());
-        buffer_ptr = 0;
-        buffer_sz = (int)buffer.size();
+        assert(length + 1 > 0);
+        line.resize((size_t)length + 1);
+        head = 0;
     }
-    void update(T &data) {
-        buffer[(size_t)buffer_ptr] = data;
-        buffer_ptr++; buffer_ptr %= buffer_sz;
-        data = buffer[(size_t)buffer_ptr];
-    }
-    T update_dont_touch(T data) {
-        buffer[(size_t)buffer_ptr] = data;
-        buffer_ptr++; buffer_ptr %= buffer_sz;
-        return buffer.at((size_t)buffer_ptr);
-    }
+    void update(T &data) { data = push(data); }
+    T update_dont_touch(T data) { return push(data); }
     int findmaxpos(T &maxval) {
-        int maxpos = 0;
-        maxval = buffer[(size_t)buffer_ptr];
-        for (int i = 0; i < buffer_sz; i++) {
-            if (buffer[(size_t)buffer_ptr] > maxval) { maxval = buffer[(size_t)buffer_ptr]; maxpos = i; }
-            buffer_ptr++; buffer_ptr %= buffer_sz;
+        const size_t n = line.size();
+        size_t best = 0;
+        maxval = line[head];
+        for (size_t i = 1; i < n; ++i) {
+            const T &v = line[(head + i) % n];
+            if (v > maxval) { maxval = v; best = i; }
         }
-        return maxpos;
+        return (int)best;
     }
 
 private:
-    std::vector<T> buffer;
-    int buffer_ptr;
-    int buffer_sz;
+    T push(const T &v) {                                   // store, advance, hand back the oldest sample
+        line[head] = v;
+        head = (head + 1) % line.size();
+        return line[head];
+    }
+    std::vector<T> line;
+    size_t head;
 };
 #endif
