@@ -42,6 +42,7 @@ constexpr int K3_WARM = 3;              // warm-up tiles in front of a span (>= 
 constexpr int K3_MAX_VFO = 16;
 constexpr int K3_LUT_STEADY = 512;      // table entries of the start-up transient (94 measured)
 constexpr int K3_MAX_SLOTS = K3_MAX_VFO * 32;
+constexpr int K3_XS = K3_TILE + 16;     // staged input samples per stream and tile: 16 in front (the windows reach back 12), then the tile
 
 #ifndef HB_P0
 #define HB_P0 0.0060431029837374152f
@@ -162,12 +163,14 @@ struct K3Hist {
 };
 
 // Shared memory of a CTA: [rrel: count*64 float2][slot table: K3_MAX_SLOTS ushort][per warp: ring of `rows` rows,
-// 32 dst pointers, 2 x 32 table anchors (float2), 32 per-stream table bases (int2)]
-K3_HD size_t k3_warp_smem_bytes(int rows) {
-    return (size_t)rows * K3_ROW * sizeof(float2) + 32 * sizeof(float2 *) + 64 * sizeof(float2) + 32 * sizeof(int2);
+// 32 dst pointers, 2 x 32 table anchors (float2), 32 per-stream table bases (int2), nsw staged input tiles of K3_XS samples,
+// one mbarrier]
+K3_HD size_t k3_warp_smem_bytes(int rows, int nsw) {
+    return (size_t)rows * K3_ROW * sizeof(float2) + 32 * sizeof(float2 *) + 64 * sizeof(float2) + 32 * sizeof(int2) +
+           (size_t)nsw * K3_XS * sizeof(float2) + 16;
 }
-K3_HD size_t k3_cta_smem_bytes(int count, int warps, int rows) {
-    return (size_t)count * K3_OUT1 * sizeof(float2) + K3_MAX_SLOTS * sizeof(unsigned short) + (size_t)warps * k3_warp_smem_bytes(rows);
+K3_HD size_t k3_cta_smem_bytes(int count, int warps, int rows, int nsw) {
+    return (size_t)count * K3_OUT1 * sizeof(float2) + K3_MAX_SLOTS * sizeof(unsigned short) + (size_t)warps * k3_warp_smem_bytes(rows, nsw);
 }
 // 8 bytes global -> shared without passing through a register (LDGSTS); k3_async_wait() makes them visible to the issuing thread
 K3_HD void k3_async_copy8(void *smem, const void *gmem) {
@@ -205,7 +208,7 @@ K3_HD void k3_prefetch_l1(const void *p) {
 //   srrel   the CTA's copy of p.rrel;  stab: slot table (v << 8 | 16-byte chunk), n_slots entries per stream
 template <int MAXS, class Env>
 K3_HD void k3_unit(Env &env, const K3Params &p, int sg, int span, int b, float2 *ring, float2 **sdst, float2 *sF, int2 *sK,
-                   const float2 *srrel, const unsigned short *stab, int n_slots) {
+                   float2 *sX, const float2 *srrel, const unsigned short *stab, int n_slots) {
     const int lane = env.lane;
     const int nv = p.count, nsw = p.nsw, B = p.block_in, L = p.lut_len;
     const int sbase = p.stream0 + sg * nsw;
@@ -246,8 +249,20 @@ K3_HD void k3_unit(Env &env, const K3Params &p, int sg, int span, int b, float2 
     k3_async_copy8(sF + lane, lutB + wrapL(kbB + (t_begin - K3_WARM) * K3_TILE));
     int fpar = 0;
     const float2 *in0 = p.in + (size_t)sbase * (size_t)p.in_stride + p.hist_in + (long long)b * B;         // sample 0 of stream sbase
-    const float2 *in_pf = in0 + K3_TILE - 16 + 16 * lane;                                                  // this lane's line of the next tile
-    const float2 *in_ln = in0 + 4 * lane;                                                                  // this lane's chunk of a tile
+    // The input of a tile (K3_XS samples per stream: 16 in front of the tile, then the tile) is staged in shared memory by the
+    // bulk-copy engine one tile ahead: one lane issues one copy per stream when role A has consumed the previous tile, the
+    // bytes land while role B runs, everybody waits on the warp's mbarrier at the next tile head.
+    int n_str = 0;
+    for (int s = 0; s < nsw && sbase + s < p.stream_end; ++s) n_str++;
+    auto stage_x = [&](int c_first) {
+        if (lane == 0) {
+            env.x_expect((unsigned)(n_str * K3_XS * sizeof(float2)));
+            for (int s = 0; s < n_str; ++s)
+                env.x_copy(sX + s * K3_XS, in0 + (size_t)s * (size_t)p.in_stride + c_first - 16, (unsigned)(K3_XS * sizeof(float2)));
+        }
+    };
+    stage_x((t_begin - K3_WARM) * K3_TILE);
+    unsigned xpar = 0;
     // Output copy, common case (at most 32 sixteen-byte chunks per stream and tile): this lane's chunk is the same for every
     // tile and stream, so its source offset and destination are kept in registers instead of being looked up per tile.
     const bool cp_fast = n_slots <= 32;
@@ -264,15 +279,12 @@ K3_HD void k3_unit(Env &env, const K3Params &p, int sg, int span, int b, float2 
     for (int t = t_begin - K3_WARM; t < t_end; ++t) {
         const int c0 = t * K3_TILE;                          // callback coordinate of the tile's first sample (may be negative)
         k3_async_wait();
+        env.x_wait(xpar);
+        xpar ^= 1u;
         env.sync();
         const float2 *sFt = sF + 32 * fpar;                  // this tile's anchors
         fpar ^= 1;
         k3_async_copy8(sF + 32 * fpar + lane, lutB + wrapL(kbB + c0 + K3_TILE));
-        // the coming tile's input lines into L1 (10 lines of 128 bytes cover 128 + 14 samples): they have this whole tile to arrive
-        if (t + 1 < t_end && lane < 10) {
-            const float2 *pf = in_pf + c0;
-            for (int s = 0; s < nsw && sbase + s < p.stream_end; ++s, pf += p.in_stride) k3_prefetch_l1(pf);
-        }
         // =============================== role A ===============================
         for (int s0 = 0; s0 < nsw; s0 += 2) {
             const int strA = sbase + s0, strB = sbase + s0 + 1;
@@ -281,8 +293,9 @@ K3_HD void k3_unit(Env &env, const K3Params &p, int sg, int span, int b, float2 
             const int kaA = wrapL(baseA.x + c0), kaB = wrapL(baseB.x + c0);      // table index of sample c0
             const bool fastA = c0 != 0 && kaA >= K3_LUT_STEADY + 16 && kaA + K3_TILE + 8 <= L;
             const bool fastB = c0 != 0 && kaB >= K3_LUT_STEADY + 16 && kaB + K3_TILE + 8 <= L;
-            const float2 *inA = in_ln + (size_t)s0 * (size_t)p.in_stride + c0;
-            const float2 *inB = in_ln + (size_t)(hasB ? s0 + 1 : s0) * (size_t)p.in_stride + c0;
+            // staged samples of the two streams: index i of a stream's buffer is sample c0 - 16 + i
+            const float2 *inA = sX + s0 * K3_XS + 16 + 4 * lane;
+            const float2 *inB = sX + (hasB ? s0 + 1 : s0) * K3_XS + 16 + 4 * lane;
             if (env.all(fastA && fastB)) {              // a vote: the compiler then knows the branch (and the VFO loop in it) is warp-uniform
                 // ---- sums and differences, once for all VFOs ----
                 // x[i] = sample c0 + 4l - 10 + i; outputs m' = 0, 1 have centres i = 5, 7
@@ -294,7 +307,7 @@ K3_HD void k3_unit(Env &env, const K3Params &p, int sg, int span, int b, float2 
                     const bool has = q ? hasB : hasA;
 #pragma unroll
                     for (int i = 0; i < 7; ++i) {
-                        const float4 v = has ? k3_ldg(xp + i) : make_float4(0.f, 0.f, 0.f, 0.f);
+                        const float4 v = has ? xp[i] : make_float4(0.f, 0.f, 0.f, 0.f);
                         x[2 * i] = make_float2(v.x, v.y);
                         x[2 * i + 1] = make_float2(v.z, v.w);
                     }
@@ -375,7 +388,7 @@ K3_HD void k3_unit(Env &env, const K3Params &p, int sg, int span, int b, float2 
                     float2 xe[16];                                           // xe[i] = sample c0 + 4l - 12 + i
 #pragma unroll
                     for (int i = 0; i < 8; ++i) {
-                        const float4 v = k3_ldg(xp + i);
+                        const float4 v = xp[i];
                         xe[2 * i] = make_float2(v.x, v.y);
                         xe[2 * i + 1] = make_float2(v.z, v.w);
                     }
@@ -403,6 +416,7 @@ K3_HD void k3_unit(Env &env, const K3Params &p, int sg, int span, int b, float2 
             }
         }
         env.sync();
+        if (t + 1 < t_end) stage_x(c0 + K3_TILE);            // role A has read this tile's samples: the next tile's may land
         // =============================== role B ===============================
         if (c0 == 0) {
             k3_head_shift(H.h2);
@@ -490,8 +504,29 @@ K3_HD void k3_unit(Env &env, const K3Params &p, int sg, int span, int b, float2 
 #ifdef __CUDACC__
 struct K3DevEnv {
     int lane;
+    unsigned long long *xbar;                              // the warp's mbarrier of the staged input
     __device__ __forceinline__ void sync() { __syncwarp(); }
     __device__ __forceinline__ bool all(bool v) { return __all_sync(0xffffffffu, v) != 0; }
+    __device__ __forceinline__ void x_expect(unsigned bytes) {
+        asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;\n" ::"r"((unsigned)__cvta_generic_to_shared(xbar)), "r"(bytes) : "memory");
+    }
+    __device__ __forceinline__ void x_copy(void *smem, const void *gmem, unsigned bytes) {
+        asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];\n" ::"r"(
+                         (unsigned)__cvta_generic_to_shared(smem)),
+                     "l"(gmem), "r"(bytes), "r"((unsigned)__cvta_generic_to_shared(xbar))
+                     : "memory");
+    }
+    __device__ __forceinline__ void x_wait(unsigned parity) {
+        asm volatile(
+            "{\n"
+            ".reg .pred p;\n"
+            "K3WAIT_%=:\n"
+            "mbarrier.try_wait.parity.shared::cta.b64 p, [%0], %1;\n"
+            "@p bra K3DONE_%=;\n"
+            "bra K3WAIT_%=;\n"
+            "K3DONE_%=:\n"
+            "}\n" ::"r"((unsigned)__cvta_generic_to_shared(xbar)), "r"(parity) : "memory");
+    }
 };
 
 constexpr int K3_WARPS = 2;                                 // default warps per CTA; the kernel works with any CTA size (independent warps that
@@ -516,14 +551,21 @@ __global__ void __maxnreg__(RC) k2a_v3(const __grid_constant__ K3Params p) {
     }
     __syncthreads();
     const int rows = p.nsw * p.count;
-    float2 *ring = reinterpret_cast<float2 *>(wbase + (size_t)warp * k3_warp_smem_bytes(rows));
+    float2 *ring = reinterpret_cast<float2 *>(wbase + (size_t)warp * k3_warp_smem_bytes(rows, p.nsw));
     float2 **sdst = reinterpret_cast<float2 **>(ring + rows * K3_ROW);
     float2 *sF = reinterpret_cast<float2 *>(sdst + 32);
     int2 *sK = reinterpret_cast<int2 *>(sF + 64);
+    float2 *sX = reinterpret_cast<float2 *>(sK + 32);
+    unsigned long long *xbar = reinterpret_cast<unsigned long long *>(sX + p.nsw * K3_XS);
+    if (lane == 0) {
+        asm volatile("mbarrier.init.shared::cta.b64 [%0], 1;\n" ::"r"((unsigned)__cvta_generic_to_shared(xbar)));
+        asm volatile("fence.mbarrier_init.release.cluster;\n" ::: "memory");
+    }
+    __syncwarp();
     const int sg = blockIdx.x * (int)(blockDim.x >> 5) + warp;
     if (p.stream0 + sg * p.nsw >= p.stream_end) return;
-    K3DevEnv env{lane};
-    k3_unit<MAXS>(env, p, sg, (int)blockIdx.y, p.b0 + (int)blockIdx.z, ring, sdst, sF, sK, srrel, stab, n_slots);
+    K3DevEnv env{lane, xbar};
+    k3_unit<MAXS>(env, p, sg, (int)blockIdx.y, p.b0 + (int)blockIdx.z, ring, sdst, sF, sK, sX, srrel, stab, n_slots);
 }
 #endif
 

@@ -21,6 +21,11 @@ struct HostEnv {
     std::barrier<> *bar;
     void sync() { bar->arrive_and_wait(); }
     bool all(bool v) { return v; }                 // every lane evaluates the same warp-uniform condition
+    // the bulk-copy engine: on the CPU the copy is done on the spot by the issuing lane; the barrier that follows every
+    // x_wait() in k3_unit orders it against the readers
+    void x_expect(unsigned) {}
+    void x_copy(void *smem, const void *gmem, unsigned bytes) { memcpy(smem, gmem, bytes); }
+    void x_wait(unsigned) {}
 };
 
 // ---- reference: one sub VFO front end over n_cb callbacks of B samples, state carried across ----
@@ -86,12 +91,13 @@ static void run_units(const K3Params &p, int n_cb, int n_spans) {
                 std::vector<float2 *> sdst(32, nullptr);
                 std::vector<float2> sF(64, make_float2(NAN, NAN));
                 std::vector<int2> sK(32, make_int2(0, 0));
+                std::vector<float2> sX((size_t)p.nsw * K3_XS, make_float2(NAN, NAN));
                 std::barrier<> bar(32);
                 std::vector<std::thread> th;
                 for (int lane = 0; lane < 32; ++lane)
                     th.emplace_back([&, lane]() {
                         HostEnv env{lane, &bar};
-                        k3_unit<MAXS>(env, p, sg, span, p.b0 + cb, ring.data(), sdst.data(), sF.data(), sK.data(), p.rrel, stab.data(), n_slots);
+                        k3_unit<MAXS>(env, p, sg, span, p.b0 + cb, ring.data(), sdst.data(), sF.data(), sK.data(), sX.data(), p.rrel, stab.data(), n_slots);
                     });
                 for (auto &t : th) t.join();
             }
