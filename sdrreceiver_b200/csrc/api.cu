@@ -628,8 +628,8 @@ extern "C" int sdrb_bank_create(const sdrb_plan *plan, int device, int n_streams
             kp.nsw = g.v3_nsw;
         }
         BANK_CU(cudaMemcpy(b->k3_rrel.p, rrel.data(), sizeof(float2) * rrel.size(), cudaMemcpyHostToDevice));
-#define K3_ATTR(S_, R_) BANK_CU((cudaFuncSetAttribute(k2a_v3<S_, R_>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)k3_cta_smem_bytes(K3_MAX_VFO, 4, 32, 8))))
-        K3_ATTR(2, 168); K3_ATTR(3, 168); K3_ATTR(5, 168); K3_ATTR(5, 200); K3_ATTR(5, 232);
+#define K3_ATTR(S_, R_, X_) BANK_CU((cudaFuncSetAttribute(k2a_v3<S_, R_, X_>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)k3_cta_smem_bytes(K3_MAX_VFO, 4, 32, 8))))
+        K3_ATTR(2, 168, false); K3_ATTR(3, 168, false); K3_ATTR(5, 168, false); K3_ATTR(5, 200, false); K3_ATTR(5, 232, true);
 #undef K3_ATTR
         if (const char *e = getenv("SDRB_K3_CTA_WARPS")) { const int v = atoi(e); if (v >= 1 && v <= 4) b->k3_cta_warps = v; }
         if (const char *e = getenv("SDRB_K3_REGS")) { const int v = atoi(e); if (v == 168 || v == 200 || v == 232) b->k3_regs5 = v; }
@@ -822,13 +822,15 @@ static int enqueue_subs(sdrb_bank *b, const CallCtx &c, int s0, int ns, cudaStre
             dim3 grid;
             const int cw = b->k3_cta_warps;
             k3_geometry(g, kp, ns, ncb, cw, &grid);
-            const size_t smem = k3_cta_smem_bytes(g.count, cw, g.v3_nsw * g.count, g.v3_nsw);
+            // staged input (bulk copies) only where registers, not shared memory, set the number of resident CTAs
+            const bool xs = g.v3_maxs == 5 && b->k3_regs5 == 232;
+            const size_t smem = k3_cta_smem_bytes(g.count, cw, g.v3_nsw * g.count, xs ? g.v3_nsw : 0);
             TimedScope t(b, st, 2);
-            if (g.v3_maxs == 2) k2a_v3<2, 168><<<grid, cw * 32, smem, st>>>(kp);
-            else if (g.v3_maxs == 3) k2a_v3<3, 168><<<grid, cw * 32, smem, st>>>(kp);
-            else if (b->k3_regs5 == 232) k2a_v3<5, 232><<<grid, cw * 32, smem, st>>>(kp);
-            else if (b->k3_regs5 == 200) k2a_v3<5, 200><<<grid, cw * 32, smem, st>>>(kp);
-            else k2a_v3<5, 168><<<grid, cw * 32, smem, st>>>(kp);
+            if (g.v3_maxs == 2) k2a_v3<2, 168, false><<<grid, cw * 32, smem, st>>>(kp);
+            else if (g.v3_maxs == 3) k2a_v3<3, 168, false><<<grid, cw * 32, smem, st>>>(kp);
+            else if (b->k3_regs5 == 232) k2a_v3<5, 232, true><<<grid, cw * 32, smem, st>>>(kp);
+            else if (b->k3_regs5 == 200) k2a_v3<5, 200, false><<<grid, cw * 32, smem, st>>>(kp);
+            else k2a_v3<5, 168, false><<<grid, cw * 32, smem, st>>>(kp);
             (*nl)++;
             continue;
         }

@@ -165,7 +165,7 @@ struct K3Hist {
 // Shared memory of a CTA: [rrel: count*64 float2][slot table: K3_MAX_SLOTS ushort][per warp: ring of `rows` rows,
 // 32 dst pointers, 2 x 32 table anchors (float2), 32 per-stream table bases (int2), nsw staged input tiles of K3_XS samples,
 // one mbarrier]
-K3_HD size_t k3_warp_smem_bytes(int rows, int nsw) {
+K3_HD size_t k3_warp_smem_bytes(int rows, int nsw) {          // nsw = 0: no staged input
     return (size_t)rows * K3_ROW * sizeof(float2) + 32 * sizeof(float2 *) + 64 * sizeof(float2) + 32 * sizeof(int2) +
            (size_t)nsw * K3_XS * sizeof(float2) + 16;
 }
@@ -206,7 +206,10 @@ K3_HD void k3_prefetch_l1(const void *p) {
 //   ring    32 rows of K3_ROW float2, private to the warp
 //   sdst    32 pointers, private to the warp
 //   srrel   the CTA's copy of p.rrel;  stab: slot table (v << 8 | 16-byte chunk), n_slots entries per stream
-template <int MAXS, class Env>
+// XS: the input tiles are staged in shared memory by the bulk-copy engine (worth it when the extra 1.2 KB per stream do not
+// cost a resident CTA: the 5-stage instantiation, which registers limit to 8 warps per SM); otherwise the lanes load their
+// windows from global memory, the lines prefetched into L1 one tile ahead.
+template <int MAXS, bool XS, class Env>
 K3_HD void k3_unit(Env &env, const K3Params &p, int sg, int span, int b, float2 *ring, float2 **sdst, float2 *sF, int2 *sK,
                    float2 *sX, const float2 *srrel, const unsigned short *stab, int n_slots) {
     const int lane = env.lane;
@@ -255,7 +258,7 @@ K3_HD void k3_unit(Env &env, const K3Params &p, int sg, int span, int b, float2 
     int n_str = 0;
     for (int s = 0; s < nsw && sbase + s < p.stream_end; ++s) n_str++;
     auto stage_x = [&](int c_first) {
-        if (lane == 0) {
+        if (XS && lane == 0) {
             env.x_expect((unsigned)(n_str * K3_XS * sizeof(float2)));
             for (int s = 0; s < n_str; ++s)
                 env.x_copy(sX + s * K3_XS, in0 + (size_t)s * (size_t)p.in_stride + c_first - 16, (unsigned)(K3_XS * sizeof(float2)));
@@ -263,6 +266,8 @@ K3_HD void k3_unit(Env &env, const K3Params &p, int sg, int span, int b, float2 
     };
     stage_x((t_begin - K3_WARM) * K3_TILE);
     unsigned xpar = 0;
+    const float2 *in_pf = in0 + K3_TILE - 16 + 16 * lane;                                                  // !XS: this lane's line of the next tile
+    const float2 *in_ln = in0 + 4 * lane;                                                                  // !XS: this lane's chunk of a tile
     // Output copy, common case (at most 32 sixteen-byte chunks per stream and tile): this lane's chunk is the same for every
     // tile and stream, so its source offset and destination are kept in registers instead of being looked up per tile.
     const bool cp_fast = n_slots <= 32;
@@ -279,12 +284,18 @@ K3_HD void k3_unit(Env &env, const K3Params &p, int sg, int span, int b, float2 
     for (int t = t_begin - K3_WARM; t < t_end; ++t) {
         const int c0 = t * K3_TILE;                          // callback coordinate of the tile's first sample (may be negative)
         k3_async_wait();
-        env.x_wait(xpar);
-        xpar ^= 1u;
+        if (XS) {
+            env.x_wait(xpar);
+            xpar ^= 1u;
+        }
         env.sync();
         const float2 *sFt = sF + 32 * fpar;                  // this tile's anchors
         fpar ^= 1;
         k3_async_copy8(sF + 32 * fpar + lane, lutB + wrapL(kbB + c0 + K3_TILE));
+        if (!XS && t + 1 < t_end && lane < 10) {             // the coming tile's lines into L1 (10 x 128 bytes cover 128 + 14 samples)
+            const float2 *pf = in_pf + c0;
+            for (int s = 0; s < n_str; ++s, pf += p.in_stride) k3_prefetch_l1(pf);
+        }
         // =============================== role A ===============================
         for (int s0 = 0; s0 < nsw; s0 += 2) {
             const int strA = sbase + s0, strB = sbase + s0 + 1;
@@ -294,8 +305,9 @@ K3_HD void k3_unit(Env &env, const K3Params &p, int sg, int span, int b, float2 
             const bool fastA = c0 != 0 && kaA >= K3_LUT_STEADY + 16 && kaA + K3_TILE + 8 <= L;
             const bool fastB = c0 != 0 && kaB >= K3_LUT_STEADY + 16 && kaB + K3_TILE + 8 <= L;
             // staged samples of the two streams: index i of a stream's buffer is sample c0 - 16 + i
-            const float2 *inA = sX + s0 * K3_XS + 16 + 4 * lane;
-            const float2 *inB = sX + (hasB ? s0 + 1 : s0) * K3_XS + 16 + 4 * lane;
+            const float2 *inA = XS ? sX + s0 * K3_XS + 16 + 4 * lane : in_ln + (size_t)s0 * (size_t)p.in_stride + c0;
+            const float2 *inB = XS ? sX + (hasB ? s0 + 1 : s0) * K3_XS + 16 + 4 * lane
+                                   : in_ln + (size_t)(hasB ? s0 + 1 : s0) * (size_t)p.in_stride + c0;
             if (env.all(fastA && fastB)) {              // a vote: the compiler then knows the branch (and the VFO loop in it) is warp-uniform
                 // ---- sums and differences, once for all VFOs ----
                 // x[i] = sample c0 + 4l - 10 + i; outputs m' = 0, 1 have centres i = 5, 7
@@ -307,7 +319,7 @@ K3_HD void k3_unit(Env &env, const K3Params &p, int sg, int span, int b, float2 
                     const bool has = q ? hasB : hasA;
 #pragma unroll
                     for (int i = 0; i < 7; ++i) {
-                        const float4 v = has ? xp[i] : make_float4(0.f, 0.f, 0.f, 0.f);
+                        const float4 v = has ? (XS ? xp[i] : k3_ldg(xp + i)) : make_float4(0.f, 0.f, 0.f, 0.f);
                         x[2 * i] = make_float2(v.x, v.y);
                         x[2 * i + 1] = make_float2(v.z, v.w);
                     }
@@ -388,7 +400,7 @@ K3_HD void k3_unit(Env &env, const K3Params &p, int sg, int span, int b, float2 
                     float2 xe[16];                                           // xe[i] = sample c0 + 4l - 12 + i
 #pragma unroll
                     for (int i = 0; i < 8; ++i) {
-                        const float4 v = xp[i];
+                        const float4 v = XS ? xp[i] : k3_ldg(xp + i);
                         xe[2 * i] = make_float2(v.x, v.y);
                         xe[2 * i + 1] = make_float2(v.z, v.w);
                     }
@@ -416,7 +428,7 @@ K3_HD void k3_unit(Env &env, const K3Params &p, int sg, int span, int b, float2 
             }
         }
         env.sync();
-        if (t + 1 < t_end) stage_x(c0 + K3_TILE);            // role A has read this tile's samples: the next tile's may land
+        if (XS && t + 1 < t_end) stage_x(c0 + K3_TILE);      // role A has read this tile's samples: the next tile's may land
         // =============================== role B ===============================
         if (c0 == 0) {
             k3_head_shift(H.h2);
@@ -534,7 +546,7 @@ constexpr int K3_WARPS = 2;                                 // default warps per
 
 // grid: x = ceil(stream groups / K3_WARPS), y = spans, z = callbacks
 // RC = register cap: 168 (12 warps per SM, the deep cascades then spill a history array), 200 (10 warps) or 232 (8 warps, no spills)
-template <int MAXS, int RC>
+template <int MAXS, int RC, bool XS>
 __global__ void __maxnreg__(RC) k2a_v3(const __grid_constant__ K3Params p) {
     extern __shared__ __align__(16) unsigned char k3_smem[];
     float2 *srrel = reinterpret_cast<float2 *>(k3_smem);
@@ -551,12 +563,12 @@ __global__ void __maxnreg__(RC) k2a_v3(const __grid_constant__ K3Params p) {
     }
     __syncthreads();
     const int rows = p.nsw * p.count;
-    float2 *ring = reinterpret_cast<float2 *>(wbase + (size_t)warp * k3_warp_smem_bytes(rows, p.nsw));
+    float2 *ring = reinterpret_cast<float2 *>(wbase + (size_t)warp * k3_warp_smem_bytes(rows, XS ? p.nsw : 0));
     float2 **sdst = reinterpret_cast<float2 **>(ring + rows * K3_ROW);
     float2 *sF = reinterpret_cast<float2 *>(sdst + 32);
     int2 *sK = reinterpret_cast<int2 *>(sF + 64);
     float2 *sX = reinterpret_cast<float2 *>(sK + 32);
-    unsigned long long *xbar = reinterpret_cast<unsigned long long *>(sX + p.nsw * K3_XS);
+    unsigned long long *xbar = reinterpret_cast<unsigned long long *>(sX + (XS ? p.nsw : 0) * K3_XS);
     if (lane == 0) {
         asm volatile("mbarrier.init.shared::cta.b64 [%0], 1;\n" ::"r"((unsigned)__cvta_generic_to_shared(xbar)));
         asm volatile("fence.mbarrier_init.release.cluster;\n" ::: "memory");
@@ -565,7 +577,7 @@ __global__ void __maxnreg__(RC) k2a_v3(const __grid_constant__ K3Params p) {
     const int sg = blockIdx.x * (int)(blockDim.x >> 5) + warp;
     if (p.stream0 + sg * p.nsw >= p.stream_end) return;
     K3DevEnv env{lane, xbar};
-    k3_unit<MAXS>(env, p, sg, (int)blockIdx.y, p.b0 + (int)blockIdx.z, ring, sdst, sF, sK, sX, srrel, stab, n_slots);
+    k3_unit<MAXS, XS>(env, p, sg, (int)blockIdx.y, p.b0 + (int)blockIdx.z, ring, sdst, sF, sK, sX, srrel, stab, n_slots);
 }
 #endif
 

@@ -73,7 +73,7 @@ static float frand() {
     return (float)((double)(rng >> 11) / 9007199254740992.0 * 2.0 - 1.0);
 }
 
-template <int MAXS>
+template <int MAXS, bool XS>
 static void run_units(const K3Params &p, int n_cb, int n_spans) {
     const int n_groups = (p.stream_end - p.stream0 + p.nsw - 1) / p.nsw;
     // slot table and rrel as the kernel builds them
@@ -97,7 +97,7 @@ static void run_units(const K3Params &p, int n_cb, int n_spans) {
                 for (int lane = 0; lane < 32; ++lane)
                     th.emplace_back([&, lane]() {
                         HostEnv env{lane, &bar};
-                        k3_unit<MAXS>(env, p, sg, span, p.b0 + cb, ring.data(), sdst.data(), sF.data(), sK.data(), sX.data(), p.rrel, stab.data(), n_slots);
+                        k3_unit<MAXS, XS>(env, p, sg, span, p.b0 + cb, ring.data(), sdst.data(), sF.data(), sK.data(), sX.data(), p.rrel, stab.data(), n_slots);
                     });
                 for (auto &t : th) t.join();
             }
@@ -157,7 +157,8 @@ int main(int argc, char **argv) {
             for (int cb = 0; cb < cb_per_call; ++cb)
                 for (int v = 0; v < nv; ++v) ref[(size_t)s][(size_t)v].process(body + (size_t)cb * B, B, ref_out[(size_t)s][(size_t)v]);
         }
-        run_units<5>(p, cb_per_call, n_spans);
+        if (call & 1) run_units<5, false>(p, cb_per_call, n_spans);      // both input paths, alternating from call to call
+        else run_units<5, true>(p, cb_per_call, n_spans);
         for (int s = 0; s < n_streams; ++s) {
             for (int v = 0; v < nv; ++v) {
                 const float2 *z = zbuf[(size_t)v].data() + (size_t)s * out_stride + OHIST;
