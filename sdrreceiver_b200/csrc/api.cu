@@ -250,6 +250,8 @@ struct sdrb_bank {
     DevBuf k3_rrel;
     bool per_cb = false;                          // SDRB_PER_CB=1: device-resident calls launch every kernel class per callback
     bool k1_bulk = true;                          // k1_v2 (64-thread CTAs) prefetches tiles with cp.async.bulk + mbarrier; SDRB_K1_BULK=0: per-thread cp.async records
+    bool k3_xs200 = false;                        // SDRB_K3_XS200=1: staged input also at the 200-register cap
+    int k3_ws = 0;                                // SDRB_K3_WS=1|2: warp-specialised k2a_v3ws (producer + consumer warp per CTA)
     int k3_cta_warps = K3_WARPS;                  // warps per k2a_v3 CTA (SDRB_K3_CTA_WARPS=1..4)
     int k3_regs5 = 232;                           // register cap of the 5-stage k2a_v3 instantiation (SDRB_K3_REGS=168|200|232)
     int dcw_ring = 2;                             // shared-memory ring depth of k0_dc_walk (SDRB_DCW_RING=4: the round-1 size)
@@ -629,8 +631,13 @@ extern "C" int sdrb_bank_create(const sdrb_plan *plan, int device, int n_streams
         }
         BANK_CU(cudaMemcpy(b->k3_rrel.p, rrel.data(), sizeof(float2) * rrel.size(), cudaMemcpyHostToDevice));
 #define K3_ATTR(S_, R_, X_) BANK_CU((cudaFuncSetAttribute(k2a_v3<S_, R_, X_>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)k3_cta_smem_bytes(K3_MAX_VFO, 4, 32, 8))))
-        K3_ATTR(2, 168, false); K3_ATTR(3, 168, false); K3_ATTR(5, 168, false); K3_ATTR(5, 200, false); K3_ATTR(5, 232, true);
+        K3_ATTR(2, 168, false); K3_ATTR(3, 168, false); K3_ATTR(5, 168, false); K3_ATTR(5, 200, false); K3_ATTR(5, 200, true); K3_ATTR(5, 232, true);
 #undef K3_ATTR
+#define K3W_ATTR(S_, R_, X_) BANK_CU((cudaFuncSetAttribute(k2a_v3ws<S_, R_, X_>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)k3ws_cta_smem_bytes(K3_MAX_VFO, 32, 8))))
+        K3W_ATTR(2, 168, false); K3W_ATTR(3, 168, false); K3W_ATTR(5, 168, false); K3W_ATTR(5, 168, true);
+#undef K3W_ATTR
+        if (const char *e = getenv("SDRB_K3_WS")) b->k3_ws = atoi(e);
+        b->k3_xs200 = getenv("SDRB_K3_XS200") && atoi(getenv("SDRB_K3_XS200")) != 0;
         if (const char *e = getenv("SDRB_K3_CTA_WARPS")) { const int v = atoi(e); if (v >= 1 && v <= 4) b->k3_cta_warps = v; }
         if (const char *e = getenv("SDRB_K3_REGS")) { const int v = atoi(e); if (v == 168 || v == 200 || v == 232) b->k3_regs5 = v; }
     }
@@ -819,16 +826,31 @@ static int enqueue_subs(sdrb_bank *b, const CallCtx &c, int s0, int ns, cudaStre
         if (g.v3) {
             K3Params &kp = b->k3[gi];
             kp.stream0 = s0; kp.stream_end = s0 + ns; kp.b0 = cb0;
+            if (b->k3_ws) {
+                // warp-specialised pair per CTA (kernels_v3.cuh: k2a_v3ws); SDRB_K3_WS=2: with staged input for the 5-stage groups
+                dim3 grid;
+                k3_geometry(g, kp, ns, ncb, 1, &grid);
+                const bool xs = b->k3_ws == 2 && g.v3_maxs == 5;
+                const size_t smem = k3ws_cta_smem_bytes(g.count, g.v3_nsw * g.count, xs ? g.v3_nsw : 0);
+                TimedScope t(b, st, 2);
+                if (g.v3_maxs == 2) k2a_v3ws<2, 168, false><<<grid, 64, smem, st>>>(kp);
+                else if (g.v3_maxs == 3) k2a_v3ws<3, 168, false><<<grid, 64, smem, st>>>(kp);
+                else if (xs) k2a_v3ws<5, 168, true><<<grid, 64, smem, st>>>(kp);
+                else k2a_v3ws<5, 168, false><<<grid, 64, smem, st>>>(kp);
+                (*nl)++;
+                continue;
+            }
             dim3 grid;
             const int cw = b->k3_cta_warps;
             k3_geometry(g, kp, ns, ncb, cw, &grid);
             // staged input (bulk copies) only where registers, not shared memory, set the number of resident CTAs
-            const bool xs = g.v3_maxs == 5 && b->k3_regs5 == 232;
+            const bool xs = g.v3_maxs == 5 && (b->k3_regs5 == 232 || b->k3_xs200);
             const size_t smem = k3_cta_smem_bytes(g.count, cw, g.v3_nsw * g.count, xs ? g.v3_nsw : 0);
             TimedScope t(b, st, 2);
             if (g.v3_maxs == 2) k2a_v3<2, 168, false><<<grid, cw * 32, smem, st>>>(kp);
             else if (g.v3_maxs == 3) k2a_v3<3, 168, false><<<grid, cw * 32, smem, st>>>(kp);
             else if (b->k3_regs5 == 232) k2a_v3<5, 232, true><<<grid, cw * 32, smem, st>>>(kp);
+            else if (b->k3_regs5 == 200 && b->k3_xs200) k2a_v3<5, 200, true><<<grid, cw * 32, smem, st>>>(kp);
             else if (b->k3_regs5 == 200) k2a_v3<5, 200, false><<<grid, cw * 32, smem, st>>>(kp);
             else k2a_v3<5, 168, false><<<grid, cw * 32, smem, st>>>(kp);
             (*nl)++;

@@ -209,7 +209,11 @@ K3_HD void k3_prefetch_l1(const void *p) {
 // XS: the input tiles are staged in shared memory by the bulk-copy engine (worth it when the extra 1.2 KB per stream do not
 // cost a resident CTA: the 5-stage instantiation, which registers limit to 8 warps per SM); otherwise the lanes load their
 // windows from global memory, the lines prefetched into L1 one tile ahead.
-template <int MAXS, bool XS, class Env>
+// ROLE: 0 = one warp plays both roles in turn (role A, warp barrier, role B); 1 / 2 = warp-specialised pair: this warp is the
+// producer (role A only, writes tile i into ring buffer i & 1) or the consumer (role B and the output copy only); the two hand the
+// buffers over with env.signal_/wait_ full/empty (named barriers of the CTA). A warp then holds only its role's registers
+// (the histories live in the consumer, the sums and differences in the producer) and tile i+1 is produced while tile i is filtered.
+template <int MAXS, bool XS, int ROLE, class Env>
 K3_HD void k3_unit(Env &env, const K3Params &p, int sg, int span, int b, float2 *ring, float2 **sdst, float2 *sF, int2 *sK,
                    float2 *sX, const float2 *srrel, const unsigned short *stab, int n_slots) {
     const int lane = env.lane;
@@ -231,10 +235,10 @@ K3_HD void k3_unit(Env &env, const K3Params &p, int sg, int span, int b, float2 
         H.h2[i] = make_float2(0.f, 0.f); H.h3[i] = make_float2(0.f, 0.f);
         H.h4[i] = make_float2(0.f, 0.f); H.h5[i] = make_float2(0.f, 0.f);
     }
-    const float2 *myrow = ring + (rowB ? lane : 0) * K3_ROW;      // lanes without a row read row 0 and store nothing
     const int SBw = rowB ? SB : 0;
+    const int ring_buf = nsw * nv * K3_ROW;                       // float2 per ring buffer (ROLE 1/2: two buffers)
     // per stream of the warp: table index of callback coordinate 0 and "this callback starts the stream" (oscillator.cpp:26-30)
-    if (lane < nsw) {
+    if (ROLE != 2 && lane < nsw) {
         int kb = 0, zero = 0;
         if (sbase + lane < p.stream_end) {
             const long long blk = k3_ldg(p.blocks_done + sbase + lane) + b;
@@ -245,11 +249,11 @@ K3_HD void k3_unit(Env &env, const K3Params &p, int sg, int span, int b, float2 
     }
     env.sync();
     const float2 *lutB = p.v[rowB ? vB : 0].lut;
-    const int kbB = sK[rowB ? sB : 0].x;
+    const int kbB = ROLE != 2 ? sK[rowB ? sB : 0].x : 0;
     auto wrapL = [L](int k) { if (k < 0) k += L; if (k >= L) k -= L; return k; };
     // the table entry of this row's (stream, VFO) at the first sample of a tile travels global -> shared one tile ahead
     // (sF is two buffers of 32 entries): no register holds it while the previous tile is being worked on
-    k3_async_copy8(sF + lane, lutB + wrapL(kbB + (t_begin - K3_WARM) * K3_TILE));
+    if (ROLE != 2) k3_async_copy8(sF + lane, lutB + wrapL(kbB + (t_begin - K3_WARM) * K3_TILE));
     int fpar = 0;
     const float2 *in0 = p.in + (size_t)sbase * (size_t)p.in_stride + p.hist_in + (long long)b * B;         // sample 0 of stream sbase
     // The input of a tile (K3_XS samples per stream: 16 in front of the tile, then the tile) is staged in shared memory by the
@@ -258,7 +262,7 @@ K3_HD void k3_unit(Env &env, const K3Params &p, int sg, int span, int b, float2 
     int n_str = 0;
     for (int s = 0; s < nsw && sbase + s < p.stream_end; ++s) n_str++;
     auto stage_x = [&](int c_first) {
-        if (XS && lane == 0) {
+        if (XS && ROLE != 2 && lane == 0) {
             env.x_expect((unsigned)(n_str * K3_XS * sizeof(float2)));
             for (int s = 0; s < n_str; ++s)
                 env.x_copy(sX + s * K3_XS, in0 + (size_t)s * (size_t)p.in_stride + c_first - 16, (unsigned)(K3_XS * sizeof(float2)));
@@ -283,19 +287,23 @@ K3_HD void k3_unit(Env &env, const K3Params &p, int sg, int span, int b, float2 
 
     for (int t = t_begin - K3_WARM; t < t_end; ++t) {
         const int c0 = t * K3_TILE;                          // callback coordinate of the tile's first sample (may be negative)
+        const int ti = t - (t_begin - K3_WARM);              // tile counter of this unit
+        float2 *rbuf = ring + (ROLE == 0 ? 0 : (ti & 1) * ring_buf);
+        const float2 *sFt = sF + 32 * fpar;                  // this tile's anchors
+        if (ROLE != 2) {
         k3_async_wait();
         if (XS) {
             env.x_wait(xpar);
             xpar ^= 1u;
         }
         env.sync();
-        const float2 *sFt = sF + 32 * fpar;                  // this tile's anchors
         fpar ^= 1;
         k3_async_copy8(sF + 32 * fpar + lane, lutB + wrapL(kbB + c0 + K3_TILE));
         if (!XS && t + 1 < t_end && lane < 10) {             // the coming tile's lines into L1 (10 x 128 bytes cover 128 + 14 samples)
             const float2 *pf = in_pf + c0;
             for (int s = 0; s < n_str; ++s, pf += p.in_stride) k3_prefetch_l1(pf);
         }
+        if (ROLE == 1 && ti >= 2) env.wait_empty(ti & 1);    // the consumer is done with the tile that used this buffer
         // =============================== role A ===============================
         for (int s0 = 0; s0 < nsw; s0 += 2) {
             const int strA = sbase + s0, strB = sbase + s0 + 1;
@@ -386,7 +394,7 @@ K3_HD void k3_unit(Env &env, const K3Params &p, int sg, int span, int b, float2 
                     for (int q = 0; q < 2; ++q) {
                         const float2 o0 = k3_cmul(G[q][0], acc[q][0]), o1 = k3_cmul(G[q][1], acc[q][1]);
                         if (q ? hasB : hasA)
-                            *reinterpret_cast<float4 *>(ring + ((s0 + q) * nv + v) * K3_ROW + 2 * lane) = make_float4(o0.x, o0.y, o1.x, o1.y);
+                            *reinterpret_cast<float4 *>(rbuf + ((s0 + q) * nv + v) * K3_ROW + 2 * lane) = make_float4(o0.x, o0.y, o1.x, o1.y);
                     }
                 }
             } else {
@@ -422,14 +430,19 @@ K3_HD void k3_unit(Env &env, const K3Params &p, int sg, int span, int b, float2 
                         float2 o1 = k3_hb(u[2], u[4], u[6], u[7], u[8], u[10], u[12]);
                         o0 = make_float2(o0.x * sc, o0.y * sc);
                         o1 = make_float2(o1.x * sc, o1.y * sc);
-                        *reinterpret_cast<float4 *>(ring + ((s0 + q) * nv + v) * K3_ROW + 2 * lane) = make_float4(o0.x, o0.y, o1.x, o1.y);
+                        *reinterpret_cast<float4 *>(rbuf + ((s0 + q) * nv + v) * K3_ROW + 2 * lane) = make_float4(o0.x, o0.y, o1.x, o1.y);
                     }
                 }
             }
         }
         env.sync();
         if (XS && t + 1 < t_end) stage_x(c0 + K3_TILE);      // role A has read this tile's samples: the next tile's may land
+        if (ROLE == 1) env.signal_full(ti & 1);
+        }                                                    // ROLE != 2
         // =============================== role B ===============================
+        if (ROLE != 1) {
+        if (ROLE == 2) env.wait_full(ti & 1);
+        const float2 *myrow = rbuf + (rowB ? lane : 0) * K3_ROW;  // lanes without a row read row 0 and store nothing
         if (c0 == 0) {
             k3_head_shift(H.h2);
             if (MAXS > 2) k3_head_shift(H.h3);
@@ -439,7 +452,7 @@ K3_HD void k3_unit(Env &env, const K3Params &p, int sg, int span, int b, float2 
 #pragma unroll
         for (int sub = 0; sub < K3_OUT1 / 16; ++sub) {
             const float4 *rp = reinterpret_cast<const float4 *>(myrow + 16 * sub);
-            float2 *wr = ring + (rowB ? lane : 0) * K3_ROW;  // outputs go to the front of the row (always behind the read position)
+            float2 *wr = rbuf + (rowB ? lane : 0) * K3_ROW;  // outputs go to the front of the row (always behind the read position)
             if (MAXS >= 2) {
                 // stage 2 in two halves of 8 inputs: only half of the 16 first-stage samples is in registers at any time
                 float2 o2[8];
@@ -489,7 +502,7 @@ K3_HD void k3_unit(Env &env, const K3Params &p, int sg, int span, int b, float2 
                 if (lane < n_slots) {
                     const long long adv = ((long long)t * K3_OUT1) >> cp_shift;      // out1 index 64 t -> index of the VFO's own output
                     for (int s = 0; s < nsw && sbase + s < p.stream_end; ++s) {
-                        const float4 v = *reinterpret_cast<const float4 *>(ring + s * nv * K3_ROW + cp_src);
+                        const float4 v = *reinterpret_cast<const float4 *>(rbuf + s * nv * K3_ROW + cp_src);
                         *reinterpret_cast<float4 *>(cp_dst + (size_t)s * (size_t)p.out_stride + adv) = v;
                     }
                 }
@@ -503,13 +516,18 @@ K3_HD void k3_unit(Env &env, const K3Params &p, int sg, int span, int b, float2 
                     for (int slot = lane; slot < n_slots; slot += 32) {
                         const unsigned e = stab[slot];
                         const int r = s * nv + (int)(e >> 8), ch = (int)(e & 0xffu);
-                        const float4 v = *reinterpret_cast<const float4 *>(ring + r * K3_ROW + 2 * ch);
+                        const float4 v = *reinterpret_cast<const float4 *>(rbuf + r * K3_ROW + 2 * ch);
                         *reinterpret_cast<float4 *>(sdst[r] + 2 * ch) = v;
                     }
                 }
             }
         }
-        env.sync();
+        if (ROLE == 2) {
+            env.sync();
+            env.signal_empty(ti & 1);
+        }
+        }                                                    // ROLE != 1
+        if (ROLE == 0) env.sync();
     }
 }
 
@@ -519,6 +537,12 @@ struct K3DevEnv {
     unsigned long long *xbar;                              // the warp's mbarrier of the staged input
     __device__ __forceinline__ void sync() { __syncwarp(); }
     __device__ __forceinline__ bool all(bool v) { return __all_sync(0xffffffffu, v) != 0; }
+    // producer/consumer hand-over of the two ring buffers (ROLE 1/2): named barriers 1..4 of the 64-thread CTA, the signalling warp
+    // arrives, the waiting warp syncs (64 = both warps)
+    __device__ __forceinline__ void signal_full(int buf) { asm volatile("bar.arrive %0, 64;\n" ::"r"(1 + buf) : "memory"); }
+    __device__ __forceinline__ void wait_full(int buf) { asm volatile("bar.sync %0, 64;\n" ::"r"(1 + buf) : "memory"); }
+    __device__ __forceinline__ void signal_empty(int buf) { asm volatile("bar.arrive %0, 64;\n" ::"r"(3 + buf) : "memory"); }
+    __device__ __forceinline__ void wait_empty(int buf) { asm volatile("bar.sync %0, 64;\n" ::"r"(3 + buf) : "memory"); }
     __device__ __forceinline__ void x_expect(unsigned bytes) {
         asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;\n" ::"r"((unsigned)__cvta_generic_to_shared(xbar)), "r"(bytes) : "memory");
     }
@@ -577,8 +601,46 @@ __global__ void __maxnreg__(RC) k2a_v3(const __grid_constant__ K3Params p) {
     const int sg = blockIdx.x * (int)(blockDim.x >> 5) + warp;
     if (p.stream0 + sg * p.nsw >= p.stream_end) return;
     K3DevEnv env{lane, xbar};
-    k3_unit<MAXS, XS>(env, p, sg, (int)blockIdx.y, p.b0 + (int)blockIdx.z, ring, sdst, sF, sK, sX, srrel, stab, n_slots);
+    k3_unit<MAXS, XS, 0>(env, p, sg, (int)blockIdx.y, p.b0 + (int)blockIdx.z, ring, sdst, sF, sK, sX, srrel, stab, n_slots);
+}
+// Warp-specialised form: a CTA is ONE unit of work handled by a producer warp (role A) and a consumer warp (role B) that hand two
+// ring buffers back and forth. grid: x = stream groups, y = spans, z = callbacks; 64 threads.
+K3_HD size_t k3ws_cta_smem_bytes(int count, int rows, int nsw) {
+    return (size_t)count * K3_OUT1 * sizeof(float2) + K3_MAX_SLOTS * sizeof(unsigned short) + (size_t)rows * K3_ROW * sizeof(float2) +
+           k3_warp_smem_bytes(rows, nsw);
+}
+template <int MAXS, int RC, bool XS>
+__global__ void __maxnreg__(RC) k2a_v3ws(const __grid_constant__ K3Params p) {
+    extern __shared__ __align__(16) unsigned char k3_smem[];
+    float2 *srrel = reinterpret_cast<float2 *>(k3_smem);
+    unsigned short *stab = reinterpret_cast<unsigned short *>(srrel + p.count * K3_OUT1);
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    for (int e = threadIdx.x; e < p.count * K3_OUT1; e += blockDim.x) srrel[e] = p.rrel[e];
+    int n_slots = 0;
+    for (int v = 0; v < p.count; ++v) {
+        const int n = 32 >> (p.v[v].S - 1);
+        for (int c = threadIdx.x; c < n; c += blockDim.x) stab[n_slots + c] = (unsigned short)((v << 8) | c);
+        n_slots += n;
+    }
+    const int rows = p.nsw * p.count;
+    float2 *ring = reinterpret_cast<float2 *>(stab + K3_MAX_SLOTS);                // two buffers of `rows` rows
+    float2 **sdst = reinterpret_cast<float2 **>(ring + 2 * rows * K3_ROW);
+    float2 *sF = reinterpret_cast<float2 *>(sdst + 32);
+    int2 *sK = reinterpret_cast<int2 *>(sF + 64);
+    float2 *sX = reinterpret_cast<float2 *>(sK + 32);
+    unsigned long long *xbar = reinterpret_cast<unsigned long long *>(sX + (XS ? p.nsw : 0) * K3_XS);
+    if (threadIdx.x == 0) {
+        asm volatile("mbarrier.init.shared::cta.b64 [%0], 1;\n" ::"r"((unsigned)__cvta_generic_to_shared(xbar)));
+        asm volatile("fence.mbarrier_init.release.cluster;\n" ::: "memory");
+    }
+    __syncthreads();
+    const int sg = blockIdx.x;
+    if (p.stream0 + sg * p.nsw >= p.stream_end) return;
+    K3DevEnv env{lane, xbar};
+    if (warp == 0) k3_unit<MAXS, XS, 1>(env, p, sg, (int)blockIdx.y, p.b0 + (int)blockIdx.z, ring, sdst, sF, sK, sX, srrel, stab, n_slots);
+    else k3_unit<MAXS, XS, 2>(env, p, sg, (int)blockIdx.y, p.b0 + (int)blockIdx.z, ring, sdst, sF, sK, sX, srrel, stab, n_slots);
 }
 #endif
+
 
 }  // namespace sdrb

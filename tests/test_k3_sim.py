@@ -35,6 +35,9 @@ def sim(built):
     (30720, 7680, 4, 2, 7, 16),      # 16 sub VFOs, ragged last span
     (30720, 7680, 3, 8, 3, 4),       # eight streams per warp
     (30720, 7680, 2, 1, 5, 16),      # one stream per warp
+    (30720, 7680, 3, 2, 4, 6, 1),    # the warp-specialised producer / consumer pair, two ring buffers
+    (30720, 7680, 4, 2, 7, 16, 1),
+    (30720, 7680, 5, 3, 1, 6, 1),
 ])
 def test_k3_unit_matches_the_plain_cascade(sim, args):
     r = subprocess.run([sim] + [str(a) for a in args], capture_output=True, text=True, timeout=600)
