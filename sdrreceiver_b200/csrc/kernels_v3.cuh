@@ -52,6 +52,15 @@ constexpr int K3_XS = K3_TILE + 16;     // staged input samples per stream and t
 #endif
 
 #define K3_HD __host__ __device__ __forceinline__
+// tuning switches of the VFO loop of role A (tools/k3_variants.sh builds the alternatives)
+#ifndef K3_PIPE
+#define K3_PIPE 1            /* 1: rotation-table pair and anchors of VFO v+1 are read while VFO v is computed */
+#endif
+#ifndef K3_VFO_UNROLL
+#define K3_VFO_UNROLL 2
+#endif
+#define K3_STR2(x) #x
+#define K3_STR(x) K3_STR2(x)
 
 struct K3Vfo {
     const float2 *lut;          // Oscillator table
@@ -348,11 +357,16 @@ K3_HD void k3_unit(Env &env, const K3Params &p, int sg, int span, int b, float2 
                 // software pipeline: the rotation-table pair and the anchors of VFO v+1 are fetched while VFO v is computed
                 float4 rr_n = *reinterpret_cast<const float4 *>(srrel + 2 * lane);
                 float2 FA_n = sFt[s0 * nv], FB_n = sFt[(hasB ? s0 + 1 : s0) * nv];
-#pragma unroll 2
+_Pragma(K3_STR(unroll K3_VFO_UNROLL))
                 for (int v = 0; v < nv; ++v) {
+#if K3_PIPE
                     const float4 rr = rr_n;
                     const float2 FA = FA_n, FB = FB_n;
-                    if (v + 1 < nv) {
+#else
+                    const float4 rr = *reinterpret_cast<const float4 *>(srrel + v * K3_OUT1 + 2 * lane);
+                    const float2 FA = sFt[s0 * nv + v], FB = sFt[(hasB ? s0 + 1 : s0) * nv + v];
+#endif
+                    if (K3_PIPE && v + 1 < nv) {
                         rr_n = *reinterpret_cast<const float4 *>(srrel + (v + 1) * K3_OUT1 + 2 * lane);
                         FA_n = sFt[s0 * nv + v + 1];
                         FB_n = sFt[(hasB ? s0 + 1 : s0) * nv + v + 1];
