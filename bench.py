@@ -222,7 +222,7 @@ def alg_tables(plan):
     hb = lambda decim: sum(20.0 / 2 ** a for a in range(1, decim + 1))
     alg_flops = {
         "dc_scan": 8.0 if plan.correct_dc else 0.0,
-        "ingest_main": 2.0 + sum(6.0 + hb(m["decim"]) for m in plan.mains),
+        "ingest_main": 10.0 + sum(6.0 + hb(m["decim"]) for m in plan.mains),     # u8->f32 2 + DC 8 + mains
         "sub_cascade": sum((s["Fs"] / fs) * (6.0 + hb(s["decim"])) for s in plan.subs),
         "late_fir": sum((s["out_rate"] / fs) * 4.0 * s["n_dec_taps"] for s in plan.subs if s["late"]),
         "usb_audio": sum((s["out_rate"] / fs) * (2.0 * 62 + 1 + 2.0 * s["n_lpf_taps"] + 2.0) for s in plan.subs),

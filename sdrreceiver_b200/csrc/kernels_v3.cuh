@@ -57,7 +57,7 @@ constexpr int K3_XS = K3_TILE + 16;     // staged input samples per stream and t
 #define K3_PIPE 1            /* 1: rotation-table pair and anchors of VFO v+1 are read while VFO v is computed */
 #endif
 #ifndef K3_VFO_UNROLL
-#define K3_VFO_UNROLL 2
+#define K3_VFO_UNROLL 4
 #endif
 #define K3_STR2(x) #x
 #define K3_STR(x) K3_STR2(x)
