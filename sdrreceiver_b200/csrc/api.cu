@@ -205,6 +205,13 @@ struct SubGroup {           // sub VFOs of one main VFO (at most V2_MAX_VFO) -> 
 
 // Rf[j] = (rot/|rot|)^j, j = -10..31 (index j + 10), rot = the float rotation the Oscillator table is
 // built from (oscillator.cpp:9-14); see kernels_v2.cuh
+void rf_table(double sample_rate, double frequency, float2 *dst);
+// the kernel-parameter form: (c, c, -s, s) per rotation (kernels_v2.cuh: RfTab)
+void rf_tab(double sample_rate, double frequency, RfTab *t) {
+    float2 rf[RF_LEN];
+    rf_table(sample_rate, frequency, rf);
+    for (int i = 0; i < RF_LEN; i++) t->q[i] = make_float4(rf[i].x, rf[i].x, -rf[i].y, rf[i].y);
+}
 void rf_table(double sample_rate, double frequency, float2 *dst) {
     const double step = 2.0 * M_PI * frequency / sample_rate;
     const float rr = (float)cos(step), ri = (float)sin(step);
@@ -254,6 +261,7 @@ struct sdrb_bank {
     int k3_ws = 0;                                // SDRB_K3_WS=1|2: warp-specialised k2a_v3ws (producer + consumer warp per CTA)
     int k3_cta_warps = K3_WARPS;                  // warps per k2a_v3 CTA (SDRB_K3_CTA_WARPS=1..4)
     int k3_regs5 = 200;                           // register cap of the 5-stage k2a_v3 instantiation (SDRB_K3_REGS=168|200|232)
+    int dc_run = 4;                               // blocks per integer solve of k0_dc_walk: 4, 2 or 1 (SDRB_DC_RUN; 1 = round-1 behaviour)
     int dcw_ring = 2;                             // shared-memory ring depth of k0_dc_walk (SDRB_DCW_RING=4: the round-1 size)
     int dbg_only = 0;                             // SDRB_DEBUG_ONLY=dc|filters: profiling aid, device-resident calls skip the other half (results are then meaningless)
     DevBuf cascdev, rfdev, latedev, usbdev, carry;
@@ -505,9 +513,7 @@ extern "C" int sdrb_bank_create(const sdrb_plan *plan, int device, int n_streams
         D.lut = (const float2 *)b->luts.p + sub_lut_off[i];
         D.out = (float2 *)b->zbuf.p + z_off[i];
         D.S = s.decim; D.block_out = s.block_z; D.hist = z_hist[i]; D.pad = 0;
-        float2 rf[RF_LEN];
-        rf_table((double)s.fs, s.mixer, rf);
-        memcpy(b->sub_rf[i].q, rf, sizeof(RfTab));
+        rf_tab((double)s.fs, s.mixer, &b->sub_rf[i]);
     }
     for (size_t i = 0; i < h.subs.size(); i++) {
         const SubVfo &s = h.subs[i];
@@ -569,7 +575,7 @@ extern "C" int sdrb_bank_create(const sdrb_plan *plan, int device, int n_streams
         q.dc_table = (const uint2 *)b->dc_table.p;
         q.dc_anchor = (const DcAnchor *)b->dc_anchor.p;
         q.blocks_done = (const long long *)b->blocks_done.p;
-        for (size_t i = 0; i < h.mains.size(); i++) memcpy(q.rf[i].q, &rfhost[i * RF_LEN], sizeof(RfTab));
+        for (size_t i = 0; i < h.mains.size(); i++) rf_tab((double)h.fs, h.mains[i].mixer, &q.rf[i]);
         q.out_stride = (long long)b->main_stride;
         q.dc_stride = b->dc_stride + DC_HALO_BLKS; q.block = h.block; q.lut_len = (int)h.mains[0].lut.size();
         q.n_main = (int)h.mains.size();
@@ -586,7 +592,7 @@ extern "C" int sdrb_bank_create(const sdrb_plan *plan, int device, int n_streams
         K2V2Params &kp = b->k2v2[gi];
         for (int v = 0; v < g.count; v++) {
             kp.vfos[v] = cascdev[(size_t)(g.first + v)];
-            memcpy(kp.rf[v].q, &rfhost[(h.mains.size() + (size_t)(g.first + v)) * RF_LEN], sizeof(RfTab));
+            kp.rf[v] = b->sub_rf[(size_t)order[(size_t)(g.first + v)]];
         }
         kp.in = (const float2 *)b->main_out.p + b->main_off[(size_t)g.main_idx];
         kp.blocks_done = (const long long *)b->blocks_done.p;
@@ -652,6 +658,7 @@ extern "C" int sdrb_bank_create(const sdrb_plan *plan, int device, int n_streams
     BANK_CU(cudaFuncSetAttribute(k0_dc_walk<2>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)dcw_smem<2>()));
     BANK_CU(cudaFuncSetAttribute(k0_dc_walk<4>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)dcw_smem<4>()));
     if (const char *e = getenv("SDRB_DCW_RING")) b->dcw_ring = atoi(e) == 4 ? 4 : 2;
+    if (const char *e = getenv("SDRB_DC_RUN")) b->dc_run = atoi(e) >= 4 ? 4 : (atoi(e) >= 2 ? 2 : 1);
     BANK_CU(cudaFuncSetAttribute(k2_late_v2<5>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)lv_smem<5>()));
     BANK_CU(cudaFuncSetAttribute(k2_late_v2<6>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)lv_smem<6>()));
     BANK_CU(cudaFuncSetAttribute(k2a_v2<64>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)V2L<64>::SMEM));
@@ -769,11 +776,11 @@ static int enqueue_dc_cb(sdrb_bank *b, const CallCtx &c, int s0, int ns, cudaStr
         if (b->dcw_ring == 4)
             k0_dc_walk<4><<<(unsigned)ns, 64, dcw_smem<4>(), sd>>>(c.d_iq, c.iq_stride, (const DcStats *)b->dc_stats.p, b->dc_stride,
                                                                   b->anchor_buf(c.par), b->qtab_buf(c.par), (float2 *)b->dc_state.p, b->table_buf(c.par),
-                                                                  b->dc_stride + DC_HALO_BLKS, cb * per_cb, per_cb, s0);
+                                                                  b->dc_stride + DC_HALO_BLKS, cb * per_cb, per_cb, s0, b->dc_run);
         else
             k0_dc_walk<2><<<(unsigned)ns, 64, dcw_smem<2>(), sd>>>(c.d_iq, c.iq_stride, (const DcStats *)b->dc_stats.p, b->dc_stride,
                                                                   b->anchor_buf(c.par), b->qtab_buf(c.par), (float2 *)b->dc_state.p, b->table_buf(c.par),
-                                                                  b->dc_stride + DC_HALO_BLKS, cb * per_cb, per_cb, s0);
+                                                                  b->dc_stride + DC_HALO_BLKS, cb * per_cb, per_cb, s0, b->dc_run);
     }
     (*nl) += 2;
     CU_TRY(cudaEventRecord(done, sd));
@@ -1657,6 +1664,32 @@ extern "C" int sdrb_usb_demod(const float *d_points, const float *d_in, float *d
     return SDRB_OK;
 }
 
+// Twiddle and window tables of the 8192-point transform, one copy per device, built on the host with the reference's own
+// expressions: exp(-2 pi i k/N) in double cast to float (kiss_fft.c:357-363), hann[i] = 0.5*(1 - cos(2 pi float(i)/(N-1)))
+// cast to float (mainwindow.cpp:284-288).
+static int fft_tables(int device, FftTables *out) {
+    static FftTables tabs[64] = {};
+    if (device < 0 || device >= 64) { set_error("fft_tables: device index out of range"); return SDRB_E_INVALID; }
+    if (!tabs[device].tw) {
+        std::vector<float2> tw((size_t)FFT_N / 2);
+        std::vector<float> hann((size_t)FFT_N);
+        const double pi = 3.14159265358979323846264338327950288;
+        for (int m = 0; m < FFT_N / 2; m++) {
+            const double phase = -2.0 * pi * (double)m / (double)FFT_N;
+            tw[(size_t)m] = make_float2((float)cos(phase), (float)sin(phase));
+        }
+        for (int i = 0; i < FFT_N; i++) hann[(size_t)i] = (float)(0.5 * (1.0 - cos(2.0 * M_PI * (double)(float)i / (FFT_N - 1.0))));
+        float2 *dtw = nullptr; float *dh = nullptr;
+        CU_TRY(cudaMalloc(&dtw, tw.size() * sizeof(float2)));
+        CU_TRY(cudaMalloc(&dh, hann.size() * sizeof(float)));
+        CU_TRY(cudaMemcpy(dtw, tw.data(), tw.size() * sizeof(float2), cudaMemcpyHostToDevice));
+        CU_TRY(cudaMemcpy(dh, hann.data(), hann.size() * sizeof(float), cudaMemcpyHostToDevice));
+        tabs[device].tw = dtw; tabs[device].hann = dh;
+    }
+    *out = tabs[device];
+    return SDRB_OK;
+}
+
 extern "C" int sdrb_spectrum_fft(const float *d_in, float *d_out, int n_batch, int nfft, int apply_hann, void *cuda_stream) {
     if (!d_in || !d_out || n_batch <= 0 || nfft != 8192) {
         set_error("sdrb_spectrum_fft: nfft must be 8192 (mainwindow.cpp:241)"); return SDRB_E_INVALID;
@@ -1666,8 +1699,10 @@ extern "C" int sdrb_spectrum_fft(const float *d_in, float *d_out, int n_batch, i
         CU_TRY(cudaFuncSetAttribute(prim_fft8192, cudaFuncAttributeMaxDynamicSharedMemorySize, 8192 * (int)sizeof(float2)));
         attr = true;
     }
+    FftTables T;
+    { int dev = 0; CU_TRY(cudaGetDevice(&dev)); const int trc = fft_tables(dev, &T); if (trc != SDRB_OK) return trc; }
     prim_fft8192<<<(unsigned)n_batch, 512, 8192 * sizeof(float2), (cudaStream_t)cuda_stream>>>(
-        (const float2 *)d_in, (float2 *)d_out, apply_hann);
+        (const float2 *)d_in, (float2 *)d_out, apply_hann, T);
     CU_TRY(cudaGetLastError());
     return SDRB_OK;
 }
@@ -1727,9 +1762,11 @@ extern "C" int sdrb_spectrum_feed_device(sdrb_spectrum *sp, const float *d_in, s
         set_error("sdrb_spectrum_feed_device: bad argument"); return SDRB_E_INVALID;
     }
     CU_TRY(cudaSetDevice(sp->device));
+    FftTables T;
+    { const int trc = fft_tables(sp->device, &T); if (trc != SDRB_OK) return trc; }
     k_spectrum_feed<<<(unsigned)sp->n, FFT_THREADS, FFT_N * sizeof(float2), (cudaStream_t)cuda_stream>>>(
         (const float2 *)d_in, (long long)in_stride, len, (float2 *)sp->inr.p, (double *)sp->pwr.p, (double *)sp->smooth.p,
-        (double *)sp->stats.p, (float2 *)d_fft_out);
+        (double *)sp->stats.p, (float2 *)d_fft_out, T);
     CU_TRY(cudaGetLastError());
     return SDRB_OK;
 }

@@ -418,13 +418,88 @@ __device__ __forceinline__ void cp_async16(void *smem, const void *gmem) {
 __device__ __forceinline__ void cp_async_commit() { asm volatile("cp.async.commit_group;\n" ::); }
 template <int N> __device__ __forceinline__ void cp_async_wait() { asm volatile("cp.async.wait_group %0;\n" ::"n"(N)); }
 
+// Integer solve of a RUN of R consecutive blocks (R * 128 samples, 4 R per lane) in one pass. The straddling blocks cluster -- the
+// state dwells near its threshold for a few blocks at a time -- and one solve of four blocks costs little more than a solve of one:
+// the same warp scan, the same fixed-point structure with 4 R dependent steps per lane and round. V_k = V + U_k - C_k with U the
+// prefix sums of the increments and C_{i+1} = C_i + [C_i <= V + U_i - T]; the lanes iterate their indicators against the counts of
+// the lanes before them (bit-sliced ballots of the per-lane counts) until nothing changes. Every state of the run must stay inside
+// [0, hiw) and no increment may be a rounding tie, otherwise the caller falls back to the single-block path.
+// On success: the block-start states go to to[0], to[2], .. (one entry per block), V becomes the state after the run.
+template <int R>
+__device__ __forceinline__ bool dc_solve_run(const unsigned char *raw, int arm, int lane, unsigned lt_mask, const int *sqt, int Tv, int hiw,
+                                             unsigned &V, uint2 *to) {
+    constexpr int NS = 4 * R;                                   // samples per lane
+    constexpr int BITS = R == 1 ? 3 : (R == 2 ? 4 : 5);         // bits of a lane's indicator count (<= NS)
+    unsigned w[NS / 2];                                         // one 32-bit word = two IQ pairs
+    if (R == 4) {
+        const uint4 a = *reinterpret_cast<const uint4 *>(raw + lane * 32), c = *reinterpret_cast<const uint4 *>(raw + lane * 32 + 16);
+        w[0] = a.x; w[1] = a.y; w[2] = a.z; w[3] = a.w; w[4 % (NS / 2)] = c.x; w[5 % (NS / 2)] = c.y; w[6 % (NS / 2)] = c.z; w[7 % (NS / 2)] = c.w;
+    } else if (R == 2) {
+        const uint4 a = *reinterpret_cast<const uint4 *>(raw + lane * 16);
+        w[0] = a.x; w[1] = a.y; w[2 % (NS / 2)] = a.z; w[3 % (NS / 2)] = a.w;
+    } else {
+        const uint2 a = *reinterpret_cast<const uint2 *>(raw + lane * 8);
+        w[0] = a.x; w[1] = a.y;
+    }
+    int p[NS + 1];
+    bool tie = false;
+    p[0] = 0;
+#pragma unroll
+    for (int i = 0; i < NS; ++i) {
+        const int d = sqt[(w[i >> 1] >> (16 * (i & 1) + 8 * arm)) & 0xffu];
+        tie |= d == DC_QTIE;
+        p[i + 1] = p[i] + d;
+    }
+    const int tot = p[NS];
+    int inc = tot;
+#pragma unroll
+    for (int o = 1; o < 32; o <<= 1) {
+        const int v = __shfl_up_sync(0xffffffffu, inc, o);
+        if (lane >= o) inc += v;
+    }
+    const int base = (int)V + (inc - tot);                      // V + U at the lane's first sample
+    int cin = 0, nl = 0;
+    for (int it = 0; it < 34; ++it) {
+        int c = cin;
+#pragma unroll
+        for (int i = 0; i < NS; ++i) c += (c <= base + p[i] - Tv) ? 1 : 0;
+        nl = c - cin;
+        int nc = 0;
+#pragma unroll
+        for (int bit = 0; bit < BITS; ++bit) nc += __popc(__ballot_sync(0xffffffffu, (nl >> bit) & 1) & lt_mask) << bit;
+        const bool changed = nc != cin;
+        cin = nc;
+        if (!__any_sync(0xffffffffu, changed)) break;
+    }
+    // final pass: every state of the lane inside the window?
+    bool inside = true;
+    {
+        int c = cin;
+#pragma unroll
+        for (int i = 0; i < NS; ++i) {
+            const int v = base + p[i] - c;
+            inside &= (v >= 0) & (v < hiw);
+            c += (c <= base + p[i] - Tv) ? 1 : 0;
+        }
+    }
+    const int total = __shfl_sync(0xffffffffu, inc, 31);
+    const int ctot = __shfl_sync(0xffffffffu, cin + nl, 31);
+    const int vend = (int)V + total - ctot;
+    const bool fine = inside && !tie;
+    if (!(__all_sync(0xffffffffu, fine) && vend >= 0 && vend < hiw)) return false;
+    constexpr int LPB = 32 / R;                                 // lanes per block
+    if ((lane & (LPB - 1)) == 0) to[(size_t)(lane / LPB) * 2] = make_uint2((unsigned)(base - cin), 0u);
+    V = (unsigned)vend;
+    return true;
+}
+
 template <int DCW_RING>
 __global__ void __launch_bounds__(64) k0_dc_walk(const uint8_t *__restrict__ iq, size_t iq_stride,
                                                   const DcStats *__restrict__ stats, int stats_stride,
                                                   const DcAnchor *__restrict__ anchors, const int *__restrict__ qtab,
                                                   float2 *__restrict__ dc_state,
                                                   uint2 *__restrict__ table, int table_stride, int blk0, int n_blk,
-                                                  int stream0) {
+                                                  int stream0, int max_run) {
     extern __shared__ __align__(16) unsigned char dcw_smem[];
     const int stream = stream0 + blockIdx.x;
     const int arm = threadIdx.x >> 5, lane = threadIdx.x & 31;
@@ -535,6 +610,15 @@ __global__ void __launch_bounds__(64) k0_dc_walk(const uint8_t *__restrict__ iq,
                 cp_async_wait<DCW_RING - 1>();                      // this batch's bytes have landed
                 __syncwarp();
                 raw_ready = true;
+            }
+            // a run of four (or two) blocks in one solve where the batch has that many left
+            if (V < win && max_run > 1) {
+                const unsigned char *rawn = reinterpret_cast<const unsigned char *>(slot + (size_t)n * (2 * DC_BLK / 16));
+                if (n + 4 <= nb && max_run >= 4) {
+                    if (dc_solve_run<4>(rawn, arm, lane, lt_mask, sqt, Tv, (int)win, V, to + (size_t)n * 2)) { j0 = n + 4; continue; }
+                } else if (n + 2 <= nb) {
+                    if (dc_solve_run<2>(rawn, arm, lane, lt_mask, sqt, Tv, (int)win, V, to + (size_t)n * 2)) { j0 = n + 2; continue; }
+                }
             }
             // the lane's 4 samples of this arm
             const uint2 rw = *reinterpret_cast<const uint2 *>(reinterpret_cast<const unsigned char *>(slot + (size_t)n * (2 * DC_BLK / 16)) + lane * 8);

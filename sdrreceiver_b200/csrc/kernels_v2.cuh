@@ -53,7 +53,15 @@ struct CascVfo {
 // kernel parameters (constant bank): the VFO index is uniform across the CTA, so the rotation
 // operands come through the uniform/constant path and cost the shared-memory pipe nothing
 // (they were 21 broadcast LDS.128 per VFO and thread; ncu had k2a at 79 % L1/shared throughput).
-struct RfTab { float4 q[RF_LEN / 2]; };
+// One float4 per rotation: (c, c, -s, s) for Rf[j] = c + j s. A complex product Rf[j] * x is then two packed operations --
+// mul2(x, (c, c)) and fma2((x.y, x.x), (-s, s), .) with the half swap folded into the FFMA2 operand by ptxas -- instead of four
+// scalar ones; the constants reach the instructions as uniform registers.
+struct RfTab { float4 q[RF_LEN]; };
+__device__ __forceinline__ float2 rot2(float4 r, float2 x) {
+    return fma2(make_float2(x.y, x.x), make_float2(r.z, r.w), mul2(x, make_float2(r.x, r.y)));
+}
+// the same with a per-thread factor F, prepared once as Fc = (F.x, F.x), Fs = (-F.y, F.y)
+__device__ __forceinline__ float2 rotF(float2 Fc, float2 Fs, float2 x) { return fma2(make_float2(x.y, x.x), Fs, mul2(x, Fc)); }
 
 // scratch layout of the array a stage reads: N samples per thread, STR float2 apart, PADT
 // never-written thread slots in front (read only by halo threads whose results are dropped)
@@ -202,10 +210,10 @@ __device__ __forceinline__ void cascade_loop(const float2 (&x)[44], const P &p, 
                 // rotating frame like the first half-band stage: lut[k0 + j] = F * Rf[j], no table reads per sample
                 // (the per-sample reads are 8-byte loads 256 bytes apart across a warp: 32 sectors per instruction)
 #pragma unroll
+                const float2 Fc = make_float2(F.x, F.x), Fs = make_float2(-F.y, F.y);
                 for (int q = 0; q < V2_CHUNK / 2; ++q) {
-                    const float4 r = p.rf[v].q[q + 5];    // Rf[2q], Rf[2q+1]
-                    const float2 a = cmul(F, cmul(make_float2(r.x, r.y), x[12 + 2 * q]));
-                    const float2 c = cmul(F, cmul(make_float2(r.z, r.w), x[13 + 2 * q]));
+                    const float2 a = rotF(Fc, Fs, rot2(p.rf[v].q[2 * q + 10], x[12 + 2 * q]));      // Rf[2q]
+                    const float2 c = rotF(Fc, Fs, rot2(p.rf[v].q[2 * q + 11], x[13 + 2 * q]));      // Rf[2q+1]
                     *reinterpret_cast<float4 *>(outp + v0 + 2 * q) = make_float4(a.x, a.y, c.x, c.y);
                 }
             } else if (store) {
@@ -234,16 +242,13 @@ __device__ __forceinline__ void cascade_loop(const float2 (&x)[44], const P &p, 
         if (fast) {
             float2 u[42];
 #pragma unroll
-            for (int q = 0; q < 21; ++q) {
-                const float4 r = p.rf[v].q[q];
-                u[2 * q] = cmul(make_float2(r.x, r.y), x[2 * q + 2]);
-                u[2 * q + 1] = cmul(make_float2(r.z, r.w), x[2 * q + 3]);
-            }
+            for (int j = 0; j < 42; ++j) u[j] = rot2(p.rf[v].q[j], x[j + 2]);
+            const float2 Fc = make_float2(F.x, F.x), Fs = make_float2(-F.y, F.y);
 #pragma unroll
             for (int k = 0; k < 8; ++k) {
                 const int r = 2 * k;
-                const float2 a = cmul(F, hb11(u[2 * r], u[2 * r + 2], u[2 * r + 4], u[2 * r + 5], u[2 * r + 6], u[2 * r + 8], u[2 * r + 10]));
-                const float2 c = cmul(F, hb11(u[2 * r + 2], u[2 * r + 4], u[2 * r + 6], u[2 * r + 7], u[2 * r + 8], u[2 * r + 10], u[2 * r + 12]));
+                const float2 a = rotF(Fc, Fs, hb11(u[2 * r], u[2 * r + 2], u[2 * r + 4], u[2 * r + 5], u[2 * r + 6], u[2 * r + 8], u[2 * r + 10]));
+                const float2 c = rotF(Fc, Fs, hb11(u[2 * r + 2], u[2 * r + 4], u[2 * r + 6], u[2 * r + 7], u[2 * r + 8], u[2 * r + 10], u[2 * r + 12]));
                 pa[k] = make_float4(a.x, a.y, c.x, c.y);
             }
         } else {

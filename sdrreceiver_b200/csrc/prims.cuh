@@ -139,44 +139,90 @@ __global__ void __launch_bounds__(256) prim_usb(const float *__restrict__ pts, c
 
 // Spectrum path: Hann window (mainwindow.cpp:284-288, 416-423) and an 8192-point forward complex
 // FFT, unscaled like kiss_fft (kiss_fft.c:339-388). One CTA per transform, whole transform in
-// shared memory: bit-reversed load, 13 radix-2 stages.
+// shared memory: bit-reversed load, then four radix-8 passes (three radix-2 stages each, on eight
+// registers per group) and one radix-2 pass -- 5 barriers instead of 13 -- with twiddles read from a
+// table the host builds like kiss_fft does (exp(-2 pi i k/N) in double, cast to float: kiss_fft.c:357-363)
+// and the Hann window from a table built with the reference's own expression (mainwindow.cpp:287).
 constexpr int FFT_N = 8192, FFT_LOGN = 13, FFT_THREADS = 512;
 
-__device__ __forceinline__ float hann8192(int i) {         // float(0.5*(1 - cos(2*pi*float(i)/(N-1)))), mainwindow.cpp:287
-    return (float)(0.5 * (1.0 - cos(2.0 * 3.14159265358979323846 * (double)(float)i / (FFT_N - 1.0))));
+struct FftTables {
+    const float2 *tw;            // [FFT_N / 2]: exp(-2 pi i m / N)
+    const float *hann;           // [FFT_N]
+};
+
+__device__ __forceinline__ float2 fft_cmul(float2 a, float2 w) { return make_float2(a.x * w.x - a.y * w.y, a.x * w.y + a.y * w.x); }
+
+// radix-2 stages st, st+1, st+2 on the eight elements base + j * 2^st of a group (decimation in time, natural order out)
+__device__ __forceinline__ void fft_radix8_group(float2 *s, const float2 *__restrict__ tw, int st, int g) {
+    const int span = 1 << st;
+    const int k0 = g & (span - 1);
+    const int base = ((g >> st) << (st + 3)) + k0;
+    float2 v[8];
+#pragma unroll
+    for (int j = 0; j < 8; ++j) v[j] = s[base + j * span];
+    // stage st: pairs (j, j+1), twiddle exponent k0 / 2^st half-turns
+    {
+        const float2 w = tw[k0 << (FFT_LOGN - 1 - st)];
+#pragma unroll
+        for (int j = 0; j < 8; j += 2) {
+            const float2 t = fft_cmul(v[j + 1], w);
+            v[j + 1] = make_float2(v[j].x - t.x, v[j].y - t.y);
+            v[j] = make_float2(v[j].x + t.x, v[j].y + t.y);
+        }
+    }
+    // stage st+1: pairs (j, j+2), k = k0 + (j & 1) * 2^st
+#pragma unroll
+    for (int q = 0; q < 2; ++q) {
+        const float2 w = tw[(k0 + q * span) << (FFT_LOGN - 2 - st)];
+#pragma unroll
+        for (int h = 0; h < 8; h += 4) {
+            const int j = h + q;
+            const float2 t = fft_cmul(v[j + 2], w);
+            v[j + 2] = make_float2(v[j].x - t.x, v[j].y - t.y);
+            v[j] = make_float2(v[j].x + t.x, v[j].y + t.y);
+        }
+    }
+    // stage st+2: pairs (j, j+4), k = k0 + j * 2^st
+#pragma unroll
+    for (int j = 0; j < 4; ++j) {
+        const float2 w = tw[(k0 + j * span) << (FFT_LOGN - 3 - st)];
+        const float2 t = fft_cmul(v[j + 4], w);
+        v[j + 4] = make_float2(v[j].x - t.x, v[j].y - t.y);
+        v[j] = make_float2(v[j].x + t.x, v[j].y + t.y);
+    }
+#pragma unroll
+    for (int j = 0; j < 8; ++j) s[base + j * span] = v[j];
 }
 
 // s[] holds the input in bit-reversed order on entry (and a __syncthreads has been passed)
-__device__ __forceinline__ void fft8192_stages(float2 *s) {
-    for (int st = 0; st < FFT_LOGN; ++st) {
-        const int half = 1 << st;
-        for (int bfly = threadIdx.x; bfly < FFT_N / 2; bfly += FFT_THREADS) {
-            const int k = bfly & (half - 1);
-            const int i0 = ((bfly >> st) << (st + 1)) + k, i1 = i0 + half;
-            float sn, cs;
-            sincospif(-(float)k / (float)half, &sn, &cs);
-            const float2 a = s[i0], b = s[i1];
-            const float2 tw = make_float2(b.x * cs - b.y * sn, b.x * sn + b.y * cs);
-            s[i0] = make_float2(a.x + tw.x, a.y + tw.y);
-            s[i1] = make_float2(a.x - tw.x, a.y - tw.y);
-        }
+__device__ __forceinline__ void fft8192_stages(float2 *s, const float2 *__restrict__ tw) {
+#pragma unroll 1
+    for (int st = 0; st < 12; st += 3) {
+        for (int g = threadIdx.x; g < FFT_N / 8; g += FFT_THREADS) fft_radix8_group(s, tw, st, g);
         __syncthreads();
     }
+    // last stage (half = 4096)
+    for (int k = threadIdx.x; k < FFT_N / 2; k += FFT_THREADS) {
+        const float2 a = s[k], t = fft_cmul(s[k + FFT_N / 2], tw[k]);
+        s[k] = make_float2(a.x + t.x, a.y + t.y);
+        s[k + FFT_N / 2] = make_float2(a.x - t.x, a.y - t.y);
+    }
+    __syncthreads();
 }
 
-__global__ void __launch_bounds__(FFT_THREADS) prim_fft8192(const float2 *__restrict__ in, float2 *__restrict__ out, int hann) {
+__global__ void __launch_bounds__(FFT_THREADS) prim_fft8192(const float2 *__restrict__ in, float2 *__restrict__ out, int hann, FftTables T) {
     extern __shared__ float2 s[];
     const float2 *x = in + (size_t)blockIdx.x * FFT_N;
     for (int i = threadIdx.x; i < FFT_N; i += FFT_THREADS) {
         float2 v = x[i];
         if (hann) {
-            const float w = hann8192(i);
+            const float w = T.hann[i];
             v.x *= w; v.y *= w;
         }
         s[__brev((unsigned)i) >> (32 - FFT_LOGN)] = v;
     }
     __syncthreads();
-    fft8192_stages(s);
+    fft8192_stages(s, T.tw);
     float2 *y = out + (size_t)blockIdx.x * FFT_N;
     for (int i = threadIdx.x; i < FFT_N; i += FFT_THREADS) y[i] = s[i];
 }
@@ -191,7 +237,7 @@ __global__ void __launch_bounds__(FFT_THREADS) prim_fft8192(const float2 *__rest
 __global__ void __launch_bounds__(FFT_THREADS) k_spectrum_feed(const float2 *__restrict__ data, long long data_stride, int len,
                                                                float2 *__restrict__ inr, double *__restrict__ pwr,
                                                                double *__restrict__ smooth, double *__restrict__ stats,
-                                                               float2 *__restrict__ fft_out) {
+                                                               float2 *__restrict__ fft_out, FftTables T) {
     extern __shared__ float2 s[];
     __shared__ double red_max[FFT_THREADS / 32], red_sum[FFT_THREADS / 32];
     const int d = blockIdx.x;
@@ -201,7 +247,7 @@ __global__ void __launch_bounds__(FFT_THREADS) k_spectrum_feed(const float2 *__r
     for (int i = threadIdx.x; i < FFT_N; i += FFT_THREADS) {
         float2 v;
         if (i < len) {
-            const float w = hann8192(i);
+            const float w = T.hann[i];
             v = x[i];
             v.x *= w; v.y *= w;
             keep[i] = v;
@@ -211,7 +257,7 @@ __global__ void __launch_bounds__(FFT_THREADS) k_spectrum_feed(const float2 *__r
         s[__brev((unsigned)i) >> (32 - FFT_LOGN)] = v;
     }
     __syncthreads();
-    fft8192_stages(s);
+    fft8192_stages(s, T.tw);
     double mx = 0.0, sum = 0.0;
     for (int i = threadIdx.x; i < FFT_N; i += FFT_THREADS) {
         const float2 X = s[i];
