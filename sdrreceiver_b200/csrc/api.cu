@@ -250,6 +250,7 @@ struct sdrb_bank {
     K1V2Params k1v2{};
     int k1_threads = 64;
     std::vector<K2V2Params> k2v2;                 // one prebuilt parameter block per sub-VFO group
+    std::vector<int> k3_slots;                    // resident CTAs of each group's k2a_v3 instantiation (-1: not asked yet)
     std::vector<K3Params> k3;                     // ... and for the groups that run k2a_v3
     std::vector<bool> sub_fused;                  // NCO mix fused into the /late FIR kernel: z exists only on demand
     std::vector<CascVfo> sub_casc;
@@ -262,6 +263,7 @@ struct sdrb_bank {
     int k3_cta_warps = K3_WARPS;                  // warps per k2a_v3 CTA (SDRB_K3_CTA_WARPS=1..4)
     int k3_regs5 = 200;                           // register cap of the 5-stage k2a_v3 instantiation (SDRB_K3_REGS=168|200|232)
     int dc_run = 4;                               // blocks per integer solve of k0_dc_walk: 4, 2 or 1 (SDRB_DC_RUN; 1 = round-1 behaviour)
+    bool dcw_bulk = false;                        // k0_dc_walk: one bulk copy per batch instead of per-lane cp.async (SDRB_DCW_BULK=1; measured neutral)
     int dcw_ring = 2;                             // shared-memory ring depth of k0_dc_walk (SDRB_DCW_RING=4: the round-1 size)
     int dbg_only = 0;                             // SDRB_DEBUG_ONLY=dc|filters: profiling aid, device-resident calls skip the other half (results are then meaningless)
     DevBuf cascdev, rfdev, latedev, usbdev, carry;
@@ -655,9 +657,11 @@ extern "C" int sdrb_bank_create(const sdrb_plan *plan, int device, int n_streams
     b->uv_warp_floats = std::max(UV_IN_FLOATS, 2 * b->uv_eo_rows * UV_ROW);
     b->uv_smem = sizeof(float) * (2 * (size_t)(64 + b->uv_np_max) + (size_t)UV_WARPS * b->uv_warp_floats);
     BANK_CU(cudaFuncSetAttribute(k2b_v2, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)b->uv_smem));
-    BANK_CU(cudaFuncSetAttribute(k0_dc_walk<2>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)dcw_smem<2>()));
-    BANK_CU(cudaFuncSetAttribute(k0_dc_walk<4>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)dcw_smem<4>()));
+    BANK_CU(cudaFuncSetAttribute(k0_dc_walk<2, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)dcw_smem<2>()));
+    BANK_CU(cudaFuncSetAttribute(k0_dc_walk<2, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)dcw_smem<2>()));
+    BANK_CU(cudaFuncSetAttribute(k0_dc_walk<4, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)dcw_smem<4>()));
     if (const char *e = getenv("SDRB_DCW_RING")) b->dcw_ring = atoi(e) == 4 ? 4 : 2;
+    if (const char *e = getenv("SDRB_DCW_BULK")) b->dcw_bulk = atoi(e) != 0;
     if (const char *e = getenv("SDRB_DC_RUN")) b->dc_run = atoi(e) >= 4 ? 4 : (atoi(e) >= 2 ? 2 : 1);
     BANK_CU(cudaFuncSetAttribute(k2_late_v2<5>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)lv_smem<5>()));
     BANK_CU(cudaFuncSetAttribute(k2_late_v2<6>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)lv_smem<6>()));
@@ -774,13 +778,17 @@ static int enqueue_dc_cb(sdrb_bank *b, const CallCtx &c, int s0, int ns, cudaStr
     {
         TimedScope t(b, sd, 0);
         if (b->dcw_ring == 4)
-            k0_dc_walk<4><<<(unsigned)ns, 64, dcw_smem<4>(), sd>>>(c.d_iq, c.iq_stride, (const DcStats *)b->dc_stats.p, b->dc_stride,
+            k0_dc_walk<4, false><<<(unsigned)ns, 64, dcw_smem<4>(), sd>>>(c.d_iq, c.iq_stride, (const DcStats *)b->dc_stats.p, b->dc_stride,
                                                                   b->anchor_buf(c.par), b->qtab_buf(c.par), (float2 *)b->dc_state.p, b->table_buf(c.par),
                                                                   b->dc_stride + DC_HALO_BLKS, cb * per_cb, per_cb, s0, b->dc_run);
+        else if (b->dcw_bulk)
+            k0_dc_walk<2, true><<<(unsigned)ns, 64, dcw_smem<2>(), sd>>>(c.d_iq, c.iq_stride, (const DcStats *)b->dc_stats.p, b->dc_stride,
+                                                                        b->anchor_buf(c.par), b->qtab_buf(c.par), (float2 *)b->dc_state.p, b->table_buf(c.par),
+                                                                        b->dc_stride + DC_HALO_BLKS, cb * per_cb, per_cb, s0, b->dc_run);
         else
-            k0_dc_walk<2><<<(unsigned)ns, 64, dcw_smem<2>(), sd>>>(c.d_iq, c.iq_stride, (const DcStats *)b->dc_stats.p, b->dc_stride,
-                                                                  b->anchor_buf(c.par), b->qtab_buf(c.par), (float2 *)b->dc_state.p, b->table_buf(c.par),
-                                                                  b->dc_stride + DC_HALO_BLKS, cb * per_cb, per_cb, s0, b->dc_run);
+            k0_dc_walk<2, false><<<(unsigned)ns, 64, dcw_smem<2>(), sd>>>(c.d_iq, c.iq_stride, (const DcStats *)b->dc_stats.p, b->dc_stride,
+                                                                         b->anchor_buf(c.par), b->qtab_buf(c.par), (float2 *)b->dc_state.p, b->table_buf(c.par),
+                                                                         b->dc_stride + DC_HALO_BLKS, cb * per_cb, per_cb, s0, b->dc_run);
     }
     (*nl) += 2;
     CU_TRY(cudaEventRecord(done, sd));
@@ -812,18 +820,30 @@ static int enqueue_ingest_cb(sdrb_bank *b, const CallCtx &c, int s0, int ns, cud
     return SDRB_OK;
 }
 
-// k2a_v3 launch geometry: one warp per (stream group, span, callback); spans are chosen so that the grid holds about
-// two warps per resident slot (148 SMs x 10 warps), never shorter than 16 tiles (3 warm-up tiles are recomputed per span)
-static void k3_geometry(const SubGroup &g, K3Params &kp, int ns, int ncb, int cta_warps, dim3 *grid) {
+// k2a_v3 launch geometry: one warp per (stream group, span, callback). `slots` = CTAs of this kernel the device holds at once
+// (occupancy x SM count): the spans are chosen so that the grid is just under SDRB_K3_WAVES (default 2) full waves of it -- the
+// 5-stage kernel holds 4 CTAs per SM (two 200-register warps per scheduler), and a grid of 2.4 waves left the last third of its run
+// 60 % empty (profiles/r02_experiments.md section 1). Never shorter than 16 tiles: 3 warm-up tiles are recomputed per span.
+static void k3_geometry(const SubGroup &g, K3Params &kp, int ns, int ncb, int cta_warps, int slots, dim3 *grid) {
     const int sgroups = (ns + g.v3_nsw - 1) / g.v3_nsw;
-    int target = 148 * 10 * 2;
-    if (const char *e = getenv("SDRB_K3_WARPS")) { const int v = atoi(e); if (v > 0) target = v; }
-    int spans = std::max(1, target / std::max(1, sgroups * ncb));
+    const int ctas_x = (sgroups + cta_warps - 1) / cta_warps;
+    static const int waves = [] { const char *e = getenv("SDRB_K3_WAVES"); const int v = e ? atoi(e) : 0; return v > 0 ? v : 2; }();
+    int target_ctas = slots > 0 ? waves * slots : 148 * 10;
+    if (const char *e = getenv("SDRB_K3_WARPS")) { const int v = atoi(e); if (v > 0) target_ctas = v / cta_warps; }
+    int spans = std::max(1, target_ctas / std::max(1, ctas_x * ncb));
     int tps = std::max(16, (kp.n_tiles + spans - 1) / spans);
     tps = std::min(tps, kp.n_tiles);
     spans = (kp.n_tiles + tps - 1) / tps;
     kp.tiles_per_span = tps;
-    *grid = dim3((unsigned)((sgroups + cta_warps - 1) / cta_warps), (unsigned)spans, (unsigned)ncb);
+    *grid = dim3((unsigned)ctas_x, (unsigned)spans, (unsigned)ncb);
+}
+
+template <class K>
+static int k3_slots(K kernel, int threads, size_t smem) {
+    int per_sm = 0, dev = 0, sms = 148;
+    if (cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, kernel, threads, smem) != cudaSuccess) return 0;
+    if (cudaGetDevice(&dev) == cudaSuccess) cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
+    return per_sm * sms;
 }
 
 // Sub-VFO cascades of callbacks cb0 .. cb0+ncb-1.
@@ -836,7 +856,7 @@ static int enqueue_subs(sdrb_bank *b, const CallCtx &c, int s0, int ns, cudaStre
             if (b->k3_ws) {
                 // warp-specialised pair per CTA (kernels_v3.cuh: k2a_v3ws); SDRB_K3_WS=2: with staged input for the 5-stage groups
                 dim3 grid;
-                k3_geometry(g, kp, ns, ncb, 1, &grid);
+                k3_geometry(g, kp, ns, ncb, 1, 0, &grid);
                 const bool xs = b->k3_ws == 2 && g.v3_maxs == 5;
                 const size_t smem = k3ws_cta_smem_bytes(g.count, g.v3_nsw * g.count, xs ? g.v3_nsw : 0);
                 TimedScope t(b, st, 2);
@@ -849,17 +869,25 @@ static int enqueue_subs(sdrb_bank *b, const CallCtx &c, int s0, int ns, cudaStre
             }
             dim3 grid;
             const int cw = b->k3_cta_warps;
-            k3_geometry(g, kp, ns, ncb, cw, &grid);
             // staged input (bulk copies) only where registers, not shared memory, set the number of resident CTAs
             const bool xs = g.v3_maxs == 5 && (b->k3_regs5 == 232 || b->k3_xs200);
             const size_t smem = k3_cta_smem_bytes(g.count, cw, g.v3_nsw * g.count, xs ? g.v3_nsw : 0);
-            TimedScope t(b, st, 2);
-            if (g.v3_maxs == 2) k2a_v3<2, 168, false><<<grid, cw * 32, smem, st>>>(kp);
-            else if (g.v3_maxs == 3) k2a_v3<3, 168, false><<<grid, cw * 32, smem, st>>>(kp);
-            else if (b->k3_regs5 == 232) k2a_v3<5, 232, true><<<grid, cw * 32, smem, st>>>(kp);
-            else if (b->k3_regs5 == 200 && b->k3_xs200) k2a_v3<5, 200, true><<<grid, cw * 32, smem, st>>>(kp);
-            else if (b->k3_regs5 == 200) k2a_v3<5, 200, false><<<grid, cw * 32, smem, st>>>(kp);
-            else k2a_v3<5, 168, false><<<grid, cw * 32, smem, st>>>(kp);
+            if (b->k3_slots.size() <= gi) b->k3_slots.resize(gi + 1, -1);
+            int &slots = b->k3_slots[gi];
+#define K3_GO(S_, R_, X_)                                                          \
+    do {                                                                           \
+        if (slots < 0) slots = k3_slots(k2a_v3<S_, R_, X_>, cw * 32, smem);        \
+        k3_geometry(g, kp, ns, ncb, cw, slots, &grid);                             \
+        TimedScope t(b, st, 2);                                                    \
+        k2a_v3<S_, R_, X_><<<grid, cw * 32, smem, st>>>(kp);                       \
+    } while (0)
+            if (g.v3_maxs == 2) K3_GO(2, 168, false);
+            else if (g.v3_maxs == 3) K3_GO(3, 168, false);
+            else if (b->k3_regs5 == 232) K3_GO(5, 232, true);
+            else if (b->k3_regs5 == 200 && b->k3_xs200) K3_GO(5, 200, true);
+            else if (b->k3_regs5 == 200) K3_GO(5, 200, false);
+            else K3_GO(5, 168, false);
+#undef K3_GO
             (*nl)++;
             continue;
         }

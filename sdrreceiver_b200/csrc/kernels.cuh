@@ -323,7 +323,10 @@ __global__ void __launch_bounds__(128) k0_dc_anchor(const float2 *__restrict__ d
 // Q = RN_even(fl(c*x)/ulp), or DC_QTIE where the rounding would be a half-way case (the block is then stepped in float).
 // One table of 256 ints per stream and arm, built once per call right after the anchor: the block statistics and the
 // walk's integer solves look increments up instead of redoing five float operations per sample.
-#define DC_QTIE ((int)0x80000000)
+// DC_QTIE is a large POSITIVE value (real increments are below 2^17 in magnitude: qmax < 1e5 is a condition of the anchor):
+// a tie then shows up in the block statistics by itself -- the prefix sums jump by 2^30 -- and costs the per-sample loop nothing.
+#define DC_QTIE ((int)0x40000000)
+#define DC_QTIE_SEEN(v) ((v) >= 0x20000000 || (v) < -0x20000000)   // a sum that contains at least one DC_QTIE (1..128 of them, wrapping)
 __global__ void __launch_bounds__(256) k0_dc_qtab(const DcAnchor *__restrict__ anchors, int *__restrict__ qtab, int stream0) {
     const int sa = 2 * stream0 + blockIdx.x;                       // (stream, arm)
     const DcAnchor A = anchors[sa];
@@ -351,8 +354,9 @@ __global__ void __launch_bounds__(128) k0_dc_blocks(const uint8_t *__restrict__ 
     if (!AI.ok && !AQ.ok) { out[0] = bad; out[1] = bad; return; }
     const uint4 *src = reinterpret_cast<const uint4 *>(iq + (size_t)stream * iq_stride + (size_t)blk * (2 * DC_BLK));
     // integer ulps: u = prefix of the increments before sample k; amax = max u, bmin/bmax = min/max of u - k
+    // (fused add + min/max: one VIADDMNMX each; ties: see DC_QTIE -- the first tie lifts every later prefix sum to ~2^30,
+    // so it is seen in amax, or in the block total if it was the last sample)
     int uI = 0, uQ = 0, amaxI = 0, amaxQ = 0, bminI = 0, bminQ = 0, bmaxI = 0, bmaxQ = 0;
-    int tieI = 0, tieQ = 0;
 #pragma unroll 2
     for (int v = 0; v < DC_BLK / 8; ++v) {
         const uint4 raw = __ldg(src + v);
@@ -361,13 +365,13 @@ __global__ void __launch_bounds__(128) k0_dc_blocks(const uint8_t *__restrict__ 
         for (int k = 0; k < 8; ++k) {
             const unsigned pr = w[k >> 1] >> (16 * (k & 1));
             const int kk = 8 * v + k;
-            amaxI = max(amaxI, uI); bminI = min(bminI, uI - kk); bmaxI = max(bmaxI, uI - kk);
-            amaxQ = max(amaxQ, uQ); bminQ = min(bminQ, uQ - kk); bmaxQ = max(bmaxQ, uQ - kk);
-            const int dI = sq[0][pr & 0xffu], dQ = sq[1][(pr >> 8) & 0xffu];
-            tieI |= (dI == DC_QTIE); tieQ |= (dQ == DC_QTIE);
-            uI += dI; uQ += dQ;
+            amaxI = max(amaxI, uI); bminI = __viaddmin_s32(uI, -kk, bminI); bmaxI = __viaddmax_s32(uI, -kk, bmaxI);
+            amaxQ = max(amaxQ, uQ); bminQ = __viaddmin_s32(uQ, -kk, bminQ); bmaxQ = __viaddmax_s32(uQ, -kk, bmaxQ);
+            uI += sq[0][pr & 0xffu];
+            uQ += sq[1][(pr >> 8) & 0xffu];
         }
     }
+    const bool tieI = DC_QTIE_SEEN(amaxI) || DC_QTIE_SEEN(uI), tieQ = DC_QTIE_SEEN(amaxQ) || DC_QTIE_SEEN(uQ);
     const bool badI = !AI.ok || tieI, badQ = !AQ.ok || tieQ;
     // amax >= 0 >= bmin by construction (the k = 0 term), so ta <= T - lo1 <= tb
     DcStats sI, sQ;
@@ -417,6 +421,31 @@ __device__ __forceinline__ void cp_async16(void *smem, const void *gmem) {
 }
 __device__ __forceinline__ void cp_async_commit() { asm volatile("cp.async.commit_group;\n" ::); }
 template <int N> __device__ __forceinline__ void cp_async_wait() { asm volatile("cp.async.wait_group %0;\n" ::"n"(N)); }
+
+// ---- mbarrier + bulk-copy (TMA engine) helpers, shared by the DC walk and k1_v2 ----
+__device__ __forceinline__ void mbar_init(unsigned long long *bar, unsigned count) {
+    asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;\n" ::"r"((unsigned)__cvta_generic_to_shared(bar)), "r"(count));
+}
+__device__ __forceinline__ void mbar_expect_tx(unsigned long long *bar, unsigned bytes) {
+    asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;\n" ::"r"((unsigned)__cvta_generic_to_shared(bar)), "r"(bytes) : "memory");
+}
+__device__ __forceinline__ void mbar_wait(unsigned long long *bar, unsigned parity) {
+    asm volatile(
+        "{\n"
+        ".reg .pred p;\n"
+        "WAIT_%=:\n"
+        "mbarrier.try_wait.parity.shared::cta.b64 p, [%0], %1;\n"
+        "@p bra DONE_%=;\n"
+        "bra WAIT_%=;\n"
+        "DONE_%=:\n"
+        "}\n" ::"r"((unsigned)__cvta_generic_to_shared(bar)), "r"(parity) : "memory");
+}
+__device__ __forceinline__ void bulk_g2s(void *smem, const void *gmem, unsigned bytes, unsigned long long *bar) {
+    asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];\n" ::"r"(
+                     (unsigned)__cvta_generic_to_shared(smem)),
+                 "l"(gmem), "r"(bytes), "r"((unsigned)__cvta_generic_to_shared(bar))
+                 : "memory");
+}
 
 // Integer solve of a RUN of R consecutive blocks (R * 128 samples, 4 R per lane) in one pass. The straddling blocks cluster -- the
 // state dwells near its threshold for a few blocks at a time -- and one solve of four blocks costs little more than a solve of one:
@@ -493,7 +522,10 @@ __device__ __forceinline__ bool dc_solve_run(const unsigned char *raw, int arm, 
     return true;
 }
 
-template <int DCW_RING>
+// BULK: a batch's raw bytes (8 KB, contiguous in the stream's row) come as ONE cp.async.bulk issued by lane 0 with an mbarrier per
+// ring slot, instead of 16 cp.async of 16 bytes per lane with their address and bounds arithmetic (a fifth of the walk's
+// instructions and of its dependent chain, profiles/r02_experiments.md section 3).
+template <int DCW_RING, bool BULK>
 __global__ void __launch_bounds__(64) k0_dc_walk(const uint8_t *__restrict__ iq, size_t iq_stride,
                                                   const DcStats *__restrict__ stats, int stats_stride,
                                                   const DcAnchor *__restrict__ anchors, const int *__restrict__ qtab,
@@ -515,19 +547,37 @@ __global__ void __launch_bounds__(64) k0_dc_walk(const uint8_t *__restrict__ iq,
     __syncwarp();
     const int *sqt = s_qtab[arm];
 
+    __shared__ unsigned long long s_bar[2][DCW_RING];              // BULK: one mbarrier per arm and ring slot
+    if (BULK) {
+        if (lane == 0) {
+#pragma unroll
+            for (int i = 0; i < DCW_RING; ++i) mbar_init(&s_bar[arm][i], 1);
+            asm volatile("fence.mbarrier_init.release.cluster;\n" ::: "memory");
+        }
+        __syncwarp();
+    }
     auto prefetch = [&](int batch) {
         if (batch < n_batch) {
             uint4 *dst = ring + (size_t)(batch % DCW_RING) * DCW_SLOT16;
             const uint4 *src = rp + (size_t)batch * DCW_SLOT16;
             const int n_valid = min(DCW_BATCH, n_blk - batch * DCW_BATCH) * (2 * DC_BLK / 16);
+            if (BULK) {
+                if (lane == 0) {
+                    mbar_expect_tx(&s_bar[arm][batch % DCW_RING], 16u * (unsigned)n_valid);
+                    bulk_g2s(dst, src, 16u * (unsigned)n_valid, &s_bar[arm][batch % DCW_RING]);
+                }
+            } else {
 #pragma unroll
-            for (int i = 0; i < DCW_SLOT16 / 32; ++i) {
-                const int e = i * 32 + lane;
-                if (e < n_valid) cp_async16(dst + e, src + e);
+                for (int i = 0; i < DCW_SLOT16 / 32; ++i) {
+                    const int e = i * 32 + lane;
+                    if (e < n_valid) cp_async16(dst + e, src + e);
+                }
             }
         }
-        cp_async_commit();
+        if (!BULK) cp_async_commit();
     };
+    // BULK: the copy of batch `batch` has landed (phase parity of its slot's barrier)
+    auto landed = [&](int batch) { mbar_wait(&s_bar[arm][batch % DCW_RING], (unsigned)((batch / DCW_RING) & 1)); };
     auto load_stats = [&](int batch) {
         DcStats S; S.D = 0; S.ta = 0xFFFFFFFFu; S.tb = 0u; S.tb_hi = 0xFFFFFFFFu;          // neutral: passes both ways
         const int j = batch * DCW_BATCH + lane;
@@ -552,7 +602,9 @@ __global__ void __launch_bounds__(64) k0_dc_walk(const uint8_t *__restrict__ iq,
     for (int i = 0; i < DCW_RING - 1; ++i) prefetch(i);
     DcStats Snext = load_stats(0);
     for (int batch = 0; batch < n_batch; ++batch) {
-        cp_async_wait<DCW_RING - 1>();                              // the slot about to be refilled has landed (and been consumed)
+        // the slot about to be refilled has landed (and been consumed): its barrier must have finished its phase before it is re-armed
+        if (BULK) { if (batch > 0) landed(batch - 1); }
+        else cp_async_wait<DCW_RING - 1>();
         __syncwarp();
         prefetch(batch + DCW_RING - 1);
         const DcStats S = Snext;
@@ -607,7 +659,8 @@ __global__ void __launch_bounds__(64) k0_dc_walk(const uint8_t *__restrict__ iq,
                 continue;
             }
             if (!raw_ready) {
-                cp_async_wait<DCW_RING - 1>();                      // this batch's bytes have landed
+                if (BULK) landed(batch);                            // this batch's bytes have landed
+                else cp_async_wait<DCW_RING - 1>();
                 __syncwarp();
                 raw_ready = true;
             }

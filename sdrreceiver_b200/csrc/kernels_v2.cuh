@@ -422,29 +422,7 @@ constexpr int K1_TPC = SDRB_K1_TPC;
 
 // ---- bulk-copy (TMA engine, cp.async.bulk + mbarrier) variant of the tile prefetch: one elected thread moves the whole
 // tile's raw bytes and DC block states with two or three bulk copies; everybody waits on the buffer's mbarrier ----
-__device__ __forceinline__ void mbar_init(unsigned long long *bar, unsigned count) {
-    asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;\n" ::"r"((unsigned)__cvta_generic_to_shared(bar)), "r"(count));
-}
-__device__ __forceinline__ void mbar_expect_tx(unsigned long long *bar, unsigned bytes) {
-    asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;\n" ::"r"((unsigned)__cvta_generic_to_shared(bar)), "r"(bytes) : "memory");
-}
-__device__ __forceinline__ void mbar_wait(unsigned long long *bar, unsigned parity) {
-    asm volatile(
-        "{\n"
-        ".reg .pred p;\n"
-        "WAIT_%=:\n"
-        "mbarrier.try_wait.parity.shared::cta.b64 p, [%0], %1;\n"
-        "@p bra DONE_%=;\n"
-        "bra WAIT_%=;\n"
-        "DONE_%=:\n"
-        "}\n" ::"r"((unsigned)__cvta_generic_to_shared(bar)), "r"(parity) : "memory");
-}
-__device__ __forceinline__ void bulk_g2s(void *smem, const void *gmem, unsigned bytes, unsigned long long *bar) {
-    asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];\n" ::"r"(
-                     (unsigned)__cvta_generic_to_shared(smem)),
-                 "l"(gmem), "r"(bytes), "r"((unsigned)__cvta_generic_to_shared(bar))
-                 : "memory");
-}
+// (mbar_init / mbar_expect_tx / mbar_wait / bulk_g2s live in kernels.cuh: the DC walk uses them too)
 template <int NT> constexpr int k1_bulk_raw_bytes() { return NT * 64 + 32; }                 // samples v0(0)-16 .. v0(NT-1)+31
 template <int NT> constexpr int k1_bulk_buf_bytes() { return k1_bulk_raw_bytes<NT>() + (NT / 4) * 16 + 16; }
 template <int NT> constexpr size_t k1v2_smem_bulk() { return V2L<NT>::SMEM + 2 * (size_t)k1_bulk_buf_bytes<NT>(); }

@@ -56,6 +56,9 @@ constexpr int K3_XS = K3_TILE + 16;     // staged input samples per stream and t
 #ifndef K3_PIPE
 #define K3_PIPE 1            /* 1: rotation-table pair and anchors of VFO v+1 are read while VFO v is computed */
 #endif
+#ifndef K3_PACKED_CMUL
+#define K3_PACKED_CMUL 1
+#endif
 #ifndef K3_VFO_UNROLL
 #define K3_VFO_UNROLL 4
 #endif
@@ -127,8 +130,20 @@ K3_HD float2 k3_fma(float2 a, float2 b, float2 c) {
     return make_float2(a.x * b.x + c.x, a.y * b.y + c.y);
 #endif
 }
-K3_HD float2 k3_cmul(float2 a, float2 b) { return make_float2(a.x * b.x - a.y * b.y, a.x * b.y + a.y * b.x); }
 K3_HD float2 k3_splat(float v) { return make_float2(v, v); }
+// complex product a * b. Device: two packed operations -- b * (a.x, a.x), then (-b.y, b.x) * (a.y, a.y) added: ptxas folds the
+// half swap, the per-half sign and the broadcast of the scalar into the operands of FMUL2 / FFMA2 (no extra registers or moves)
+K3_HD float2 k3_cmul(float2 a, float2 b) {
+#if defined(__CUDA_ARCH__) && K3_PACKED_CMUL
+    unsigned long long r, bx = *reinterpret_cast<unsigned long long *>(&b);
+    float2 sx = make_float2(a.x, a.x), sy = make_float2(a.y, a.y), bs = make_float2(-b.y, b.x);
+    asm("mul.rn.f32x2 %0, %1, %2;" : "=l"(r) : "l"(bx), "l"(*reinterpret_cast<unsigned long long *>(&sx)));
+    asm("fma.rn.f32x2 %0, %1, %2, %0;" : "+l"(r) : "l"(*reinterpret_cast<unsigned long long *>(&bs)), "l"(*reinterpret_cast<unsigned long long *>(&sy)));
+    return *reinterpret_cast<float2 *>(&r);
+#else
+    return make_float2(a.x * b.x - a.y * b.y, a.x * b.y + a.y * b.x);
+#endif
+}
 template <class T> K3_HD T k3_ldg(const T *p) {
 #ifdef __CUDA_ARCH__
     return __ldg(p);
