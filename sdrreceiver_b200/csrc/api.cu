@@ -261,7 +261,9 @@ struct sdrb_bank {
     bool k3_xs200 = false;                        // SDRB_K3_XS200=1: staged input also at the 200-register cap
     int k3_ws = 0;                                // SDRB_K3_WS=1|2: warp-specialised k2a_v3ws (producer + consumer warp per CTA)
     int k3_cta_warps = K3_WARPS;                  // warps per k2a_v3 CTA (SDRB_K3_CTA_WARPS=1..4)
-    int k3_regs5 = 200;                           // register cap of the 5-stage k2a_v3 instantiation (SDRB_K3_REGS=168|200|232)
+    int k3_cta_warps2 = K3_WARPS;                 // ... of the groups with at most 3 stages (SDRB_K3_CTA_WARPS2=1..12): their 160-register warps fit
+                                                  // three to a scheduler, shared memory per CTA (the rotation table is per CTA) decides
+    int k3_regs5 = 200;                           // register cap of the 5-stage k2a_v3 instantiation (SDRB_K3_REGS=168|200|232|255; 200..255 all hold two warps per scheduler)
     int dc_run = 4;                               // blocks per integer solve of k0_dc_walk: 4, 2 or 1 (SDRB_DC_RUN; 1 = round-1 behaviour)
     bool dcw_bulk = false;                        // k0_dc_walk: one bulk copy per batch instead of per-lane cp.async (SDRB_DCW_BULK=1; measured neutral)
     int dcw_ring = 2;                             // shared-memory ring depth of k0_dc_walk (SDRB_DCW_RING=4: the round-1 size)
@@ -638,8 +640,8 @@ extern "C" int sdrb_bank_create(const sdrb_plan *plan, int device, int n_streams
             kp.nsw = g.v3_nsw;
         }
         BANK_CU(cudaMemcpy(b->k3_rrel.p, rrel.data(), sizeof(float2) * rrel.size(), cudaMemcpyHostToDevice));
-#define K3_ATTR(S_, R_, X_) BANK_CU((cudaFuncSetAttribute(k2a_v3<S_, R_, X_>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)k3_cta_smem_bytes(K3_MAX_VFO, 4, 32, 8))))
-        K3_ATTR(2, 168, false); K3_ATTR(3, 168, false); K3_ATTR(5, 168, false); K3_ATTR(5, 200, false); K3_ATTR(5, 200, true); K3_ATTR(5, 232, true);
+#define K3_ATTR(S_, R_, X_) BANK_CU((cudaFuncSetAttribute(k2a_v3<S_, R_, X_>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024)))
+        K3_ATTR(2, 168, false); K3_ATTR(3, 168, false); K3_ATTR(5, 168, false); K3_ATTR(5, 200, false); K3_ATTR(5, 200, true); K3_ATTR(5, 232, true); K3_ATTR(5, 255, false);
 #undef K3_ATTR
 #define K3W_ATTR(S_, R_, X_) BANK_CU((cudaFuncSetAttribute(k2a_v3ws<S_, R_, X_>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)k3ws_cta_smem_bytes(K3_MAX_VFO, 32, 8))))
         K3W_ATTR(2, 168, false); K3W_ATTR(3, 168, false); K3W_ATTR(5, 168, false); K3W_ATTR(5, 168, true);
@@ -647,7 +649,8 @@ extern "C" int sdrb_bank_create(const sdrb_plan *plan, int device, int n_streams
         if (const char *e = getenv("SDRB_K3_WS")) b->k3_ws = atoi(e);
         b->k3_xs200 = getenv("SDRB_K3_XS200") && atoi(getenv("SDRB_K3_XS200")) != 0;
         if (const char *e = getenv("SDRB_K3_CTA_WARPS")) { const int v = atoi(e); if (v >= 1 && v <= 4) b->k3_cta_warps = v; }
-        if (const char *e = getenv("SDRB_K3_REGS")) { const int v = atoi(e); if (v == 168 || v == 200 || v == 232) b->k3_regs5 = v; }
+        if (const char *e = getenv("SDRB_K3_CTA_WARPS2")) { const int v = atoi(e); if (v >= 1 && v <= 12) b->k3_cta_warps2 = v; }
+        if (const char *e = getenv("SDRB_K3_REGS")) { const int v = atoi(e); if (v == 168 || v == 200 || v == 232 || v == 255) b->k3_regs5 = v; }
     }
     if (!latedev.empty()) BANK_CU(cudaMemcpy(b->latedev.p, latedev.data(), sizeof(LateDev) * latedev.size(), cudaMemcpyHostToDevice));
     if (!usbdev.empty()) BANK_CU(cudaMemcpy(b->usbdev.p, usbdev.data(), sizeof(UsbDev) * usbdev.size(), cudaMemcpyHostToDevice));
@@ -868,7 +871,7 @@ static int enqueue_subs(sdrb_bank *b, const CallCtx &c, int s0, int ns, cudaStre
                 continue;
             }
             dim3 grid;
-            const int cw = b->k3_cta_warps;
+            const int cw = g.v3_maxs <= 3 ? b->k3_cta_warps2 : b->k3_cta_warps;
             // staged input (bulk copies) only where registers, not shared memory, set the number of resident CTAs
             const bool xs = g.v3_maxs == 5 && (b->k3_regs5 == 232 || b->k3_xs200);
             const size_t smem = k3_cta_smem_bytes(g.count, cw, g.v3_nsw * g.count, xs ? g.v3_nsw : 0);
@@ -884,6 +887,7 @@ static int enqueue_subs(sdrb_bank *b, const CallCtx &c, int s0, int ns, cudaStre
             if (g.v3_maxs == 2) K3_GO(2, 168, false);
             else if (g.v3_maxs == 3) K3_GO(3, 168, false);
             else if (b->k3_regs5 == 232) K3_GO(5, 232, true);
+            else if (b->k3_regs5 == 255) K3_GO(5, 255, false);
             else if (b->k3_regs5 == 200 && b->k3_xs200) K3_GO(5, 200, true);
             else if (b->k3_regs5 == 200) K3_GO(5, 200, false);
             else K3_GO(5, 168, false);
