@@ -391,7 +391,11 @@ def b200_arm(args):
     zmq_leg = None
     if not args.no_e2e and not args.no_zmq:
         try:
-            zmq_leg = publish_leg(B, plan, bank, host_bufs, row, S, NB, rank, args)
+            n_sock = max(1, min(8, (os.cpu_count() or 8) // max(1, 2 * args.gpus)))
+            zmq_leg = publish_leg(B, plan, bank, host_bufs, row, S, NB, rank, args, n_sock)
+            if n_sock > 1:                    # the reference's shape beside it: one socket, one sender thread
+                one = publish_leg(B, plan, bank, host_bufs, row, S, NB, rank, args, 1)
+                zmq_leg["single_socket"] = {k: one[k] for k in ("value", "ms_per_step", "messages_per_s", "messages_received")}
         except Exception as ex:           # reported, never required for the GPU number
             zmq_leg = {"value": None, "error": str(ex)[:200]}
 
@@ -565,36 +569,44 @@ def extra_plan(B, torch, shard, name, S, NB, dev, local_rank, peak, fp32_peak, b
     return out
 
 
-def publish_leg(B, plan, bank, host_bufs, row, S, NB, rank, args):
+def publish_leg(B, plan, bank, host_bufs, row, S, NB, rank, args, n_sockets=8):
     """The path's last hop: every callback record of every receiver is sent as the reference does (3 frames per sub VFO:
-    topic, rate, int16 payload) into a SUB socket of this process over ipc. Timed with the host call that produces the
-    records: K steps of process_host_async (two in flight) + sdrb_publisher_send_block for the step that just completed."""
+    topic, rate, int16 payload) into SUB sockets of this process over ipc. Timed with the host call that produces the
+    records: K steps of process_host_async (two in flight) + sdrb_publisher_pool_send_call for the step that just completed.
+    n_sockets PUB sockets with one sender thread each (receiver s on socket s % n_sockets); 1 = the reference's single socket."""
     import ctypes as C
     import threading
     import zmq
     lib = B.lib()
-    ep = "ipc:///tmp/sdrb_bench_%d_%d" % (os.getpid(), rank)
+    base = "ipc:///tmp/sdrb_bench_%d_%d_%d" % (os.getpid(), rank, n_sockets)
+    pool = C.c_void_p()
+    B._check(lib.sdrb_publisher_pool_open(base.encode(), 1, n_sockets, C.byref(pool)), "sdrb_publisher_pool_open")
     ctx = zmq.Context.instance()
-    sub = ctx.socket(zmq.SUB)
-    sub.setsockopt(zmq.RCVHWM, 0)
-    sub.setsockopt(zmq.SUBSCRIBE, b"")
-    n_rx = [0, 0]
+    n_rx = [[0, 0] for _ in range(n_sockets)]
     stop = [False]
+    subs, threads = [], []
 
-    def drain():
+    def drain(sub, acc):
         while not stop[0]:
             try:
-                parts = sub.recv_multipart(flags=zmq.NOBLOCK, copy=False)
-                n_rx[0] += 1
-                n_rx[1] += len(parts[2].buffer) if len(parts) == 3 else 0
+                parts = sub.recv_multipart(copy=False)
+                acc[0] += 1
+                acc[1] += len(parts[2].buffer) if len(parts) == 3 else 0
             except zmq.Again:
-                time.sleep(0.0002)
+                pass
 
-    pub = C.c_void_p()
-    B._check(lib.sdrb_publisher_open(ep.encode(), 1, C.byref(pub)), "sdrb_publisher_open")
-    sub.connect(ep)
-    th = threading.Thread(target=drain, daemon=True)
-    th.start()
+    for k in range(n_sockets):
+        buf = C.create_string_buffer(256)
+        B._check(lib.sdrb_publisher_pool_address(pool, k, buf, 256), "sdrb_publisher_pool_address")
+        sub = ctx.socket(zmq.SUB)
+        sub.setsockopt(zmq.RCVHWM, 0)
+        sub.setsockopt(zmq.RCVTIMEO, 50)
+        sub.setsockopt(zmq.SUBSCRIBE, b"")
+        sub.connect(buf.value.decode())
+        subs.append(sub)
+        threads.append(threading.Thread(target=drain, args=(sub, n_rx[k]), daemon=True))
+    for th in threads:
+        th.start()
     time.sleep(0.3)
     steps = max(2, min(args.steps, 10))
     sent = 0
@@ -607,14 +619,8 @@ def publish_leg(B, plan, bank, host_bufs, row, S, NB, rank, args):
         bank.host_wait(1)
 
     def publish(o):
-        n = 0
-        for s in range(S):
-            for cb in range(NB):
-                rec = o + 2 * (s * NB + cb) * plan.pcm_per_block
-                if lib.sdrb_publisher_send_block(pub, plan.h, C.c_void_p(rec)) != 0:
-                    raise RuntimeError("sdrb_publisher_send_block failed")
-                n += len(plan.subs)
-        return n
+        B._check(lib.sdrb_publisher_pool_send_call(pool, plan.h, C.c_void_p(o), S, NB), "sdrb_publisher_pool_send_call")
+        return S * NB * len(plan.subs)
 
     one()
     bank.host_wait(0)
@@ -626,13 +632,18 @@ def publish_leg(B, plan, bank, host_bufs, row, S, NB, rank, args):
     secs = time.perf_counter() - t0
     time.sleep(0.5)
     stop[0] = True
-    th.join(timeout=2)
-    lib.sdrb_publisher_close(pub)
-    sub.close(0)
+    for th in threads:
+        th.join(timeout=2)
+    lib.sdrb_publisher_pool_close(pool)
+    for sub in subs:
+        sub.close(0)
     samples = S * NB * plan.block * steps
     return {"value": samples / secs / 1e6, "unit": "MS/s", "realtime_x": samples / secs / plan.fs, "steps": steps,
-            "messages_sent": sent, "messages_per_s": sent / secs, "messages_received": n_rx[0], "payload_bytes_received": n_rx[1],
-            "transport": "ipc PUB -> SUB in this process, one publisher thread", "ms_per_step": 1e3 * secs / steps}
+            "messages_sent": sent, "messages_per_s": sent / secs, "messages_received": sum(a[0] for a in n_rx),
+            "payload_bytes_received": sum(a[1] for a in n_rx), "sockets": n_sockets,
+            "transport": "ipc PUB -> SUB in this process, %d publisher socket(s) with one sender thread each "
+                         "(sdrb_publisher_pool), one python drain thread per socket" % n_sockets,
+            "ms_per_step": 1e3 * secs / steps}
 
 
 def main():

@@ -320,6 +320,18 @@ int sdrb_publisher_send_block(sdrb_publisher *p, const sdrb_plan *plan, const in
  * dropped): close() does the same with ZMQ_LINGER 0. Set SDRB_ZMQ_LINGER_MS (milliseconds, -1 = wait for ever, libzmq's
  * default) before sdrb_publisher_open to let queued frames drain first. */
 void sdrb_publisher_close(sdrb_publisher *p);
+/* A pool of publishers: n_sockets PUB sockets, one sender thread each. The reference runs one process -- one ZmqPublisher
+ * (zmqpublisher.cpp:15-96), one address -- per dongle; a bank holds hundreds of receivers, and a single socket fed by a single
+ * thread caps the publish leg far below the rest of the path. Receiver s is sent on socket s % n_sockets, its callbacks in order,
+ * every message in the reference's three-frame format. Socket k's address: "%d" in `address` replaced by k; else a tcp port
+ * + k; else ".k" appended (n_sockets == 1: `address` as it is). sdrb_publisher_pool_send_call takes the [n_streams][n_blocks]
+ * [pcm_per_block] result of one process_host call and returns when every frame has been handed to libzmq. */
+typedef struct sdrb_publisher_pool sdrb_publisher_pool;
+int sdrb_publisher_pool_open(const char *address, int bind, int n_sockets, sdrb_publisher_pool **out);
+int sdrb_publisher_pool_sockets(const sdrb_publisher_pool *pool);
+int sdrb_publisher_pool_address(const sdrb_publisher_pool *pool, int k, char *buf, size_t len);
+int sdrb_publisher_pool_send_call(sdrb_publisher_pool *pool, const sdrb_plan *plan, const int16_t *h_pcm, int n_streams, int n_blocks);
+void sdrb_publisher_pool_close(sdrb_publisher_pool *pool);
 
 /* ---- ingest front ends, host side (the library opens no socket and no dongle) ---- */
 /* rtl_tcp client protocol as spoken by sdrj (sdrj.cpp:31-74, 125-188). Feed whatever the socket

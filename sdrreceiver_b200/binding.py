@@ -143,6 +143,11 @@ def lib():
         "sdrb_publisher_send": (i, [vp, C.c_char_p, C.c_uint32, vp, C.c_uint32]),
         "sdrb_publisher_send_block": (i, [vp, vp, vp]),
         "sdrb_publisher_close": (None, [vp]),
+        "sdrb_publisher_pool_open": (i, [C.c_char_p, i, i, P(vp)]),
+        "sdrb_publisher_pool_sockets": (i, [vp]),
+        "sdrb_publisher_pool_address": (i, [vp, i, C.c_char_p, C.c_size_t]),
+        "sdrb_publisher_pool_send_call": (i, [vp, vp, vp, i, i]),
+        "sdrb_publisher_pool_close": (None, [vp]),
         "sdrb_last_error": (C.c_char_p, []),
         "sdrb_version": (C.c_char_p, []),
     }

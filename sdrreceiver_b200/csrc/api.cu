@@ -250,6 +250,7 @@ struct sdrb_bank {
     K1V2Params k1v2{};
     int k1_threads = 64;
     std::vector<K2V2Params> k2v2;                 // one prebuilt parameter block per sub-VFO group
+    std::vector<int> k3_cw;                       // warps per CTA chosen for each group's k2a_v3 launches
     std::vector<int> k3_slots;                    // resident CTAs of each group's k2a_v3 instantiation (-1: not asked yet)
     std::vector<K3Params> k3;                     // ... and for the groups that run k2a_v3
     std::vector<bool> sub_fused;                  // NCO mix fused into the /late FIR kernel: z exists only on demand
@@ -261,7 +262,7 @@ struct sdrb_bank {
     bool k3_xs200 = false;                        // SDRB_K3_XS200=1: staged input also at the 200-register cap
     int k3_ws = 0;                                // SDRB_K3_WS=1|2: warp-specialised k2a_v3ws (producer + consumer warp per CTA)
     int k3_cta_warps = K3_WARPS;                  // warps per k2a_v3 CTA (SDRB_K3_CTA_WARPS=1..4)
-    int k3_cta_warps2 = K3_WARPS;                 // ... of the groups with at most 3 stages (SDRB_K3_CTA_WARPS2=1..12): their 160-register warps fit
+    int k3_cta_warps2 = 0;                        // ... of the groups with at most 3 stages (SDRB_K3_CTA_WARPS2=1..12; 0 = the size with the most resident warps): their 160-register warps fit
                                                   // three to a scheduler, shared memory per CTA (the rotation table is per CTA) decides
     int k3_regs5 = 200;                           // register cap of the 5-stage k2a_v3 instantiation (SDRB_K3_REGS=168|200|232|255; 200..255 all hold two warps per scheduler)
     int dc_run = 4;                               // blocks per integer solve of k0_dc_walk: 4, 2 or 1 (SDRB_DC_RUN; 1 = round-1 behaviour)
@@ -871,18 +872,34 @@ static int enqueue_subs(sdrb_bank *b, const CallCtx &c, int s0, int ns, cudaStre
                 continue;
             }
             dim3 grid;
-            const int cw = g.v3_maxs <= 3 ? b->k3_cta_warps2 : b->k3_cta_warps;
             // staged input (bulk copies) only where registers, not shared memory, set the number of resident CTAs
             const bool xs = g.v3_maxs == 5 && (b->k3_regs5 == 232 || b->k3_xs200);
-            const size_t smem = k3_cta_smem_bytes(g.count, cw, g.v3_nsw * g.count, xs ? g.v3_nsw : 0);
-            if (b->k3_slots.size() <= gi) b->k3_slots.resize(gi + 1, -1);
+            if (b->k3_slots.size() <= gi) { b->k3_slots.resize(gi + 1, -1); b->k3_cw.resize(gi + 1, 0); }
             int &slots = b->k3_slots[gi];
-#define K3_GO(S_, R_, X_)                                                          \
-    do {                                                                           \
-        if (slots < 0) slots = k3_slots(k2a_v3<S_, R_, X_>, cw * 32, smem);        \
-        k3_geometry(g, kp, ns, ncb, cw, slots, &grid);                             \
-        TimedScope t(b, st, 2);                                                    \
-        k2a_v3<S_, R_, X_><<<grid, cw * 32, smem, st>>>(kp);                       \
+            int &cw = b->k3_cw[gi];
+            size_t smem = 0;
+            // First launch of the group: CTA size and resident CTAs. The 5-stage kernels hold two warps per scheduler whatever the CTA
+            // size (registers); the shorter cascades fit three, and how many CTAs fit is a matter of shared memory (the rotation table is
+            // per CTA, a ring per warp): take the CTA size with the most resident warps (25E's 15 two-stage VFOs: 6 warps, 12 per SM).
+#define K3_GO(S_, R_, X_)                                                                                   \
+    do {                                                                                                    \
+        if (slots < 0) {                                                                                    \
+            cw = g.v3_maxs <= 3 ? b->k3_cta_warps2 : b->k3_cta_warps;                                       \
+            if (cw == 0) {                                                                                  \
+                int best = 0;                                                                               \
+                for (int c : {2, 3, 4, 6}) {                                                                \
+                    const int w = c * k3_slots(k2a_v3<S_, R_, X_>, c * 32,                                  \
+                                               k3_cta_smem_bytes(g.count, c, g.v3_nsw * g.count, xs ? g.v3_nsw : 0)); \
+                    if (w > best) { best = w; cw = c; }                                                     \
+                }                                                                                           \
+                if (cw == 0) cw = K3_WARPS;                                                                 \
+            }                                                                                               \
+            slots = k3_slots(k2a_v3<S_, R_, X_>, cw * 32, k3_cta_smem_bytes(g.count, cw, g.v3_nsw * g.count, xs ? g.v3_nsw : 0)); \
+        }                                                                                                   \
+        smem = k3_cta_smem_bytes(g.count, cw, g.v3_nsw * g.count, xs ? g.v3_nsw : 0);                       \
+        k3_geometry(g, kp, ns, ncb, cw, slots, &grid);                                                      \
+        TimedScope t(b, st, 2);                                                                             \
+        k2a_v3<S_, R_, X_><<<grid, cw * 32, smem, st>>>(kp);                                                \
     } while (0)
             if (g.v3_maxs == 2) K3_GO(2, 168, false);
             else if (g.v3_maxs == 3) K3_GO(3, 168, false);

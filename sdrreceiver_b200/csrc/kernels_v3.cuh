@@ -471,7 +471,9 @@ _Pragma(K3_STR(unroll K3_VFO_UNROLL))
         // =============================== role B ===============================
         if (ROLE != 1) {
         if (ROLE == 2) env.wait_full(ti & 1);
-        const float2 *myrow = rbuf + (rowB ? lane : 0) * K3_ROW;  // lanes without a row read row 0 and store nothing
+        // lanes without a row store nothing and read the (read-only, >= 64 entries) rotation table instead of somebody's row: a row is
+        // rewritten in place by its owner while it is read, and a second reader would be a data race (compute-sanitizer racecheck)
+        const float2 *myrow = rowB ? rbuf + lane * K3_ROW : srrel;
         if (c0 == 0) {
             k3_head_shift(H.h2);
             if (MAXS > 2) k3_head_shift(H.h3);

@@ -6,9 +6,14 @@
 #include <dlfcn.h>
 #include <glob.h>
 
+#include <condition_variable>
+#include <cstdio>
 #include <cstring>
 #include <cstdlib>
+#include <mutex>
 #include <string>
+#include <thread>
+#include <vector>
 
 #include "plan.hpp"
 
@@ -133,4 +138,120 @@ extern "C" void sdrb_publisher_close(sdrb_publisher *p) {
     if (p->sock && g_zmq.close) g_zmq.close(p->sock);
     if (p->ctx && g_zmq.ctx_term) g_zmq.ctx_term(p->ctx);
     delete p;
+}
+
+// ---- a pool of publishers: one PUB socket and one sender thread per stream group ----
+// A reference deployment runs one SDRReceiver process -- one ZmqPublisher, one address -- per dongle; a bank holds hundreds of
+// receivers, and one socket fed by one thread caps the publish leg far below the GPU path (profiles/r02_experiments.md section 6:
+// zmq_send copies every payload, 224 MB per bench step). The pool keeps the reference's wire format per message
+// (zmqpublisher.cpp:82-96) and the per-receiver order of callbacks; receiver s goes out on socket s % n_sockets.
+struct sdrb_publisher_pool {
+    std::vector<sdrb_publisher *> pubs;
+    std::vector<std::string> addrs;
+    std::vector<std::thread> workers;
+    std::mutex mu;
+    std::condition_variable cv_go, cv_done;
+    unsigned long long gen = 0;
+    int pending = 0, failed = 0;
+    bool quit = false;
+    // the job of the current generation
+    const sdrb_plan *plan = nullptr;
+    const int16_t *pcm = nullptr;
+    int n_streams = 0, n_blocks = 0;
+    std::string error;
+};
+
+namespace {
+std::string pool_address(const char *address, int k) {
+    std::string a(address);
+    const size_t at = a.find("%d");
+    if (at != std::string::npos) return a.substr(0, at) + std::to_string(k) + a.substr(at + 2);
+    // tcp://host:port -> port + k; anything else (ipc, inproc): ".k" appended
+    const size_t colon = a.rfind(':');
+    if (a.compare(0, 6, "tcp://") == 0 && colon != std::string::npos && colon > 5) {
+        char *end = nullptr;
+        const long port = strtol(a.c_str() + colon + 1, &end, 10);
+        if (end && *end == 0 && port > 0) return a.substr(0, colon + 1) + std::to_string(port + k);
+    }
+    return a + "." + std::to_string(k);
+}
+
+void pool_worker(sdrb_publisher_pool *pool, int k) {
+    unsigned long long seen = 0;
+    for (;;) {
+        const sdrb_plan *plan; const int16_t *pcm; int ns, nb;
+        {
+            std::unique_lock<std::mutex> lk(pool->mu);
+            pool->cv_go.wait(lk, [&] { return pool->quit || pool->gen != seen; });
+            if (pool->quit) return;
+            seen = pool->gen;
+            plan = pool->plan; pcm = pool->pcm; ns = pool->n_streams; nb = pool->n_blocks;
+        }
+        int rc = SDRB_OK;
+        const size_t rec = (size_t)plan->h.pcm_per_block;
+        const int n = (int)pool->pubs.size();
+        for (int s = k; s < ns && rc == SDRB_OK; s += n)
+            for (int cb = 0; cb < nb && rc == SDRB_OK; ++cb)
+                rc = sdrb_publisher_send_block(pool->pubs[(size_t)k], plan, pcm + ((size_t)s * nb + cb) * rec);
+        {
+            std::lock_guard<std::mutex> lk(pool->mu);
+            if (rc != SDRB_OK) { pool->failed = rc; pool->error = sdrb_last_error(); }
+            if (--pool->pending == 0) pool->cv_done.notify_all();
+        }
+    }
+}
+}  // namespace
+
+extern "C" int sdrb_publisher_pool_open(const char *address, int bind, int n_sockets, sdrb_publisher_pool **out) {
+    if (!address || !out || n_sockets < 1 || n_sockets > 256) { sdrb::set_error("sdrb_publisher_pool_open: bad argument"); return SDRB_E_INVALID; }
+    *out = nullptr;
+    sdrb_publisher_pool *pool = new sdrb_publisher_pool();
+    for (int k = 0; k < n_sockets; ++k) {
+        pool->addrs.push_back(n_sockets == 1 ? std::string(address) : pool_address(address, k));
+        sdrb_publisher *p = nullptr;
+        const int rc = sdrb_publisher_open(pool->addrs.back().c_str(), bind, &p);
+        if (rc != SDRB_OK) {
+            for (sdrb_publisher *q : pool->pubs) sdrb_publisher_close(q);
+            delete pool;
+            return rc;
+        }
+        pool->pubs.push_back(p);
+    }
+    for (int k = 0; k < n_sockets; ++k) pool->workers.emplace_back(pool_worker, pool, k);
+    *out = pool;
+    return SDRB_OK;
+}
+
+extern "C" int sdrb_publisher_pool_sockets(const sdrb_publisher_pool *pool) { return pool ? (int)pool->pubs.size() : 0; }
+
+extern "C" int sdrb_publisher_pool_address(const sdrb_publisher_pool *pool, int k, char *buf, size_t len) {
+    if (!pool || !buf || len == 0 || k < 0 || k >= (int)pool->addrs.size()) { sdrb::set_error("sdrb_publisher_pool_address: bad argument"); return SDRB_E_INVALID; }
+    snprintf(buf, len, "%s", pool->addrs[(size_t)k].c_str());
+    return SDRB_OK;
+}
+
+extern "C" int sdrb_publisher_pool_send_call(sdrb_publisher_pool *pool, const sdrb_plan *plan, const int16_t *h_pcm, int n_streams, int n_blocks) {
+    if (!pool || !plan || (!h_pcm && n_streams > 0 && n_blocks > 0)) { sdrb::set_error("sdrb_publisher_pool_send_call: NULL argument"); return SDRB_E_INVALID; }
+    if (n_streams <= 0 || n_blocks <= 0) return SDRB_OK;
+    std::unique_lock<std::mutex> lk(pool->mu);
+    pool->plan = plan; pool->pcm = h_pcm; pool->n_streams = n_streams; pool->n_blocks = n_blocks;
+    pool->pending = (int)pool->workers.size();
+    pool->failed = 0;
+    ++pool->gen;
+    pool->cv_go.notify_all();
+    pool->cv_done.wait(lk, [&] { return pool->pending == 0; });
+    if (pool->failed) { sdrb::set_error(pool->error); return pool->failed; }
+    return SDRB_OK;
+}
+
+extern "C" void sdrb_publisher_pool_close(sdrb_publisher_pool *pool) {
+    if (!pool) return;
+    {
+        std::lock_guard<std::mutex> lk(pool->mu);
+        pool->quit = true;
+    }
+    pool->cv_go.notify_all();
+    for (std::thread &t : pool->workers) t.join();
+    for (sdrb_publisher *p : pool->pubs) sdrb_publisher_close(p);
+    delete pool;
 }

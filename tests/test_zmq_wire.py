@@ -75,3 +75,66 @@ def test_bad_address_is_an_error_code_not_a_crash():
     h = C.c_void_p()
     rc = B.lib().sdrb_publisher_open(b"notaproto://x", 1, C.byref(h))
     assert rc == -5 and not h.value
+
+
+def test_publisher_pool_keeps_format_and_per_receiver_order(tmp_path):
+    """sdrb_publisher_pool_*: n sockets, one sender thread each; receiver s on socket s % n, its callbacks in order, every message
+    the reference's three frames (zmqpublisher.cpp:82-96). One SUB socket per pool address plays the decoders."""
+    L = B.lib()
+    base = "ipc://" + str(tmp_path / "pool.sock")
+    pool = C.c_void_p()
+    rc = L.sdrb_publisher_pool_open(base.encode(), 1, 3, C.byref(pool))
+    if rc == -5:
+        pytest.skip("libzmq not loadable here: " + L.sdrb_last_error().decode())
+    assert rc == 0, L.sdrb_last_error()
+    assert L.sdrb_publisher_pool_sockets(pool) == 3
+    ctx = zmq.Context()
+    subs = []
+    for k in range(3):
+        buf = C.create_string_buffer(256)
+        assert L.sdrb_publisher_pool_address(pool, k, buf, 256) == 0
+        assert buf.value.decode() == base + ".%d" % k
+        sub = ctx.socket(zmq.SUB)
+        sub.setsockopt(zmq.SUBSCRIBE, b"")
+        sub.setsockopt(zmq.RCVTIMEO, 5000)
+        sub.connect(buf.value.decode())
+        subs.append(sub)
+    time.sleep(0.4)
+    plan = B.Plan(plan_path("54W_288K"))
+    n_streams, n_blocks = 5, 2
+    pcm = (np.arange(n_streams * n_blocks * plan.pcm_per_block, dtype=np.int64) % 30011 - 15000).astype(np.int16)
+    pcm = pcm.reshape(n_streams, n_blocks, plan.pcm_per_block)
+    for rep in range(2):                                         # the workers are reused from call to call
+        assert L.sdrb_publisher_pool_send_call(pool, plan.h, pcm.ctypes.data_as(C.c_void_p), n_streams, n_blocks) == 0
+        for k, sub in enumerate(subs):
+            for s in range(k, n_streams, 3):                     # a worker sends its receivers one after the other
+                for cb in range(n_blocks):
+                    for v in plan.subs:
+                        topic, rate, payload = sub.recv_multipart()
+                        assert topic == v["topic"].encode()[:5].ljust(5, b"\0")
+                        assert int.from_bytes(rate, "little") == v["out_rate"]
+                        want = pcm[s, cb, v["pcm_offset"]:v["pcm_offset"] + v["samples_out"]]
+                        assert np.array_equal(np.frombuffer(payload, dtype="<i2"), want)
+    assert L.sdrb_publisher_pool_send_call(pool, plan.h, None, 0, 0) == 0          # nothing to send
+    assert L.sdrb_publisher_pool_send_call(pool, plan.h, None, 2, 2) == -1         # NULL records
+    L.sdrb_publisher_pool_close(pool)
+    for sub in subs:
+        sub.close(0)
+    ctx.term()
+
+
+def test_publisher_pool_address_rules(tmp_path):
+    L = B.lib()
+    for base, want in (("ipc://" + str(tmp_path / "a%d.sock"), "ipc://" + str(tmp_path / "a1.sock")),
+                       ("tcp://127.0.0.1:45731", "tcp://127.0.0.1:45732")):
+        pool = C.c_void_p()
+        rc = L.sdrb_publisher_pool_open(base.encode(), 1, 2, C.byref(pool))
+        if rc == -5 and b"libzmq" in L.sdrb_last_error():
+            pytest.skip("libzmq not loadable here")
+        assert rc == 0, L.sdrb_last_error()
+        buf = C.create_string_buffer(256)
+        assert L.sdrb_publisher_pool_address(pool, 1, buf, 256) == 0 and buf.value.decode() == want
+        assert L.sdrb_publisher_pool_address(pool, 2, buf, 256) == -1
+        L.sdrb_publisher_pool_close(pool)
+    pool = C.c_void_p()
+    assert L.sdrb_publisher_pool_open(b"ipc:///tmp/x", 1, 0, C.byref(pool)) == -1 and not pool.value
