@@ -581,32 +581,46 @@ def publish_leg(B, plan, bank, host_bufs, row, S, NB, rank, args, n_sockets=8):
     base = "ipc:///tmp/sdrb_bench_%d_%d_%d" % (os.getpid(), rank, n_sockets)
     pool = C.c_void_p()
     B._check(lib.sdrb_publisher_pool_open(base.encode(), 1, n_sockets, C.byref(pool)), "sdrb_publisher_pool_open")
-    ctx = zmq.Context.instance()
-    n_rx = [[0, 0] for _ in range(n_sockets)]
-    stop = [False]
-    subs, threads = [], []
-
-    def drain(sub, acc):
-        while not stop[0]:
-            try:
-                parts = sub.recv_multipart(copy=False)
-                acc[0] += 1
-                acc[1] += len(parts[2].buffer) if len(parts) == 3 else 0
-            except zmq.Again:
-                pass
-
+    addrs = []
     for k in range(n_sockets):
         buf = C.create_string_buffer(256)
         B._check(lib.sdrb_publisher_pool_address(pool, k, buf, 256), "sdrb_publisher_pool_address")
-        sub = ctx.socket(zmq.SUB)
-        sub.setsockopt(zmq.RCVHWM, 0)
-        sub.setsockopt(zmq.RCVTIMEO, 50)
-        sub.setsockopt(zmq.SUBSCRIBE, b"")
-        sub.connect(buf.value.decode())
-        subs.append(sub)
-        threads.append(threading.Thread(target=drain, args=(sub, n_rx[k]), daemon=True))
-    for th in threads:
-        th.start()
+        addrs.append(buf.value.decode())
+    # the receiving side: tools/zmq_sink.cpp (built next to the library) in its own process, one thread per address; a python
+    # SUB socket per address with a drain thread each if the binary is missing
+    sink_bin = os.path.join(os.path.dirname(os.path.abspath(__file__)), "sdrreceiver_b200", "zmq_sink")
+    sink = None
+    n_rx = [[0, 0] for _ in range(n_sockets)]
+    stop = [False]
+    subs, threads = [], []
+    if os.access(sink_bin, os.X_OK):
+        import subprocess
+        sink = subprocess.Popen([sink_bin] + addrs, stdin=subprocess.PIPE, stdout=subprocess.PIPE, text=True)
+        if sink.stdout.readline().strip() != "ready":
+            sink.kill()
+            sink = None
+    if sink is None:
+        ctx = zmq.Context.instance()
+
+        def drain(sub, acc):
+            while not stop[0]:
+                try:
+                    parts = sub.recv_multipart(copy=False)
+                    acc[0] += 1
+                    acc[1] += len(parts[2].buffer) if len(parts) == 3 else 0
+                except zmq.Again:
+                    pass
+
+        for k in range(n_sockets):
+            sub = ctx.socket(zmq.SUB)
+            sub.setsockopt(zmq.RCVHWM, 0)
+            sub.setsockopt(zmq.RCVTIMEO, 50)
+            sub.setsockopt(zmq.SUBSCRIBE, b"")
+            sub.connect(addrs[k])
+            subs.append(sub)
+            threads.append(threading.Thread(target=drain, args=(sub, n_rx[k]), daemon=True))
+        for th in threads:
+            th.start()
     time.sleep(0.3)
     steps = max(2, min(args.steps, 10))
     sent = 0
@@ -631,18 +645,25 @@ def publish_leg(B, plan, bank, host_bufs, row, S, NB, rank, args, n_sockets=8):
     bank.host_wait(0)
     secs = time.perf_counter() - t0
     time.sleep(0.5)
-    stop[0] = True
-    for th in threads:
-        th.join(timeout=2)
+    if sink is not None:
+        out, _ = sink.communicate("", timeout=20)              # EOF on stdin: the sink prints its counts and leaves
+        got = json.loads(out.strip().splitlines()[-1])
+        received, received_bytes = got["messages"], got["payload_bytes"]
+        side = "tools/zmq_sink.cpp in its own process, one SUB socket and thread per address"
+    else:
+        stop[0] = True
+        for th in threads:
+            th.join(timeout=2)
+        for sub in subs:
+            sub.close(0)
+        received, received_bytes = sum(a[0] for a in n_rx), sum(a[1] for a in n_rx)
+        side = "python SUB sockets in this process, one drain thread per address"
     lib.sdrb_publisher_pool_close(pool)
-    for sub in subs:
-        sub.close(0)
     samples = S * NB * plan.block * steps
     return {"value": samples / secs / 1e6, "unit": "MS/s", "realtime_x": samples / secs / plan.fs, "steps": steps,
-            "messages_sent": sent, "messages_per_s": sent / secs, "messages_received": sum(a[0] for a in n_rx),
-            "payload_bytes_received": sum(a[1] for a in n_rx), "sockets": n_sockets,
-            "transport": "ipc PUB -> SUB in this process, %d publisher socket(s) with one sender thread each "
-                         "(sdrb_publisher_pool), one python drain thread per socket" % n_sockets,
+            "messages_sent": sent, "messages_per_s": sent / secs, "messages_received": received,
+            "payload_bytes_received": received_bytes, "sockets": n_sockets,
+            "transport": "ipc, %d PUB socket(s) with one sender thread each (sdrb_publisher_pool) -> %s" % (n_sockets, side),
             "ms_per_step": 1e3 * secs / steps}
 
 

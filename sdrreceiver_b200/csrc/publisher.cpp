@@ -66,7 +66,8 @@ bool load_zmq() {
 }
 // libzmq 4.x constants (zmq.h)
 constexpr int kPUB = 1, kSNDMORE = 2, kRECONNECT_IVL = 18, kRECONNECT_IVL_MAX = 21;
-constexpr int kKEEPALIVE = 34, kKEEPALIVE_CNT = 35, kKEEPALIVE_IDLE = 36, kKEEPALIVE_INTVL = 37, kLINGER = 17;
+constexpr int kKEEPALIVE = 34, kKEEPALIVE_CNT = 35, kKEEPALIVE_IDLE = 36, kKEEPALIVE_INTVL = 37, kLINGER = 17, kSNDHWM = 23;
+int g_pool_sndhwm = 0;                                           // > 0 while sdrb_publisher_pool_open creates its sockets
 }  // namespace
 
 struct sdrb_publisher {
@@ -95,6 +96,13 @@ extern "C" int sdrb_publisher_open(const char *address, int bind, sdrb_publisher
     g_zmq.setsockopt(p->sock, kRECONNECT_IVL, &reconnect, sizeof(int));
     g_zmq.setsockopt(p->sock, kRECONNECT_IVL_MAX, &reconnect_max, sizeof(int));
     g_zmq.setsockopt(p->sock, kLINGER, &linger, sizeof(int));
+    // Send high-water mark: the reference keeps libzmq's default (1000 messages per subscriber), enough for one receiver's 27
+    // messages per callback. A pool socket carries the callbacks of a whole call for its share of the receivers in one burst
+    // (1728 messages for 25E, 128 receivers, 4 callbacks, 8 sockets): everything past the mark would be dropped before the I/O
+    // thread has had a chance to write it. SDRB_ZMQ_SNDHWM overrides both (0 = no limit).
+    int sndhwm = g_pool_sndhwm;
+    if (const char *e = getenv("SDRB_ZMQ_SNDHWM")) sndhwm = atoi(e);
+    if (sndhwm > 0 || getenv("SDRB_ZMQ_SNDHWM")) g_zmq.setsockopt(p->sock, kSNDHWM, &sndhwm, sizeof(int));
     const int rc = bind ? g_zmq.bind(p->sock, address) : g_zmq.connect(p->sock, address);
     if (rc < 0) {
         sdrb::set_error(std::string("ZeroMQ could not ") + (bind ? "bind to " : "connect to ") + address +
@@ -206,6 +214,7 @@ extern "C" int sdrb_publisher_pool_open(const char *address, int bind, int n_soc
     if (!address || !out || n_sockets < 1 || n_sockets > 256) { sdrb::set_error("sdrb_publisher_pool_open: bad argument"); return SDRB_E_INVALID; }
     *out = nullptr;
     sdrb_publisher_pool *pool = new sdrb_publisher_pool();
+    g_pool_sndhwm = 65536;
     for (int k = 0; k < n_sockets; ++k) {
         pool->addrs.push_back(n_sockets == 1 ? std::string(address) : pool_address(address, k));
         sdrb_publisher *p = nullptr;
@@ -213,10 +222,12 @@ extern "C" int sdrb_publisher_pool_open(const char *address, int bind, int n_soc
         if (rc != SDRB_OK) {
             for (sdrb_publisher *q : pool->pubs) sdrb_publisher_close(q);
             delete pool;
+            g_pool_sndhwm = 0;
             return rc;
         }
         pool->pubs.push_back(p);
     }
+    g_pool_sndhwm = 0;
     for (int k = 0; k < n_sockets; ++k) pool->workers.emplace_back(pool_worker, pool, k);
     *out = pool;
     return SDRB_OK;

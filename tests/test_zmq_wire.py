@@ -138,3 +138,38 @@ def test_publisher_pool_address_rules(tmp_path):
         L.sdrb_publisher_pool_close(pool)
     pool = C.c_void_p()
     assert L.sdrb_publisher_pool_open(b"ipc:///tmp/x", 1, 0, C.byref(pool)) == -1 and not pool.value
+
+
+def test_pool_delivers_a_whole_call_to_the_counting_sink(tmp_path):
+    """A call's burst (here 8 receivers x 2 callbacks x 27 messages on 2 sockets, three times) reaches tools/zmq_sink.cpp -- the
+    counting subscriber bench.py uses for its publish leg -- completely: message count and payload bytes."""
+    import json
+    import os
+    import subprocess
+    sink_bin = os.path.join(os.path.dirname(os.path.abspath(B.__file__)), "zmq_sink")
+    if not os.access(sink_bin, os.X_OK):
+        pytest.skip("zmq_sink not built (make -C sdrreceiver_b200/csrc)")
+    L = B.lib()
+    pool = C.c_void_p()
+    rc = L.sdrb_publisher_pool_open(("ipc://" + str(tmp_path / "sink%d.sock")).encode(), 1, 2, C.byref(pool))
+    if rc == -5:
+        pytest.skip("libzmq not loadable here")
+    assert rc == 0, L.sdrb_last_error()
+    addrs = []
+    for k in range(2):
+        buf = C.create_string_buffer(256)
+        assert L.sdrb_publisher_pool_address(pool, k, buf, 256) == 0
+        addrs.append(buf.value.decode())
+    sink = subprocess.Popen([sink_bin] + addrs, stdin=subprocess.PIPE, stdout=subprocess.PIPE, text=True)
+    assert sink.stdout.readline().strip() == "ready"
+    time.sleep(0.4)
+    plan = B.Plan(plan_path("25E"))
+    pcm = np.ones((8, 2, plan.pcm_per_block), dtype=np.int16)
+    for _ in range(3):
+        assert L.sdrb_publisher_pool_send_call(pool, plan.h, pcm.ctypes.data_as(C.c_void_p), 8, 2) == 0
+    time.sleep(0.5)
+    out, _ = sink.communicate("", timeout=20)
+    got = json.loads(out.strip().splitlines()[-1])
+    L.sdrb_publisher_pool_close(pool)
+    assert got["messages"] == 3 * 8 * 2 * len(plan.subs)
+    assert got["payload_bytes"] == 3 * 8 * 2 * 2 * sum(v["samples_out"] for v in plan.subs)
