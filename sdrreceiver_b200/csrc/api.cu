@@ -810,7 +810,7 @@ static int enqueue_ingest_cb(sdrb_bank *b, const CallCtx &c, int s0, int ns, cud
     if (c.d_cf) {
         const int k1_tiles = (h.block + K1_TILE - 1) / K1_TILE;
         TimedScope t(b, st, 1);
-        k1_ingest_main<false><<<dim3((unsigned)ns, (unsigned)k1_tiles, 1u), K1_THREADS, 0, st>>>(k1);
+        k1_ingest_main<<<dim3((unsigned)ns, (unsigned)k1_tiles, 1u), K1_THREADS, 0, st>>>(k1);
     } else {
         K1V2Params q = b->k1v2;
         q.iq = c.d_iq; q.iq_stride = c.iq_stride; q.stream0 = s0; q.b0 = cb;

@@ -6,7 +6,7 @@
 //                                           ahead on a side stream
 //   k1_v2 (v2)                              u8 -> f32 (sdr.cpp:43-49), DC, per main VFO NCO mix (vfo.cpp:237-245) +
 //                                           11-tap half-band cascade (halfbanddecimator.cpp:43-72) -> cf32 main output
-//   k1_ingest_main<false>                   the same for cf32 input (vfo::process on a main VFO: no u8, no DC)
+//   k1_ingest_main                          the same for cf32 input (vfo::process on a main VFO: no u8, no DC)
 //   k2a_v2 (v2)                             all sub VFOs of a main VFO: NCO mix + S half-band stages -> cf32 z
 //   k2_late_v2 (v2) / k2_late_fir           /5 or /6 decimating FIR (vfo.cpp:334-387); the second is the fallback
 //   k2b_v2 (v2)                             delay62 - Hilbert125 (vfo.cpp:316-324), optional low-pass, gain, int16
@@ -756,14 +756,14 @@ __global__ void __launch_bounds__(64) k0_dc_walk(const uint8_t *__restrict__ iq,
 }
 
 // ------------------------------------------------------------------------------------
-// K1: fused ingest + main VFOs.
+// K1 for cf32 input (vfo::process on a main VFO, vfo.cpp:235: no byte conversion, no DC removal): main VFOs only. The uint8
+// path is k1_v2 (kernels_v2.cuh); round 1's uint8 branch of this kernel is gone with its DC consumer.
 // CTA = 9 warps: warp 0 recomputes the 256 samples in front of the tile (filter halo, or
 // the tail of the previous callback for tile 0), warps 1..8 own 256 samples each; every
 // thread owns 8 consecutive samples = one 16-byte load.
 // ------------------------------------------------------------------------------------
 constexpr int K1_A0_STR = 10, K1_A1_STR = 6, K1_A2_STR = 2;
 
-template <bool RAW>
 __global__ void __launch_bounds__(K1_THREADS, 2) k1_ingest_main(const K1Params p) {
     __shared__ __align__(16) float2 sA0[(K1_THREADS + HB_PAD) * K1_A0_STR];
     __shared__ __align__(16) float2 sA1[(K1_THREADS + HB_PAD) * K1_A1_STR];
@@ -783,7 +783,7 @@ __global__ void __launch_bounds__(K1_THREADS, 2) k1_ingest_main(const K1Params p
     float2 x[8];
 #pragma unroll
     for (int k = 0; k < 8; ++k) x[k] = make_float2(0.f, 0.f);
-    if (exists && !RAW) {
+    if (exists) {
         // cf32 input (what vfo::process receives, vfo.cpp:235): no byte conversion, no DC removal
         const float2 *csrc = (b == 0 && i0 < 0)
             ? p.cf_tail + (size_t)stream * RAW_TAIL + (RAW_TAIL + i0)
@@ -794,63 +794,6 @@ __global__ void __launch_bounds__(K1_THREADS, 2) k1_ingest_main(const K1Params p
             const float4 v = __ldg(c4 + k);
             x[2 * k] = make_float2(v.x, v.y);
             x[2 * k + 1] = make_float2(v.z, v.w);
-        }
-    }
-    if (exists && RAW) {
-        const uint8_t *src = (b == 0 && i0 < 0)
-            ? p.tail + (size_t)stream * (2 * RAW_TAIL) + (2 * RAW_TAIL + 2 * i0)
-            : p.iq + (size_t)stream * p.iq_stride + ((size_t)b * B + i0) * 2;
-        const uint4 raw = __ldg(reinterpret_cast<const uint4 *>(src));
-        unpack8(raw, x);
-        if (p.correct_dc) {
-            // avept for each of this lane's 8 samples, bit-exact: start from the state the walk
-            // kernel left at the head of the DC block (DC_BLK samples = 16 lanes), advance to this lane's
-            // chunk -- by translation in integer ulps when the block was a translation, by real
-            // float steps over the preceding samples otherwise -- then 8 real float steps.
-            const int dblk = (b * B + i0 + RAW_TAIL) / DC_BLK;                   // table index incl. halo entries
-            const int m = (i0 >> 3) & (DC_BLK / 8 - 1);                            // chunk inside the DC block
-            const uint2 *te = p.dc_table + ((size_t)stream * p.dc_stride + dblk) * 2;
-            const uint2 eI = __ldg(te), eQ = __ldg(te + 1);
-            const DcAnchor AI = p.dc_anchor[2 * stream], AQ = p.dc_anchor[2 * stream + 1];
-            // both arms packed (FMUL2/FADD2): q = fl(c*x) is shared by the increment and the step
-            const float2 sgn2 = make_float2(AI.sgn, AQ.sgn), invu2 = make_float2(AI.inv_u, AQ.inv_u);
-            float2 q[8], d2 = make_float2(0.f, 0.f);
-#pragma unroll
-            for (int k = 0; k < 8; ++k) {
-                q[k] = mul2(splat2(DC_C), x[k]);
-                const float2 y = mul2(mul2(q[k], sgn2), invu2);                   // sign flip and 1/ulp are exact
-                d2 = add2(d2, add2(add2(y, splat2(DC_MAGIC)), splat2(-DC_MAGIC)));
-            }
-            const float dI = d2.x - 8.f * (float)AI.r0, dQ = d2.y - 8.f * (float)AQ.r0;
-            // exclusive prefix over the 16 lanes of the DC block
-            float pI = dI, pQ = dQ;
-#pragma unroll
-            for (int d = 1; d < DC_BLK / 8; d <<= 1) {
-                const float vI = __shfl_up_sync(0xffffffffu, pI, d, DC_BLK / 8);
-                const float vQ = __shfl_up_sync(0xffffffffu, pQ, d, DC_BLK / 8);
-                if (m >= d) { pI += vI; pQ += vQ; }
-            }
-            pI -= dI; pQ -= dQ;
-            float sI = __uint_as_float(eI.x), sQ = __uint_as_float(eQ.x);
-            if (eI.y < 2u) sI = AI.sgn * __uint_as_float(eI.x + AI.lo + 1u + (unsigned)((int)pI - (eI.y ? 8 * m : 0)));
-            if (eQ.y < 2u) sQ = AQ.sgn * __uint_as_float(eQ.x + AQ.lo + 1u + (unsigned)((int)pQ - (eQ.y ? 8 * m : 0)));
-            if ((eI.y == 2u || eQ.y == 2u) && m > 0) {
-                for (int j = m; j > 0; --j) {                                     // preceding chunks of the block
-                    float2 y[8];
-                    unpack8(__ldg(reinterpret_cast<const uint4 *>(src) - j), y);
-#pragma unroll
-                    for (int k = 0; k < 8; ++k) {
-                        if (eI.y == 2u) sI = dc_step(sI, y[k].x);
-                        if (eQ.y == 2u) sQ = dc_step(sQ, y[k].y);
-                    }
-                }
-            }
-            float2 s2 = make_float2(sI, sQ);
-#pragma unroll
-            for (int k = 0; k < 8; ++k) {
-                s2 = add2(mul2(s2, splat2(DC_A)), q[k]);                          // sdrj.cpp:281, both arms
-                x[k] = add2(x[k], make_float2(-s2.x, -s2.y));
-            }
         }
     }
     const long long n_abs = blk * (long long)B + i0;

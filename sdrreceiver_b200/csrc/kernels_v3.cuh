@@ -56,6 +56,12 @@ constexpr int K3_XS = K3_TILE + 16;     // staged input samples per stream and t
 #ifndef K3_PIPE
 #define K3_PIPE 1            /* 1: rotation-table pair and anchors of VFO v+1 are read while VFO v is computed */
 #endif
+// K3_XPF: how the coming tile's input reaches the SM ahead of time (no staged input): 0 = prefetch.global.L1 of its lines one tile
+// ahead; 1 = real 16-byte loads of those lines into a scratch register (a prefetch instruction may stop at L2); 2 = 0 + the first
+// stream's loads of a tile issued at the very top of the tile, above the warp barrier and the bookkeeping
+#ifndef K3_XPF
+#define K3_XPF 0
+#endif
 #ifndef K3_PACKED_CMUL
 #define K3_PACKED_CMUL 1
 #endif
@@ -144,6 +150,14 @@ K3_HD float2 k3_cmul(float2 a, float2 b) {
     return make_float2(a.x * b.x - a.y * b.y, a.x * b.y + a.y * b.x);
 #endif
 }
+// 16-byte store to GLOBAL memory (the compiler then knows it cannot alias the shared-memory loads around it)
+K3_HD void k3_store_global16(float2 *dst, float4 v) {
+#ifdef __CUDA_ARCH__
+    asm volatile("st.global.v4.f32 [%0], {%1, %2, %3, %4};" ::"l"(__cvta_generic_to_global(dst)), "f"(v.x), "f"(v.y), "f"(v.z), "f"(v.w));
+#else
+    *reinterpret_cast<float4 *>(dst) = v;
+#endif
+}
 template <class T> K3_HD T k3_ldg(const T *p) {
 #ifdef __CUDA_ARCH__
     return __ldg(p);
@@ -221,6 +235,16 @@ K3_HD void k3_async_wait() {
 K3_HD void k3_prefetch_l1(const void *p) {
 #ifdef __CUDA_ARCH__
     asm volatile("prefetch.global.L1 [%0];" ::"l"(p));
+#else
+    (void)p;
+#endif
+}
+
+// a 16-byte load whose value nobody uses: brings the line into L1 like a real load does
+K3_HD void k3_touch16(const void *p) {
+#ifdef __CUDA_ARCH__
+    float a, b, c, d;
+    asm volatile("ld.global.nc.v4.f32 {%0, %1, %2, %3}, [%4];" : "=f"(a), "=f"(b), "=f"(c), "=f"(d) : "l"(p));
 #else
     (void)p;
 #endif
@@ -314,6 +338,13 @@ K3_HD void k3_unit(Env &env, const K3Params &p, int sg, int span, int b, float2 
         const int ti = t - (t_begin - K3_WARM);              // tile counter of this unit
         float2 *rbuf = ring + (ROLE == 0 ? 0 : (ti & 1) * ring_buf);
         const float2 *sFt = sF + 32 * fpar;                  // this tile's anchors
+        // K3_XPF == 2: the first stream's samples of this tile, requested before anything else of the tile
+        float4 xa0[7];
+        if (K3_XPF == 2 && !XS && ROLE != 2) {
+            const float4 *xp = reinterpret_cast<const float4 *>(in_ln + c0 - 10);
+#pragma unroll
+            for (int i = 0; i < 7; ++i) xa0[i] = sbase < p.stream_end ? k3_ldg(xp + i) : make_float4(0.f, 0.f, 0.f, 0.f);   // the address role A reads anyway
+        }
         if (ROLE != 2) {
         k3_async_wait();
         if (XS) {
@@ -325,7 +356,10 @@ K3_HD void k3_unit(Env &env, const K3Params &p, int sg, int span, int b, float2 
         k3_async_copy8(sF + 32 * fpar + lane, lutB + wrapL(kbB + c0 + K3_TILE));
         if (!XS && t + 1 < t_end && lane < 10) {             // the coming tile's lines into L1 (10 x 128 bytes cover 128 + 14 samples)
             const float2 *pf = in_pf + c0;
-            for (int s = 0; s < n_str; ++s, pf += p.in_stride) k3_prefetch_l1(pf);
+            for (int s = 0; s < n_str; ++s, pf += p.in_stride) {
+                if (K3_XPF == 1) k3_touch16(pf);
+                else k3_prefetch_l1(pf);
+            }
         }
         if (ROLE == 1 && ti >= 2) env.wait_empty(ti & 1);    // the consumer is done with the tile that used this buffer
         // =============================== role A ===============================
@@ -351,7 +385,8 @@ K3_HD void k3_unit(Env &env, const K3Params &p, int sg, int span, int b, float2 
                     const bool has = q ? hasB : hasA;
 #pragma unroll
                     for (int i = 0; i < 7; ++i) {
-                        const float4 v = has ? (XS ? xp[i] : k3_ldg(xp + i)) : make_float4(0.f, 0.f, 0.f, 0.f);
+                        const float4 v = (K3_XPF == 2 && !XS && q == 0 && s0 == 0) ? xa0[i]
+                                                                                    : has ? (XS ? xp[i] : k3_ldg(xp + i)) : make_float4(0.f, 0.f, 0.f, 0.f);
                         x[2 * i] = make_float2(v.x, v.y);
                         x[2 * i + 1] = make_float2(v.z, v.w);
                     }
@@ -534,7 +569,7 @@ _Pragma(K3_STR(unroll K3_VFO_UNROLL))
                     const long long adv = ((long long)t * K3_OUT1) >> cp_shift;      // out1 index 64 t -> index of the VFO's own output
                     for (int s = 0; s < nsw && sbase + s < p.stream_end; ++s) {
                         const float4 v = *reinterpret_cast<const float4 *>(rbuf + s * nv * K3_ROW + cp_src);
-                        *reinterpret_cast<float4 *>(cp_dst + (size_t)s * (size_t)p.out_stride + adv) = v;
+                        k3_store_global16(cp_dst + (size_t)s * (size_t)p.out_stride + adv, v);
                     }
                 }
             } else {
@@ -542,13 +577,27 @@ _Pragma(K3_STR(unroll K3_VFO_UNROLL))
                 sdst[lane] = outB + (((long long)t * K3_OUT1) >> (SB - 1));
                 env.sync();
                 // cooperative, coalesced copy: slot -> (VFO, 16-byte chunk); chunks of a row are consecutive slots
+                // Four slots per lane and trip, in three phases (slot table, then chunk + destination, then the stores): the chain
+                // slot -> row -> chunk -> store is three dependent shared loads long, and with one slot per trip it was a fifth of the
+                // 2-stage kernel's time (profiles/r02_experiments.md section 1). The stores are st.global: a generic store would keep the
+                // compiler from moving the next shared loads above it.
                 for (int s = 0; s < nsw; ++s) {
                     if (sbase + s >= p.stream_end) break;
-                    for (int slot = lane; slot < n_slots; slot += 32) {
-                        const unsigned e = stab[slot];
-                        const int r = s * nv + (int)(e >> 8), ch = (int)(e & 0xffu);
-                        const float4 v = *reinterpret_cast<const float4 *>(rbuf + r * K3_ROW + 2 * ch);
-                        *reinterpret_cast<float4 *>(sdst[r] + 2 * ch) = v;
+                    for (int slot0 = lane; slot0 < n_slots; slot0 += 128) {
+                        int e[4];
+                        float4 v[4];
+                        float2 *d[4];
+#pragma unroll
+                        for (int u = 0; u < 4; ++u) e[u] = slot0 + 32 * u < n_slots ? (int)stab[slot0 + 32 * u] : -1;
+#pragma unroll
+                        for (int u = 0; u < 4; ++u) {
+                            const int r = s * nv + (e[u] >= 0 ? (e[u] >> 8) : 0), ch = e[u] >= 0 ? (e[u] & 0xff) : 0;
+                            v[u] = *reinterpret_cast<const float4 *>(rbuf + r * K3_ROW + 2 * ch);
+                            d[u] = sdst[r] + 2 * ch;
+                        }
+#pragma unroll
+                        for (int u = 0; u < 4; ++u)
+                            if (e[u] >= 0) k3_store_global16(d[u], v[u]);
                     }
                 }
             }
