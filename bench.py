@@ -308,7 +308,8 @@ def canary_check(B, plan, local_rank):
     if not os.path.exists(gold):
         return None, "no golden file for this plan"
     g = np.load(gold)
-    iq = synth.make_iq(plan.fs, plan.block, synth.carriers_for_plan(plan.center, plan.subs), stream=0)
+    level = 0.5 if any(s["late"] for s in plan.subs) else 1.0          # as tools/make_golden.py (the /late plans clip at full level)
+    iq = synth.make_iq(plan.fs, plan.block, synth.carriers_for_plan(plan.center, plan.subs), level=level, stream=0)
     if not np.array_equal(np.frombuffer(hashlib.sha256(iq.tobytes()).digest(), np.uint8), g["input_sha256"]):
         return None, "synthetic input differs from the golden file's"
     bank = B.Bank(plan, 1, 1, device=local_rank)
@@ -566,6 +567,11 @@ def extra_plan(B, torch, shard, name, S, NB, dev, local_rank, peak, fp32_peak, b
         out["spectrum_feed_ms_per_step"] = spec_ms
         out["spectrum_feeds_per_step"] = "%d displays x (%d sub-VFO feeds + 1 Main feed)" % (S, NB)
     R.bank.close()
+    # the same parity check as the headline plan's: one callback of a fresh receiver against the unmodified reference's int16
+    lsb, what = canary_check(B, plan, local_rank)
+    out["parity_ok"] = lsb is not None and lsb <= 1
+    out["canary_max_lsb_vs_reference"] = lsb
+    out["parity_what"] = what
     return out
 
 

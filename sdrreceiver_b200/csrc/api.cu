@@ -273,6 +273,7 @@ struct sdrb_bank {
     std::vector<SubGroup> groups;
     int n_late = 0, n_usb = 0, n_carry = 0;
     int max_usb_samples = 0, max_late_samples = 0;
+    int late_taps_per_phase = 0;    // taps per polyphase branch if all late VFOs share it (10 or 13 select a compile-time instantiation), else -1
     int late_factor = 0;            // the plan's /late factor if all late VFOs share it and their taps fit k2_late_v2, else -1
     int uv_np_max = 0, uv_eo_rows = 0, uv_warp_floats = 0, uv_tiles = 0;   // k2b_v2 launch geometry
     std::vector<unsigned short> uv_vfo_tiles;                              // tiles per callback of each USB VFO
@@ -468,7 +469,10 @@ extern "C" int sdrb_bank_create(const sdrb_plan *plan, int device, int n_streams
         if (s.late > 0) {
             const int lf = ((int)s.dec_taps.size() <= s.late * LV_AMAX) ? s.late : -1;
             b->late_factor = (b->late_factor == 0 || b->late_factor == lf) ? lf : -1;
+            const int tpp = ((int)s.dec_taps.size() + s.late - 1) / s.late;
+            b->late_taps_per_phase = (b->late_taps_per_phase == 0 || b->late_taps_per_phase == tpp) ? tpp : -1;
         }
+    if (const char *e = getenv("SDRB_LATE_GENERIC")) { if (atoi(e) != 0) b->late_taps_per_phase = -1; }
     {
         const char *ef = getenv("SDRB_FUSE_LATE");
         const bool want = !(ef && atoi(ef) == 0) && (b->late_factor == 5 || b->late_factor == 6);
@@ -667,8 +671,10 @@ extern "C" int sdrb_bank_create(const sdrb_plan *plan, int device, int n_streams
     if (const char *e = getenv("SDRB_DCW_RING")) b->dcw_ring = atoi(e) == 4 ? 4 : 2;
     if (const char *e = getenv("SDRB_DCW_BULK")) b->dcw_bulk = atoi(e) != 0;
     if (const char *e = getenv("SDRB_DC_RUN")) b->dc_run = atoi(e) >= 4 ? 4 : (atoi(e) >= 2 ? 2 : 1);
-    BANK_CU(cudaFuncSetAttribute(k2_late_v2<5>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)lv_smem<5>()));
-    BANK_CU(cudaFuncSetAttribute(k2_late_v2<6>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)lv_smem<6>()));
+    BANK_CU((cudaFuncSetAttribute(k2_late_v2<5, 0>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)lv_smem<5>())));
+    BANK_CU((cudaFuncSetAttribute(k2_late_v2<6, 0>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)lv_smem<6>())));
+    BANK_CU((cudaFuncSetAttribute(k2_late_v2<5, 10>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)lv_smem<5>())));
+    BANK_CU((cudaFuncSetAttribute(k2_late_v2<6, 13>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)lv_smem<6>())));
     BANK_CU(cudaFuncSetAttribute(k2a_v2<64>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)V2L<64>::SMEM));
     BANK_CU(cudaFuncSetAttribute(k2a_v2<96>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)V2L<96>::SMEM));
     BANK_CU(cudaFuncSetAttribute(k2a_v2<128>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)V2L<128>::SMEM));
@@ -932,8 +938,12 @@ static int enqueue_audio(sdrb_bank *b, const CallCtx &c, int s0, int ns, cudaStr
         TimedScope t(b, st, 3);
         if (b->late_factor == 5 || b->late_factor == 6) {           // every late VFO of the plan divides by the same 5 or 6
             const dim3 grid((unsigned)ns, (unsigned)b->n_late, (unsigned)((ncb * b->max_late_samples + LV_TILE - 1) / LV_TILE));
-            if (b->late_factor == 5) k2_late_v2<5><<<grid, LV_THREADS, lv_smem<5>(), st>>>((const LateDev *)b->latedev.p, cb0, ncb, s0);
-            else k2_late_v2<6><<<grid, LV_THREADS, lv_smem<6>(), st>>>((const LateDev *)b->latedev.p, cb0, ncb, s0);
+            // late_taps_per_phase: the reference's 49-tap /5 and 73-tap /6 filters get their tap loops at compile time
+            const LateDev *ld = (const LateDev *)b->latedev.p;
+            if (b->late_factor == 5 && b->late_taps_per_phase == 10) k2_late_v2<5, 10><<<grid, LV_THREADS, lv_smem<5>(), st>>>(ld, cb0, ncb, s0);
+            else if (b->late_factor == 5) k2_late_v2<5, 0><<<grid, LV_THREADS, lv_smem<5>(), st>>>(ld, cb0, ncb, s0);
+            else if (b->late_taps_per_phase == 13) k2_late_v2<6, 13><<<grid, LV_THREADS, lv_smem<6>(), st>>>(ld, cb0, ncb, s0);
+            else k2_late_v2<6, 0><<<grid, LV_THREADS, lv_smem<6>(), st>>>(ld, cb0, ncb, s0);
         } else {
             const int tiles = (ncb * b->max_late_samples + LATE_TILE - 1) / LATE_TILE;
             k2_late_fir<<<dim3((unsigned)ns, (unsigned)b->n_late, (unsigned)tiles), LATE_TILE, 0, st>>>(

@@ -854,7 +854,9 @@ template <int L> constexpr size_t lv_smem() {
     return (size_t)(lv_span<L>() + lv_span<L>() / (L * LV_R) + 2) * sizeof(float2) + (size_t)L * LV_AMAX * sizeof(float2);
 }
 
-template <int L>
+// AT: taps per phase at compile time (10 for the reference's 49 taps / 5, 13 for 73 / 6) when every late VFO of the plan has that
+// many; 0 = read from the descriptor (the FIR loops are then predicated per tap: a third more instructions)
+template <int L, int AT>
 __global__ void __launch_bounds__(LV_THREADS, 4) k2_late_v2(const LateDev *__restrict__ devs, int cb0, int ncb, int stream0) {
     extern __shared__ __align__(16) unsigned char lv_raw[];
     constexpr int SEG = L * LV_R;                           // samples per thread segment
@@ -868,7 +870,7 @@ __global__ void __launch_bounds__(LV_THREADS, 4) k2_late_v2(const LateDev *__res
     const int stream = stream0 + blockIdx.x;
     const int t = threadIdx.x;
     const int N = D.ntaps;
-    const int A = (N + L - 1) / L;                          // taps per phase (10 for 49/5, 13 for 73/6)
+    const int A = AT > 0 ? AT : (N + L - 1) / L;            // taps per phase (10 for 49/5, 13 for 73/6)
     const int span = L * LV_TILE + L * A;
     const long long zlo = (long long)L * m0 - N;            // may be negative: history
     const long long zmax = (long long)(cb0 + ncb) * D.block_z;
@@ -884,20 +886,37 @@ __global__ void __launch_bounds__(LV_THREADS, 4) k2_late_v2(const LateDev *__res
         // for stream sample 0 (oscillator.cpp:26-30,42-48). History in front of the call (zi < 0) is the parent's own history.
         const int len = D.lut_len;
         const long long n0 = D.blocks_done[stream] * (long long)D.block_z;
-        int k = (int)(((n0 + zlo + t) % len + len) % len);
-        const int kstep = LV_THREADS % len;
-#pragma unroll 4
-        for (int e = t; e < span; e += LV_THREADS) {
-            const long long zi = zlo + e;
-            float2 v = make_float2(0.f, 0.f);
-            if (zi < zmax) {
-                const float2 x = __ldg(zp + zi);
-                const float2 r = __ldg(D.mix_lut + ((n0 + zi == 0) ? len - 1 : k));
-                v = cmul(r, x);
+        const long long first = n0 + zlo;                    // stream sample of element 0 of the tile
+        if (first > 0 && zlo + span <= zmax && span < len) {
+            // the usual tile: every element exists, stream sample 0 is not in it, the table wraps at most once. Per element two
+            // 8-byte loads, one compare-and-subtract for the wrap and a complex product as two packed operations -- the staging
+            // loop used to cost more instructions than the FIR behind it (16 per element against 13 per element for /5, 49 taps)
+            const int k0 = (int)(first % len);
+            const float2 *__restrict__ xp = zp + zlo;
+            const float2 *__restrict__ lut = D.mix_lut;
+#pragma unroll 8
+            for (int e = t; e < span; e += LV_THREADS) {
+                int k = k0 + e;
+                if (k >= len) k -= len;
+                const float2 x = __ldg(xp + e), r = __ldg(lut + k);
+                sz[e + e / SEG] = fma2(make_float2(-x.y, x.x), make_float2(r.y, r.y), mul2(x, make_float2(r.x, r.x)));
             }
-            sz[e + e / SEG] = v;
-            k += kstep;
-            if (k >= len) k -= len;
+        } else {
+            int k = (int)(((first + t) % len + len) % len);
+            const int kstep = LV_THREADS % len;
+#pragma unroll 4
+            for (int e = t; e < span; e += LV_THREADS) {
+                const long long zi = zlo + e;
+                float2 v = make_float2(0.f, 0.f);
+                if (zi < zmax) {
+                    const float2 x = __ldg(zp + zi);
+                    const float2 r = __ldg(D.mix_lut + ((n0 + zi == 0) ? len - 1 : k));
+                    v = fma2(make_float2(-x.y, x.x), make_float2(r.y, r.y), mul2(x, make_float2(r.x, r.x)));
+                }
+                sz[e + e / SEG] = v;
+                k += kstep;
+                if (k >= len) k -= len;
+            }
         }
     }
     for (int e = t; e < L * LV_AMAX; e += LV_THREADS) {
@@ -913,13 +932,14 @@ __global__ void __launch_bounds__(LV_THREADS, 4) k2_late_v2(const LateDev *__res
     const float2 *base = sz + t * (SEG + 1);                // logical sample L*(t*R) of the tile
 #pragma unroll 1
     for (int r = 0; r < L; ++r) {
-        float2 w[LV_R + LV_AMAX - 1];
+        constexpr int AU = AT > 0 ? AT : LV_AMAX;             // unrolled extent
+        float2 w[LV_R + AU - 1];
 #pragma unroll
-        for (int j = 0; j < LV_R + LV_AMAX - 1; ++j)
-            if (j < LV_R + A - 1) w[j] = base[L * j + r + j / LV_R];          // + one pad per segment crossed
+        for (int j = 0; j < LV_R + AU - 1; ++j)
+            if (AT > 0 || j < LV_R + A - 1) w[j] = base[L * j + r + j / LV_R];          // + one pad per segment crossed
 #pragma unroll
-        for (int a = 0; a < LV_AMAX; ++a) {
-            if (a < A) {
+        for (int a = 0; a < AU; ++a) {
+            if (AT > 0 || a < A) {
                 const float2 c2 = sc[L * a + r];
 #pragma unroll
                 for (int k = 0; k < LV_R; ++k) acc[k] = fma2(c2, w[k + a], acc[k]);

@@ -71,3 +71,18 @@ def test_plan_digests(name):
         assert hashlib.sha256(orc.pcm(k).tobytes()).hexdigest() == dig["pcm_sha256"][s["topic"]], s["topic"]
         assert dig["frames"][k] == [s["topic"][:5], s["out_rate"], 2 * s["samples_out"], 3]
     orc.close()
+
+
+@pytest.mark.parametrize("name", ["25E", "54W_288K", "54W_all", "CBAND_143E"])
+def test_bench_canaries(name):
+    """tests/golden/canary_<plan>_1block.npz -- what bench.py's parity verdict compares the GPU with (first callback of a reset
+    receiver, int16 of the unmodified reference): the restatement reproduces them bit for bit from the same synthetic input."""
+    g = np.load(os.path.join(GOLD, "canary_%s_1block.npz" % name))
+    op = OP.build_plan(plan_path(name))
+    iq = synth.make_iq(op["Fs"], op["block"], synth.carriers_for_plan(op["center"], op["subs"]), level=level_for(op), stream=0)
+    assert np.array_equal(np.frombuffer(hashlib.sha256(iq.tobytes()).digest(), np.uint8), g["input_sha256"])
+    orc = O.Oracle(op)
+    orc.process(iq)
+    for k, s in enumerate(op["subs"]):
+        assert np.array_equal(orc.pcm(k), g["pcm_" + s["topic"]]), s["topic"]
+    orc.close()

@@ -340,7 +340,9 @@ def test_dc_state_is_bit_identical(dc, sigma, n_blocks, splits):
 @pytest.mark.gpu
 @pytest.mark.parametrize("k1_threads,k2a_threads,extra", [(128, 64, {}), (96, 96, {"SDRB_K2A_V3": "0"}), (64, 128, {"SDRB_K1_BULK": "0"}),
                                                           (64, 64, {"SDRB_K2A_V3": "0", "SDRB_FUSE_LATE": "0", "SDRB_PER_CB": "1"}),
-                                                          (64, 64, {"SDRB_K3_REGS": "168", "SDRB_K3_CTA_WARPS": "4", "SDRB_DCW_RING": "4"})])
+                                                          (64, 64, {"SDRB_K3_REGS": "168", "SDRB_K3_CTA_WARPS": "4", "SDRB_DCW_RING": "4"}),
+                                                          (64, 64, {"SDRB_LATE_GENERIC": "1", "SDRB_DC_RUN": "1", "SDRB_DCW_BULK": "1",
+                                                                    "SDRB_K3_CTA_WARPS2": "3", "SDRB_K3_WAVES": "3"})])
 def test_every_cta_size_of_the_cascade_kernels(k1_threads, k2a_threads, extra):
     """k1_v2 / k2a_v2 exist for 64-, 96- and 128-thread CTAs and the host picks one per launch
     (api.cu: v2_pick_threads). SDRB_K1_THREADS / SDRB_K2A_THREADS force a size: every instantiation

@@ -30,6 +30,15 @@ def plan_input(name, n_blocks):
     return op, synth.make_iq(op["Fs"], op["block"] * n_blocks, synth.carriers_for_plan(op["center"], op["subs"]), level=level)
 
 
+def write_canaries(names=("25E", "54W_288K", "54W_all", "CBAND_143E")):
+    for name in names:
+        op, iq = plan_input(name, 1)
+        outs, _, _ = O.run_ref(os.path.join(ROOT, "plans", name + ".ini"), iq)
+        np.savez_compressed(os.path.join(GOLD, "canary_%s_1block.npz" % name),
+                            input_sha256=np.frombuffer(hashlib.sha256(iq.tobytes()).digest(), np.uint8),
+                            **{"pcm_" + k: v for k, v in outs.items()})
+
+
 def main():
     assert O.have_ref(), "build oracle/_ref first (make -C oracle)"
     os.makedirs(GOLD, exist_ok=True)
@@ -85,11 +94,8 @@ def main():
             "tap_l2": {k: float(np.linalg.norm(v.astype(np.float64))) for k, v in taps.items()},
             "pcm_head": {k: v[:8].tolist() for k, v in outs.items()},
         }
-    # ---- the bench's canary: first callback of stream 0 of the 25E plan from a reset receiver, full int16 ----
-    op, iq = plan_input("25E", 1)
-    outs, _, _ = O.run_ref(os.path.join(ROOT, "plans", "25E.ini"), iq)
-    np.savez_compressed(os.path.join(GOLD, "canary_25E_1block.npz"), input_sha256=np.frombuffer(hashlib.sha256(iq.tobytes()).digest(), np.uint8),
-                        **{"pcm_" + k: v for k, v in outs.items()})
+    # ---- the bench's canaries: first callback of stream 0 of a plan from a reset receiver, full int16 (bench.py canary_check) ----
+    write_canaries()
     with open(os.path.join(GOLD, "plan_digests.json"), "w") as f:
         json.dump(dig, f, indent=1, sort_keys=True)
     print("golden written to", GOLD)
