@@ -393,6 +393,8 @@ def b200_arm(args):
     if not args.no_e2e and not args.no_zmq:
         try:
             n_sock = max(1, min(8, (os.cpu_count() or 8) // max(1, 2 * args.gpus)))
+            if os.environ.get("SDRB_BENCH_SOCKETS"):
+                n_sock = max(1, int(os.environ["SDRB_BENCH_SOCKETS"]))
             zmq_leg = publish_leg(B, plan, bank, host_bufs, row, S, NB, rank, args, n_sock)
             if n_sock > 1:                    # the reference's shape beside it: one socket, one sender thread
                 one = publish_leg(B, plan, bank, host_bufs, row, S, NB, rank, args, 1)

@@ -67,14 +67,14 @@ bool load_zmq() {
 // libzmq 4.x constants (zmq.h)
 constexpr int kPUB = 1, kSNDMORE = 2, kRECONNECT_IVL = 18, kRECONNECT_IVL_MAX = 21;
 constexpr int kKEEPALIVE = 34, kKEEPALIVE_CNT = 35, kKEEPALIVE_IDLE = 36, kKEEPALIVE_INTVL = 37, kLINGER = 17, kSNDHWM = 23;
-int g_pool_sndhwm = 0;                                           // > 0 while sdrb_publisher_pool_open creates its sockets
 }  // namespace
 
 struct sdrb_publisher {
     void *ctx = nullptr, *sock = nullptr;
 };
 
-extern "C" int sdrb_publisher_open(const char *address, int bind, sdrb_publisher **out) {
+// default_sndhwm: 0 = leave libzmq's default (what the reference does), > 0 = the pool's mark
+static int publisher_open(const char *address, int bind, int default_sndhwm, sdrb_publisher **out) {
     if (!address || !out) { sdrb::set_error("sdrb_publisher_open: NULL argument"); return SDRB_E_INVALID; }
     *out = nullptr;
     if (!load_zmq()) return SDRB_E_ZMQ;
@@ -100,7 +100,7 @@ extern "C" int sdrb_publisher_open(const char *address, int bind, sdrb_publisher
     // messages per callback. A pool socket carries the callbacks of a whole call for its share of the receivers in one burst
     // (1728 messages for 25E, 128 receivers, 4 callbacks, 8 sockets): everything past the mark would be dropped before the I/O
     // thread has had a chance to write it. SDRB_ZMQ_SNDHWM overrides both (0 = no limit).
-    int sndhwm = g_pool_sndhwm;
+    int sndhwm = default_sndhwm;
     if (const char *e = getenv("SDRB_ZMQ_SNDHWM")) sndhwm = atoi(e);
     if (sndhwm > 0 || getenv("SDRB_ZMQ_SNDHWM")) g_zmq.setsockopt(p->sock, kSNDHWM, &sndhwm, sizeof(int));
     const int rc = bind ? g_zmq.bind(p->sock, address) : g_zmq.connect(p->sock, address);
@@ -115,6 +115,8 @@ extern "C" int sdrb_publisher_open(const char *address, int bind, sdrb_publisher
     *out = p;
     return SDRB_OK;
 }
+
+extern "C" int sdrb_publisher_open(const char *address, int bind, sdrb_publisher **out) { return publisher_open(address, bind, 0, out); }
 
 extern "C" int sdrb_publisher_send(sdrb_publisher *p, const char *topic, uint32_t rate, const void *payload, uint32_t len) {
     if (!p || !topic || (!payload && len)) { sdrb::set_error("sdrb_publisher_send: NULL argument"); return SDRB_E_INVALID; }
@@ -214,20 +216,17 @@ extern "C" int sdrb_publisher_pool_open(const char *address, int bind, int n_soc
     if (!address || !out || n_sockets < 1 || n_sockets > 256) { sdrb::set_error("sdrb_publisher_pool_open: bad argument"); return SDRB_E_INVALID; }
     *out = nullptr;
     sdrb_publisher_pool *pool = new sdrb_publisher_pool();
-    g_pool_sndhwm = 65536;
     for (int k = 0; k < n_sockets; ++k) {
         pool->addrs.push_back(n_sockets == 1 ? std::string(address) : pool_address(address, k));
         sdrb_publisher *p = nullptr;
-        const int rc = sdrb_publisher_open(pool->addrs.back().c_str(), bind, &p);
+        const int rc = publisher_open(pool->addrs.back().c_str(), bind, 65536, &p);
         if (rc != SDRB_OK) {
             for (sdrb_publisher *q : pool->pubs) sdrb_publisher_close(q);
             delete pool;
-            g_pool_sndhwm = 0;
             return rc;
         }
         pool->pubs.push_back(p);
     }
-    g_pool_sndhwm = 0;
     for (int k = 0; k < n_sockets; ++k) pool->workers.emplace_back(pool_worker, pool, k);
     *out = pool;
     return SDRB_OK;
