@@ -56,12 +56,6 @@ constexpr int K3_XS = K3_TILE + 16;     // staged input samples per stream and t
 #ifndef K3_PIPE
 #define K3_PIPE 1            /* 1: rotation-table pair and anchors of VFO v+1 are read while VFO v is computed */
 #endif
-// K3_XPF: how the coming tile's input reaches the SM ahead of time (no staged input): 0 = prefetch.global.L1 of its lines one tile
-// ahead; 1 = real 16-byte loads of those lines into a scratch register (a prefetch instruction may stop at L2); 2 = 0 + the first
-// stream's loads of a tile issued at the very top of the tile, above the warp barrier and the bookkeeping
-#ifndef K3_XPF
-#define K3_XPF 0
-#endif
 #ifndef K3_PACKED_CMUL
 #define K3_PACKED_CMUL 1
 #endif
@@ -240,16 +234,6 @@ K3_HD void k3_prefetch_l1(const void *p) {
 #endif
 }
 
-// a 16-byte load whose value nobody uses: brings the line into L1 like a real load does
-K3_HD void k3_touch16(const void *p) {
-#ifdef __CUDA_ARCH__
-    float a, b, c, d;
-    asm volatile("ld.global.nc.v4.f32 {%0, %1, %2, %3}, [%4];" : "=f"(a), "=f"(b), "=f"(c), "=f"(d) : "l"(p));
-#else
-    (void)p;
-#endif
-}
-
 // One warp's work: streams sbase .. sbase+nsw-1, tiles of span `span` of callback b.
 //   ring    32 rows of K3_ROW float2, private to the warp
 //   sdst    32 pointers, private to the warp
@@ -338,13 +322,6 @@ K3_HD void k3_unit(Env &env, const K3Params &p, int sg, int span, int b, float2 
         const int ti = t - (t_begin - K3_WARM);              // tile counter of this unit
         float2 *rbuf = ring + (ROLE == 0 ? 0 : (ti & 1) * ring_buf);
         const float2 *sFt = sF + 32 * fpar;                  // this tile's anchors
-        // K3_XPF == 2: the first stream's samples of this tile, requested before anything else of the tile
-        float4 xa0[7];
-        if (K3_XPF == 2 && !XS && ROLE != 2) {
-            const float4 *xp = reinterpret_cast<const float4 *>(in_ln + c0 - 10);
-#pragma unroll
-            for (int i = 0; i < 7; ++i) xa0[i] = sbase < p.stream_end ? k3_ldg(xp + i) : make_float4(0.f, 0.f, 0.f, 0.f);   // the address role A reads anyway
-        }
         if (ROLE != 2) {
         k3_async_wait();
         if (XS) {
@@ -354,12 +331,12 @@ K3_HD void k3_unit(Env &env, const K3Params &p, int sg, int span, int b, float2 
         env.sync();
         fpar ^= 1;
         k3_async_copy8(sF + 32 * fpar + lane, lutB + wrapL(kbB + c0 + K3_TILE));
-        if (!XS && t + 1 < t_end && lane < 10) {             // the coming tile's lines into L1 (10 x 128 bytes cover 128 + 14 samples)
+        // The coming tile's lines into L1 (10 x 128 bytes cover 128 + 14 samples). Measured and not kept (profiles/r02_experiments.md
+        // section 1): a request per 32-byte sector, real "touch" loads instead of the prefetch instruction, the first stream's loads
+        // hoisted above the barrier, staged input -- none of them moves the kernel's time.
+        if (!XS && t + 1 < t_end && lane < 10) {
             const float2 *pf = in_pf + c0;
-            for (int s = 0; s < n_str; ++s, pf += p.in_stride) {
-                if (K3_XPF == 1) k3_touch16(pf);
-                else k3_prefetch_l1(pf);
-            }
+            for (int s = 0; s < n_str; ++s, pf += p.in_stride) k3_prefetch_l1(pf);
         }
         if (ROLE == 1 && ti >= 2) env.wait_empty(ti & 1);    // the consumer is done with the tile that used this buffer
         // =============================== role A ===============================
@@ -385,8 +362,7 @@ K3_HD void k3_unit(Env &env, const K3Params &p, int sg, int span, int b, float2 
                     const bool has = q ? hasB : hasA;
 #pragma unroll
                     for (int i = 0; i < 7; ++i) {
-                        const float4 v = (K3_XPF == 2 && !XS && q == 0 && s0 == 0) ? xa0[i]
-                                                                                    : has ? (XS ? xp[i] : k3_ldg(xp + i)) : make_float4(0.f, 0.f, 0.f, 0.f);
+                        const float4 v = has ? (XS ? xp[i] : k3_ldg(xp + i)) : make_float4(0.f, 0.f, 0.f, 0.f);
                         x[2 * i] = make_float2(v.x, v.y);
                         x[2 * i + 1] = make_float2(v.z, v.w);
                     }
