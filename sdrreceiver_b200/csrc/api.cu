@@ -609,6 +609,7 @@ extern "C" int sdrb_bank_create(const sdrb_plan *plan, int device, int n_streams
         kp.count = g.count; kp.lut_len = g.lut_len; kp.block_in = g.block_in; kp.HT = g.halo;
     }
     // k2a_v3 parameter blocks: folded taps and rotation tables per sub VFO (kernels_v3.cuh)
+    static_assert(K3_MAX_VFO >= V2_MAX_VFO, "a sub-VFO group (at most V2_MAX_VFO) must fit K3Params::v");
     {
         const char *ev3 = getenv("SDRB_K2A_V3");
         const bool want_v3 = !(ev3 && atoi(ev3) == 0);
