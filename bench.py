@@ -304,7 +304,7 @@ def canary_check(B, plan, local_rank):
     tests/golden/canary_25E_1block.npz (int16 of the unmodified reference, tools/make_golden.py): +-1 LSB."""
     import hashlib
     from sdrreceiver_b200 import synth
-    gold = os.path.join(ROOT, "tests", "golden", "canary_%s_1block.npz" % os.path.basename(plan.path).replace(".ini", ""))
+    gold = os.path.join(ROOT, "tests", "golden", "canary_%s_1block.npz" % os.path.basename(plan.path or "").replace(".ini", ""))
     if not os.path.exists(gold):
         return None, "no golden file for this plan"
     g = np.load(gold)
@@ -336,7 +336,6 @@ def b200_arm(args):
     numa = bind_to_gpu_cpus(local_rank)          # before the pinned buffers are allocated (first touch)
     plan_path = os.path.join(ROOT, "plans", args.plan + ".ini")
     plan = B.Plan(plan_path)
-    plan.path = plan_path
     S, NB, Bk = args.streams, args.blocks, plan.block
 
     def barrier():

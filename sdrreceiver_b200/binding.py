@@ -174,6 +174,7 @@ class Plan:
         else:
             _check(L.sdrb_plan_create(C.byref(desc), C.byref(h)), "sdrb_plan_create")
         self.h = h
+        self.path = None if ini_path is None else os.fspath(ini_path)      # the ini this plan came from (None: built from a descriptor)
         info = PlanInfo()
         _check(L.sdrb_plan_get_info(h, C.byref(info)), "sdrb_plan_get_info")
         self.info = info

@@ -393,3 +393,27 @@ def test_bench_line_on_the_gpu():
     assert set(d["plans"]) == {"54W_288K", "54W_all", "CBAND_143E"} and all(v.get("value", 0) > 0 for v in d["plans"].values())
     assert d["plans"]["CBAND_143E"]["spectrum_feed_ms_per_step"] > 0
     assert d["e2e_zmq"]["value"] > 0 and d["e2e_zmq"]["messages_received"] > 0
+
+
+@pytest.mark.gpu
+def test_twenty_sub_vfos_on_one_main_vfo(tmp_path):
+    """A plan the sample inis do not contain: 20 sub VFOs on ONE main VFO (the sub-VFO kernels take at most 16 per launch, so the
+    parent's subs are split into a group of 16 and a group of 4, whose warps then own 8 streams each) with 5-, 4-, 3- and 2-stage
+    cascades side by side, plus a second main VFO with a single sub. 3 ragged streams, 6 callbacks in two calls, DC removal on."""
+    lines = ["sample_rate=1536000", "center_frequency=1545600000", "zmq_address=tcp://*:6003", "correct_dc_bias=1", "mix_offset=0", "",
+             "[main_vfos]", "size=2", "1\\frequency=1545116000", "1\\out_rate=384000", "2\\frequency=1546096000", "2\\out_rate=192000", "",
+             "[vfos]", "size=21"]
+    rates = [600, 600, 1200, 600, 10500, 1200, 600, 600, 8400, 600, 1200, 600, 600, 10500, 600, 600, 1200, 600, 8400, 600]
+    for k, dr in enumerate(rates):
+        f = 1545116000 - 150000 + 15000 * k + 137 * k
+        lines += ["%d\\frequency=%d" % (k + 1, f), "%d\\gain=5" % (k + 1), "%d\\data_rate=%d" % (k + 1, dr), "%d\\topic=V%02d" % (k + 1, k + 1)]
+    lines += ["21\\frequency=1546096000", "21\\gain=3", "21\\data_rate=10500", "21\\topic=V21"]
+    ini = tmp_path / "many.ini"
+    ini.write_text("\n".join(lines) + "\n")
+    op = OP.build_plan(str(ini)); plan = B.Plan(str(ini))
+    assert sum(1 for s in op["subs"] if s["main"] == 0) == 20 and {s["decim"] for s in op["subs"]} == {2, 3, 4, 5}
+    n_streams = 3
+    iqs = np.stack([make_input(op, 6, stream=s) for s in range(n_streams)])
+    pcm, tap, _ = run_gpu(plan, iqs, [4, 2])
+    for s in range(n_streams):
+        check_against_oracle(plan, op, iqs[s], pcm[s], tap[s], None)
