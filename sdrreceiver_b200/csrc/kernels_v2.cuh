@@ -856,8 +856,11 @@ template <int L> constexpr size_t lv_smem() {
 
 // AT: taps per phase at compile time (10 for the reference's 49 taps / 5, 13 for 73 / 6) when every late VFO of the plan has that
 // many; 0 = read from the descriptor (the FIR loops are then predicated per tap: a third more instructions)
+#ifndef LV_MINB
+#define LV_MINB 4
+#endif
 template <int L, int AT>
-__global__ void __launch_bounds__(LV_THREADS, 4) k2_late_v2(const LateDev *__restrict__ devs, int cb0, int ncb, int stream0) {
+__global__ void __launch_bounds__(LV_THREADS, LV_MINB) k2_late_v2(const LateDev *__restrict__ devs, int cb0, int ncb, int stream0) {
     extern __shared__ __align__(16) unsigned char lv_raw[];
     constexpr int SEG = L * LV_R;                           // samples per thread segment
     float2 *sz = reinterpret_cast<float2 *>(lv_raw);
@@ -894,12 +897,42 @@ __global__ void __launch_bounds__(LV_THREADS, 4) k2_late_v2(const LateDev *__res
             const int k0 = (int)(first % len);
             const float2 *__restrict__ xp = zp + zlo;
             const float2 *__restrict__ lut = D.mix_lut;
+            if (AT > 0 && k0 + span <= len) {
+                // ... and the table does not wrap inside the tile (all tiles but one per second of signal), tile length known at
+                // compile time: a thread's elements are e = t + 128 i. Both loads then are one base pointer plus an immediate, and
+                // so is the padded destination e + e / SEG: 128 * P is a whole number of segments for P = SEG / gcd(128, SEG)
+                // (5 for /5, 3 for /6), so only the first P destinations are computed, the others are those plus a constant.
+                // Per element: two loads, two packed operations, one store (the address arithmetic used to be 12 integer
+                // instructions per element, profiles/r02_experiments.md section 5).
+                constexpr int SPAN_C = L * LV_TILE + L * AT;
+                constexpr int G = (SEG % 16 == 0) ? 16 : 8;      // gcd(128, SEG) for SEG = 40 (8) and 48 (16)
+                static_assert(SEG % G == 0 && LV_THREADS % G == 0 && (SEG / G) % 2 == 1, "period of the padded layout");
+                constexpr int P = SEG / G;
+                constexpr int ADV = LV_THREADS * P + LV_THREADS * P / SEG;
+                constexpr int NFULL = SPAN_C / LV_THREADS;
+                int dbase[P];
+#pragma unroll
+                for (int u = 0; u < P; ++u) dbase[u] = (t + LV_THREADS * u) + (t + LV_THREADS * u) / SEG;
+                const float2 *__restrict__ xq = xp + t;
+                const float2 *__restrict__ lq = lut + k0 + t;
+#pragma unroll
+                for (int i = 0; i < NFULL; ++i) {
+                    const float2 x = __ldg(xq + LV_THREADS * i), r = __ldg(lq + LV_THREADS * i);
+                    sz[dbase[i % P] + (i / P) * ADV] = fma2(make_float2(-x.y, x.x), make_float2(r.y, r.y), mul2(x, make_float2(r.x, r.x)));
+                }
+                const int e = t + LV_THREADS * NFULL;
+                if (e < SPAN_C) {
+                    const float2 x = __ldg(xp + e), r = __ldg(lut + k0 + e);
+                    sz[e + e / SEG] = fma2(make_float2(-x.y, x.x), make_float2(r.y, r.y), mul2(x, make_float2(r.x, r.x)));
+                }
+            } else {
 #pragma unroll 8
-            for (int e = t; e < span; e += LV_THREADS) {
-                int k = k0 + e;
-                if (k >= len) k -= len;
-                const float2 x = __ldg(xp + e), r = __ldg(lut + k);
-                sz[e + e / SEG] = fma2(make_float2(-x.y, x.x), make_float2(r.y, r.y), mul2(x, make_float2(r.x, r.x)));
+                for (int e = t; e < span; e += LV_THREADS) {
+                    int k = k0 + e;
+                    if (k >= len) k -= len;
+                    const float2 x = __ldg(xp + e), r = __ldg(lut + k);
+                    sz[e + e / SEG] = fma2(make_float2(-x.y, x.x), make_float2(r.y, r.y), mul2(x, make_float2(r.x, r.x)));
+                }
             }
         } else {
             int k = (int)(((first + t) % len + len) % len);
