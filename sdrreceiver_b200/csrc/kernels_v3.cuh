@@ -9,7 +9,8 @@
 //         y = lut[kc] * ( h5 x[c] + sum_{d=1,3,5} h_d cos(wd) (x[c+d] + x[c-d]) + j h_d sin(wd) (x[c+d] - x[c-d]) ),
 //     and the sums and differences do NOT depend on the VFO: they are formed once per tile and stream and
 //     reused by all 12-15 sub VFOs. Per VFO and output: 6 FFMA2 + one complex multiply by the table entry
-//     (instead of 21 complex multiplies + 7 packed operations per 16 outputs and VFO in k2a_v2).
+//     (instead of 21 complex multiplies + 7 packed operations per 16 outputs and VFO in k2a_v2); the complex
+//     multiplies are two packed operations each (k3_cmul).
 //     Taps are doubled (2 h5 = 1: the centre term costs nothing) and the factor 2^-S of the S stages is
 //     folded into the rotation table, which is exact in binary floating point.
 //   B (VFO-parallel, later stages): lane = (stream, VFO) row. The row's 64 first-stage outputs of the tile
@@ -625,7 +626,8 @@ constexpr int K3_WARPS = 2;                                 // default warps per
                                                             // only share the read-only tables)
 
 // grid: x = ceil(stream groups / K3_WARPS), y = spans, z = callbacks
-// RC = register cap: 168 (12 warps per SM, the deep cascades then spill a history array), 200 (10 warps) or 232 (8 warps, no spills)
+// RC = register cap: 168 (three warps per scheduler = 12 per SM, the deep cascades then spill a history array); 200, 232 and 255 all hold two
+// warps per scheduler = 8 per SM (the register file is per scheduler: 16384 registers), without spills
 template <int MAXS, int RC, bool XS>
 __global__ void __maxnreg__(RC) k2a_v3(const __grid_constant__ K3Params p) {
     extern __shared__ __align__(16) unsigned char k3_smem[];
