@@ -692,7 +692,10 @@ __device__ __noinline__ void uv_store_ragged(const float *v, int k0, int tile_ou
     }
 }
 
-__global__ void __launch_bounds__(UV_WARPS * 32, 4) k2b_v2(const __grid_constant__ K2bV2Params p) {
+#ifndef UV_MINB
+#define UV_MINB 4
+#endif
+__global__ void __launch_bounds__(UV_WARPS * 32, UV_MINB) k2b_v2(const __grid_constant__ K2bV2Params p) {
     extern __shared__ __align__(16) float uv_smem[];
     if (blockIdx.z >= p.tiles[blockIdx.y]) return;          // grid.z is the longest VFO's tile count
     const UsbDev &D = p.devs[blockIdx.y];
