@@ -140,9 +140,10 @@ def test_whole_plan_bit_identical(name):
     orc.close()
 
 
-@pytest.mark.parametrize("name,n_blocks", [("25E", 16), ("CBAND_143E", 13)])
+@pytest.mark.parametrize("name,n_blocks", [("25E", 16), ("CBAND_143E", 13), ("54W_all", 9), ("54W_288K", 12)])
 def test_whole_plan_bit_identical_over_seconds(name, n_blocks):
-    """The restatement against the unmodified reference over 4 s (25E) / 3.25 s (CBAND_143E) of signal: every
+    """The restatement against the unmodified reference over 4 s (25E) / 3.25 s (CBAND_143E) / 2.25 s (54W_all) / 2.4 s (54W_288K:
+    five callbacks per second) of signal: every
     Oscillator table wraps three or four times (the tables are one second long), the DC recursion passes its approach
     and sits in the lock-in regime for the last second or more (it starts from zero; lock-in after about 2.3 s at a
     bias of 0.5 LSB), and every half-band stage sees 12-15 callback edges. int16, float tap and both main-VFO taps
