@@ -325,7 +325,10 @@ void sdrb_publisher_close(sdrb_publisher *p);
  * thread caps the publish leg far below the rest of the path. Receiver s is sent on socket s % n_sockets, its callbacks in order,
  * every message in the reference's three-frame format. Socket k's address: "%d" in `address` replaced by k; else a tcp port
  * + k; else ".k" appended (n_sockets == 1: `address` as it is). sdrb_publisher_pool_send_call takes the [n_streams][n_blocks]
- * [pcm_per_block] result of one process_host call and returns when every frame has been handed to libzmq. */
+ * [pcm_per_block] result of one process_host call and returns when every frame has been handed to libzmq; one caller at a time.
+ * Socket options are the reference's (zmqpublisher.cpp:24-37) except the send high-water mark: a pool socket queues a whole call's
+ * burst before its I/O thread has written any of it, so it is 65536 messages instead of libzmq's 1000 per subscriber
+ * (SDRB_ZMQ_SNDHWM overrides it for pool and single publishers alike, 0 = no limit). */
 typedef struct sdrb_publisher_pool sdrb_publisher_pool;
 int sdrb_publisher_pool_open(const char *address, int bind, int n_sockets, sdrb_publisher_pool **out);
 int sdrb_publisher_pool_sockets(const sdrb_publisher_pool *pool);
