@@ -417,3 +417,16 @@ def test_twenty_sub_vfos_on_one_main_vfo(tmp_path):
     pcm, tap, _ = run_gpu(plan, iqs, [4, 2])
     for s in range(n_streams):
         check_against_oracle(plan, op, iqs[s], pcm[s], tap[s], None)
+
+
+@pytest.mark.gpu
+def test_ten_seconds_in_uneven_calls():
+    """40 callbacks (10 s of signal: every Oscillator table wraps ten times, the DC recursion spends seven seconds in its lock-in
+    regime) handed over in calls of 1..4 callbacks in an irregular order -- the span geometry of the sub-VFO kernels, the DC
+    double buffering and every carried tail change from call to call -- against the restatement over the whole run."""
+    op = OP.build_plan(plan_path("25E")); plan = B.Plan(plan_path("25E"))
+    splits = [1, 3, 4, 2, 4, 4, 1, 4, 2, 3, 4, 4, 1, 3]
+    assert sum(splits) == 40
+    iq = make_input(op, 40)
+    pcm, tap, _ = run_gpu(plan, iq[None, :], splits)
+    check_against_oracle(plan, op, iq, pcm[0], tap[0], None)
